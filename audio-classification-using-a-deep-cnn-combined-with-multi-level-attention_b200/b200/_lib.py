@@ -1,0 +1,86 @@
+"""ctypes binding of libvggish_mla_b200.so (include/vggish_mla_b200.h).
+
+The library is the product: if it is missing, or a call fails, we raise — there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvggish_mla_b200.so")
+
+_c_p = C.c_void_p
+_ll = C.c_longlong
+_int = C.c_int
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); mirrors the header one to one.
+SIGNATURES = {
+    "vmb_last_error": (C.c_char_p, []),
+    "vmb_abi_version": (_int, []),
+    "vmb_device_arch": (_int, [_int]),
+    "vmb_num_frames": (_ll, [_ll]),
+    "vmb_num_examples": (_ll, [_ll]),
+    "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
+    "vmb_front_end_tables": (_int, [_c_p, _c_p]),
+    "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
+    "vmb_conv3x3_relu": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _int, _int, _int, _int, _c_p]),
+    "vmb_linear": (_int, [_c_p, _c_p, _c_p, _c_p, _int, _int, _ll, _int, _int, _c_p]),
+    "vmb_postprocess": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
+    "vmb_vggish_create": (_int, [C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p),
+                                 C.POINTER(_c_p), _c_p]),
+    "vmb_vggish_destroy": (None, [_c_p]),
+    "vmb_vggish_workspace_bytes": (_sz, [_ll]),
+    "vmb_vggish_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "vmb_mla_create": (_int, [C.POINTER(_c_p), _int, C.POINTER(_int), _int, _int, _int, _int, _c_p, _ll, _c_p]),
+    "vmb_mla_destroy": (None, [_c_p]),
+    "vmb_mla_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int]),
+    "vmb_mla_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
+    "vmb_pipeline_workspace_bytes": (_sz, [_ll, _ll]),
+    "vmb_pipeline_forward": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
+    "vmb_pipeline_forward_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),
+}
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    """A C-ABI call returned non-zero; the message is vmb_last_error()."""
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                "(there is no CPU fallback for this path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().vmb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise B200Error(f"{what} failed: {last_error()}")
+
+
+def ptr(t) -> int:
+    """data_ptr of a CUDA tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

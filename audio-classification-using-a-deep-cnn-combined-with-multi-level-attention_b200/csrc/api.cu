@@ -1,0 +1,120 @@
+// extern "C" boundary (include/vggish_mla_b200.h): argument checks, error strings, dispatch into the kernels.
+#include "../../include/vggish_mla_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+
+namespace {
+thread_local char g_api_err[768] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_api_err, sizeof g_api_err, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+int fail_from(const char* where, const char* inner) { return fail("%s: %s", where, inner); }
+
+cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+}  // namespace
+
+namespace vmb {
+void set_api_error(const char* msg) { snprintf(g_api_err, sizeof g_api_err, "%s", msg); }
+}  // namespace vmb
+
+extern "C" {
+
+const char* vmb_last_error(void) { return g_api_err; }
+int vmb_abi_version(void) { return 1; }
+
+int vmb_device_arch(int device) {
+  int major = 0, minor = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) {
+    fail("vmb_device_arch: no CUDA device %d (%s)", device, cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  return major * 10 + minor;
+}
+
+long long vmb_num_frames(long long n_samples) {
+  // mel_features.py:42  1 + int(floor((num_samples - window_length) / hop_length)), floor division
+  const long long d = n_samples - 400;
+  long long q = d / 160;
+  if (d % 160 != 0 && d < 0) --q;
+  return 1 + q;
+}
+
+long long vmb_num_examples(long long n_samples) {
+  const long long f = vmb_num_frames(n_samples);
+  if (f < 96) return f < 0 ? -1 : 0;
+  return 1 + (f - 96) / 96;  // vggish_input.py:73-76 via mel_features.py:42 with window = hop = 96
+}
+
+int vmb_logmel(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+               long long frames_out, float* logmel, void* stream) {
+  if (n_clips < 0 || frames_out < 0) return fail("vmb_logmel: negative size");
+  const long long nf = vmb_num_frames(samples_per_clip);
+  if (nf < 1) return fail("vmb_logmel: %lld samples is shorter than one 400-sample window", samples_per_clip);
+  if (frames_out > nf) return fail("vmb_logmel: frames_out %lld > available frames %lld", frames_out, nf);
+  if (clip_stride < samples_per_clip) return fail("vmb_logmel: clip_stride < samples_per_clip");
+  if (n_clips == 0 || frames_out == 0) return 0;
+  if (!wave || !logmel) return fail("vmb_logmel: null pointer");
+  if (vmb::logmel_forward(wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, S(stream)))
+    return fail_from("vmb_logmel", vmb::kernels_last_error());
+  return 0;
+}
+
+int vmb_front_end_tables(double* hann400, double* mel257x64) {
+  vmb::front_end_tables_host(hann400, mel257x64);
+  return 0;
+}
+
+int vmb_conv1_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n, void* stream) {
+  if (n < 0) return fail("vmb_conv1_relu_pool: negative n");
+  if (n == 0) return 0;
+  if (!examples || !w || !b || !out) return fail("vmb_conv1_relu_pool: null pointer");
+  if (vmb::conv1_relu_pool(examples, w, b, out, n, S(stream)))
+    return fail_from("vmb_conv1_relu_pool", vmb::kernels_last_error());
+  return 0;
+}
+
+int vmb_conv3x3_relu(const void* act, const void* w, const float* bias, void* out, long long n, int H, int W, int C_in,
+                     int C_out, int pool, void* stream) {
+  if (n < 0 || n > 0x7fffffffLL / 4096) return fail("vmb_conv3x3_relu: bad n %lld", n);
+  if (n == 0) return 0;
+  if (!act || !w || !bias || !out) return fail("vmb_conv3x3_relu: null pointer");
+  if (pool && ((H | W) & 1)) return fail("vmb_conv3x3_relu: pooling needs even H, W");
+  if (vmb::igemm_conv3x3(act, w, bias, out, int(n), H, W, C_in, C_out, pool, S(stream)))
+    return fail_from("vmb_conv3x3_relu", vmb::igemm_last_error());
+  return 0;
+}
+
+int vmb_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, long long M, int N,
+               int K, void* stream) {
+  if (M < 0 || M > 0x7fffffffLL) return fail("vmb_linear: bad M %lld", M);
+  if (M == 0) return 0;
+  if (!a || !w || !bias || !out) return fail("vmb_linear: null pointer");
+  if (vmb::igemm_linear(a, w, bias, out, out_f32, relu, int(M), N, K, S(stream)))
+    return fail_from("vmb_linear", vmb::igemm_last_error());
+  return 0;
+}
+
+int vmb_postprocess(const float* emb, const float* eigen, const float* means, float* out_f32, uint8_t* out_u8,
+                    long long n, void* stream) {
+  if (n < 0) return fail("vmb_postprocess: negative n");
+  if (n == 0) return 0;
+  if (!emb || !eigen || !means) return fail("vmb_postprocess: null pointer");
+  if (vmb::postprocess(emb, eigen, means, out_f32, out_u8, n, S(stream)))
+    return fail_from("vmb_postprocess", vmb::kernels_last_error());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// tcgen05 implicit-GEMM kernel + host launchers.  See igemm_sm100.cuh for the design notes.
+#include "igemm_sm100.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "sm100_ptx.cuh"
+
+namespace vmb {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                          // 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KiB
+constexpr int kQuarterBytes = 32 * kBlockK * 2;      // one 32-row quarter of A (one TMA box in CONV mode)
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBiasBytes + kBarBytes;
+};
+
+template <int BLOCK_N, bool CONV, bool POOL, bool OUT_F32>
+__global__ void __launch_bounds__(kNumThreads, 1)
+igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const IgemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint8_t* stage_base = smem;
+  float* bias_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kBiasBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        int bx[4], by[4], bn[4];
+        if (CONV) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int g = m_tile * 4 + q;
+            const int n_img = g / p.boxes_per_img;
+            const int r = g - n_img * p.boxes_per_img;
+            const int yy = r / p.boxes_per_row;
+            bn[q] = n_img;
+            by[q] = yy * p.Hb;
+            bx[q] = (r - yy * p.boxes_per_row) * p.Wb;
+          }
+        }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = stage_base + stage * C::kStageBytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (CONV) {
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tma_load_4d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[q] + dw,
+                          by[q] + dh, bn[q]);
+            if (++cb == p.cblks) { cb = 0; ++tap; }
+          } else {
+            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
+          }
+          tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(stage_base + stage * C::kStageBytes);
+          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int ep_tid = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int n0 = n_tile * BLOCK_N;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      float* bias_t = bias_s + acc * BLOCK_N;
+      for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads) bias_t[i] = __ldg(p.bias + n0 + i);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      // Where does this thread's accumulator row go?
+      bool valid;
+      size_t out_off;  // element offset of column n0 for this thread's output row / pooled pixel
+      int sub = 0;
+      if (CONV) {
+        const int g = m_tile * 4 + q;
+        const int n_img = g / p.boxes_per_img;
+        const int r = g - n_img * p.boxes_per_img;
+        const int yy = r / p.boxes_per_row;
+        const int hh = lane / p.Wb, ww = lane - hh * p.Wb;
+        const int h = yy * p.Hb + hh;
+        const int w = (r - yy * p.boxes_per_row) * p.Wb + ww;
+        valid = n_img < p.M;
+        if (POOL) {
+          sub = (ww & 1) | ((hh & 1) << 1);
+          out_off = ((static_cast<size_t>(n_img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.N + n0;
+        } else {
+          out_off = ((static_cast<size_t>(n_img) * p.H + h) * p.W + w) * p.N + n0;
+        }
+      } else {
+        const int row = m_tile * kBlockM + q * 32 + lane;
+        valid = row < p.M;
+        out_off = static_cast<size_t>(row) * p.ldo + n0;
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + ch * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_t + ch * 32 + j);
+          f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (OUT_F32) {
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
+          if (POOL) {
+            // 2x2 window = lanes {l, l^1, l^Wb, l^1^Wb}; max commutes with the monotone bf16 rounding.
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+              pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], p.Wb));
+            }
+            // the four lanes of a window each store a different 8-channel (16 B) slice
+            uint4 o;
+            o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
+            o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
+            o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
+            o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
+            if (valid) *reinterpret_cast<uint4*>(outp + sub * 8) = o;
+          } else if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(outp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+thread_local char g_err[512] = "";
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// rank-`rank` bf16 tensor map, 128-byte swizzle, zero OOB fill.  strides_bytes has rank-1 entries.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d)", int(r), rank);
+    return 1;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool CONV, bool POOL, bool OUT_F32>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
+  auto kern = igemm_bf16_kernel<BLOCK_N, CONV, POOL, OUT_F32>;
+  static bool attr_set = false;
+  constexpr int smem = Cfg<BLOCK_N>::kSmemBytes;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "igemm launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+const char* igemm_last_error() { return g_err; }
+
+int igemm_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, int M, int N,
+                 int K, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBlockK != 0 || N % 128 != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_linear: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
+    return 1;
+  }
+  const int block_n = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
+    uint64_t str[1] = {uint64_t(K) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (make_tmap_bf16(&ta, a, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
+    uint64_t str[1] = {uint64_t(K) * 2};
+    uint32_t box[2] = {kBlockK, uint32_t(block_n)};
+    if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.num_kb = K / kBlockK;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.num_n_tiles = N / block_n;
+  p.relu = relu;
+  p.ldo = N;
+  p.bias = bias;
+  p.out = out;
+  if (block_n == 256)
+    return out_f32 ? launch<256, false, false, true>(ta, tb, p, stream)
+                   : launch<256, false, false, false>(ta, tb, p, stream);
+  return out_f32 ? launch<128, false, false, true>(ta, tb, p, stream)
+                 : launch<128, false, false, false>(ta, tb, p, stream);
+}
+
+int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
+                  int C_out, int pool, cudaStream_t stream) {
+  if (n_img <= 0) return 0;
+  const int Wb = (W % 16 == 0) ? 16 : 8;
+  const int Hb = 32 / Wb;
+  if (C_in % kBlockK != 0 || C_out % 128 != 0 || W % Wb != 0 || H % Hb != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_conv3x3: unsupported geometry H=%d W=%d C_in=%d C_out=%d", H, W, C_in, C_out);
+    return 1;
+  }
+  const int block_n = (C_out % 256 == 0) ? 256 : 128;
+  const int K = 9 * C_in;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {uint64_t(C_in), uint64_t(W), uint64_t(H), uint64_t(n_img)};
+    uint64_t str[3] = {uint64_t(C_in) * 2, uint64_t(W) * C_in * 2, uint64_t(H) * W * C_in * 2};
+    uint32_t box[4] = {kBlockK, uint32_t(Wb), uint32_t(Hb), 1};
+    if (make_tmap_bf16(&ta, act, 4, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(C_out)};
+    uint64_t str[1] = {uint64_t(K) * 2};
+    uint32_t box[2] = {kBlockK, uint32_t(block_n)};
+    if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = n_img;
+  p.N = C_out;
+  p.num_kb = K / kBlockK;
+  p.cblks = C_in / kBlockK;
+  p.H = H;
+  p.W = W;
+  p.Hb = Hb;
+  p.Wb = Wb;
+  p.boxes_per_row = W / Wb;
+  p.boxes_per_img = (H / Hb) * (W / Wb);
+  p.total_boxes = n_img * p.boxes_per_img;
+  p.num_m_tiles = (p.total_boxes + 3) / 4;
+  p.num_n_tiles = C_out / block_n;
+  p.relu = 1;
+  p.ldo = C_out;
+  p.bias = bias;
+  p.out = out;
+  if (block_n == 256)
+    return pool ? launch<256, true, true, false>(ta, tb, p, stream) : launch<256, true, false, false>(ta, tb, p, stream);
+  return pool ? launch<128, true, true, false>(ta, tb, p, stream) : launch<128, true, false, false>(ta, tb, p, stream);
+}
+
+}  // namespace vmb

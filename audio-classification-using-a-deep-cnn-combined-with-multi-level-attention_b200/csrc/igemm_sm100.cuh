@@ -1,0 +1,53 @@
+// Implicit-GEMM engine for the VGGish conv3x3 / FC layers on sm_100a (tcgen05 + TMEM + TMA).
+//
+//   D[M x N] = act( A[M x K] * B[N x K]^T + bias[N] ),  A, B bf16 (K-major), accumulation fp32 in TMEM.
+//
+// Two A-operand modes share one kernel:
+//   * PLAIN : A is a row-major [M][K] bf16 matrix (the FC layers, reference vggish.py:13-19).
+//   * CONV  : A is never materialised.  The activation tensor is NHWC bf16 and the K axis runs over
+//             (tap, c_in) = (kh*3+kw)*C_in + c.  For K-block kb the producer issues four 4-D TMA box loads
+//             (64 channels x Wb x Hb pixels, Wb*Hb = 32) at the tap-shifted coordinates; TMA zero-fills the
+//             out-of-range halo, which is exactly Conv2d(padding=1) (reference vggish.py:113).  Each box is
+//             one 32-row quarter of the 128-row UMMA tile, so one epilogue warp owns whole 2x2 pooling
+//             windows and MaxPool2d(2,2) (vggish.py:111) is a pair of warp shuffles.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-5 = epilogue (TMEM -> regs -> bias/ReLU/pool -> global).  Persistent over tiles, accumulators
+// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace vmb {
+
+struct IgemmParams {
+  int M;             // PLAIN: rows of A / D.  CONV: number of images.
+  int N;             // output columns (C_out)
+  int num_kb;        // K / 64
+  int cblks;         // CONV: C_in / 64
+  int H, W;          // CONV: input (= conv output) spatial size
+  int Hb, Wb;        // CONV: box = Hb x Wb pixels, Hb*Wb == 32, both even
+  int boxes_per_row; // W / Wb
+  int boxes_per_img; // (H / Hb) * (W / Wb)
+  int total_boxes;   // M * boxes_per_img
+  int num_m_tiles;
+  int num_n_tiles;
+  int relu;
+  long long ldo;     // PLAIN: output row stride (elements)
+  const float* bias; // [N]
+  void* out;         // bf16 (or fp32 when OUT_F32)
+};
+
+// Launchers (defined in igemm_sm100.cu).  All return cudaError_t-compatible ints; 0 = ok.
+// PLAIN: out[M][N] (+ldo) = act(A[M][K] B[N][K]^T + bias).  K % 64 == 0, N % block_n == 0.
+int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int out_f32, int relu,
+                 int M, int N, int K, cudaStream_t stream);
+// CONV 3x3 pad 1 (+bias, ReLU, optional 2x2 maxpool): act NHWC bf16 [n][H][W][C_in], weights [C_out][9*C_in]
+// ((kh,kw,c) order), out NHWC bf16 [n][H or H/2][W or W/2][C_out].  C_in % 64 == 0, C_out % 128 == 0.
+int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
+                  int W, int C_in, int C_out, int pool, cudaStream_t stream);
+
+const char* igemm_last_error();
+
+}  // namespace vmb

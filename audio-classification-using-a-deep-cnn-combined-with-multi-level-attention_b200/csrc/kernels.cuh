@@ -1,0 +1,31 @@
+// Internal (C++) launch interfaces of the non-GEMM kernels.  Every function returns 0 on success; on failure
+// kernels_last_error() holds the reason.  Device pointers throughout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace vmb {
+
+const char* kernels_last_error();
+void set_kernel_error(const char* fmt, ...);
+// cudaGetLastError() -> 0 / 1 with the message recorded.
+int check_launch(const char* what);
+
+// ---- front end (frontend.cu)
+// Constant tables exactly as mel_features.py builds them (float64): periodic_hann(400) and
+// spectrogram_to_mel_matrix(64, 257, 16000, 125, 7500).
+void front_end_tables_host(double* hann400, double* mel257x64);
+int logmel_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                   long long frames_out, float* logmel, cudaStream_t stream);
+
+// ---- VGGish odd layers (layers.cu)
+int conv1_relu_pool(const float* examples, const float* w, const float* b, void* out_bf16, long long n,
+                    cudaStream_t stream);
+int postprocess(const float* emb, const float* eigen, const float* means, float* out_f32, uint8_t* out_u8,
+                long long n, cudaStream_t stream);
+// OIHW fp32 [C_out][C_in][3][3] -> bf16 [C_out][(kh*3+kw)*C_in + c]
+int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream);
+// fp32 -> bf16 elementwise
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+
+}  // namespace vmb

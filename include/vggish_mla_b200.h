@@ -1,0 +1,126 @@
+/* vggish_mla_b200.h — C-ABI of the B200-native waveform -> log-mel -> VGGish -> multi-level-attention path.
+ *
+ * This is the drop-in boundary behind the reference's Python import surface (the reference has no FFI of
+ * its own).  Every entry point below names the reference code it replaces
+ * (paths relative to the reference root).  All pointers named *_dev are CUDA device pointers owned by the
+ * caller (the Python shims pass torch tensors' data_ptr()); `stream` is a cudaStream_t passed as void*.
+ * Functions return 0 on success and non-zero on failure; vmb_last_error() then returns a message
+ * (thread-local).  Nothing here falls back to the CPU: without a CUDA device every compute entry point fails.
+ *
+ * Build: libvggish_mla_b200.so, compiled for sm_100a only (see __graft_entry__.build()).
+ */
+#ifndef VGGISH_MLA_B200_H_
+#define VGGISH_MLA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vmb_vggish vmb_vggish_t;
+typedef struct vmb_mla vmb_mla_t;
+
+/* ------------------------------------------------------------------------------------------ misc */
+const char* vmb_last_error(void);
+int vmb_abi_version(void);
+/* Compute capability of `device` as major*10+minor (100 on B200), or a negative value on error. */
+int vmb_device_arch(int device);
+
+/* ------------------------------------------------------------------------------------------ front end
+ * torchvggish/mel_features.py:21-45 (frame), :48-68 (periodic_hann), :71-92 (stft_magnitude),
+ * :114-189 (spectrogram_to_mel_matrix), :192-223 (log_mel_spectrogram) and the example framing of
+ * torchvggish/vggish_input.py:66-76, with the constants of torchvggish/vggish_params.py:22-36.       */
+
+/* frame(): 1 + floor((n - 400) / 160); negative when n < 400 (the reference raises ValueError there). */
+long long vmb_num_frames(long long n_samples);
+/* Number of 96-frame examples waveform_to_examples() yields for n_samples at 16 kHz (0 if < 15 600). */
+long long vmb_num_examples(long long n_samples);
+
+/* log_mel_spectrogram() for n_clips equally long mono 16 kHz fp32 clips.
+ *   wave_dev   [n_clips][clip_stride] fp32 (first samples_per_clip samples of each row are used)
+ *   logmel_dev [n_clips][frames_out][64] fp32 where frames_out <= vmb_num_frames(samples_per_clip)
+ * Only the first frames_out frames of each clip are produced (pass 96*vmb_num_examples(..) to get the
+ * (n_examples, 96, 64) example tensor of waveform_to_examples, vggish_input.py:73-80).                 */
+int vmb_logmel(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
+               long long frames_out, float* logmel_dev, void* stream);
+
+/* The constant tables the kernel uses (host copies, for the parity tests against mel_features.py):
+ * periodic Hann (400 doubles) and the 257x64 HTK mel matrix (row-major doubles).                      */
+int vmb_front_end_tables(double* hann400, double* mel257x64);
+
+/* ------------------------------------------------------------------------------------------ VGGish layers
+ * Layer-level entry points (used by the per-layer parity tests and by vmb_vggish_forward).            */
+
+/* features.0 + ReLU + MaxPool (vggish.py:108-118, first conv, C_in = 1): examples fp32 [n][96][64] ->
+ * NHWC bf16 [n][48][32][64].  w_dev fp32 [64][9] (OIHW with I = 1), b_dev fp32 [64].                 */
+int vmb_conv1_relu_pool(const float* examples_dev, const float* w_dev, const float* b_dev, void* out_bf16_dev,
+                        long long n, void* stream);
+
+/* Conv2d(3x3, padding=1) + ReLU (+ MaxPool2d(2,2) when pool != 0) as a tcgen05 implicit GEMM.
+ *   act_bf16_dev NHWC bf16 [n][H][W][C_in]; w_bf16_dev bf16 [C_out][9*C_in] in (kh, kw, c_in) order;
+ *   out NHWC bf16 [n][H(/2)][W(/2)][C_out].  C_in % 64 == 0, C_out % 128 == 0.                       */
+int vmb_conv3x3_relu(const void* act_bf16_dev, const void* w_bf16_dev, const float* bias_dev, void* out_bf16_dev,
+                     long long n, int H, int W, int C_in, int C_out, int pool, void* stream);
+
+/* Linear (+ReLU when relu != 0): out[M][N] = act(A[M][K] W[N][K]^T + b).  A, W bf16; out bf16, or fp32 when
+ * out_f32 != 0.  K % 64 == 0, N % 128 == 0 (vggish.py:13-19).                                          */
+int vmb_linear(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, void* out_dev, int out_f32,
+               int relu, long long M, int N, int K, void* stream);
+
+/* Postprocessor.postprocess (vggish.py:62-102): out = round((clamp(E (x - mu), -2, 2) + 2) * 63.75), values
+ * 0..255 stored as fp32 like the reference (F6) and optionally also as uint8.  emb_dev fp32 [n][128],
+ * eigen_dev fp32 [128][128], means_dev fp32 [128].  Either output may be NULL.                          */
+int vmb_postprocess(const float* emb_dev, const float* eigen_dev, const float* means_dev, float* out_f32_dev,
+                    uint8_t* out_u8_dev, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ VGGish model
+ * VGG.forward (vggish.py:21-31) with weights taken from a reference state_dict (SURVEY.md §8b keys).
+ * conv_w_dev[i]: fp32 OIHW, i = features.{0,3,6,8,11,13}; fc_w_dev[i]: fp32 [out][in], i = embeddings.{0,2,4}.
+ * The handle owns bf16 re-laid-out copies; the caller's tensors are not referenced after create returns.   */
+int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w_dev[6], const float* const conv_b_dev[6],
+                      const float* const fc_w_dev[3], const float* const fc_b_dev[3], void* stream);
+void vmb_vggish_destroy(vmb_vggish_t* handle);
+/* Scratch bytes vmb_vggish_forward needs for n examples (caller allocates, 1024-byte aligned). */
+size_t vmb_vggish_workspace_bytes(long long n_examples);
+/* examples_dev fp32 [n][96][64] -> emb_dev fp32 [n][128] (post-ReLU embeddings, vggish.py:31).
+ * If bottleneck_bf16_dev != NULL the (h,w,c)-flattened conv features [n][12288] bf16 (vggish.py:26-29) are
+ * copied there as well (the reference's just_bottlenecks variant, model.py:162-167).                      */
+int vmb_vggish_forward(vmb_vggish_t* handle, const float* examples_dev, long long n, float* emb_dev,
+                       void* bottleneck_bf16_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ MLA head
+ * MultiLevelAttention.forward in eval mode (model.py:258-269; EmbeddedMapping :217-222, AttentionModule
+ * :236-242).  `params_dev` is one flat fp32 device buffer holding, in this order (T = time steps):
+ *   for each level l:  norm0 {weight[T], bias[T], running_mean[T], running_var[T]}
+ *                      for each fc j of the level: W[H][in] bias[H] norm {weight, bias, mean, var}[T each]
+ *   for each level l:  fcv W[K][H] bias[K]; normv {w,b,mean,var}[T]; normf {w,b,mean,var}[T]
+ *   fc W[K][L*K] bias[K]; norm {weight, bias, running_mean, running_var}[K each]
+ * (fcf is constructed by the reference but never used in forward, model.py:231,238 — it is not passed.) */
+int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes,
+                   int t_steps, const float* params_dev, long long n_params, void* stream);
+void vmb_mla_destroy(vmb_mla_t* handle);
+long long vmb_mla_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps);
+/* emb_dev fp32 [B][T][emb_in] -> scores_dev fp32 [B][K] (sigmoid outputs, model.py:268). */
+int vmb_mla_forward(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------ whole path
+ * Ensemble.forward for cnn_type == "vggish" (model.py:58-62) fed from raw audio:
+ * wave [n_clips][samples_per_clip] fp32 16 kHz -> scores [n_clips][K].  samples_per_clip must yield exactly
+ * T examples (10 s -> 10).  Device-resident variant: everything already in HBM.                         */
+size_t vmb_pipeline_workspace_bytes(long long n_clips, long long samples_per_clip);
+int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_dev, long long n_clips,
+                         long long samples_per_clip, float* scores_dev, float* emb_dev_or_null,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Host-buffer variant (the end-to-end number of bench.py): wave_host / scores_host are HOST pointers
+ * (pinned for full speed); the call copies H2D, runs the path on `stream` in micro-batches of
+ * `clips_per_batch`, copies the scores D2H and synchronises the stream before returning.               */
+int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                              long long samples_per_clip, float* scores_host, long long clips_per_batch,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGGISH_MLA_B200_H_ */
