@@ -35,6 +35,7 @@ SIGNATURES = {
     "vmb_vggish_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_mla_create": (_int, [C.POINTER(_c_p), _int, C.POINTER(_int), _int, _int, _int, _int, _c_p, _ll, _c_p]),
     "vmb_mla_destroy": (None, [_c_p]),
+    "vmb_mla_num_classes": (_int, [_c_p]),
     "vmb_mla_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int]),
     "vmb_mla_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
     "vmb_pipeline_workspace_bytes": (_sz, [_ll, _ll]),

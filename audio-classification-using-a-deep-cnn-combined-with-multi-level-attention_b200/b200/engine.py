@@ -1,0 +1,280 @@
+"""Host side of the B200 path: thin, typed wrappers that hand torch CUDA tensors to the C-ABI library.
+
+torch is plumbing here (device memory, streams); all arithmetic happens in libvggish_mla_b200.so.  Every wrapper
+validates shapes / dtypes / devices in Python and raises; nothing falls back to torch ops or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import B200Error, check, ptr, stream_ptr
+
+CONV_KEYS = (0, 3, 6, 8, 11, 13)
+FC_KEYS = (0, 2, 4)
+WIN, HOP, FRAMES_PER_EXAMPLE, MEL = 400, 160, 96, 64
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise B200Error(f"{name} must live on a CUDA device (no CPU path exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def require_b200(device: Optional[torch.device] = None) -> None:
+    """Fail loudly unless a sm_100 device is present and the library loads."""
+    if not torch.cuda.is_available():
+        raise B200Error("no CUDA device: the B200 path has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    arch = _lib.lib().vmb_device_arch(idx)
+    if arch != 100:
+        raise B200Error(f"device {idx} has compute capability {arch}; the kernels are built for sm_100a only")
+
+
+def num_frames(n_samples: int) -> int:
+    return int(_lib.lib().vmb_num_frames(int(n_samples)))
+
+
+def num_examples(n_samples: int) -> int:
+    return int(_lib.lib().vmb_num_examples(int(n_samples)))
+
+
+def logmel(wave: torch.Tensor, frames_out: Optional[int] = None) -> torch.Tensor:
+    """wave (n_clips, n_samples) or (n_samples,) fp32 CUDA -> (n_clips, frames_out, 64) fp32 log-mel."""
+    wave = _need_cuda(wave, "wave")
+    if wave.dim() == 1:
+        wave = wave[None]
+    if wave.dim() != 2:
+        raise ValueError("wave must be (n_clips, n_samples)")
+    n_clips, n_samples = wave.shape
+    nf = num_frames(n_samples)
+    if nf < 0:
+        raise ValueError("negative dimensions are not allowed")  # what the reference's frame() raises (F10)
+    if frames_out is None:
+        frames_out = nf
+    out = torch.empty((n_clips, frames_out, MEL), device=wave.device, dtype=torch.float32)
+    with torch.cuda.device(wave.device):
+        for c0 in range(0, n_clips, 32768):
+            nc = min(32768, n_clips - c0)
+            check(_lib.lib().vmb_logmel(ptr(wave[c0:]), nc, n_samples, wave.stride(0), frames_out, ptr(out[c0:]),
+                                        stream_ptr()), "vmb_logmel")
+    return out
+
+
+def examples_from_wave(wave: torch.Tensor) -> torch.Tensor:
+    """(n_clips, n_samples) fp32 CUDA -> (n_clips * examples_per_clip, 96, 64) fp32 (vggish_input.py:66-76)."""
+    if wave.dim() == 1:
+        wave = wave[None]
+    per = num_examples(wave.shape[-1])
+    if per < 0:
+        raise ValueError("negative dimensions are not allowed")
+    lm = logmel(wave, per * FRAMES_PER_EXAMPLE)
+    return lm.view(wave.shape[0] * per, FRAMES_PER_EXAMPLE, MEL)
+
+
+def front_end_tables():
+    """(hann[400], mel[257, 64]) float64 numpy arrays as built inside the library."""
+    import numpy as np
+    hann = np.empty(400, dtype=np.float64)
+    mel = np.empty((257, 64), dtype=np.float64)
+    check(_lib.lib().vmb_front_end_tables(hann.ctypes.data, mel.ctypes.data), "vmb_front_end_tables")
+    return hann, mel
+
+
+def postprocess(emb: torch.Tensor, eigen: torch.Tensor, means: torch.Tensor, want_u8: bool = False):
+    emb = _need_cuda(emb, "embeddings")
+    eigen = _need_cuda(eigen, "pca_eigen_vectors")
+    means = _need_cuda(means.reshape(-1), "pca_means")
+    n = emb.shape[0]
+    out = torch.empty((n, 128), device=emb.device, dtype=torch.float32)
+    u8 = torch.empty((n, 128), device=emb.device, dtype=torch.uint8) if want_u8 else None
+    with torch.cuda.device(emb.device):
+        check(_lib.lib().vmb_postprocess(ptr(emb), ptr(eigen), ptr(means), ptr(out), ptr(u8), n, stream_ptr()),
+              "vmb_postprocess")
+    return (out, u8) if want_u8 else out
+
+
+class VggishHandle:
+    """Owns the library-side VGGish weights (bf16, implicit-GEMM layout) built from a reference state_dict."""
+
+    def __init__(self, state_dict: dict, device: torch.device):
+        require_b200(device)
+        self.device = device
+        self._h = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        with torch.cuda.device(device):
+            keep = []
+
+            def dev(key):
+                t = state_dict[key].detach().to(device=device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                return t.data_ptr()
+
+            cw = (C.c_void_p * 6)(*[dev(f"features.{k}.weight") for k in CONV_KEYS])
+            cb = (C.c_void_p * 6)(*[dev(f"features.{k}.bias") for k in CONV_KEYS])
+            fw = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.weight") for k in FC_KEYS])
+            fb = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.bias") for k in FC_KEYS])
+            check(_lib.lib().vmb_vggish_create(C.byref(self._h), cw, cb, fw, fb, stream_ptr()), "vmb_vggish_create")
+            del keep
+
+    @property
+    def raw(self) -> C.c_void_p:
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().vmb_vggish_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes + 1024:
+            self._ws = None
+            self._ws = torch.empty(nbytes + 1024, device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def forward(self, examples: torch.Tensor, want_bottleneck: bool = False):
+        """examples (n, 96, 64) or (n, 1, 96, 64) fp32 CUDA -> (n, 128) fp32 post-ReLU embeddings."""
+        examples = _need_cuda(examples, "examples")
+        if examples.dim() == 4 and examples.shape[1] == 1:
+            examples = examples[:, 0]
+        if examples.dim() != 3 or tuple(examples.shape[1:]) != (96, 64):
+            raise ValueError(f"examples must be (n, 1, 96, 64) or (n, 96, 64), got {tuple(examples.shape)}")
+        examples = examples.contiguous()
+        n = examples.shape[0]
+        emb = torch.empty((n, 128), device=self.device, dtype=torch.float32)
+        bott = torch.empty((n, 12288), device=self.device, dtype=torch.bfloat16) if want_bottleneck else None
+        if n == 0:
+            return (emb, bott) if want_bottleneck else emb
+        with torch.cuda.device(self.device):
+            need = int(_lib.lib().vmb_vggish_workspace_bytes(n))
+            ws = self._workspace(need)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            check(_lib.lib().vmb_vggish_forward(self._h, ptr(examples), n, ptr(emb), ptr(bott), base, need, stream_ptr()),
+                  "vmb_vggish_forward")
+        return (emb, bott) if want_bottleneck else emb
+
+
+def pack_mla_params(sd: dict, model_conf: Sequence[int], device: torch.device) -> torch.Tensor:
+    """Flatten a MultiLevelAttention state_dict into the layout documented in vggish_mla_b200.h."""
+    parts = []
+
+    def add(key):
+        parts.append(sd[key].detach().to(device=device, dtype=torch.float32).reshape(-1))
+
+    def add_bn(prefix):
+        for s in ("weight", "bias", "running_mean", "running_var"):
+            add(f"{prefix}.{s}")
+
+    for lvl, n_fc in enumerate(model_conf):
+        p = f"embedded_mappings.{lvl}"
+        add_bn(p + ".norm0")
+        for j in range(n_fc):
+            add(f"{p}.fc.{j}.weight")
+            add(f"{p}.fc.{j}.bias")
+            add_bn(f"{p}.norms.{j}")
+    for lvl in range(len(model_conf)):
+        p = f"attention_modules.{lvl}"
+        add(p + ".fcv.weight")
+        add(p + ".fcv.bias")
+        add_bn(p + ".normv")
+        add_bn(p + ".normf")
+    add("fc.weight")
+    add("fc.bias")
+    add_bn("norm")
+    return torch.cat(parts).contiguous()
+
+
+class MlaHandle:
+    """Library-side multi-level attention head (eval mode) built from a reference state_dict."""
+
+    def __init__(self, state_dict: dict, model_conf: Sequence[int], emb_in: int, hidden: int, n_classes: int,
+                 t_steps: int, device: torch.device):
+        require_b200(device)
+        self.device = device
+        self.n_classes = n_classes
+        self.t_steps = t_steps
+        self.emb_in = emb_in
+        self._h = C.c_void_p()
+        conf = (C.c_int * len(model_conf))(*[int(v) for v in model_conf])
+        with torch.cuda.device(device):
+            flat = pack_mla_params(state_dict, model_conf, device)
+            expect = _lib.lib().vmb_mla_param_count(len(model_conf), conf, emb_in, hidden, n_classes, t_steps)
+            if expect != flat.numel():
+                raise B200Error(f"head parameter count {flat.numel()} != expected {expect} for this configuration")
+            check(_lib.lib().vmb_mla_create(C.byref(self._h), len(model_conf), conf, emb_in, hidden, n_classes, t_steps,
+                                            ptr(flat), flat.numel(), stream_ptr()), "vmb_mla_create")
+
+    @property
+    def raw(self) -> C.c_void_p:
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().vmb_mla_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def forward(self, emb: torch.Tensor) -> torch.Tensor:
+        emb = _need_cuda(emb, "embeddings")
+        if emb.dim() != 3 or emb.shape[1] != self.t_steps or emb.shape[2] != self.emb_in:
+            raise ValueError(f"expected (B, {self.t_steps}, {self.emb_in}), got {tuple(emb.shape)}")
+        out = torch.empty((emb.shape[0], self.n_classes), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().vmb_mla_forward(self._h, ptr(emb), emb.shape[0], ptr(out), stream_ptr()), "vmb_mla_forward")
+        return out
+
+
+class Pipeline:
+    """waveform (n_clips, 160000) -> scores (n_clips, K): log-mel + VGGish + head, all inside the library."""
+
+    def __init__(self, vggish: VggishHandle, mla: MlaHandle):
+        if vggish.device != mla.device:
+            raise ValueError("both handles must live on the same device")
+        self.vggish, self.mla, self.device = vggish, mla, vggish.device
+        self._ws: Optional[torch.Tensor] = None
+
+    def forward(self, wave: torch.Tensor, want_embeddings: bool = False):
+        wave = _need_cuda(wave, "wave")
+        if wave.dim() != 2:
+            raise ValueError("wave must be (n_clips, n_samples)")
+        n, ns = wave.shape
+        if num_examples(ns) != self.mla.t_steps:
+            raise ValueError(f"{ns} samples give {num_examples(ns)} examples per clip, the head needs {self.mla.t_steps}")
+        scores = torch.empty((n, self.mla.n_classes), device=self.device, dtype=torch.float32)
+        emb = torch.empty((n * self.mla.t_steps, 128), device=self.device, dtype=torch.float32) if want_embeddings else None
+        if n == 0:
+            return (scores, emb) if want_embeddings else scores
+        with torch.cuda.device(self.device):
+            need = int(_lib.lib().vmb_pipeline_workspace_bytes(n, ns))
+            if self._ws is None or self._ws.numel() < need + 1024:
+                self._ws = None
+                self._ws = torch.empty(need + 1024, device=self.device, dtype=torch.uint8)
+            base = (self._ws.data_ptr() + 1023) // 1024 * 1024
+            check(_lib.lib().vmb_pipeline_forward(self.vggish.raw, self.mla.raw, ptr(wave), n, ns, ptr(scores), ptr(emb),
+                                                  base, need, stream_ptr()), "vmb_pipeline_forward")
+        return (scores, emb) if want_embeddings else scores
+
+    def forward_host(self, wave_host: torch.Tensor, scores_host: Optional[torch.Tensor] = None,
+                     clips_per_batch: int = 256) -> torch.Tensor:
+        """End-to-end call with HOST buffers: H2D copy, compute and D2H copy all happen inside the library."""
+        if wave_host.is_cuda or wave_host.dtype != torch.float32 or wave_host.dim() != 2:
+            raise ValueError("wave_host must be a (n_clips, n_samples) fp32 CPU tensor (pinned for full speed)")
+        wave_host = wave_host.contiguous()
+        n, ns = wave_host.shape
+        if scores_host is None:
+            scores_host = torch.empty((n, self.mla.n_classes), dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().vmb_pipeline_forward_host(self.vggish.raw, self.mla.raw, wave_host.data_ptr(), n, ns,
+                                                       scores_host.data_ptr(), clips_per_batch, stream_ptr()),
+                  "vmb_pipeline_forward_host")
+        return scores_host

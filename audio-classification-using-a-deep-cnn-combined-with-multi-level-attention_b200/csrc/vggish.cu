@@ -1,0 +1,289 @@
+// VGGish model handle (reference torchvggish/vggish.py:9-31, 108-118) and the whole waveform -> scores pipeline
+// (model.py:58-62 fed by vggish_input.py:30-82).  The handle owns bf16 weights re-laid-out for the implicit-GEMM
+// kernels; activations ping-pong between two caller-provided workspace regions in NHWC bf16.
+#include <cuda_bf16.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/vggish_mla_b200.h"
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+
+namespace vmb {
+void set_api_error(const char* msg);
+}
+
+// Cached staging of vmb_pipeline_forward_host (grown on demand, freed with the handle).
+struct HostStage {
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t fence = nullptr, wave_ready[2] = {}, wave_free[2] = {};
+  float* d_wave[2] = {};
+  size_t wave_cap[2] = {};
+  float* d_scores = nullptr;
+  size_t scores_cap = 0;
+  void* d_ws = nullptr;
+  size_t ws_cap = 0;
+};
+
+struct vmb_vggish {
+  float* conv1_w = nullptr;  // fp32 [64][9]
+  float* conv_b[6] = {};     // fp32 biases (index 0 = conv1)
+  void* conv_w[6] = {};      // bf16 [C_out][9*C_in], index 1..5
+  void* fc_w[3] = {};        // bf16 [out][in]
+  float* fc_b[3] = {};
+  HostStage stage;
+};
+
+namespace {
+
+struct ConvGeom { int H, W, C_in, C_out, pool; };
+// features.{3,6,8,11,13}: input geometry of each tensor-core conv (after the preceding pools)
+constexpr ConvGeom kConv[5] = {{48, 32, 64, 128, 1}, {24, 16, 128, 256, 0}, {24, 16, 256, 256, 1},
+                               {12, 8, 256, 512, 0}, {12, 8, 512, 512, 1}};
+constexpr int kFcIn[3] = {12288, 4096, 4096};
+constexpr int kFcOut[3] = {4096, 4096, 128};
+constexpr size_t kBufA = 196608;  // bytes per example: largest activation (48x32x64 or 24x16x256 bf16)
+constexpr size_t kBufB = 98304;   // 24x16x128 / 12x8x512 bf16
+
+int fail(const char* fmt, const char* detail = "") {
+  char buf[640];
+  snprintf(buf, sizeof buf, fmt, detail);
+  vmb::set_api_error(buf);
+  return 1;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w[6], const float* const conv_b[6],
+                      const float* const fc_w[3], const float* const fc_b[3], void* stream) {
+  if (!handle || !conv_w || !conv_b || !fc_w || !fc_b) return fail("vmb_vggish_create: null argument");
+  for (int i = 0; i < 6; ++i)
+    if (!conv_w[i] || !conv_b[i]) return fail("vmb_vggish_create: null conv tensor");
+  for (int i = 0; i < 3; ++i)
+    if (!fc_w[i] || !fc_b[i]) return fail("vmb_vggish_create: null fc tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vmb_vggish* h = new vmb_vggish();
+  bool ok = true;
+  auto dmalloc = [&](void** p, size_t bytes) { ok = ok && cudaMalloc(p, bytes) == cudaSuccess; };
+  auto dcopy = [&](void* d, const void* s, size_t bytes) {
+    ok = ok && cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+  };
+  dmalloc(reinterpret_cast<void**>(&h->conv1_w), 64 * 9 * 4);
+  dmalloc(reinterpret_cast<void**>(&h->conv_b[0]), 64 * 4);
+  if (ok) {
+    dcopy(h->conv1_w, conv_w[0], 64 * 9 * 4);
+    dcopy(h->conv_b[0], conv_b[0], 64 * 4);
+  }
+  for (int i = 0; i < 5 && ok; ++i) {
+    const ConvGeom& g = kConv[i];
+    dmalloc(&h->conv_w[i + 1], size_t(g.C_out) * 9 * g.C_in * 2);
+    dmalloc(reinterpret_cast<void**>(&h->conv_b[i + 1]), size_t(g.C_out) * 4);
+    if (!ok) break;
+    dcopy(h->conv_b[i + 1], conv_b[i + 1], size_t(g.C_out) * 4);
+    ok = ok && vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st) == 0;
+  }
+  for (int i = 0; i < 3 && ok; ++i) {
+    dmalloc(&h->fc_w[i], size_t(kFcOut[i]) * kFcIn[i] * 2);
+    dmalloc(reinterpret_cast<void**>(&h->fc_b[i]), size_t(kFcOut[i]) * 4);
+    if (!ok) break;
+    dcopy(h->fc_b[i], fc_b[i], size_t(kFcOut[i]) * 4);
+    ok = ok && vmb::cast_f32_to_bf16(fc_w[i], h->fc_w[i], static_cast<long long>(kFcOut[i]) * kFcIn[i], st) == 0;
+  }
+  ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) {
+    const char* why = cudaGetErrorString(cudaGetLastError());
+    vmb_vggish_destroy(h);
+    return fail("vmb_vggish_create: allocation / re-layout failed (%s)", why);
+  }
+  *handle = h;
+  return 0;
+}
+
+void vmb_vggish_destroy(vmb_vggish_t* h) {
+  if (!h) return;
+  cudaFree(h->conv1_w);
+  for (int i = 0; i < 6; ++i) {
+    cudaFree(h->conv_b[i]);
+    cudaFree(h->conv_w[i]);
+  }
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(h->fc_w[i]);
+    cudaFree(h->fc_b[i]);
+  }
+  HostStage& hs = h->stage;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(hs.d_wave[i]);
+    if (hs.wave_ready[i]) cudaEventDestroy(hs.wave_ready[i]);
+    if (hs.wave_free[i]) cudaEventDestroy(hs.wave_free[i]);
+  }
+  cudaFree(hs.d_scores);
+  cudaFree(hs.d_ws);
+  if (hs.fence) cudaEventDestroy(hs.fence);
+  if (hs.copy_st) cudaStreamDestroy(hs.copy_st);
+  delete h;
+}
+
+size_t vmb_vggish_workspace_bytes(long long n) {
+  if (n <= 0) return 0;
+  return align_up(size_t(n) * kBufA, 1024) + align_up(size_t(n) * kBufB, 1024);
+}
+
+int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, float* emb, void* bottleneck,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return fail("vmb_vggish_forward: null handle");
+  if (n < 0) return fail("vmb_vggish_forward: negative n");
+  if (n == 0) return 0;
+  if (n > 1000000) return fail("vmb_vggish_forward: at most 1 000 000 examples per call (chunk on the host)");
+  if (!examples || !emb || !workspace) return fail("vmb_vggish_forward: null pointer");
+  if (workspace_bytes < vmb_vggish_workspace_bytes(n)) return fail("vmb_vggish_forward: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_vggish_forward: workspace must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* A = static_cast<char*>(workspace);
+  char* B = A + align_up(size_t(n) * kBufA, 1024);
+
+  if (vmb::conv1_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
+    return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
+  char* src = A;
+  char* dst = B;
+  for (int i = 0; i < 5; ++i) {
+    const ConvGeom& g = kConv[i];
+    if (vmb::igemm_conv3x3(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in, g.C_out, g.pool, st))
+      return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+    char* t = src; src = dst; dst = t;
+  }
+  // src == B now holds the NHWC [n][6][4][512] features == the (h,w,c)-flattened [n][12288] matrix (vggish.py:26-29)
+  if (bottleneck &&
+      cudaMemcpyAsync(bottleneck, src, size_t(n) * 12288 * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return fail("vmb_vggish_forward: bottleneck copy failed");
+  // fc1: B -> A, fc2: A -> B, fc3: B -> emb (fp32)
+  if (vmb::igemm_linear(src, h->fc_w[0], h->fc_b[0], dst, 0, 1, int(n), kFcOut[0], kFcIn[0], st) ||
+      vmb::igemm_linear(dst, h->fc_w[1], h->fc_b[1], src, 0, 1, int(n), kFcOut[1], kFcIn[1], st) ||
+      vmb::igemm_linear(src, h->fc_w[2], h->fc_b[2], emb, 1, 1, int(n), kFcOut[2], kFcIn[2], st))
+    return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ whole path
+namespace {
+struct PipeLayout { size_t examples, emb, vgg, total; long long n_ex; };
+PipeLayout pipe_layout(long long n_clips, long long samples_per_clip) {
+  PipeLayout L{};
+  const long long per = vmb_num_examples(samples_per_clip);
+  L.n_ex = per > 0 ? per * n_clips : 0;
+  L.examples = 0;
+  L.emb = align_up(size_t(L.n_ex) * 96 * 64 * 4, 1024);
+  L.vgg = L.emb + align_up(size_t(L.n_ex) * 128 * 4, 1024);
+  L.total = L.vgg + vmb_vggish_workspace_bytes(L.n_ex);
+  return L;
+}
+}  // namespace
+
+size_t vmb_pipeline_workspace_bytes(long long n_clips, long long samples_per_clip) {
+  if (n_clips <= 0) return 0;
+  return pipe_layout(n_clips, samples_per_clip).total;
+}
+
+int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave, long long n_clips,
+                         long long samples_per_clip, float* scores, float* emb_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!vggish || !mla) return fail("vmb_pipeline_forward: null handle");
+  if (n_clips < 0) return fail("vmb_pipeline_forward: negative n_clips");
+  if (n_clips == 0) return 0;
+  if (!wave || !scores || !workspace) return fail("vmb_pipeline_forward: null pointer");
+  const long long per = vmb_num_examples(samples_per_clip);
+  if (per != 10)
+    return fail("vmb_pipeline_forward: samples_per_clip must yield exactly T = 10 examples (params.py:26)");
+  const PipeLayout L = pipe_layout(n_clips, samples_per_clip);
+  if (workspace_bytes < L.total) return fail("vmb_pipeline_forward: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_pipeline_forward: workspace must be 1024-byte aligned");
+  char* ws = static_cast<char*>(workspace);
+  float* examples = reinterpret_cast<float*>(ws + L.examples);
+  float* emb = reinterpret_cast<float*>(ws + L.emb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // log-mel of the first 96*10 frames of every clip == the (n_clips*10, 96, 64) example tensor
+  for (long long c0 = 0; c0 < n_clips; c0 += 32768) {
+    const long long nc = n_clips - c0 < 32768 ? n_clips - c0 : 32768;
+    if (vmb_logmel(wave + c0 * samples_per_clip, nc, samples_per_clip, samples_per_clip, per * 96,
+                   examples + c0 * per * 96 * 64, stream))
+      return 1;
+  }
+  if (vmb_vggish_forward(vggish, examples, L.n_ex, emb, nullptr, ws + L.vgg, workspace_bytes - L.vgg, stream)) return 1;
+  if (emb_out && cudaMemcpyAsync(emb_out, emb, size_t(L.n_ex) * 128 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return fail("vmb_pipeline_forward: embedding copy failed");
+  return vmb_mla_forward(mla, emb, n_clips, scores, stream);
+}
+
+int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                              long long samples_per_clip, float* scores_host, long long clips_per_batch,
+                              void* stream) {
+  if (!vggish || !mla) return fail("vmb_pipeline_forward_host: null handle");
+  if (n_clips < 0 || clips_per_batch <= 0) return fail("vmb_pipeline_forward_host: bad sizes");
+  if (n_clips == 0) return 0;
+  if (!wave_host || !scores_host) return fail("vmb_pipeline_forward_host: null pointer");
+  if (vmb_num_examples(samples_per_clip) != 10)
+    return fail("vmb_pipeline_forward_host: samples_per_clip must yield exactly T = 10 examples (params.py:26)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (clips_per_batch > n_clips) clips_per_batch = n_clips;
+  const int n_classes = vmb_mla_num_classes(mla);
+  HostStage& hs = vggish->stage;
+  // (re)size the cached staging buffers: two wave buffers so the H2D copy of batch i+1 overlaps compute of batch i
+  const size_t wave_bytes = size_t(clips_per_batch) * samples_per_clip * 4;
+  const size_t ws_bytes = vmb_pipeline_workspace_bytes(clips_per_batch, samples_per_clip);
+  const size_t score_bytes = size_t(n_clips) * n_classes * 4;
+  bool ok = true;
+  if (!hs.copy_st) {
+    ok = cudaStreamCreateWithFlags(&hs.copy_st, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&hs.fence, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&hs.wave_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&hs.wave_free[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  auto grow = [&](void** p, size_t* cap, size_t need) {
+    if (!ok || *cap >= need) return;
+    cudaStreamSynchronize(st);
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    ok = cudaMalloc(p, need) == cudaSuccess;
+    if (ok) *cap = need;
+  };
+  grow(reinterpret_cast<void**>(&hs.d_wave[0]), &hs.wave_cap[0], wave_bytes);
+  grow(reinterpret_cast<void**>(&hs.d_wave[1]), &hs.wave_cap[1], wave_bytes);
+  grow(&hs.d_ws, &hs.ws_cap, ws_bytes);
+  grow(reinterpret_cast<void**>(&hs.d_scores), &hs.scores_cap, score_bytes);
+  if (!ok) return fail("vmb_pipeline_forward_host: staging allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+
+  // the copy stream must not run ahead of work already queued on `stream`
+  cudaEventRecord(hs.fence, st);
+  cudaStreamWaitEvent(hs.copy_st, hs.fence, 0);
+  int rc = 0;
+  long long b = 0;
+  for (long long c0 = 0; c0 < n_clips && rc == 0; c0 += clips_per_batch, ++b) {
+    const int s = int(b & 1);
+    const long long nc = n_clips - c0 < clips_per_batch ? n_clips - c0 : clips_per_batch;
+    if (b >= 2) cudaStreamWaitEvent(hs.copy_st, hs.wave_free[s], 0);
+    if (cudaMemcpyAsync(hs.d_wave[s], wave_host + c0 * samples_per_clip, size_t(nc) * samples_per_clip * 4,
+                        cudaMemcpyHostToDevice, hs.copy_st) != cudaSuccess) {
+      rc = fail("vmb_pipeline_forward_host: H2D copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    cudaEventRecord(hs.wave_ready[s], hs.copy_st);
+    cudaStreamWaitEvent(st, hs.wave_ready[s], 0);
+    rc = vmb_pipeline_forward(vggish, mla, hs.d_wave[s], nc, samples_per_clip, hs.d_scores + c0 * n_classes, nullptr,
+                              hs.d_ws, hs.ws_cap, stream);
+    cudaEventRecord(hs.wave_free[s], st);
+  }
+  if (rc == 0 && cudaMemcpyAsync(scores_host, hs.d_scores, score_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    rc = fail("vmb_pipeline_forward_host: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  cudaStreamSynchronize(hs.copy_st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0)
+    rc = fail("vmb_pipeline_forward_host: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+}  // extern "C"

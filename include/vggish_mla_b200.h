@@ -101,6 +101,7 @@ int vmb_vggish_forward(vmb_vggish_t* handle, const float* examples_dev, long lon
 int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes,
                    int t_steps, const float* params_dev, long long n_params, void* stream);
 void vmb_mla_destroy(vmb_mla_t* handle);
+int vmb_mla_num_classes(const vmb_mla_t* handle);
 long long vmb_mla_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps);
 /* emb_dev fp32 [B][T][emb_in] -> scores_dev fp32 [B][K] (sigmoid outputs, model.py:268). */
 int vmb_mla_forward(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
