@@ -20,6 +20,9 @@ SIGNATURES = {
     "vmb_last_error": (C.c_char_p, []),
     "vmb_abi_version": (_int, []),
     "vmb_device_arch": (_int, [_int]),
+    "vmb_launch_count": (_ll, []),
+    "vmb_profile_enable": (_int, [_int]),
+    "vmb_profile_collect": (_int, [_c_p, _c_p, _int]),
     "vmb_num_frames": (_ll, [_ll]),
     "vmb_num_examples": (_ll, [_ll]),
     "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),

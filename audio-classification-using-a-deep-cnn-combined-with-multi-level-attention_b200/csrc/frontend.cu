@@ -230,6 +230,7 @@ int logmel_forward(const float* wave, long long n_clips, long long samples_per_c
   dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(n_clips));
   logmel_kernel<<<grid, kThreads, 0, stream>>>(wave, samples_per_clip, clip_stride, frames_out, t->basis, t->melw,
                                                logmel);
+  count_launch();
   return check_launch("logmel_kernel");
 }
 

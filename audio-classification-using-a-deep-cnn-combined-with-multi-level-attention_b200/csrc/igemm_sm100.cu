@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "kernels.cuh"
 #include "sm100_ptx.cuh"
 
 namespace vmb {
@@ -308,6 +309,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, c
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm launch failed: %s", cudaGetErrorString(e));

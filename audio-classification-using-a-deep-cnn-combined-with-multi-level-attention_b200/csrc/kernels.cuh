@@ -11,6 +11,23 @@ void set_kernel_error(const char* fmt, ...);
 // cudaGetLastError() -> 0 / 1 with the message recorded.
 int check_launch(const char* what);
 
+// ---- accounting (profile.cu)
+// Every kernel launcher calls count_launch(); StageTimer brackets one stage with CUDA events when profiling is on.
+void count_launch(int n = 1);
+class StageTimer {
+ public:
+  StageTimer(int stage, cudaStream_t st);
+  ~StageTimer();
+  StageTimer(const StageTimer&) = delete;
+  StageTimer& operator=(const StageTimer&) = delete;
+
+ private:
+  int stage_;
+  cudaStream_t st_;
+  bool on_;
+  cudaEvent_t a_ = nullptr, b_ = nullptr;
+};
+
 // ---- front end (frontend.cu)
 // Constant tables exactly as mel_features.py builds them (float64): periodic_hann(400) and
 // spectrogram_to_mel_matrix(64, 257, 16000, 125, 7500).

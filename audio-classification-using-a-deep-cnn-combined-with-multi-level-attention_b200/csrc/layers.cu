@@ -139,6 +139,7 @@ int conv1_relu_pool(const float* examples, const float* w, const float* b, void*
     dim3 grid(kInH / 2 / kPRows, static_cast<unsigned>(chunk));
     conv1_kernel<<<grid, 256, 0, stream>>>(examples + done * kInH * kInW, w, b,
                                            static_cast<__nv_bfloat16*>(out) + done * (kInH / 2) * (kInW / 2) * kC1);
+    count_launch();
     if (check_launch("conv1_kernel")) return 1;
     done += chunk;
   }
@@ -149,16 +150,19 @@ int postprocess(const float* emb, const float* eigen, const float* means, float*
                 long long n, cudaStream_t stream) {
   const long long blocks = (n + 7) / 8;
   postprocess_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(emb, eigen, means, out_f32, out_u8, n);
+  count_launch();
   return check_launch("postprocess_kernel");
 }
 
 int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream) {
   relayout_conv_kernel<<<1024, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(w_bf16), C_out, C_in);
+  count_launch();
   return check_launch("relayout_conv_kernel");
 }
 
 int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
   cast_bf16_kernel<<<2048, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  count_launch();
   return check_launch("cast_bf16_kernel");
 }
 

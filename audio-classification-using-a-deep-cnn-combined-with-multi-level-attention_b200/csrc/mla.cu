@@ -400,6 +400,7 @@ int vmb_mla_forward(vmb_mla_t* h, const float* emb, long long batch, float* scor
     const unsigned grid = static_cast<unsigned>((batch + 3) / 4);
     mla_forward_kernel<4><<<grid, kThreads, head_smem_bytes(4, ystride), st>>>(h->dev, emb, batch, scores, ystride);
   }
+  vmb::count_launch();
   if (vmb::check_launch("mla_forward_kernel")) return fail(vmb::kernels_last_error());
   return 0;
 }

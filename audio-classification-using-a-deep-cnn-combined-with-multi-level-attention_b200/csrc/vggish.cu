@@ -146,25 +146,32 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
   char* A = static_cast<char*>(workspace);
   char* B = A + align_up(size_t(n) * kBufA, 1024);
 
-  if (vmb::conv1_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
-    return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
+  {
+    vmb::StageTimer t(VMB_STAGE_CONV1, st);
+    if (vmb::conv1_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
+      return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
+  }
   char* src = A;
   char* dst = B;
   for (int i = 0; i < 5; ++i) {
     const ConvGeom& g = kConv[i];
+    vmb::StageTimer t(VMB_STAGE_CONV2 + i, st);
     if (vmb::igemm_conv3x3(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in, g.C_out, g.pool, st))
       return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
-    char* t = src; src = dst; dst = t;
+    char* sw = src; src = dst; dst = sw;
   }
   // src == B now holds the NHWC [n][6][4][512] features == the (h,w,c)-flattened [n][12288] matrix (vggish.py:26-29)
   if (bottleneck &&
       cudaMemcpyAsync(bottleneck, src, size_t(n) * 12288 * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return fail("vmb_vggish_forward: bottleneck copy failed");
   // fc1: B -> A, fc2: A -> B, fc3: B -> emb (fp32)
-  if (vmb::igemm_linear(src, h->fc_w[0], h->fc_b[0], dst, 0, 1, int(n), kFcOut[0], kFcIn[0], st) ||
-      vmb::igemm_linear(dst, h->fc_w[1], h->fc_b[1], src, 0, 1, int(n), kFcOut[1], kFcIn[1], st) ||
-      vmb::igemm_linear(src, h->fc_w[2], h->fc_b[2], emb, 1, 1, int(n), kFcOut[2], kFcIn[2], st))
-    return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+  const void* fc_in[3] = {src, dst, src};
+  void* fc_out[3] = {dst, src, emb};
+  for (int i = 0; i < 3; ++i) {
+    vmb::StageTimer t(VMB_STAGE_FC1 + i, st);
+    if (vmb::igemm_linear(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], i == 2, 1, int(n), kFcOut[i], kFcIn[i], st))
+      return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+  }
   return 0;
 }
 
@@ -208,6 +215,7 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   // log-mel of the first 96*10 frames of every clip == the (n_clips*10, 96, 64) example tensor
   for (long long c0 = 0; c0 < n_clips; c0 += 32768) {
     const long long nc = n_clips - c0 < 32768 ? n_clips - c0 : 32768;
+    vmb::StageTimer t(VMB_STAGE_LOGMEL, st);
     if (vmb_logmel(wave + c0 * samples_per_clip, nc, samples_per_clip, samples_per_clip, per * 96,
                    examples + c0 * per * 96 * 64, stream))
       return 1;
@@ -215,6 +223,7 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   if (vmb_vggish_forward(vggish, examples, L.n_ex, emb, nullptr, ws + L.vgg, workspace_bytes - L.vgg, stream)) return 1;
   if (emb_out && cudaMemcpyAsync(emb_out, emb, size_t(L.n_ex) * 128 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
     return fail("vmb_pipeline_forward: embedding copy failed");
+  vmb::StageTimer t(VMB_STAGE_MLA, st);
   return vmb_mla_forward(mla, emb, n_clips, scores, stream);
 }
 

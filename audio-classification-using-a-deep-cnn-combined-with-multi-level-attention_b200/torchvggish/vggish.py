@@ -1,0 +1,158 @@
+"""Drop-in for torchvggish/vggish.py: `VGG`, `Postprocessor`, `make_layers`, `VGGish` with the reference's
+constructor signatures and state_dict keys (vggish.py:9-184), computing on the B200 library.
+
+The nn.Conv2d / nn.Linear children exist only to own the parameters under the reference's key names
+(`features.{0,3,6,8,11,13}.*`, `embeddings.{0,2,4}.*`, `pproc.pca_*`): forward never runs them.  On the first
+call (and whenever the parameters change) the weights are handed to the library, which keeps bf16 copies in its
+implicit-GEMM layout; the forward pass is conv1 -> 5 tcgen05 implicit-GEMM convs with fused ReLU / max-pool ->
+3 tcgen05 FC layers (csrc/vggish.cu).  There is no CPU path: a module that is not on a CUDA device raises.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from b200 import engine as _engine
+from b200._lib import B200Error
+
+from . import vggish_input, vggish_params
+
+_CONV_PLAN = (64, "M", 128, "M", 256, 256, "M", 512, 512, "M")   # vggish.py:111
+
+
+def make_layers():
+    """Parameter holders for the conv stack, laid out so the state_dict keys match vggish.py:108-118."""
+    mods, c_in = [], 1
+    for item in _CONV_PLAN:
+        if item == "M":
+            mods.append(nn.MaxPool2d(kernel_size=2, stride=2))
+        else:
+            mods.extend((nn.Conv2d(c_in, item, kernel_size=3, padding=1), nn.ReLU(inplace=True)))
+            c_in = item
+    return nn.Sequential(*mods)
+
+
+def _param_fingerprint(module):
+    return tuple((p.data_ptr(), p._version, str(p.device)) for p in module.parameters())
+
+
+class VGG(nn.Module):
+    """VGGish body: (N, 1, 96, 64) log-mel examples -> (N, 128) post-ReLU embeddings (vggish.py:9-31)."""
+
+    def __init__(self, features):
+        super().__init__()
+        self.features = features
+        fc_dims = ((512 * 4 * 6, 4096), (4096, 4096), (4096, vggish_params.EMBEDDING_SIZE))
+        mods = []
+        for fin, fout in fc_dims:
+            mods.extend((nn.Linear(fin, fout), nn.ReLU(True)))
+        self.embeddings = nn.Sequential(*mods)
+        self._handle = None
+        self._handle_key = None
+
+    # -- library handle, rebuilt when a parameter was modified in place, replaced or moved
+    def _b200_handle(self):
+        dev = next(self.features.parameters()).device
+        if dev.type != "cuda":
+            raise B200Error("VGGish parameters are on %s: move the module to a CUDA device (.to('cuda')); this build "
+                            "has no CPU path" % dev)
+        body = {k: v for k, v in self.state_dict().items() if k.startswith(("features.", "embeddings."))}
+        key = tuple((v.data_ptr(), v._version) for v in body.values()) + (str(dev),)
+        if self._handle is None or key != self._handle_key:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = _engine.VggishHandle(body, dev)
+            self._handle_key = key
+        return self._handle
+
+    def forward(self, x):
+        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("training the VGGish body is outside the B200 path (the reference freezes it, "
+                                      "model.py:159-160); call set_requires_grad(module, False) or .eval()")
+        h = self._b200_handle()
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a (N, 1, 96, 64) tensor")
+        x = x.detach().to(device=h.device, dtype=torch.float32)
+        return h.forward(x)
+
+    def bottlenecks(self, x):
+        """(N, 12288) bf16 conv features in (h, w, c) order (the flatten of vggish.py:26-29)."""
+        h = self._b200_handle()
+        return h.forward(x.detach().to(device=h.device, dtype=torch.float32), want_bottleneck=True)[1]
+
+
+class Postprocessor(nn.Module):
+    """PCA (+ whitening) and 8-bit quantisation of the embeddings (vggish.py:34-105): returns FLOAT32 values in
+    0..255, squeezed, like the reference."""
+
+    def __init__(self):
+        super().__init__()
+        n = vggish_params.EMBEDDING_SIZE
+        self.pca_eigen_vectors = nn.Parameter(torch.empty((n, n), dtype=torch.float), requires_grad=False)
+        self.pca_means = nn.Parameter(torch.empty((n, 1), dtype=torch.float), requires_grad=False)
+
+    def postprocess(self, embeddings_batch):
+        assert len(embeddings_batch.shape) == 2, "Expected 2-d batch, got %r" % (embeddings_batch.shape,)
+        assert embeddings_batch.shape[1] == vggish_params.EMBEDDING_SIZE, "Bad batch shape: %r" % (
+            embeddings_batch.shape,)
+        dev = self.pca_eigen_vectors.device
+        if dev.type != "cuda":
+            raise B200Error("Postprocessor parameters are on %s: this build has no CPU path" % dev)
+        q = _engine.postprocess(embeddings_batch.detach().to(device=dev, dtype=torch.float32),
+                                self.pca_eigen_vectors.data, self.pca_means.data)
+        return torch.squeeze(q)
+
+    def quantized_uint8(self, embeddings_batch):
+        """Same values as postprocess() but as a uint8 tensor (N, 128) — the AudioSet release format."""
+        dev = self.pca_eigen_vectors.device
+        return _engine.postprocess(embeddings_batch.detach().to(device=dev, dtype=torch.float32),
+                                   self.pca_eigen_vectors.data, self.pca_means.data, want_u8=True)[1]
+
+    def forward(self, x):
+        return self.postprocess(x)
+
+
+def _vgg():
+    return VGG(make_layers())
+
+
+class VGGish(VGG):
+    """VGGish with optional waveform pre-processing and PCA post-processing (vggish.py:143-184).
+
+    `pretrained=True` needs network access to the URLs in `urls` exactly like the reference
+    (torch.hub.load_state_dict_from_url); offline, build with pretrained=False and load_state_dict()."""
+
+    def __init__(self, urls, pretrained=True, preprocess=True, postprocess=True, progress=True):
+        super().__init__(make_layers())
+        if pretrained:
+            from torch import hub
+            super().load_state_dict(hub.load_state_dict_from_url(urls["vggish"], progress=progress))
+        self.preprocess = preprocess
+        self.postprocess = postprocess
+        if self.postprocess:
+            self.pproc = Postprocessor()
+            if pretrained:
+                from torch import hub
+                sd = hub.load_state_dict_from_url(urls["pca"], progress=progress)
+                self.pproc.load_state_dict({
+                    vggish_params.PCA_EIGEN_VECTORS_NAME: torch.as_tensor(
+                        sd[vggish_params.PCA_EIGEN_VECTORS_NAME], dtype=torch.float),
+                    vggish_params.PCA_MEANS_NAME: torch.as_tensor(
+                        sd[vggish_params.PCA_MEANS_NAME].reshape(-1, 1), dtype=torch.float)})
+
+    def forward(self, x, fs=None):
+        if self.preprocess:
+            x = self._preprocess(x, fs)
+        x = VGG.forward(self, x)
+        if self.postprocess:
+            x = self._postprocess(x)
+        return x
+
+    def _preprocess(self, x, fs):
+        if isinstance(x, np.ndarray):
+            return vggish_input.waveform_to_examples(x, fs)
+        if isinstance(x, str):
+            return vggish_input.wavfile_to_examples(x)
+        raise AttributeError
+
+    def _postprocess(self, x):
+        return self.pproc(x)

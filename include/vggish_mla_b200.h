@@ -28,6 +28,22 @@ int vmb_abi_version(void);
 /* Compute capability of `device` as major*10+minor (100 on B200), or a negative value on error. */
 int vmb_device_arch(int device);
 
+/* ------------------------------------------------------------------------------------------ accounting
+ * (no reference counterpart: the reference only wall-clocks whole epochs, train.py:71,164-165)
+ * Number of CUDA kernels this library has launched in this process.                                   */
+long long vmb_launch_count(void);
+/* Per-stage device timing with CUDA events recorded on the caller's stream around each stage of
+ * vmb_vggish_forward / vmb_pipeline_forward.  Stage ids: */
+enum {
+  VMB_STAGE_LOGMEL = 0, VMB_STAGE_CONV1 = 1, VMB_STAGE_CONV2 = 2, VMB_STAGE_CONV3_1 = 3, VMB_STAGE_CONV3_2 = 4,
+  VMB_STAGE_CONV4_1 = 5, VMB_STAGE_CONV4_2 = 6, VMB_STAGE_FC1 = 7, VMB_STAGE_FC2 = 8, VMB_STAGE_FC3 = 9,
+  VMB_STAGE_MLA = 10, VMB_STAGE_POSTPROCESS = 11, VMB_NUM_STAGES = 12
+};
+int vmb_profile_enable(int on);
+/* Synchronises the recorded events, adds them to the running totals and copies the totals out
+ * (milliseconds and call counts per stage, VMB_NUM_STAGES entries each; either may be NULL).           */
+int vmb_profile_collect(double* ms_per_stage, long long* calls_per_stage, int reset);
+
 /* ------------------------------------------------------------------------------------------ front end
  * torchvggish/mel_features.py:21-45 (frame), :48-68 (periodic_hann), :71-92 (stft_magnitude),
  * :114-189 (spectrogram_to_mel_matrix), :192-223 (log_mel_spectrogram) and the example framing of

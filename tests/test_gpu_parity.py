@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star):
+  * frame indexing, tables: bit-exact
+  * log-mel: <= 1e-4 absolute against the float64 reference
+  * conv / FC layers (bf16 operands, fp32 accumulation): per layer max-abs <= 1.5 % of the layer's max activation
+    and cosine >= 0.9999 against the fp32 oracle; embeddings the same
+  * head (fp32 CUDA cores): <= 2e-5 absolute on the sigmoid scores given identical embeddings
+  * postprocessor: bit-exact on identical fp32 embeddings except where fp32 summation order straddles a
+    quantisation boundary (+-1 LSB, counted and bounded)
+  * mAP on the fixed synthetic label set: identical to 3 decimals
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from b200 import _lib, engine, sharding, synth
+from oracle import frontend_np, model_torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def vgg_handle(vgg_sd):
+    h = engine.VggishHandle(vgg_sd, DEV)
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="module")
+def head_handle(head_sd):
+    h = engine.MlaHandle(head_sd, (2, 1), 128, 600, 527, 10, DEV)
+    yield h
+    h.close()
+
+
+def test_library_is_the_thing_that_runs():
+    engine.require_b200(DEV)
+    before = _lib.lib().vmb_launch_count()
+    engine.logmel(torch.zeros(1, 16000, device=DEV))
+    torch.cuda.synchronize()
+    assert _lib.lib().vmb_launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------------------ front end
+def test_logmel_golden(golden_front):
+    waves = torch.from_numpy(golden_front["waves_f32"]).to(DEV)
+    lm = engine.logmel(waves).cpu().numpy().astype(np.float64)
+    ref = golden_front["logmel_f64"]
+    assert lm.shape == ref.shape == (4, 118, 64)
+    err = np.abs(lm - ref).max(axis=(1, 2))
+    print("log-mel max-abs error per signal family:", err)
+    assert err.max() <= 1e-4
+
+
+@pytest.mark.parametrize("first", [0, 4])
+def test_logmel_full_clips_vs_oracle(first):
+    waves = synth.make_clips(first, 4)                                   # 10 s clips, all four families
+    got = engine.logmel(torch.from_numpy(waves).to(DEV)).cpu().numpy().astype(np.float64)
+    assert got.shape == (4, 998, 64)
+    for i in range(4):
+        ref = frontend_np.log_mel_spectrogram(waves[i].astype(np.float64))
+        assert np.abs(got[i] - ref).max() <= 1e-4
+
+
+def test_examples_shape_indexing_and_edges():
+    waves = synth.make_clips(0, 2)
+    ex = engine.examples_from_wave(torch.from_numpy(waves).to(DEV))
+    assert tuple(ex.shape) == (20, 96, 64) and ex.dtype == torch.float32
+    ref = frontend_np.waveform_to_examples(waves[1].astype(np.float64))
+    assert np.abs(ex[10:].cpu().numpy() - ref).max() <= 1e-4
+    # frame i of the log-mel starts at sample 160 i: computing a shifted slice reproduces shifted frames exactly
+    w = torch.from_numpy(waves[0]).to(DEV)
+    whole = engine.logmel(w)[0]
+    part = engine.logmel(w[160 * 37:160 * 37 + 16000])[0]
+    assert torch.equal(part, whole[37:37 + part.shape[0]])
+    # lengths around the edges (F10)
+    assert engine.logmel(torch.zeros(400, device=DEV)).shape == (1, 1, 64)
+    assert engine.logmel(torch.zeros(559, device=DEV)).shape == (1, 1, 64)
+    assert engine.logmel(torch.zeros(560, device=DEV)).shape == (1, 2, 64)
+    assert engine.examples_from_wave(torch.zeros(15599, device=DEV)).shape[0] == 0
+    assert engine.examples_from_wave(torch.zeros(15600, device=DEV)).shape[0] == 1
+    with pytest.raises(ValueError):
+        engine.logmel(torch.zeros(100, device=DEV))
+    # silence: log(0 + 0.01)
+    z = engine.logmel(torch.zeros(1, 4000, device=DEV))
+    assert torch.allclose(z, torch.full_like(z, float(np.log(0.01))), atol=1e-6)
+    # strided rows (clip_stride > samples_per_clip) are honoured
+    big = torch.from_numpy(waves).to(DEV)
+    assert torch.equal(engine.logmel(big[:, :32000]), engine.logmel(big[:, :32000].contiguous()))
+
+
+def test_reference_named_front_end_api(golden_front):
+    from torchvggish import mel_features, vggish_input
+    w = golden_front["waves_f32"][0].astype(np.float64)
+    t = vggish_input.waveform_to_examples(w, 16000)
+    assert tuple(t.shape) == (1, 1, 96, 64) and t.dtype == torch.float32 and t.is_cuda
+    assert np.abs(t.cpu().numpy() - golden_front["examples_tensor_f32"]).max() <= 1e-4
+    a = vggish_input.waveform_to_examples(w, 16000, return_tensor=False)
+    assert a.dtype == np.float64 and a.shape == (1, 96, 64)
+    stereo = np.stack([golden_front["waves_f32"][0], golden_front["waves_f32"][2]], axis=1).astype(np.float64)
+    s = vggish_input.waveform_to_examples(stereo, 16000, return_tensor=False)
+    assert np.abs(s - golden_front["stereo_examples_f64"]).max() <= 1e-4
+    lm = mel_features.log_mel_spectrogram(w, audio_sample_rate=16000, log_offset=0.01, window_length_secs=0.025,
+                                          hop_length_secs=0.010, num_mel_bins=64, lower_edge_hertz=125,
+                                          upper_edge_hertz=7500)
+    assert np.abs(lm - golden_front["logmel_f64"][0]).max() <= 1e-4
+    with pytest.raises(NotImplementedError):
+        vggish_input.waveform_to_examples(w, 22050)
+    with pytest.raises(ValueError):
+        vggish_input.waveform_to_examples(np.zeros(100), 16000)
+
+
+# ------------------------------------------------------------------------------------------------ VGGish layers
+def _layer_check(got, ref, name, rel_tol=0.015, cos_tol=0.9999):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    rel = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+    cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    print(f"{name}: rel-max-err {rel:.3e} cos {cos:.6f}")
+    assert not torch.isnan(got).any()
+    assert rel <= rel_tol and cos >= cos_tol, name
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,pool", [(3, 48, 32, 64, 128, 1), (3, 24, 16, 128, 256, 0),
+                                                 (3, 24, 16, 256, 256, 1), (5, 12, 8, 256, 512, 0),
+                                                 (5, 12, 8, 512, 512, 1), (1, 12, 8, 256, 512, 0)])
+def test_conv3x3_layer(n, H, W, Cin, Cout, pool):
+    g = torch.Generator().manual_seed(H * 7 + Cin + n)
+    x = torch.randn(n, Cin, H, W, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(DEV).bfloat16()
+    b = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_k = w.permute(0, 2, 3, 1).contiguous().reshape(Cout, 9 * Cin)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.full((n, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    engine.check(_lib.lib().vmb_conv3x3_relu(x_nhwc.data_ptr(), w_k.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W,
+                                             Cin, Cout, pool, engine.stream_ptr()), "vmb_conv3x3_relu")
+    ref = F.relu(F.conv2d(x.float(), w.float(), b, padding=1))           # same bf16-rounded operands, fp32 math
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    _layer_check(out.permute(0, 3, 1, 2), ref, f"conv {H}x{W} {Cin}->{Cout} pool={pool}", rel_tol=0.005)
+
+
+@pytest.mark.parametrize("M,N,K,f32", [(1, 128, 64, 1), (10, 4096, 12288, 0), (130, 256, 512, 0), (257, 128, 4096, 1)])
+def test_linear_layer(M, N, K, f32):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
+    b = torch.randn(N, generator=g).to(DEV)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+    engine.check(_lib.lib().vmb_linear(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), f32, 1, M, N, K,
+                                       engine.stream_ptr()), "vmb_linear")
+    ref = F.relu(a.float() @ w.float().t() + b)
+    _layer_check(out, ref, f"linear {M}x{N}x{K}", rel_tol=1e-5 if f32 else 0.005)
+
+
+def test_conv1_layer(vgg_sd):
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(7, 96, 64, generator=g) * 2 - 3).to(DEV)
+    w, b = vgg_sd["features.0.weight"].to(DEV), vgg_sd["features.0.bias"].to(DEV)
+    out = torch.empty(7, 48, 32, 64, device=DEV, dtype=torch.bfloat16)
+    engine.check(_lib.lib().vmb_conv1_relu_pool(x.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(), out.data_ptr(), 7,
+                                                engine.stream_ptr()), "vmb_conv1_relu_pool")
+    ref = F.max_pool2d(F.relu(F.conv2d(x[:, None], w, b, padding=1)), 2, 2)
+    _layer_check(out.permute(0, 3, 1, 2), ref, "conv1", rel_tol=0.005)
+
+
+def test_vggish_embeddings_vs_golden_and_oracle(golden_front, golden_vggish, vgg_handle, vgg_sd):
+    x = torch.from_numpy(golden_front["examples_f64"][:, 0]).float().to(DEV)
+    emb, bott = vgg_handle.forward(x, want_bottleneck=True)
+    _layer_check(emb, torch.from_numpy(golden_vggish["embeddings"]), "embeddings vs reference golden")
+    with torch.no_grad():
+        feats = model_torch.vgg_flatten(model_torch.vgg_features(vgg_sd, x.cpu()[:, None]))
+    _layer_check(bott, feats, "conv features (h,w,c) flatten order")
+    assert tuple(vgg_handle.forward(x[:, None]).shape) == (4, 128)
+    assert vgg_handle.forward(torch.empty(0, 96, 64, device=DEV)).shape == (0, 128)
+    with pytest.raises(ValueError):
+        vgg_handle.forward(torch.zeros(2, 64, 96, device=DEV))
+
+
+def test_vggish_batch_invariance(vgg_handle):
+    """An example's embedding must not depend on its position in the batch or on the batch size (sharding relies
+    on it): bit-identical."""
+    ex = engine.examples_from_wave(torch.from_numpy(synth.make_clips(0, 3)).to(DEV))      # 30 examples
+    full = vgg_handle.forward(ex)
+    assert torch.equal(vgg_handle.forward(ex[7:19]), full[7:19])
+    assert torch.equal(vgg_handle.forward(ex[29:30]), full[29:30])
+
+
+def test_postprocessor(golden_vggish):
+    eig, means = synth.pca_params(1)
+    emb = torch.from_numpy(golden_vggish["embeddings"])
+    out, u8 = engine.postprocess(emb.to(DEV), eig.to(DEV), means.to(DEV), want_u8=True)
+    ref = golden_vggish["postprocessed"]
+    diff = np.abs(out.cpu().numpy() - ref)
+    print("postprocess: LSB histogram on identical fp32 embeddings:", np.bincount(diff.astype(np.int64).ravel()))
+    assert diff.max() <= 1 and (diff > 0).mean() <= 0.01
+    assert u8.dtype == torch.uint8 and np.array_equal(u8.cpu().numpy().astype(np.float32), out.cpu().numpy())
+    # larger random batch against the oracle, incl. values that clamp at both ends
+    g = torch.Generator().manual_seed(9)
+    big = torch.randn(1001, 128, generator=g).abs() * 6
+    got = engine.postprocess(big.to(DEV), eig.to(DEV), means.to(DEV)).cpu()
+    want = model_torch.postprocess(eig, means, big)
+    d = (got - want).abs()
+    assert d.max() <= 1 and (d > 0).float().mean() <= 0.01
+    assert got.min() >= 0 and got.max() <= 255 and (got == 0).any() and (got == 255).any()
+
+
+def test_reference_named_vggish_module(golden_front, golden_vggish, vgg_sd):
+    from torchvggish.vggish import VGGish
+    eig, means = synth.pca_params(1)
+    net = VGGish(urls={}, pretrained=False, preprocess=True, postprocess=True)
+    net.load_state_dict({**vgg_sd, "pproc.pca_eigen_vectors": eig, "pproc.pca_means": means})
+    net = net.to(DEV).eval()
+    out = net(golden_front["waves_f32"][2].astype(np.float64), 16000)
+    assert tuple(out.shape) == (128,) and out.dtype == torch.float32                  # squeeze + float 0..255 (F6)
+    ref = golden_vggish["preprocess_postprocess"]
+    d = np.abs(out.cpu().numpy() - ref)
+    print("VGGish(preprocess, postprocess) vs reference: LSB histogram", np.bincount(d.astype(np.int64)))
+    assert (d <= 1).mean() >= 0.5 and d.max() <= 16       # bf16 body: honest LSB spread, bounded
+    plain = VGGish(urls={}, pretrained=False, preprocess=False, postprocess=False)
+    plain.load_state_dict(vgg_sd)
+    plain = plain.to(DEV).eval()
+    x = torch.from_numpy(golden_front["examples_tensor_f32"]).to(DEV)
+    _layer_check(plain(x), torch.from_numpy(golden_vggish["embeddings"][:1]), "VGGish module")
+    # in-place weight update invalidates the cached library handle
+    with torch.no_grad():
+        plain.embeddings[4].bias.add_(1.0)
+    assert (plain(x) - torch.from_numpy(golden_vggish["embeddings"][:1]).to(DEV)).min() > 0.5
+
+
+# ------------------------------------------------------------------------------------------------ head
+@pytest.mark.parametrize("tag,K,conf,seed", [("k527", 527, (2, 1), 2), ("k10", 10, (2, 1), 2), ("c121", 10, (1, 2, 1), 5)])
+def test_head_vs_golden(golden_head, tag, K, conf, seed):
+    sd = synth.mla_state_dict(conf, 128, 600, K, 10, seed=seed)
+    h = engine.MlaHandle(sd, conf, 128, 600, K, 10, DEV)
+    x = torch.from_numpy(golden_head[f"x_{tag}"]).to(DEV)
+    y = h.forward(x).cpu().numpy()
+    ref = golden_head[f"y_{tag}"]
+    print(f"head {tag}: max-abs-err {np.abs(y - ref).max():.3e}")
+    assert np.abs(y - ref).max() <= 2e-5
+    # odd batch sizes and both CTA shapes
+    xb = x.repeat(120, 1, 1)[:601]
+    yb = h.forward(xb).cpu().numpy()
+    assert np.abs(yb - np.tile(ref, (120, 1))[:601]).max() <= 2e-5
+    assert h.forward(x[:1]).shape == (1, K)
+    h.close()
+
+
+def test_reference_named_head_module(golden_head):
+    import model
+    old = model.K
+    try:
+        model.K = 527
+        m = model.MultiLevelAttention([2, 1], 128)
+    finally:
+        model.K = old
+    m.load_state_dict(synth.mla_state_dict((2, 1), 128, 600, 527, 10, seed=2))
+    m = m.to(DEV).eval()
+    y = m(torch.from_numpy(golden_head["x_k527"]).to(DEV))
+    assert np.abs(y.cpu().numpy() - golden_head["y_k527"]).max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def test_pipeline_vs_reference_golden(golden_ensemble, vgg_handle, head_handle):
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    waves = torch.from_numpy(synth.make_clips(4, 2)).to(DEV)
+    scores, emb = pipe.forward(waves, want_embeddings=True)
+    _layer_check(emb, torch.from_numpy(golden_ensemble["embeddings"]), "pipeline embeddings vs reference")
+    d = np.abs(scores.cpu().numpy() - golden_ensemble["scores"]).max()
+    print(f"pipeline scores vs reference Ensemble: max-abs-err {d:.3e}")
+    assert d <= 2e-2
+    # host-buffer entry point gives the same bits as the device-resident one
+    host = pipe.forward_host(torch.from_numpy(synth.make_clips(4, 2)).pin_memory(), clips_per_batch=1)
+    assert torch.equal(host, scores.cpu())
+
+
+def test_ensemble_module_matches_pipeline(golden_ensemble, vgg_sd, head_sd):
+    import model
+    old = model.K
+    try:
+        model.K = 527
+        conf = dict(cnn_type="vggish", num_classes=527, use_pretrained=False, just_bottlenecks=False,
+                    cnn_trainable=False, first_cnn_layer_trainable=False, in_channels=1)
+        ens = model.Ensemble("repeat", conf, [2, 1], DEV)
+    finally:
+        model.K = old
+    ens.cnn.cnn_model.load_state_dict(vgg_sd)
+    ens.mla.load_state_dict(head_sd)
+    ens = ens.to(DEV).eval()
+    from torchvggish.vggish_input import waveform_to_examples
+    waves = synth.make_clips(4, 2)
+    ex = torch.stack([waveform_to_examples(w.astype(np.float64), 16000) for w in waves])     # (2, 10, 1, 96, 64)
+    y = ens(ex)
+    assert tuple(y.shape) == (2, 527)
+    assert np.abs(y.cpu().numpy() - golden_ensemble["scores"]).max() <= 2e-2
+    assert torch.equal(ens.forward_waveform(torch.from_numpy(waves).to(DEV)), y)
+
+
+def test_map_identical_to_three_decimals(vgg_handle, head_handle, vgg_sd, head_sd):
+    """mAP on a fixed synthetic label set: B200 scores vs the fp32 CPU oracle on the same 24 clips."""
+    n = 24
+    waves = synth.make_clips(100, n)
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    got = pipe.forward(torch.from_numpy(waves).to(DEV)).cpu().numpy()
+    ex = np.concatenate([frontend_np.waveform_to_examples(w.astype(np.float64)) for w in waves]).astype(np.float32)
+    with torch.no_grad():
+        emb = model_torch.vgg_forward(vgg_sd, torch.from_numpy(ex)[:, None])
+        want = model_torch.mla_forward(head_sd, emb.reshape(n, 10, 128), (2, 1)).numpy()
+    labels = synth.multihot_labels(n, 527, p=0.2, seed=3)
+    a, b = synth.mean_average_precision(labels, got), synth.mean_average_precision(labels, want)
+    print(f"mAP B200 {a:.5f} oracle {b:.5f}; scores max-abs-err {np.abs(got - want).max():.3e}")
+    assert round(a, 3) == round(b, 3)
+
+
+def test_shard_invariance(vgg_handle, head_handle):
+    """Results must be bit-identical however the batch is cut (1/2/4/8-way contiguous shards)."""
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    waves = torch.from_numpy(synth.make_clips(200, 8)).to(DEV)
+    whole = pipe.forward(waves)
+    for world in (2, 4, 8):
+        parts = [pipe.forward(waves[slice(*sharding.shard_bounds(8, r, world))]).clone() for r in range(world)]
+        assert torch.equal(torch.cat(parts), whole)
+
+
+def test_stream_embeddings_chunking_is_exact(vgg_handle):
+    """Long-stream path (config 4 shape, shortened): chunked at multiples of 15 360 samples == unchunked."""
+    n_ex = 41
+    rng = np.random.default_rng(7)
+    stream = (rng.standard_normal(15360 * (n_ex - 1) + 15600 + 777) * 0.1).astype(np.float32)
+    assert sharding.num_examples(len(stream)) == n_ex
+    w = torch.from_numpy(stream).to(DEV)
+    whole = vgg_handle.forward(engine.examples_from_wave(w))
+    eig, means = synth.pca_params(1)
+    q_whole = engine.postprocess(whole, eig.to(DEV), means.to(DEV), want_u8=True)[1]
+    parts = []
+    for rank in range(3):
+        for e0, e1, s0, s1 in sharding.stream_chunks(len(stream), 6, rank, 3):
+            parts.append(vgg_handle.forward(engine.examples_from_wave(w[s0:s1])))
+    emb = torch.cat(parts)
+    assert torch.equal(emb, whole)
+    assert torch.equal(engine.postprocess(emb, eig.to(DEV), means.to(DEV), want_u8=True)[1], q_whole)
