@@ -230,7 +230,9 @@ def test_reference_named_vggish_module(golden_front, golden_vggish, vgg_sd):
     # in-place weight update invalidates the cached library handle
     with torch.no_grad():
         plain.embeddings[4].bias.add_(1.0)
-    assert (plain(x) - torch.from_numpy(golden_vggish["embeddings"][:1]).to(DEV)).min() > 0.5
+    ref1 = torch.from_numpy(golden_vggish["embeddings"][:1]).to(DEV)
+    moved = plain(x) - ref1
+    assert (moved[ref1 > 0] > 0.9).all() and (moved >= 0).all()
 
 
 # ------------------------------------------------------------------------------------------------ head
