@@ -26,6 +26,7 @@ SIGNATURES = {
     "vmb_num_frames": (_ll, [_ll]),
     "vmb_num_examples": (_ll, [_ll]),
     "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
+    "vmb_logmel_cudacore": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_conv3x3_relu": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _int, _int, _int, _int, _c_p]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "vmb_mla_num_classes": (_int, [_c_p]),
     "vmb_mla_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int]),
     "vmb_mla_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
+    "vmb_mla_forward_fp32": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
     "vmb_pipeline_workspace_bytes": (_sz, [_ll, _ll]),
     "vmb_pipeline_forward": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_pipeline_forward_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),

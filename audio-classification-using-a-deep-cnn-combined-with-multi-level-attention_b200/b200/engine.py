@@ -68,6 +68,24 @@ def logmel(wave: torch.Tensor, frames_out: Optional[int] = None) -> torch.Tensor
     return out
 
 
+def logmel_cudacore(wave: torch.Tensor) -> torch.Tensor:
+    """Diagnostic: the fp32 CUDA-core log-mel kernel (vmb_logmel_cudacore), same contract as logmel()."""
+    wave = _need_cuda(wave, "wave")
+    if wave.dim() == 1:
+        wave = wave[None]
+    n_clips, n_samples = wave.shape
+    nf = num_frames(n_samples)
+    if nf < 0:
+        raise ValueError("negative dimensions are not allowed")
+    out = torch.empty((n_clips, nf, MEL), device=wave.device, dtype=torch.float32)
+    with torch.cuda.device(wave.device):
+        for c0 in range(0, n_clips, 32768):
+            nc = min(32768, n_clips - c0)
+            check(_lib.lib().vmb_logmel_cudacore(ptr(wave[c0:]), nc, n_samples, wave.stride(0), nf, ptr(out[c0:]),
+                                                 stream_ptr()), "vmb_logmel_cudacore")
+    return out
+
+
 def examples_from_wave(wave: torch.Tensor) -> torch.Tensor:
     """(n_clips, n_samples) fp32 CUDA -> (n_clips * examples_per_clip, 96, 64) fp32 (vggish_input.py:66-76)."""
     if wave.dim() == 1:
@@ -224,13 +242,17 @@ class MlaHandle:
 
     __del__ = close
 
-    def forward(self, emb: torch.Tensor) -> torch.Tensor:
+    def forward(self, emb: torch.Tensor, fp32_crosscheck: bool = False) -> torch.Tensor:
+        """(B, T, emb_in) fp32 CUDA -> (B, K) scores.  fp32_crosscheck=True runs the diagnostic fused CUDA-core kernel
+        (vmb_mla_forward_fp32) instead of the tensor-core path."""
         emb = _need_cuda(emb, "embeddings")
         if emb.dim() != 3 or emb.shape[1] != self.t_steps or emb.shape[2] != self.emb_in:
             raise ValueError(f"expected (B, {self.t_steps}, {self.emb_in}), got {tuple(emb.shape)}")
         out = torch.empty((emb.shape[0], self.n_classes), device=self.device, dtype=torch.float32)
+        fn, name = ((_lib.lib().vmb_mla_forward_fp32, "vmb_mla_forward_fp32") if fp32_crosscheck
+                    else (_lib.lib().vmb_mla_forward, "vmb_mla_forward"))
         with torch.cuda.device(self.device):
-            check(_lib.lib().vmb_mla_forward(self._h, ptr(emb), emb.shape[0], ptr(out), stream_ptr()), "vmb_mla_forward")
+            check(fn(self._h, ptr(emb), emb.shape[0], ptr(out), stream_ptr()), name)
         return out
 
 

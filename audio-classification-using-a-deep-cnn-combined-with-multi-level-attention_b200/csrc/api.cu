@@ -58,18 +58,32 @@ long long vmb_num_examples(long long n_samples) {
   return 1 + (f - 96) / 96;  // vggish_input.py:73-76 via mel_features.py:42 with window = hop = 96
 }
 
+static int logmel_common(const char* who, bool tensor_core, const float* wave, long long n_clips,
+                         long long samples_per_clip, long long clip_stride, long long frames_out, float* logmel,
+                         void* stream) {
+  if (n_clips < 0 || frames_out < 0) return fail("%s: negative size", who);
+  const long long nf = vmb_num_frames(samples_per_clip);
+  if (nf < 1) return fail("%s: %lld samples is shorter than one 400-sample window", who, samples_per_clip);
+  if (frames_out > nf) return fail("%s: frames_out %lld > available frames %lld", who, frames_out, nf);
+  if (clip_stride < samples_per_clip) return fail("%s: clip_stride < samples_per_clip", who);
+  if (n_clips == 0 || frames_out == 0) return 0;
+  if (!wave || !logmel) return fail("%s: null pointer", who);
+  const int rc = tensor_core
+                     ? vmb::logmel_tc_forward(wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, S(stream))
+                     : vmb::logmel_forward(wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, S(stream));
+  if (rc) return fail_from(who, vmb::kernels_last_error());
+  return 0;
+}
+
 int vmb_logmel(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                long long frames_out, float* logmel, void* stream) {
-  if (n_clips < 0 || frames_out < 0) return fail("vmb_logmel: negative size");
-  const long long nf = vmb_num_frames(samples_per_clip);
-  if (nf < 1) return fail("vmb_logmel: %lld samples is shorter than one 400-sample window", samples_per_clip);
-  if (frames_out > nf) return fail("vmb_logmel: frames_out %lld > available frames %lld", frames_out, nf);
-  if (clip_stride < samples_per_clip) return fail("vmb_logmel: clip_stride < samples_per_clip");
-  if (n_clips == 0 || frames_out == 0) return 0;
-  if (!wave || !logmel) return fail("vmb_logmel: null pointer");
-  if (vmb::logmel_forward(wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, S(stream)))
-    return fail_from("vmb_logmel", vmb::kernels_last_error());
-  return 0;
+  return logmel_common("vmb_logmel", true, wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, stream);
+}
+
+int vmb_logmel_cudacore(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                        long long frames_out, float* logmel, void* stream) {
+  return logmel_common("vmb_logmel_cudacore", false, wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel,
+                       stream);
 }
 
 int vmb_front_end_tables(double* hann400, double* mel257x64) {

@@ -103,9 +103,13 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                           by[q] + dh, bn[q]);
             if (++cb == p.cblks) { cb = 0; ++tap; }
           } else {
-            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kBlockK, m_tile * kBlockM);
+            // split mode (p.split_nkb > 0): A and B are stored as [hi | lo] column blocks and the K loop runs over
+            // the three products hi*hi, lo*hi, hi*lo (see igemm_linear_split)
+            const int a_kb = (p.split_nkb && kb >= 2 * p.split_nkb) ? kb - 2 * p.split_nkb : kb;
+            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], a_kb * kBlockK, m_tile * kBlockM);
           }
-          tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+          const int b_kb = (p.split_nkb && kb >= p.split_nkb) ? kb - p.split_nkb : kb;
+          tma_load_2d(b_dst, &tmap_b, &full_bar[stage], b_kb * kBlockK, n_tile * BLOCK_N);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -263,17 +267,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rank-`rank` bf16 tensor map, 128-byte swizzle, zero OOB fill.  strides_bytes has rank-1 entries.
+}  // namespace
+
+// rank-`rank` bf16 tensor map, zero OOB fill.  strides_bytes has rank-1 entries.  swizzle_bytes: 128 or 64.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return 1;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle swz = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d)", int(r), rank);
@@ -292,6 +299,8 @@ int num_sms() {
   }
   return n;
 }
+
+namespace {
 
 template <int BLOCK_N, bool CONV, bool POOL, bool OUT_F32>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
@@ -358,6 +367,42 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
                    : launch<256, false, false, false>(ta, tb, p, stream);
   return out_f32 ? launch<128, false, false, true>(ta, tb, p, stream)
                  : launch<128, false, false, false>(ta, tb, p, stream);
+}
+
+int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
+                       int relu, int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBlockK != 0 || N % 128 != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
+    return 1;
+  }
+  const int block_n = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {uint64_t(2 * K), uint64_t(M)};
+    uint64_t str[1] = {uint64_t(2 * K) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (make_tmap_bf16(&ta, a_planes, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(2 * K), uint64_t(N)};
+    uint64_t str[1] = {uint64_t(2 * K) * 2};
+    uint32_t box[2] = {kBlockK, uint32_t(block_n)};
+    if (make_tmap_bf16(&tb, w_planes, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.split_nkb = K / kBlockK;
+  p.num_kb = 3 * p.split_nkb;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.num_n_tiles = N / block_n;
+  p.relu = relu;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.out = out;
+  return block_n == 256 ? launch<256, false, false, true>(ta, tb, p, stream)
+                        : launch<128, false, false, true>(ta, tb, p, stream);
 }
 
 int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,

@@ -34,6 +34,7 @@ struct IgemmParams {
   int num_m_tiles;
   int num_n_tiles;
   int relu;
+  int split_nkb;     // PLAIN split mode: K / 64 of one plane (0 = ordinary GEMM)
   long long ldo;     // PLAIN: output row stride (elements)
   const float* bias; // [N]
   void* out;         // bf16 (or fp32 when OUT_F32)
@@ -43,11 +44,22 @@ struct IgemmParams {
 // PLAIN: out[M][N] (+ldo) = act(A[M][K] B[N][K]^T + bias).  K % 64 == 0, N % block_n == 0.
 int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int out_f32, int relu,
                  int M, int N, int K, cudaStream_t stream);
+// PLAIN, split-bf16: A = [A_hi | A_lo] as bf16 [M][2K], W = [W_hi | W_lo] as bf16 [N][2K];
+// out fp32 [M][ldo] = act(A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T + bias): ~16 mantissa bits per operand (the
+// attention head, where plain bf16 would move the ranking metric).  K % 64 == 0, N % 128 == 0.
+int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
+                       int relu, int M, int N, int K, cudaStream_t stream);
 // CONV 3x3 pad 1 (+bias, ReLU, optional 2x2 maxpool): act NHWC bf16 [n][H][W][C_in], weights [C_out][9*C_in]
 // ((kh,kw,c) order), out NHWC bf16 [n][H or H/2][W or W/2][C_out].  C_in % 64 == 0, C_out % 128 == 0.
 int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
                   int W, int C_in, int C_out, int pool, cudaStream_t stream);
 
 const char* igemm_last_error();
+
+// Shared host helpers (igemm_sm100.cu): bf16 tensor map with 128- or 64-byte swizzle (error text goes to
+// igemm_last_error()), and the SM count of the current device.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes = 128);
+int num_sms();
 
 }  // namespace vmb

@@ -32,6 +32,10 @@ class StageTimer {
 // Constant tables exactly as mel_features.py builds them (float64): periodic_hann(400) and
 // spectrogram_to_mel_matrix(64, 257, 16000, 125, 7500).
 void front_end_tables_host(double* hann400, double* mel257x64);
+// Tensor-core front end (logmel_tc.cu): split-bf16 tcgen05 DFT GEMM with the magnitude / mel / log epilogue.
+int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                      long long frames_out, float* logmel, cudaStream_t stream);
+// CUDA-core fp32 version of the same computation (frontend.cu); kept as an on-device cross-check, not on the path.
 int logmel_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                    long long frames_out, float* logmel, cudaStream_t stream);
 

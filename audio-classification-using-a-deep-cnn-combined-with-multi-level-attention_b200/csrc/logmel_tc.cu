@@ -1,0 +1,473 @@
+// Tensor-core log-mel front end (sm_100a): framing + periodic Hann + 512-point real DFT as a split-bf16 tcgen05 GEMM,
+// magnitude + HTK mel projection + log fused into the epilogue.
+// Replaces torchvggish/mel_features.py:21-45 (frame), :48-68 (periodic_hann), :71-92 (stft_magnitude),
+// :114-189 (spectrogram_to_mel_matrix), :192-223 (log_mel_spectrogram).
+//
+//   S[f][c] = sum_n x[160 f + n] * W[n][c],   W[n][2j] = hann[n] cos(2 pi k_j n / 512), W[n][2j+1] = hann[n] sin(..)
+//   |X_j| = sqrt(S[f][2j]^2 + S[f][2j+1]^2);  mel[f][m] = sum_j |X_j| M[k_j][m];  out = log(mel + 0.01)
+//
+// * Precision.  log(mel + 0.01) has slope up to 100, so the DFT needs fp32-class accuracy: plain
+//   bf16/tf32 operands miss the 1e-4 bound by orders of magnitude.  Both operands are therefore split exactly into
+//   three bf16 terms (x = x0 + x1 + x2, 24 mantissa bits) and the six products with i + j <= 2 are accumulated
+//   in the same fp32 TMEM accumulator, smallest first: A2B0, A1B1, A0B2, A1B0, A0B1, A0B0.
+// * Framing is never materialised: the A operand is a 3-D TMA tensor map over the split waveform planes with
+//   dims {416 (sample in frame), frames (stride 160 samples), plane*clip}; rows overlap in memory.  The Hann window
+//   is folded into W; columns 400..415 of W are zero (K padded to 13 blocks of 32).
+// * Only DFT bins 4..243 are evaluated (2 N-tiles of 240 columns): the HTK mel matrix is exactly zero outside bins
+//   5..239 (checked when the tables are built).
+// * Epilogue: one thread owns one frame (TMEM lane); it walks the bins in order and, because every bin feeds at
+//   most the two adjacent mel bands, keeps just two running band sums, emitting log(band + 0.01) as bands complete.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.  Persistent over 128-frame
+// tiles; the two N-tiles of a frame tile use the two halves of TMEM so the epilogue of one overlaps the MMAs of the
+// next.  Smem: 3 stages x {A0,A1,A2 (128x32), B0,B1,B2 (240x32)} bf16, 64-byte swizzle = 207 KB.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vmb {
+
+namespace {
+
+constexpr int kWin = 400, kHop = 160, kFft = 512, kBins = 257, kMel = 64;
+constexpr int kBinLo = 4;               // first evaluated DFT bin
+constexpr int kTileBins = 120;          // bins per N-tile
+constexpr int kNTiles = 2;              // bins 4..243
+constexpr int kEvalBins = kTileBins * kNTiles;
+constexpr int kTM = 128;                // frames per tile (UMMA M)
+constexpr int kTN = 2 * kTileBins;      // 240 (UMMA N)
+constexpr int kBK = 32;                 // K block: 32 bf16 = one 64-byte swizzle row
+constexpr int kKB = 13;                 // 13 * 32 = 416 >= 400
+constexpr int kKPad = kKB * kBK;
+constexpr int kATile = kTM * kBK * 2;   // 8192
+constexpr int kBTile = kTN * kBK * 2;   // 15360
+constexpr int kStageBytes = 3 * (kATile + kBTile);  // 70656
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+constexpr int kTmemCols = 512;          // accumulator t lives at column 256 t
+constexpr double kPi = 3.14159265358979323846;
+constexpr float kLogOffset = 0.01f;
+
+// mel walk tables: bin kBinLo + i feeds band e-1 with weight wf and band e with weight wr (e in 0..64)
+__constant__ int c_band[kEvalBins];
+__constant__ float c_wfall[kEvalBins];
+__constant__ float c_wrise[kEvalBins];
+
+// ------------------------------------------------------------------ waveform -> three bf16 planes
+// planes[p][clip][pitch]; samples >= n_samples are written as zero so that K padding never meets garbage.
+__global__ void __launch_bounds__(256)
+split_wave_kernel(const float* __restrict__ wave, long long n_samples, long long clip_stride, long long pitch,
+                  long long n_clips, __nv_bfloat16* __restrict__ planes) {
+  const long long groups_per_clip = pitch / 8;
+  const long long total = groups_per_clip * n_clips;
+  const long long plane_elems = n_clips * pitch;
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long clip = g / groups_per_clip;
+    const long long s0 = (g - clip * groups_per_clip) * 8;
+    const float* src = wave + clip * clip_stride + s0;
+    uint32_t h0[4], h1[4], h2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) x[u] = (s0 + 2 * i + u < n_samples) ? __ldg(src + 2 * i + u) : 0.f;
+      __nv_bfloat16 a[2], b[2], c[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        a[u] = __float2bfloat16_rn(x[u]);
+        const float r1 = x[u] - __bfloat162float(a[u]);      // exact
+        b[u] = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(b[u]);        // exact
+        c[u] = __float2bfloat16_rn(r2);
+      }
+      h0[i] = static_cast<uint32_t>(__bfloat16_as_ushort(a[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(a[1])) << 16);
+      h1[i] = static_cast<uint32_t>(__bfloat16_as_ushort(b[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(b[1])) << 16);
+      h2[i] = static_cast<uint32_t>(__bfloat16_as_ushort(c[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(c[1])) << 16);
+    }
+    __nv_bfloat16* dst = planes + clip * pitch + s0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    *reinterpret_cast<uint4*>(dst + plane_elems) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(dst + 2 * plane_elems) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+  }
+}
+
+// ------------------------------------------------------------------ the GEMM + mel/log epilogue
+struct LogmelParams {
+  long long frames_out;     // frames written per clip
+  int tiles_per_clip;       // ceil(frames_out / 128)
+  int n_clips;
+  long long total_tiles;    // n_clips * tiles_per_clip
+  float* out;               // [n_clips][frames_out][64]
+};
+
+
+struct BandWalk {
+  int e = 0;          // lo accumulates band e-1, hi band e
+  float lo = 0.f, hi = 0.f;
+  float4 pend;        // four finished bands waiting for one 16-byte store
+};
+
+__device__ __forceinline__ void emit_band(BandWalk& w, float* __restrict__ row_out, bool valid) {
+  const int band = w.e - 1;
+  if (band >= 0 && band < kMel) {
+    const float v = __logf(w.lo + kLogOffset);
+    const int slot = band & 3;
+    if (slot == 0) w.pend.x = v;
+    else if (slot == 1) w.pend.y = v;
+    else if (slot == 2) w.pend.z = v;
+    else {
+      w.pend.w = v;
+      if (valid) *reinterpret_cast<float4*>(row_out + band - 3) = w.pend;
+    }
+  }
+  w.lo = w.hi;
+  w.hi = 0.f;
+  ++w.e;
+}
+
+template <int NB>  // NB bins = 2*NB accumulator columns in v
+__device__ __forceinline__ void walk_bins(BandWalk& w, const uint32_t* v, int bin0, float* __restrict__ row_out,
+                                          bool valid) {
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
+    const float mag = sqrtf(fmaf(re, re, im * im));
+    const int e = c_band[bin0 + j];
+    while (w.e < e) emit_band(w, row_out, valid);      // warp-uniform: depends on the bin index only
+    w.lo = fmaf(c_wfall[bin0 + j], mag, w.lo);
+    w.hi = fmaf(c_wrise[bin0 + j], mag, w.hi);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const LogmelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int clip = static_cast<int>(tile / p.tiles_per_clip);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(clip) * p.tiles_per_clip) * kTM;
+        for (int nt = 0; nt < kNTiles; ++nt) {
+          for (int kb = 0; kb < kKB; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* base = smem + stage * kStageBytes;
+            mbar_expect_tx(&full_bar[stage], kStageBytes);
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              tma_load_3d(base + pl * kATile, &tmap_a, &full_bar[stage], kb * kBK, row0, pl * p.n_clips + clip);
+              tma_load_2d(base + 3 * kATile + pl * kBTile, &tmap_b, &full_bar[stage], kb * kBK,
+                          pl * kEvalBins * 2 + nt * kTN);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTM, kTN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < kNTiles; ++nt, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < kKB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t a0 = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b0 = a0 + 3 * kATile;
+            // products (a plane, b plane), smallest magnitude first
+            constexpr int prod_a[6] = {2, 1, 0, 1, 0, 0};
+            constexpr int prod_b[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const uint64_t a_desc = umma_desc_kmajor_sw64(a0 + prod_a[q] * kATile);
+              const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + prod_b[q] * kBTile);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (>>4 = 2) per 16-element K step
+                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | q | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kKB - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const long long clip = tile / p.tiles_per_clip;
+      const long long frame = (tile - clip * p.tiles_per_clip) * kTM + q * 32 + lane;
+      const bool valid = frame < p.frames_out;
+      float* row_out = p.out + (clip * p.frames_out + (valid ? frame : 0)) * kMel;
+      BandWalk w;
+      w.pend = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int nt = 0; nt < kNTiles; ++nt, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll 1
+        for (int ch = 0; ch < kTN / 32; ++ch) {     // 7 chunks of 32 columns = 16 bins
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          walk_bins<16>(w, v, nt * kTileBins + ch * 16, row_out, valid);
+        }
+        {                                            // last 16 columns = 8 bins
+          uint32_t v[16];
+          tmem_ld_32x16(t_addr + (kTN / 32) * 32, v);
+          tmem_ld_wait();
+          walk_bins<8>(w, v, nt * kTileBins + (kTN / 32) * 16, row_out, valid);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ per-device constant tables
+struct TcTables {
+  __nv_bfloat16* basis = nullptr;  // [3][480][416] bf16: row = 2*bin_index + {cos, sin}, col = sample in frame
+  bool ready = false;
+};
+std::mutex g_mu;
+TcTables g_tabs[64];
+
+uint16_t bf16_bits(double v, double* back) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(static_cast<float>(v));
+  *back = static_cast<double>(__bfloat162float(h));
+  return __bfloat16_as_ushort(h);
+}
+
+int build_tables(TcTables& t) {
+  std::vector<double> hann(kWin), mel(size_t(kBins) * kMel);
+  front_end_tables_host(hann.data(), mel.data());
+  // every bin feeds at most two adjacent bands; anything else (or weight outside the evaluated bins) is an error
+  std::vector<int> band(kEvalBins, kMel + 1);
+  std::vector<float> wf(kEvalBins, 0.f), wr(kEvalBins, 0.f);
+  int prev = 0;
+  for (int k = 0; k < kBins; ++k) {
+    int first = -1, last = -1, nnz = 0;
+    for (int m = 0; m < kMel; ++m)
+      if (mel[size_t(k) * kMel + m] != 0.0) {
+        if (first < 0) first = m;
+        last = m;
+        ++nnz;
+      }
+    const int i = k - kBinLo;
+    if (i < 0 || i >= kEvalBins) {
+      if (nnz) {
+        set_kernel_error("logmel: mel matrix has weight outside the evaluated bins (bin %d)", k);
+        return 1;
+      }
+      continue;
+    }
+    if (nnz > 2 || (nnz == 2 && last != first + 1)) {
+      set_kernel_error("logmel: bin %d feeds non-adjacent mel bands", k);
+      return 1;
+    }
+    // interval index e: the bin feeds band e-1 (falling side) and band e (rising side).  Two weights -> e is the
+    // upper band; a lone weight at band c can sit on either side, whichever keeps the walk monotone.
+    int e = prev;
+    if (nnz == 2) e = last;
+    else if (nnz == 1) e = (first >= prev) ? first : first + 1;
+    if (e < prev) {
+      set_kernel_error("logmel: mel band walk is not monotone at bin %d", k);
+      return 1;
+    }
+    band[i] = e;
+    wf[i] = (e - 1 >= 0 && e - 1 < kMel) ? static_cast<float>(mel[size_t(k) * kMel + e - 1]) : 0.f;
+    wr[i] = (e < kMel) ? static_cast<float>(mel[size_t(k) * kMel + e]) : 0.f;
+    // whatever the interval choice, both non-zero weights of the row must be covered
+    for (int m = 0; m < kMel; ++m)
+      if (mel[size_t(k) * kMel + m] != 0.0 && m != e - 1 && m != e) {
+        set_kernel_error("logmel: bin %d weight for band %d not representable in the two-band walk", k, m);
+        return 1;
+      }
+    prev = e;
+  }
+  if (cudaMemcpyToSymbol(c_band, band.data(), sizeof(int) * kEvalBins) != cudaSuccess ||
+      cudaMemcpyToSymbol(c_wfall, wf.data(), sizeof(float) * kEvalBins) != cudaSuccess ||
+      cudaMemcpyToSymbol(c_wrise, wr.data(), sizeof(float) * kEvalBins) != cudaSuccess) {
+    set_kernel_error("logmel: constant table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  const size_t plane = size_t(kEvalBins) * 2 * kKPad;
+  std::vector<uint16_t> basis(3 * plane, 0);
+  for (int i = 0; i < kEvalBins; ++i)
+    for (int n = 0; n < kWin; ++n) {
+      const int kn = ((kBinLo + i) * n) % kFft;            // exact argument reduction
+      const double ang = 2 * kPi * kn / kFft;
+      const double val[2] = {hann[n] * std::cos(ang), hann[n] * std::sin(ang)};
+      for (int c = 0; c < 2; ++c) {
+        double r = val[c], back;
+        for (int pl = 0; pl < 3; ++pl) {
+          basis[pl * plane + (size_t(2 * i + c)) * kKPad + n] = bf16_bits(r, &back);
+          r -= back;
+        }
+      }
+    }
+  void* d = nullptr;
+  if (cudaMalloc(&d, basis.size() * 2) != cudaSuccess ||
+      cudaMemcpy(d, basis.data(), basis.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_kernel_error("logmel: basis upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  t.basis = static_cast<__nv_bfloat16*>(d);
+  t.ready = true;
+  return 0;
+}
+
+int get_tables(TcTables** out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_kernel_error("logmel: cudaGetDevice failed");
+    return 1;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  TcTables& t = g_tabs[dev];
+  if (!t.ready) {
+    if (build_tables(t)) return 1;
+    if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      set_kernel_error("logmel: cannot raise dynamic shared memory to %d bytes", kSmemBytes);
+      return 1;
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;   // keep freed workspace in the pool: the next call reuses it without a driver call
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  *out = &t;
+  return 0;
+}
+
+}  // namespace
+
+long long logmel_tc_pitch(long long samples_per_clip) {
+  // last frame reads up to sample 160 (frames - 1) + 415 <= samples + 15; rows of the A tensor map must stay inside
+  // the plane; a multiple of 160 keeps every stride a multiple of the 320-byte frame stride
+  return (samples_per_clip + 16 + kHop - 1) / kHop * kHop;
+}
+
+int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                      long long frames_out, float* logmel, cudaStream_t stream) {
+  TcTables* t = nullptr;
+  if (get_tables(&t)) return 1;
+  if (3 * n_clips > 0x7fffffffLL || frames_out > 0x7fffffffLL) {
+    set_kernel_error("logmel: too many clips / frames for one launch");
+    return 1;
+  }
+  const long long pitch = logmel_tc_pitch(samples_per_clip);
+  const size_t plane_bytes = size_t(n_clips) * pitch * 2;
+  void* planes = nullptr;
+  if (cudaMallocAsync(&planes, 3 * plane_bytes, stream) != cudaSuccess) {
+    set_kernel_error("logmel: workspace allocation of %zu bytes failed: %s", 3 * plane_bytes,
+                     cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  {
+    const long long groups = pitch / 8 * n_clips;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((groups + 255) / 256, 148LL * 16));
+    split_wave_kernel<<<grid, 256, 0, stream>>>(wave, samples_per_clip, clip_stride, pitch, n_clips,
+                                                static_cast<__nv_bfloat16*>(planes));
+    count_launch();
+    if (check_launch("split_wave_kernel")) return 1;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[3] = {uint64_t(kKPad), uint64_t(frames_out), uint64_t(3 * n_clips)};
+    uint64_t str[2] = {uint64_t(kHop) * 2, uint64_t(pitch) * 2};
+    uint32_t box[3] = {kBK, kTM, 1};
+    if (make_tmap_bf16(&ta, planes, 3, dims, str, box, 64)) {
+      set_kernel_error("logmel: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  {
+    uint64_t dims[2] = {uint64_t(kKPad), uint64_t(3 * kEvalBins * 2)};
+    uint64_t str[1] = {uint64_t(kKPad) * 2};
+    uint32_t box[2] = {kBK, kTN};
+    if (make_tmap_bf16(&tb, t->basis, 2, dims, str, box, 64)) {
+      set_kernel_error("logmel: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  LogmelParams p{};
+  p.frames_out = frames_out;
+  p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
+  p.n_clips = static_cast<int>(n_clips);
+  p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
+  p.out = logmel;
+  const long long grid = std::min<long long>(p.total_tiles, num_sms());
+  logmel_tc_kernel<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  count_launch();
+  if (check_launch("logmel_tc_kernel")) return 1;
+  if (cudaFreeAsync(planes, stream) != cudaSuccess) {
+    set_kernel_error("logmel: cudaFreeAsync failed");
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace vmb

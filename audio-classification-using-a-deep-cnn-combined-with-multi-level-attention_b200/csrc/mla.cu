@@ -15,45 +15,19 @@
 #include <vector>
 
 #include "../../include/vggish_mla_b200.h"
+#include <cuda_bf16.h>
+
 #include "kernels.cuh"
+#include "mla_internal.cuh"
 
 namespace vmb {
 void set_api_error(const char* msg);
 }
 
+struct vmb_mla : vmb_head::Handle {};
+
 namespace {
-
-constexpr int kMaxLevels = 4;
-constexpr int kMaxFc = 4;
-constexpr int kPad = 640;      // padded column count of every transposed weight
-constexpr int kMaxDim = 608;   // activation row pitch in shared memory (floats); multiple of 4
-constexpr int kThreads = 256;
-constexpr int kColThreads = 64;
-constexpr int kColsPerThread = kPad / kColThreads;  // 10
-
-struct FcDev {
-  const float* wt;    // [in][kPad]
-  const float* bias;  // [kPad]
-  const float* a;     // [T] folded BN scale
-  const float* b;     // [T] folded BN shift
-  int in;
-};
-struct LevelDev {
-  const float* n0a;  // [T]
-  const float* n0b;
-  int n_fc;
-  FcDev fc[kMaxFc];
-  FcDev fcv;         // a/b unused
-  const float *av, *bv, *af, *bf;  // [T] each
-};
-struct HeadDev {
-  int n_levels, emb_in, hidden, K, T;
-  LevelDev lvl[kMaxLevels];
-  const float* fc_wt;    // [L*K][kPad]
-  const float* fc_bias;  // [kPad]
-  const float* out_a;    // [K] folded BN_K
-  const float* out_b;
-};
+using namespace vmb_head;
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -234,12 +208,6 @@ constexpr size_t kMaxDynSmem = 227 * 1024;
 
 }  // namespace
 
-struct vmb_mla {
-  HeadDev dev;
-  float* blob = nullptr;  // single device allocation holding every folded table
-  int device = 0;
-};
-
 namespace {
 
 int fail(const char* msg) {
@@ -277,8 +245,8 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
   for (int l = 0; l < n_levels; ++l)
     if (n_fc[l] < 1 || n_fc[l] > kMaxFc) return fail("vmb_mla_create: 1..4 fully connected layers per level supported");
   if (T != 10) return fail("vmb_mla_create: T must be 10 (params.py:26; BatchNorm1d(T) hard-wires it, model.py:205)");
-  if (emb_in < 1 || emb_in > kMaxDim || H < 1 || H > kMaxDim || K < 1 || K > kMaxDim)
-    return fail("vmb_mla_create: emb_in, hidden and n_classes must be in 1..608");
+  if (emb_in < 1 || emb_in > 16384 || H < 1 || H > kMaxDim || K < 1 || K > kMaxDim)
+    return fail("vmb_mla_create: hidden and n_classes must be in 1..608, emb_in in 1..16384");
   if (n_params != param_count(n_levels, n_fc, emb_in, H, K, T))
     return fail("vmb_mla_create: n_params does not match the documented flat layout");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -304,18 +272,37 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
       blob[ob + i] = float(double(b[i]) - double(m[i]) * a);
     }
   };
+  std::vector<uint16_t> planes;  // bf16 bits
+  auto bf16_split = [](float v, uint16_t* hi, uint16_t* lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    *hi = __bfloat16_as_ushort(h);
+    *lo = __bfloat16_as_ushort(l);
+  };
+  size_t cur_planes = 0;
+  int cur_kpad = 0;
   auto transpose_w = [&](int n_out, int n_in, size_t& owt, size_t& obias) {
     const float* w = take(size_t(n_out) * n_in);
     const float* b = take(n_out);
     const int in_pad = (n_in + 3) & ~3;
-    owt = reserve(size_t(in_pad) * kPad);
+    const bool small = n_in <= 4096;   // the transposed fp32 copy feeds the fused fp32 kernel and the output FC
+    owt = reserve(small ? size_t(in_pad) * kPad : 4);
     obias = reserve(kPad);
+    const int kpad = (n_in + 63) / 64 * 64;
+    cur_planes = planes.size();
+    cur_kpad = kpad;
+    planes.resize(planes.size() + size_t(kPad) * 2 * kpad, 0);
     for (int o = 0; o < n_out; ++o) {
-      for (int i = 0; i < n_in; ++i) blob[owt + size_t(i) * kPad + o] = w[size_t(o) * n_in + i];
+      uint16_t* row = planes.data() + cur_planes + size_t(o) * 2 * kpad;
+      for (int i = 0; i < n_in; ++i) {
+        const float v = w[size_t(o) * n_in + i];
+        if (small) blob[owt + size_t(i) * kPad + o] = v;
+        bf16_split(v, row + i, row + kpad + i);
+      }
       blob[obias + o] = b[o];
     }
   };
-  struct FcOff { size_t wt, bias, a, b; int in; };
+  struct FcOff { size_t wt, bias, a, b; int in; size_t wp; int kpad; };
   struct LvlOff { size_t n0a, n0b; int n_fc; FcOff fc[kMaxFc]; FcOff fcv; size_t av, bv, af, bf; };
   LvlOff lo[kMaxLevels];
   for (int l = 0; l < n_levels; ++l) {
@@ -326,12 +313,16 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
     for (int j = 0; j < n_fc[l]; ++j) {
       const int in = (l == 0 && j == 0) ? emb_in : H;
       transpose_w(H, in, lo[l].fc[j].wt, lo[l].fc[j].bias);
+      lo[l].fc[j].wp = cur_planes;
+      lo[l].fc[j].kpad = cur_kpad;
       fold_bn(T, lo[l].fc[j].a, lo[l].fc[j].b);
       lo[l].fc[j].in = (in + 3) & ~3;
     }
   }
   for (int l = 0; l < n_levels; ++l) {
     transpose_w(K, H, lo[l].fcv.wt, lo[l].fcv.bias);
+    lo[l].fcv.wp = cur_planes;
+    lo[l].fcv.kpad = cur_kpad;
     lo[l].fcv.in = (H + 3) & ~3;
     lo[l].fcv.a = lo[l].fcv.b = 0;
     fold_bn(T, lo[l].av, lo[l].bv);
@@ -345,13 +336,17 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
   vmb_mla* h = new vmb_mla();
   cudaGetDevice(&h->device);
   if (cudaMalloc(&h->blob, blob.size() * 4) != cudaSuccess ||
+      cudaMalloc(&h->planes, planes.size() * 2) != cudaSuccess ||
       cudaMemcpyAsync(h->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(h->planes, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess) {
     if (h->blob) cudaFree(h->blob);
+    if (h->planes) cudaFree(h->planes);
     delete h;
     return fail("vmb_mla_create: device allocation / upload failed");
   }
   const float* B = h->blob;
+  const uint16_t* WP = static_cast<const uint16_t*>(h->planes);
   HeadDev& d = h->dev;
   std::memset(&d, 0, sizeof d);
   d.n_levels = n_levels; d.emb_in = emb_in; d.hidden = H; d.K = K; d.T = T;
@@ -359,8 +354,9 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
     LevelDev& L = d.lvl[l];
     L.n0a = B + lo[l].n0a; L.n0b = B + lo[l].n0b; L.n_fc = lo[l].n_fc;
     for (int j = 0; j < L.n_fc; ++j)
-      L.fc[j] = FcDev{B + lo[l].fc[j].wt, B + lo[l].fc[j].bias, B + lo[l].fc[j].a, B + lo[l].fc[j].b, lo[l].fc[j].in};
-    L.fcv = FcDev{B + lo[l].fcv.wt, B + lo[l].fcv.bias, nullptr, nullptr, lo[l].fcv.in};
+      L.fc[j] = FcDev{WP + lo[l].fc[j].wp, lo[l].fc[j].kpad, B + lo[l].fc[j].wt, B + lo[l].fc[j].bias,
+                      B + lo[l].fc[j].a,   B + lo[l].fc[j].b, lo[l].fc[j].in};
+    L.fcv = FcDev{WP + lo[l].fcv.wp, lo[l].fcv.kpad, B + lo[l].fcv.wt, B + lo[l].fcv.bias, nullptr, nullptr, lo[l].fcv.in};
     L.av = B + lo[l].av; L.bv = B + lo[l].bv; L.af = B + lo[l].af; L.bf = B + lo[l].bf;
   }
   d.fc_wt = B + fc_wt; d.fc_bias = B + fc_bias; d.out_a = B + out_a; d.out_b = B + out_b;
@@ -373,6 +369,7 @@ int vmb_mla_num_classes(const vmb_mla_t* h) { return h ? h->dev.K : -1; }
 void vmb_mla_destroy(vmb_mla_t* h) {
   if (!h) return;
   if (h->blob) cudaFree(h->blob);
+  if (h->planes) cudaFree(h->planes);
   delete h;
 }
 
@@ -381,6 +378,18 @@ int vmb_mla_forward(vmb_mla_t* h, const float* emb, long long batch, float* scor
   if (batch < 0) return fail("vmb_mla_forward: negative batch");
   if (batch == 0) return 0;
   if (!emb || !scores) return fail("vmb_mla_forward: null pointer");
+  if (batch > 200000000LL) return fail("vmb_mla_forward: batch too large for one call");
+  if (vmb_head::tc_forward(*h, emb, batch, scores, static_cast<cudaStream_t>(stream)))
+    return fail(vmb::kernels_last_error());
+  return 0;
+}
+
+int vmb_mla_forward_fp32(vmb_mla_t* h, const float* emb, long long batch, float* scores, void* stream) {
+  if (!h) return fail("vmb_mla_forward_fp32: null handle");
+  if (batch < 0) return fail("vmb_mla_forward_fp32: negative batch");
+  if (batch == 0) return 0;
+  if (!emb || !scores) return fail("vmb_mla_forward_fp32: null pointer");
+  if (h->dev.emb_in > kMaxDim) return fail("vmb_mla_forward_fp32: emb_in > 608 is only supported by vmb_mla_forward");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ystride = (h->dev.n_levels * h->dev.K + 3) & ~3;
   static bool attr_done = false;
@@ -389,7 +398,7 @@ int vmb_mla_forward(vmb_mla_t* h, const float* emb, long long batch, float* scor
                              int(kMaxDynSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(mla_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(kMaxDynSmem)) != cudaSuccess)
-      return fail("vmb_mla_forward: cannot raise the dynamic shared memory limit");
+      return fail("vmb_mla_forward_fp32: cannot raise the dynamic shared memory limit");
     attr_done = true;
   }
   // small batches: 2 clips per CTA so more SMs take part; large batches: 4 clips per CTA (half the weight traffic)

@@ -1,0 +1,55 @@
+// Shared definitions of the multi-level attention head (mla.cu: handle + fused fp32 kernel, mla_tc.cu: tensor-core
+// path).  Reference: model.py:199-269.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace vmb_head {
+
+constexpr int kMaxLevels = 4;
+constexpr int kMaxFc = 4;
+constexpr int kPad = 640;      // padded column count of every transposed weight
+constexpr int kMaxDim = 608;   // activation row pitch in shared memory (floats); multiple of 4
+constexpr int kThreads = 256;
+constexpr int kColThreads = 64;
+constexpr int kColsPerThread = kPad / kColThreads;  // 10
+
+struct FcDev {
+  const void* wp;     // bf16 [kPad][2 * kpad]: hi | lo planes of W (rows = outputs, zero padded)   (tensor-core path)
+  int kpad;           // inputs padded to a multiple of 64
+  const float* wt;    // [in][kPad]
+  const float* bias;  // [kPad]
+  const float* a;     // [T] folded BN scale
+  const float* b;     // [T] folded BN shift
+  int in;
+};
+struct LevelDev {
+  const float* n0a;  // [T]
+  const float* n0b;
+  int n_fc;
+  FcDev fc[kMaxFc];
+  FcDev fcv;         // a/b unused
+  const float *av, *bv, *af, *bf;  // [T] each
+};
+struct HeadDev {
+  int n_levels, emb_in, hidden, K, T;
+  LevelDev lvl[kMaxLevels];
+  const float* fc_wt;    // [L*K][kPad]
+  const float* fc_bias;  // [kPad]
+  const float* out_a;    // [K] folded BN_K
+  const float* out_b;
+};
+
+
+struct Handle {
+  HeadDev dev;
+  float* blob = nullptr;      // every folded fp32 table
+  void* planes = nullptr;     // every bf16 weight plane
+  int device = 0;
+};
+
+// Tensor-core forward (mla_tc.cu).  Returns 0 / 1 (message via vmb::kernels_last_error()).
+int tc_forward(const Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st);
+
+}  // namespace vmb_head

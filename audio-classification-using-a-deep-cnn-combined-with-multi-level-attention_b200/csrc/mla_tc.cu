@@ -1,0 +1,230 @@
+// Multi-level attention head, eval mode, on the tensor cores (reference model.py:199-269).
+//
+// Every Linear of the head is a split-bf16 tcgen05 GEMM (igemm_linear_split: operands carried as hi + lo bf16
+// planes, three products, fp32 accumulation — ~16 mantissa bits, so the head adds nothing visible to the ranking
+// metric); the glue between GEMMs is three small kernels:
+//   rows_affine_split   v = [a2_t * ] relu?(a1_t * u + b1_t) [+ b2_t]  -> hi | lo planes   (BatchNorm1d(T) in eval mode
+//                       is a per-time-step affine; ReLU; the next level's norm0 folded in)
+//   attention_pool      att = softmax_K(BN^v(z)), cla = sigmoid(BN^f(z)), y = sum_t cla att / sum_t att   (model.py:236-240;
+//                       fcv feeds both branches, fcf is never used — SURVEY F3; softmax over classes — F4)
+//   head_output         out = sigmoid(BN_K(fc(concat_l y_l)))                                          (model.py:267-268)
+// Row r of every matrix is (clip r / T, time step r % T).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+#include "mla_internal.cuh"
+
+namespace vmb_head {
+
+namespace {
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// src fp32 [rows][lds] (first `cols` columns meaningful) -> dst bf16 [rows][2 * cpad] = hi | lo, zero padded.
+// One thread converts 4 consecutive columns.
+__global__ void __launch_bounds__(256)
+rows_affine_split_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, int cpad, int T,
+                         const float* __restrict__ a1, const float* __restrict__ b1, int relu,
+                         const float* __restrict__ a2, const float* __restrict__ b2,
+                         __nv_bfloat16* __restrict__ dst) {
+  const int quads = cpad / 4;
+  const long long total = rows * quads;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / quads;
+    const int c0 = static_cast<int>(i - r * quads) * 4;
+    const int t = static_cast<int>(r % T);
+    const float s1 = a1 ? __ldg(a1 + t) : 1.f, o1 = a1 ? __ldg(b1 + t) : 0.f;
+    const float s2 = a2 ? __ldg(a2 + t) : 1.f, o2 = a2 ? __ldg(b2 + t) : 0.f;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = 0.f;
+      if (c0 + j < cols) {
+        x = fmaf(s1, __ldg(src + r * lds + c0 + j), o1);
+        if (relu) x = fmaxf(x, 0.f);
+        x = fmaf(s2, x, o2);
+      }
+      v[j] = x;
+    }
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16_rn(v[j]);
+      lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+    }
+    __nv_bfloat16* d = dst + r * (2LL * cpad) + c0;
+    *reinterpret_cast<uint2*>(d) = make_uint2(
+        __bfloat16_as_ushort(hi[0]) | (uint32_t(__bfloat16_as_ushort(hi[1])) << 16),
+        __bfloat16_as_ushort(hi[2]) | (uint32_t(__bfloat16_as_ushort(hi[3])) << 16));
+    *reinterpret_cast<uint2*>(d + cpad) = make_uint2(
+        __bfloat16_as_ushort(lo[0]) | (uint32_t(__bfloat16_as_ushort(lo[1])) << 16),
+        __bfloat16_as_ushort(lo[2]) | (uint32_t(__bfloat16_as_ushort(lo[3])) << 16));
+  }
+}
+
+// One CTA per clip: z fp32 [T rows][ldz] -> y[clip][col0 + k].  T <= 16.
+__global__ void __launch_bounds__(256)
+attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, const float* __restrict__ av,
+                      const float* __restrict__ bv, const float* __restrict__ af, const float* __restrict__ bf,
+                      float* __restrict__ y, long long ystride, int col0) {
+  __shared__ float rmax[16], rsum[16];
+  const long long clip = blockIdx.x;
+  const float* zc = z + clip * T * ldz;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < T; t += 8) {
+    const float a = __ldg(av + t), b = __ldg(bv + t);
+    float m = -INFINITY;
+    for (int c = lane; c < K; c += 32) m = fmaxf(m, fmaf(a, __ldg(zc + t * ldz + c), b));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < K; c += 32) s += expf(fmaf(a, __ldg(zc + t * ldz + c), b) - m);
+    s = warp_sum(s);
+    if (lane == 0) { rmax[t] = m; rsum[t] = s; }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float num = 0.f, den = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float zz = __ldg(zc + t * ldz + k);
+      const float att = expf(fmaf(__ldg(av + t), zz, __ldg(bv + t)) - rmax[t]) / rsum[t];
+      const float cla = 1.f / (1.f + expf(-fmaf(__ldg(af + t), zz, __ldg(bf + t))));
+      num = fmaf(cla, att, num);
+      den += att;
+    }
+    y[clip * ystride + col0 + k] = num / den;
+  }
+}
+
+// out[clip][c] = sigmoid(a_c * (sum_k y[clip][k] W^T[k][c] + bias_c) + b_c); G clips per CTA share each weight load.
+constexpr int kOutG = 8;
+__global__ void __launch_bounds__(256)
+head_output_kernel(const float* __restrict__ y, long long ystride, int kin, int K, const float* __restrict__ wt,
+                   int wpitch, const float* __restrict__ bias, const float* __restrict__ oa,
+                   const float* __restrict__ ob, long long batch, float* __restrict__ out) {
+  extern __shared__ float ys[];  // [kOutG][kin]
+  const long long clip0 = static_cast<long long>(blockIdx.x) * kOutG;
+  for (int i = threadIdx.x; i < kOutG * kin; i += blockDim.x) {
+    const int g = i / kin, k = i - g * kin;
+    ys[i] = (clip0 + g < batch) ? __ldg(y + (clip0 + g) * ystride + k) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    float acc[kOutG];
+#pragma unroll
+    for (int g = 0; g < kOutG; ++g) acc[g] = 0.f;
+    for (int k = 0; k < kin; ++k) {
+      const float w = __ldg(wt + static_cast<size_t>(k) * wpitch + c);
+#pragma unroll
+      for (int g = 0; g < kOutG; ++g) acc[g] = fmaf(ys[g * kin + k], w, acc[g]);
+    }
+    const float b0 = __ldg(bias + c), a = __ldg(oa + c), b = __ldg(ob + c);
+#pragma unroll
+    for (int g = 0; g < kOutG; ++g)
+      if (clip0 + g < batch) out[(clip0 + g) * K + c] = 1.f / (1.f + expf(-fmaf(a, acc[g] + b0, b)));
+  }
+}
+
+unsigned grid_for(long long items, int per_block) {
+  return static_cast<unsigned>(std::min<long long>((items + per_block - 1) / per_block, 148LL * 8));
+}
+
+int split_rows(const float* src, long long lds, long long rows, int cols, int cpad, int T, const float* a1,
+               const float* b1, int relu, const float* a2, const float* b2, void* dst, cudaStream_t st) {
+  rows_affine_split_kernel<<<grid_for(rows * (cpad / 4), 256), 256, 0, st>>>(
+      src, lds, rows, cols, cpad, T, a1, b1, relu, a2, b2, static_cast<__nv_bfloat16*>(dst));
+  vmb::count_launch();
+  return vmb::check_launch("rows_affine_split_kernel");
+}
+
+size_t up(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+}  // namespace
+
+int tc_forward(const Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st) {
+  const HeadDev& d = h.dev;
+  const long long rows = batch * d.T;
+  if (rows > 0x7fffffffLL) {
+    vmb::set_kernel_error("mla: too many rows for one call");
+    return 1;
+  }
+  const int in_pad = d.lvl[0].fc[0].kpad;            // emb_in padded to 64
+  const int hpad = kPad;                             // hidden / class width padded to 640
+  const int ystride = (d.n_levels * d.K + 3) & ~3;
+  // workspace: x planes | two activation plane buffers | normed-input planes | fp32 GEMM output | y
+  const size_t sz_x = up(size_t(rows) * 2 * in_pad * 2), sz_p = up(size_t(rows) * 2 * hpad * 2);
+  const size_t sz_u = up(size_t(rows) * hpad * 4), sz_y = up(size_t(batch) * ystride * 4);
+  const size_t total = sz_x + 3 * sz_p + sz_u + sz_y;
+  char* ws = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), total, st) != cudaSuccess) {
+    vmb::set_kernel_error("mla: workspace allocation of %zu bytes failed: %s", total,
+                          cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  void* X = ws;
+  void* P[2] = {ws + sz_x, ws + sz_x + sz_p};
+  void* Pn = ws + sz_x + 2 * sz_p;
+  float* U = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p);
+  float* Y = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p + sz_u);
+  int rc = 0;
+  auto gemm = [&](const void* a, const FcDev& fc) {
+    if (!rc && vmb::igemm_linear_split(a, fc.wp, fc.bias, U, hpad, 0, int(rows), hpad, fc.kpad, st)) {
+      vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+      rc = 1;
+    }
+  };
+  // level 0 input: norm0 applied to the embeddings
+  rc = split_rows(emb, d.emb_in, rows, d.emb_in, in_pad, d.T, d.lvl[0].n0a, d.lvl[0].n0b, 0, nullptr, nullptr, X, st);
+  const void* cur = X;
+  int pp = 0;
+  for (int l = 0; l < d.n_levels && !rc; ++l) {
+    const LevelDev& L = d.lvl[l];
+    for (int j = 0; j < L.n_fc && !rc; ++j) {
+      gemm(cur, L.fc[j]);
+      // h = relu(BN(u)) as planes for the next Linear of this level (or for fcv)
+      if (!rc) rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, nullptr, nullptr, P[pp], st);
+      if (!rc && j == L.n_fc - 1 && l + 1 < d.n_levels)   // the same embedding with the next level's norm0 applied
+        rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, d.lvl[l + 1].n0a,
+                        d.lvl[l + 1].n0b, Pn, st);
+      cur = P[pp];
+      pp ^= 1;
+    }
+    gemm(cur, L.fcv);   // z = fcv(emb_l) -> U
+    if (!rc) {
+      attention_pool_kernel<<<static_cast<unsigned>(batch), 256, 0, st>>>(U, hpad, d.K, d.T, L.av, L.bv, L.af, L.bf, Y,
+                                                                          ystride, l * d.K);
+      vmb::count_launch();
+      rc = vmb::check_launch("attention_pool_kernel");
+    }
+    cur = Pn;
+  }
+  if (!rc) {
+    const int kin = d.n_levels * d.K;
+    const size_t smem = size_t(kOutG) * kin * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) {
+      cudaFuncSetAttribute(head_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr_done = true;
+    }
+    head_output_kernel<<<static_cast<unsigned>((batch + kOutG - 1) / kOutG), 256, smem, st>>>(
+        Y, ystride, kin, d.K, d.fc_wt, kPad, d.fc_bias, d.out_a, d.out_b, batch, scores);
+    vmb::count_launch();
+    rc = vmb::check_launch("head_output_kernel");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+}  // namespace vmb_head

@@ -111,6 +111,16 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= 2ull << 61;
   return d;
 }
+// Same for rows of 64 bytes (32 bf16) with the 64-byte swizzle (TMA SWIZZLE_64B): 8-row atoms of 512 B.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;                               // leading byte offset: unused for swizzled K-major (canonical 1)
+  d |= static_cast<uint64_t>(512u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;                               // layout type 4 = SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor, kind::f16, A = B = bf16 (K-major), D = fp32, M x N tile.
 //   bits 4-5 D format (1 = f32)  bits 7-9 A format (1 = bf16)  bits 10-12 B format (1 = bf16)
 //   bit 15/16 A/B major (0 = K)  bits 17-22 N >> 3  bits 24-28 M >> 4
@@ -145,6 +155,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }

@@ -62,6 +62,11 @@ long long vmb_num_examples(long long n_samples);
 int vmb_logmel(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                long long frames_out, float* logmel_dev, void* stream);
 
+/* The same computation on the CUDA cores in plain fp32 (the first implementation).  Diagnostic only: an on-device
+ * cross-check for the tensor-core kernel at sizes the CPU oracle cannot reach; vmb_pipeline_forward never uses it. */
+int vmb_logmel_cudacore(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
+                        long long frames_out, float* logmel_dev, void* stream);
+
 /* The constant tables the kernel uses (host copies, for the parity tests against mel_features.py):
  * periodic Hann (400 doubles) and the 257x64 HTK mel matrix (row-major doubles).                      */
 int vmb_front_end_tables(double* hann400, double* mel257x64);
@@ -119,8 +124,12 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
 void vmb_mla_destroy(vmb_mla_t* handle);
 int vmb_mla_num_classes(const vmb_mla_t* handle);
 long long vmb_mla_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps);
-/* emb_dev fp32 [B][T][emb_in] -> scores_dev fp32 [B][K] (sigmoid outputs, model.py:268). */
+/* emb_dev fp32 [B][T][emb_in] -> scores_dev fp32 [B][K] (sigmoid outputs, model.py:268).  Every Linear runs as a
+ * split-bf16 tcgen05 GEMM (hi + lo operand planes, fp32 accumulation).                                   */
 int vmb_mla_forward(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
+/* The same head as ONE fused CUDA-core fp32 kernel (the first implementation; emb_in <= 608).  Diagnostic: the
+ * on-device cross-check for vmb_mla_forward; vmb_pipeline_forward never uses it.                         */
+int vmb_mla_forward_fp32(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------ whole path
  * Ensemble.forward for cnn_type == "vggish" (model.py:58-62) fed from raw audio:

@@ -43,7 +43,7 @@ def test_library_is_the_thing_that_runs():
     before = _lib.lib().vmb_launch_count()
     engine.logmel(torch.zeros(1, 16000, device=DEV))
     torch.cuda.synchronize()
-    assert _lib.lib().vmb_launch_count() == before + 1
+    assert _lib.lib().vmb_launch_count() == before + 2          # split kernel + tcgen05 DFT/mel kernel
 
 
 # ------------------------------------------------------------------------------------------------ front end
@@ -65,6 +65,19 @@ def test_logmel_full_clips_vs_oracle(first):
     for i in range(4):
         ref = frontend_np.log_mel_spectrogram(waves[i].astype(np.float64))
         assert np.abs(got[i] - ref).max() <= 1e-4
+
+
+def test_logmel_full_batch_tensor_core_vs_cuda_core():
+    """Full bench size (256 clips): the tcgen05 kernel against the independent fp32 CUDA-core kernel on the device
+    (both are within 1e-4 of the float64 reference, so they must agree within 2e-4), plus row independence."""
+    waves = synth.fast_clips(0, 256).to(DEV)
+    a = engine.logmel(waves)
+    b = engine.logmel_cudacore(waves)
+    assert a.shape == b.shape == (256, 998, 64)
+    d = (a - b).abs().max().item()
+    print(f"log-mel tensor-core vs CUDA-core over 256 clips: max-abs diff {d:.3e}")
+    assert d <= 2e-4 and torch.isfinite(a).all()
+    assert torch.equal(engine.logmel(waves[200:203]), a[200:203])
 
 
 def test_examples_shape_indexing_and_edges():
@@ -243,8 +256,10 @@ def test_head_vs_golden(golden_head, tag, K, conf, seed):
     x = torch.from_numpy(golden_head[f"x_{tag}"]).to(DEV)
     y = h.forward(x).cpu().numpy()
     ref = golden_head[f"y_{tag}"]
-    print(f"head {tag}: max-abs-err {np.abs(y - ref).max():.3e}")
-    assert np.abs(y - ref).max() <= 2e-5
+    y32 = h.forward(x, fp32_crosscheck=True).cpu().numpy()
+    print(f"head {tag}: max-abs-err tensor-core path {np.abs(y - ref).max():.3e}, fused fp32 kernel "
+          f"{np.abs(y32 - ref).max():.3e}")
+    assert np.abs(y - ref).max() <= 2e-5 and np.abs(y32 - ref).max() <= 2e-5
     # odd batch sizes and both CTA shapes
     xb = x.repeat(120, 1, 1)[:601]
     yb = h.forward(xb).cpu().numpy()
@@ -304,8 +319,10 @@ def test_ensemble_module_matches_pipeline(golden_ensemble, vgg_sd, head_sd):
 
 
 def test_map_identical_to_three_decimals(vgg_handle, head_handle, vgg_sd, head_sd):
-    """mAP on a fixed synthetic label set: B200 scores vs the fp32 CPU oracle on the same 24 clips."""
-    n = 24
+    """mAP on a fixed synthetic label set: B200 scores vs the fp32 CPU oracle on the same 128 clips.  "Identical to
+    3 decimals" is checked as |mAP_b200 - mAP_oracle| < 0.0005 (half a unit of the third decimal): the labels are
+    random, so this is the worst case for ranking flips caused by the bf16 VGGish body."""
+    n = 128
     waves = synth.make_clips(100, n)
     pipe = engine.Pipeline(vgg_handle, head_handle)
     got = pipe.forward(torch.from_numpy(waves).to(DEV)).cpu().numpy()
@@ -316,7 +333,7 @@ def test_map_identical_to_three_decimals(vgg_handle, head_handle, vgg_sd, head_s
     labels = synth.multihot_labels(n, 527, p=0.2, seed=3)
     a, b = synth.mean_average_precision(labels, got), synth.mean_average_precision(labels, want)
     print(f"mAP B200 {a:.5f} oracle {b:.5f}; scores max-abs-err {np.abs(got - want).max():.3e}")
-    assert round(a, 3) == round(b, 3)
+    assert abs(a - b) < 5e-4
 
 
 def test_shard_invariance(vgg_handle, head_handle):
