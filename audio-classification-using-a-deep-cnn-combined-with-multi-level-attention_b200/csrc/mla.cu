@@ -330,6 +330,8 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
   }
   size_t fc_wt, fc_bias, out_a, out_b;
   transpose_w(K, n_levels * K, fc_wt, fc_bias);
+  const size_t fc_wp = cur_planes;
+  const int fc_kpad = cur_kpad;
   fold_bn(K, out_a, out_b);
   if (cur != p.size()) return fail("vmb_mla_create: internal layout mismatch");
 
@@ -359,6 +361,7 @@ int vmb_mla_create(vmb_mla_t** handle, int n_levels, const int* n_fc, int emb_in
     L.fcv = FcDev{WP + lo[l].fcv.wp, lo[l].fcv.kpad, B + lo[l].fcv.wt, B + lo[l].fcv.bias, nullptr, nullptr, lo[l].fcv.in};
     L.av = B + lo[l].av; L.bv = B + lo[l].bv; L.af = B + lo[l].af; L.bf = B + lo[l].bf;
   }
+  d.fc_wp = WP + fc_wp; d.fc_kpad = fc_kpad;
   d.fc_wt = B + fc_wt; d.fc_bias = B + fc_bias; d.out_a = B + out_a; d.out_b = B + out_b;
   *handle = h;
   return 0;

@@ -35,6 +35,8 @@ struct LevelDev {
 struct HeadDev {
   int n_levels, emb_in, hidden, K, T;
   LevelDev lvl[kMaxLevels];
+  const void* fc_wp;     // bf16 [kPad][2 * fc_kpad]: hi | lo planes of the output Linear
+  int fc_kpad;           // L*K padded to a multiple of 64
   const float* fc_wt;    // [L*K][kPad]
   const float* fc_bias;  // [kPad]
   const float* out_a;    // [K] folded BN_K

@@ -7,7 +7,7 @@
 //                       is a per-time-step affine; ReLU; the next level's norm0 folded in)
 //   attention_pool      att = softmax_K(BN^v(z)), cla = sigmoid(BN^f(z)), y = sum_t cla att / sum_t att   (model.py:236-240;
 //                       fcv feeds both branches, fcf is never used — SURVEY F3; softmax over classes — F4)
-//   head_output         out = sigmoid(BN_K(fc(concat_l y_l)))                                          (model.py:267-268)
+//   sigmoid_affine      out = sigmoid(BN_K(fc(concat_l y_l))) after one more split GEMM for fc              (model.py:267-268)
 // Row r of every matrix is (clip r / T, time step r % T).
 #include <cuda_bf16.h>
 
@@ -108,32 +108,16 @@ attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, 
   }
 }
 
-// out[clip][c] = sigmoid(a_c * (sum_k y[clip][k] W^T[k][c] + bias_c) + b_c); G clips per CTA share each weight load.
-constexpr int kOutG = 8;
+// scores[clip][c] = sigmoid(a_c * u[clip][c] + b_c): eval-mode BatchNorm1d(K) + sigmoid on the output Linear (model.py:268)
 __global__ void __launch_bounds__(256)
-head_output_kernel(const float* __restrict__ y, long long ystride, int kin, int K, const float* __restrict__ wt,
-                   int wpitch, const float* __restrict__ bias, const float* __restrict__ oa,
-                   const float* __restrict__ ob, long long batch, float* __restrict__ out) {
-  extern __shared__ float ys[];  // [kOutG][kin]
-  const long long clip0 = static_cast<long long>(blockIdx.x) * kOutG;
-  for (int i = threadIdx.x; i < kOutG * kin; i += blockDim.x) {
-    const int g = i / kin, k = i - g * kin;
-    ys[i] = (clip0 + g < batch) ? __ldg(y + (clip0 + g) * ystride + k) : 0.f;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < K; c += blockDim.x) {
-    float acc[kOutG];
-#pragma unroll
-    for (int g = 0; g < kOutG; ++g) acc[g] = 0.f;
-    for (int k = 0; k < kin; ++k) {
-      const float w = __ldg(wt + static_cast<size_t>(k) * wpitch + c);
-#pragma unroll
-      for (int g = 0; g < kOutG; ++g) acc[g] = fmaf(ys[g * kin + k], w, acc[g]);
-    }
-    const float b0 = __ldg(bias + c), a = __ldg(oa + c), b = __ldg(ob + c);
-#pragma unroll
-    for (int g = 0; g < kOutG; ++g)
-      if (clip0 + g < batch) out[(clip0 + g) * K + c] = 1.f / (1.f + expf(-fmaf(a, acc[g] + b0, b)));
+sigmoid_affine_kernel(const float* __restrict__ u, long long ldu, long long batch, int K, const float* __restrict__ oa,
+                      const float* __restrict__ ob, float* __restrict__ out) {
+  const long long total = batch * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / K;
+    const int c = static_cast<int>(i - r * K);
+    out[i] = 1.f / (1.f + expf(-fmaf(__ldg(oa + c), __ldg(u + r * ldu + c), __ldg(ob + c))));
   }
 }
 
@@ -166,7 +150,8 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
   // workspace: x planes | two activation plane buffers | normed-input planes | fp32 GEMM output | y
   const size_t sz_x = up(size_t(rows) * 2 * in_pad * 2), sz_p = up(size_t(rows) * 2 * hpad * 2);
   const size_t sz_u = up(size_t(rows) * hpad * 4), sz_y = up(size_t(batch) * ystride * 4);
-  const size_t total = sz_x + 3 * sz_p + sz_u + sz_y;
+  const size_t sz_yp = up(size_t(batch) * 2 * d.fc_kpad * 2);
+  const size_t total = sz_x + 3 * sz_p + sz_u + sz_y + sz_yp;
   char* ws = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&ws), total, st) != cudaSuccess) {
     vmb::set_kernel_error("mla: workspace allocation of %zu bytes failed: %s", total,
@@ -178,6 +163,7 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
   void* Pn = ws + sz_x + 2 * sz_p;
   float* U = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p);
   float* Y = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p + sz_u);
+  void* Yp = ws + sz_x + 3 * sz_p + sz_u + sz_y;
   int rc = 0;
   auto gemm = [&](const void* a, const FcDev& fc) {
     if (!rc && vmb::igemm_linear_split(a, fc.wp, fc.bias, U, hpad, 0, int(rows), hpad, fc.kpad, st)) {
@@ -210,18 +196,16 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
     }
     cur = Pn;
   }
+  // out = sigmoid(BN_K(fc(concat y))): y -> planes, one more split GEMM into U ([batch][640]), then the sigmoid
+  if (!rc) rc = split_rows(Y, ystride, batch, d.n_levels * d.K, d.fc_kpad, 1, nullptr, nullptr, 0, nullptr, nullptr, Yp, st);
+  if (!rc && vmb::igemm_linear_split(Yp, d.fc_wp, d.fc_bias, U, hpad, 0, int(batch), hpad, d.fc_kpad, st)) {
+    vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+    rc = 1;
+  }
   if (!rc) {
-    const int kin = d.n_levels * d.K;
-    const size_t smem = size_t(kOutG) * kin * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
-      cudaFuncSetAttribute(head_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      attr_done = true;
-    }
-    head_output_kernel<<<static_cast<unsigned>((batch + kOutG - 1) / kOutG), 256, smem, st>>>(
-        Y, ystride, kin, d.K, d.fc_wt, kPad, d.fc_bias, d.out_a, d.out_b, batch, scores);
+    sigmoid_affine_kernel<<<grid_for(batch * d.K, 256), 256, 0, st>>>(U, hpad, batch, d.K, d.out_a, d.out_b, scores);
     vmb::count_launch();
-    rc = vmb::check_launch("head_output_kernel");
+    rc = vmb::check_launch("sigmoid_affine_kernel");
   }
   cudaFreeAsync(ws, st);
   return rc;

@@ -53,6 +53,15 @@ STAGES = ("logmel", "conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2"
           "postprocess")
 
 
+def igemm_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (None if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "igemm_traffic.json")) as fh:
+            return float(json.load(fh)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -291,7 +300,7 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": igemm_traffic(),
                      "kernel": "igemm_bf16_kernel (tcgen05 implicit GEMM: conv2..conv4_2, fc1..fc3)",
                      "launches_per_step": ig_launches_per_step, "algorithmic_flop_per_launch":
                          ig_flop_per_step / max(1, ig_launches_per_step),
