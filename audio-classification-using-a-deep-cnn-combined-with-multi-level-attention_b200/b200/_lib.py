@@ -43,6 +43,14 @@ SIGNATURES = {
     "vmb_mla_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int]),
     "vmb_mla_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
     "vmb_mla_forward_fp32": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
+    "vmb_mla_train_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int, C.POINTER(_ll)]),
+    "vmb_mla_trainer_create": (_int, [C.POINTER(_c_p), _int, C.POINTER(_int), _int, _int, _int, _int, _ll, _c_p]),
+    "vmb_mla_trainer_destroy": (None, [_c_p]),
+    "vmb_mla_train_step": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p, _c_p, _c_p]),
+    "vmb_mla_train_forward": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p]),
+    "vmb_mla_train_backward": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p]),
+    "vmb_adam_step": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _ll,
+                             C.c_float, _c_p]),
     "vmb_pipeline_workspace_bytes": (_sz, [_ll, _ll]),
     "vmb_pipeline_forward": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_pipeline_forward_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),

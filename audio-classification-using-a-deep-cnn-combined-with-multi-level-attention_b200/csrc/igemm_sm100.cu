@@ -151,7 +151,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n0 = n_tile * BLOCK_N;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       float* bias_t = bias_s + acc * BLOCK_N;
-      for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads) bias_t[i] = __ldg(p.bias + n0 + i);
+      for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads) bias_t[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
       // Where does this thread's accumulator row go?

@@ -1,0 +1,1073 @@
+// Multi-level attention head: one training step (forward in train mode + backward) on the B200.
+// Reference semantics: model.py:200-269 run under train.py:119-138 — BatchNorm1d(T) with batch statistics per time
+// step over (batch, features), Dropout(p) after each ReLU, fcv feeding both attention branches and fcf
+// never used (F3: no gradient), softmax over the class axis (F4), BatchNorm1d(K) + sigmoid on the output Linear,
+// nn.CrossEntropyLoss applied to the sigmoid outputs (train.py:131,372).  Running statistics are updated like
+// nn.BatchNorm1d does (momentum 0.1, unbiased variance).
+//
+// Every Linear (forward, dX and dW) is a split-bf16 tcgen05 GEMM (igemm_linear_split); everything between GEMMs
+// is fp32 CUDA-core work in a handful of kernels:
+//   bn_time_stats / bn_col_stats   sum and sum-of-squares per time step (or per class), finalised by the last block
+//   tile_split<Functor>            32x32 tiles: evaluate an element-wise functor (BN + ReLU + dropout, BN backward, ...),
+//                                  write hi|lo bf16 planes row-major AND transposed (the dW GEMMs contract over rows),
+//                                  optionally the fp32 values and the column sums (bias gradients)
+//   att_forward / att_backward     attention pooling over the T time steps of one clip per CTA
+//   out_loss_rows / out_bn_backward  sigmoid + cross-entropy + BatchNorm1d(K) backward
+// Gradients land in one flat fp32 buffer with the layout of the parameters (vmb_mla_train_layout), ready for a single
+// NCCL all-reduce; vmb_adam_step applies torch.optim.Adam's update to the flat buffers.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/vggish_mla_b200.h"
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+
+namespace vmb {
+void set_api_error(const char* msg);
+}
+
+namespace {
+
+constexpr int kMaxLevels = 4, kMaxFc = 4, kMaxBn = kMaxLevels * (1 + kMaxFc) + 2 * kMaxLevels + 1;
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+
+int fail(const char* fmt, const char* detail = "") {
+  char buf[640];
+  snprintf(buf, sizeof buf, fmt, detail);
+  vmb::set_api_error(buf);
+  return 1;
+}
+int pad128(int v) { return (v + 127) / 128 * 128; }
+long long pad64(long long v) { return (v + 63) / 64 * 64; }
+size_t up(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+// ------------------------------------------------------------------ statistics
+// acc[ch] = {sum, sum of squares}; stat[ch] = {mean, rstd}.  The last block to finish turns acc into stat and
+// updates the running statistics.
+struct StatJob {
+  double* acc;          // [channels][2], zeroed at step start
+  float* stat;          // [channels][2]
+  unsigned* counter;    // zeroed at step start
+  float* run_mean;      // may be null
+  float* run_var;
+  double count;         // elements per channel
+  int channels;
+};
+
+__device__ void finalize_stats(const StatJob& j) {
+  for (int c = threadIdx.x; c < j.channels; c += blockDim.x) {
+    const double mean = j.acc[2 * c] / j.count;
+    double var = j.acc[2 * c + 1] / j.count - mean * mean;
+    if (var < 0) var = 0;
+    j.stat[2 * c] = static_cast<float>(mean);
+    j.stat[2 * c + 1] = static_cast<float>(1.0 / sqrt(var + double(kBnEps)));
+    if (j.run_mean) {
+      const double unbiased = j.count > 1 ? var * j.count / (j.count - 1) : var;
+      j.run_mean[c] = (1.f - kBnMomentum) * j.run_mean[c] + kBnMomentum * static_cast<float>(mean);
+      j.run_var[c] = (1.f - kBnMomentum) * j.run_var[c] + kBnMomentum * static_cast<float>(unbiased);
+    }
+  }
+}
+
+__device__ bool last_block_done(unsigned* counter, unsigned total) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == total - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// BatchNorm1d(T) on [rows = (b, t)][F]: channel = r % T.  grid = (chunks, T); block 256.
+__global__ void __launch_bounds__(256)
+bn_time_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int F, int T, StatJob job) {
+  const int t = blockIdx.y;
+  const long long per_t = batch * F;
+  double s1 = 0, s2 = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_t;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / F;
+    const int c = static_cast<int>(i - b * F);
+    const float v = __ldg(x + (b * T + t) * ld + c);
+    s1 += v;
+    s2 += double(v) * v;
+  }
+  __shared__ double r1[8], r2[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += r1[w]; b += r2[w]; }
+    atomicAdd(job.acc + 2 * t, a);
+    atomicAdd(job.acc + 2 * t + 1, b);
+  }
+  if (last_block_done(job.counter, gridDim.x * gridDim.y)) finalize_stats(job);
+}
+
+// normf normalises the same tensor as normv: re-derive the statistics and update ITS running buffers
+__global__ void bn_running_only_kernel(StatJob job) { finalize_stats(job); }
+
+// BatchNorm1d(K) on [batch][K]: channel = column.  grid = ceil(K / 32); block (32, 8).
+__global__ void __launch_bounds__(256)
+bn_col_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int K, StatJob job) {
+  const int c = blockIdx.x * 32 + threadIdx.x % 32, ty = threadIdx.x / 32;
+  double s1 = 0, s2 = 0;
+  if (c < K)
+    for (long long b = ty; b < batch; b += 8) {
+      const float v = __ldg(x + b * ld + c);
+      s1 += v;
+      s2 += double(v) * v;
+    }
+  __shared__ double r1[8][32], r2[8][32];
+  r1[ty][threadIdx.x % 32] = s1;
+  r2[ty][threadIdx.x % 32] = s2;
+  __syncthreads();
+  if (ty == 0 && c < K) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += r1[w][threadIdx.x]; b += r2[w][threadIdx.x]; }
+    job.acc[2 * c] = a;
+    job.acc[2 * c + 1] = b;
+  }
+  if (last_block_done(job.counter, gridDim.x)) finalize_stats(job);
+}
+
+// ------------------------------------------------------------------ dropout (counter-based, recomputed in backward)
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned layer, unsigned long long idx, float p) {
+  if (p <= 0.f) return 1.f;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + (static_cast<unsigned long long>(layer) << 56);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? 1.f / (1.f - p) : 0.f;
+}
+
+// ------------------------------------------------------------------ 32x32 tile kernel with element functor
+struct TileOut {
+  __nv_bfloat16* planes;    // [rows_pad][2 * cols_pad] hi | lo   (may be null)
+  __nv_bfloat16* planes_t;  // [cols_pad][2 * rows_pad] hi | lo   (may be null)
+  float* f32;               // [rows][ld_f32]                     (may be null)
+  long long ld_f32;
+  float* col_sum;           // [cols] += sum over rows (atomic)   (may be null)
+  long long rows, rows_pad;
+  int cols, cols_pad;
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
+  __shared__ float tile[32][33];
+  f.prologue();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long r0 = static_cast<long long>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long r = r0 + ty + 8 * i;
+    const int c = c0 + tx;
+    const float v = (r < o.rows && c < o.cols) ? f(r, c) : 0.f;
+    tile[ty + 8 * i][tx] = v;
+    if (r < o.rows_pad && c < o.cols_pad) {
+      if (o.planes) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        o.planes[r * (2LL * o.cols_pad) + c] = hi;
+        o.planes[r * (2LL * o.cols_pad) + o.cols_pad + c] = lo;
+      }
+      if (o.f32 && r < o.rows) o.f32[r * o.ld_f32 + c] = v;
+    }
+  }
+  __syncthreads();
+  if (o.planes_t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i;
+      const long long r = r0 + tx;
+      if (c < o.cols_pad && r < o.rows_pad) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(tile[tx][ty + 8 * i], hi, lo);
+        o.planes_t[c * (2LL * o.rows_pad) + r] = hi;
+        o.planes_t[c * (2LL * o.rows_pad) + o.rows_pad + r] = lo;
+      }
+    }
+  }
+  if (o.col_sum && ty == 0 && c0 + tx < o.cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += tile[j][tx];
+    atomicAdd(o.col_sum + c0 + tx, s);
+  }
+}
+
+// identity (weights, plain copies)
+struct FIdentity {
+  const float* x; long long ld;
+  const float* bias_src = nullptr; float* bias_dst = nullptr; int n_bias = 0;   // block (0,0) copies the bias
+  __device__ void prologue() {
+    if (bias_dst && blockIdx.x == 0 && blockIdx.y == 0)
+      for (int i = threadIdx.x; i < n_bias; i += blockDim.x) bias_dst[i] = bias_src[i];
+  }
+  __device__ float operator()(long long r, int c) const { return __ldg(x + r * ld + c); }
+};
+
+// forward: a = dropout(relu?(gamma_t * (u - mu_t) * rstd_t + beta_t))
+struct FBnAct {
+  const float* u; long long ld; int T, F;
+  const float* stat; const float* gamma; const float* beta;
+  int relu; float p; unsigned long long seed; unsigned layer;
+  __device__ void prologue() {}
+  __device__ float operator()(long long r, int c) const {
+    const int t = static_cast<int>(r % T);
+    float v = fmaf(__ldg(gamma + t) * __ldg(stat + 2 * t + 1), __ldg(u + r * ld + c) - __ldg(stat + 2 * t), __ldg(beta + t));
+    if (relu) v = fmaxf(v, 0.f);
+    return v * dropout_scale(seed, layer, static_cast<unsigned long long>(r) * F + c, p);
+  }
+};
+
+// upstream gradient of a BN(+ReLU+dropout) block: g = (da1 + da2) * dropout * [v > 0]
+struct GradIn {
+  const float* da1; long long ld1; const float* da2; long long ld2;   // da2 may be null
+  const float* u; long long ldu; int T, F;
+  const float* stat; const float* gamma; const float* beta;
+  int relu; float p; unsigned long long seed; unsigned layer;
+  __device__ __forceinline__ float xhat(long long r, int c) const {
+    const int t = static_cast<int>(r % T);
+    return (__ldg(u + r * ldu + c) - __ldg(stat + 2 * t)) * __ldg(stat + 2 * t + 1);
+  }
+  __device__ __forceinline__ float g(long long r, int c, float xh) const {
+    const int t = static_cast<int>(r % T);
+    float d = __ldg(da1 + r * ld1 + c);
+    if (da2) d += __ldg(da2 + r * ld2 + c);
+    if (relu && fmaf(__ldg(gamma + t), xh, __ldg(beta + t)) <= 0.f) return 0.f;
+    return d * dropout_scale(seed, layer, static_cast<unsigned long long>(r) * F + c, p);
+  }
+};
+
+// phase A of BN backward: S1_t = sum g, S2_t = sum g * xhat  (double atomics), grid = (chunks, T)
+__global__ void __launch_bounds__(256)
+bn_time_backward_reduce_kernel(GradIn in, long long batch, double* __restrict__ acc) {
+  const int t = blockIdx.y;
+  const long long per_t = batch * in.F;
+  double s1 = 0, s2 = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_t;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / in.F;
+    const int c = static_cast<int>(i - b * in.F);
+    const long long r = b * in.T + t;
+    const float xh = in.xhat(r, c);
+    const float g = in.g(r, c, xh);
+    s1 += g;
+    s2 += double(g) * xh;
+  }
+  __shared__ double r1[8], r2[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += r1[w]; b += r2[w]; }
+    atomicAdd(acc + 2 * t, a);
+    atomicAdd(acc + 2 * t + 1, b);
+  }
+}
+
+// phase B: du = gamma_t * rstd_t * (g - S1_t / n - xhat * S2_t / n); block (0,0) also writes dgamma = S2, dbeta = S1
+struct FBnBackward {
+  GradIn in; const double* acc; double n; float* dgamma; float* dbeta;
+  __device__ void prologue() {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < in.T) {
+      dbeta[threadIdx.x] = static_cast<float>(acc[2 * threadIdx.x]);
+      dgamma[threadIdx.x] = static_cast<float>(acc[2 * threadIdx.x + 1]);
+    }
+  }
+  __device__ float operator()(long long r, int c) const {
+    const int t = static_cast<int>(r % in.T);
+    const float xh = in.xhat(r, c);
+    const float g = in.g(r, c, xh);
+    const float m1 = static_cast<float>(acc[2 * t] / n), m2 = static_cast<float>(acc[2 * t + 1] / n);
+    return __ldg(in.gamma + t) * __ldg(in.stat + 2 * t + 1) * (g - m1 - xh * m2);
+  }
+};
+
+// ------------------------------------------------------------------ attention (one CTA per clip)
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct AttParams {
+  const float* z; long long ldz; int K, T;
+  const float* stat;                       // [T][2] batch statistics of z (shared by both branches)
+  const float *gv, *bv, *gf, *bf;          // normv / normf affine parameters [T]
+};
+
+// y[clip][col0 + k] = sum_t cla * att / sum_t att; row_stats[r] = {max, sum} of the class softmax of row r
+__global__ void __launch_bounds__(256)
+att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int col0, float* __restrict__ row_stats) {
+  __shared__ float rmax[16], rsum[16], sa_v[16], sb_v[16], sa_f[16], sb_f[16];
+  const long long clip = blockIdx.x;
+  const float* zc = a.z + clip * a.T * a.ldz;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < a.T) {
+    const int t = threadIdx.x;
+    const float mu = a.stat[2 * t], rs = a.stat[2 * t + 1];
+    sa_v[t] = a.gv[t] * rs; sb_v[t] = a.bv[t] - a.gv[t] * rs * mu;
+    sa_f[t] = a.gf[t] * rs; sb_f[t] = a.bf[t] - a.gf[t] * rs * mu;
+  }
+  __syncthreads();
+  for (int t = warp; t < a.T; t += 8) {
+    float m = -INFINITY;
+    for (int c = lane; c < a.K; c += 32) m = fmaxf(m, fmaf(sa_v[t], __ldg(zc + t * a.ldz + c), sb_v[t]));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < a.K; c += 32) s += expf(fmaf(sa_v[t], __ldg(zc + t * a.ldz + c), sb_v[t]) - m);
+    s = warp_sum(s);
+    if (lane == 0) {
+      rmax[t] = m; rsum[t] = s;
+      row_stats[2 * (clip * a.T + t)] = m;
+      row_stats[2 * (clip * a.T + t) + 1] = s;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+    float num = 0.f, den = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+      const float zz = __ldg(zc + t * a.ldz + k);
+      const float att = expf(fmaf(sa_v[t], zz, sb_v[t]) - rmax[t]) / rsum[t];
+      const float cla = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
+      num = fmaf(cla, att, num);
+      den += att;
+    }
+    y[clip * ystride + col0 + k] = num / den;
+  }
+}
+
+// Backward of the pooling for one clip: writes gv = d(BN^v output), gf = d(BN^f output) as fp32 [rows][ldg] and adds
+// the four BatchNorm reductions (sum g, sum g * zhat for both branches) to acc_v / acc_f.
+__global__ void __launch_bounds__(256)
+att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __restrict__ dy, long long ystride, int col0,
+                    const float* __restrict__ row_stats, float* __restrict__ gv, float* __restrict__ gf, long long ldg,
+                    double* __restrict__ acc_v, double* __restrict__ acc_f) {
+  __shared__ float sa_v[16], sb_v[16], sa_f[16], sb_f[16], dot[16];
+  __shared__ double red[8][4];
+  const long long clip = blockIdx.x;
+  const float* zc = a.z + clip * a.T * a.ldz;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < a.T) {
+    const int t = threadIdx.x;
+    const float mu = a.stat[2 * t], rs = a.stat[2 * t + 1];
+    sa_v[t] = a.gv[t] * rs; sb_v[t] = a.bv[t] - a.gv[t] * rs * mu;
+    sa_f[t] = a.gf[t] * rs; sb_f[t] = a.bf[t] - a.gf[t] * rs * mu;
+    dot[t] = 0.f;
+  }
+  __syncthreads();
+  // s[k] = sum_t att; datt = dy (cla - y) / s; dot[t] = sum_k datt * att  (the softmax backward needs it per row)
+  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+      const float* rs2 = row_stats + 2 * (clip * a.T + t);
+      s += expf(fmaf(sa_v[t], __ldg(zc + t * a.ldz + k), sb_v[t]) - rs2[0]) / rs2[1];
+    }
+    const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
+    for (int t = 0; t < a.T; ++t) {
+      const float* rs2 = row_stats + 2 * (clip * a.T + t);
+      const float zz = __ldg(zc + t * a.ldz + k);
+      const float att = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
+      const float cla = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
+      atomicAdd(&dot[t], d * (cla - yy) / s * att);
+    }
+  }
+  __syncthreads();
+  double s1v = 0, s2v = 0, s1f = 0, s2f = 0;
+  // second pass, one time step per iteration so the BatchNorm reductions stay per t
+  for (int t = 0; t < a.T; ++t) {
+    const float* rs2 = row_stats + 2 * (clip * a.T + t);
+    const float mu = a.stat[2 * t], rstd = a.stat[2 * t + 1];
+    double p1v = 0, p2v = 0, p1f = 0, p2f = 0;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+      float s = 0.f;
+      for (int tt = 0; tt < a.T; ++tt) {
+        const float* r3 = row_stats + 2 * (clip * a.T + tt);
+        s += expf(fmaf(sa_v[tt], __ldg(zc + tt * a.ldz + k), sb_v[tt]) - r3[0]) / r3[1];
+      }
+      const float zz = __ldg(zc + t * a.ldz + k);
+      const float att = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
+      const float cla = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
+      const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
+      const float dcla = d * att / s;
+      const float datt = d * (cla - yy) / s;
+      const float g_f = dcla * cla * (1.f - cla);
+      const float g_v = att * (datt - dot[t]);
+      const long long r = clip * a.T + t;
+      gv[r * ldg + k] = g_v;
+      gf[r * ldg + k] = g_f;
+      const float zh = (zz - mu) * rstd;
+      p1v += g_v; p2v += double(g_v) * zh;
+      p1f += g_f; p2f += double(g_f) * zh;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      p1v += __shfl_xor_sync(0xffffffffu, p1v, o);
+      p2v += __shfl_xor_sync(0xffffffffu, p2v, o);
+      p1f += __shfl_xor_sync(0xffffffffu, p1f, o);
+      p2f += __shfl_xor_sync(0xffffffffu, p2f, o);
+    }
+    if (lane == 0) { red[warp][0] = p1v; red[warp][1] = p2v; red[warp][2] = p1f; red[warp][3] = p2f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s1v = s2v = s1f = s2f = 0;
+      for (int w = 0; w < 8; ++w) { s1v += red[w][0]; s2v += red[w][1]; s1f += red[w][2]; s2f += red[w][3]; }
+      atomicAdd(acc_v + 2 * t, s1v);
+      atomicAdd(acc_v + 2 * t + 1, s2v);
+      atomicAdd(acc_f + 2 * t, s1f);
+      atomicAdd(acc_f + 2 * t + 1, s2f);
+    }
+    __syncthreads();
+  }
+}
+
+// dz = gamma^v rstd (gv - S1v/n - zhat S2v/n) + gamma^f rstd (gf - S1f/n - zhat S2f/n); block (0,0) writes the four
+// affine-parameter gradients
+struct FAttCombine {
+  AttParams a; const float* gv; const float* gf; long long ldg;
+  const double* acc_v; const double* acc_f; double n;
+  float *dgv, *dbv, *dgf, *dbf;
+  __device__ void prologue() {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.T) {
+      const int t = threadIdx.x;
+      dbv[t] = static_cast<float>(acc_v[2 * t]); dgv[t] = static_cast<float>(acc_v[2 * t + 1]);
+      dbf[t] = static_cast<float>(acc_f[2 * t]); dgf[t] = static_cast<float>(acc_f[2 * t + 1]);
+    }
+  }
+  __device__ float operator()(long long r, int c) const {
+    const int t = static_cast<int>(r % a.T);
+    const float rstd = __ldg(a.stat + 2 * t + 1);
+    const float zh = (__ldg(a.z + r * a.ldz + c) - __ldg(a.stat + 2 * t)) * rstd;
+    const float v = __ldg(a.gv + t) * rstd *
+                    (__ldg(gv + r * ldg + c) - float(acc_v[2 * t] / n) - zh * float(acc_v[2 * t + 1] / n));
+    const float f = __ldg(a.gf + t) * rstd *
+                    (__ldg(gf + r * ldg + c) - float(acc_f[2 * t] / n) - zh * float(acc_f[2 * t + 1] / n));
+    return v + f;
+  }
+};
+
+// ------------------------------------------------------------------ output layer: BN_K + sigmoid + cross-entropy
+// one block per batch row: out = sigmoid(BN_K(o)); lse[b] = log sum_k exp(out); loss += (lse - out[label]) / B
+__global__ void __launch_bounds__(256)
+out_loss_rows_kernel(const float* __restrict__ o, long long ldo, int K, const float* __restrict__ stat,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, const long long* __restrict__ labels,
+                     long long batch, float* __restrict__ scores, float* __restrict__ lse, float* __restrict__ loss) {
+  const long long b = blockIdx.x;
+  __shared__ float red[8];
+  __shared__ float s_lab;
+  if (threadIdx.x == 0) s_lab = 0.f;
+  __syncthreads();
+  const long long lab = labels ? labels[b] : -1;
+  float m = 0.f, picked = 0.f;  // outputs are in (0, 1): exp() cannot overflow, no max shift needed
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float p = fmaf(gamma[k] * stat[2 * k + 1], o[b * ldo + k] - stat[2 * k], beta[k]);
+    const float s = 1.f / (1.f + expf(-p));
+    if (scores) scores[b * K + k] = s;
+    m += expf(s);
+    if (k == lab) picked = s;
+  }
+  m = warp_sum(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  if (lab >= 0 && lab < K && threadIdx.x == lab % blockDim.x) s_lab = picked;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float l = logf(tot);
+    lse[b] = l;
+    if (labels) atomicAdd(loss, (l - s_lab) / static_cast<float>(batch));
+  }
+}
+
+// dp[b][k] = dout * out (1 - out) with dout = (exp(out - lse_b) - [k == label_b]) / B (cross-entropy on the sigmoid
+// outputs) or an externally supplied d(loss)/d(scores); BN_K backward over the batch per class:
+// do = gamma rstd (dp - mean_b dp - xhat mean_b(dp xhat)).  grid = ceil(K/32), block (32, 8); writes do fp32 [B][ld].
+__global__ void __launch_bounds__(256)
+out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const float* __restrict__ stat,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const long long* __restrict__ labels, const float* __restrict__ lse,
+                       const float* __restrict__ dscores, long long batch, float* __restrict__ d_o, long long ldd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
+  __shared__ double r1[8][32], r2[8][32];
+  __shared__ float m1[32], m2[32];
+  const bool ok = k < K;
+  const float mu = ok ? stat[2 * k] : 0.f, rstd = ok ? stat[2 * k + 1] : 0.f, g = ok ? gamma[k] : 0.f,
+              be = ok ? beta[k] : 0.f;
+  auto dp_of = [&](long long b, float& xh) {
+    xh = (o[b * ldo + k] - mu) * rstd;
+    const float s = 1.f / (1.f + expf(-fmaf(g, xh, be)));
+    const float dout = dscores ? dscores[b * K + k]
+                               : (expf(s - lse[b]) - (labels[b] == k ? 1.f : 0.f)) / static_cast<float>(batch);
+    return dout * s * (1.f - s);
+  };
+  double s1 = 0, s2 = 0;
+  if (ok)
+    for (long long b = ty; b < batch; b += 8) {
+      float xh;
+      const float dp = dp_of(b, xh);
+      s1 += dp;
+      s2 += double(dp) * xh;
+    }
+  r1[ty][tx] = s1;
+  r2[ty][tx] = s2;
+  __syncthreads();
+  if (ty == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += r1[w][tx]; b += r2[w][tx]; }
+    m1[tx] = static_cast<float>(a / double(batch));
+    m2[tx] = static_cast<float>(b / double(batch));
+    if (ok) { dbeta[k] = static_cast<float>(a); dgamma[k] = static_cast<float>(b); }
+  }
+  __syncthreads();
+  if (ok)
+    for (long long b = ty; b < batch; b += 8) {
+      float xh;
+      const float dp = dp_of(b, xh);
+      d_o[b * ldd + k] = g * rstd * (dp - m1[tx] - xh * m2[tx]);
+    }
+}
+
+// ------------------------------------------------------------------ Adam (torch.optim.Adam, amsgrad = False)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float gr = g[i] * gscale;
+    if (wd != 0.f) gr = fmaf(wd, p[i], gr);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gr);       // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gr * gr);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ trainer handle
+// offsets into params (gamma, beta) / running (mean; var = mean + n); statistic slots for the forward batch statistics
+// and for the backward reductions
+struct BnRef { long long g, b, rm; int n; int slot, bslot; };
+struct FcRef {
+  long long w, b; int n_out, n_in, n_out_pad, n_in_pad;
+  float* bias_pad;      // [n_out_pad] zero-padded copy of the bias (the GEMM epilogue reads whole tiles)
+  __nv_bfloat16* wp;    // [n_out_pad][2 n_in_pad]
+  __nv_bfloat16* wtp;   // [n_in_pad][2 n_out_pad]
+};
+struct LevelRef { BnRef norm0; int n_fc; FcRef fc[kMaxFc]; BnRef norms[kMaxFc]; FcRef fcv; BnRef normv, normf; };
+
+struct vmb_mla_trainer {
+  int n_levels, emb_in, H, K, T;
+  long long max_batch;
+  LevelRef lvl[kMaxLevels];
+  FcRef fc_out;
+  BnRef norm_out;
+  long long n_params = 0, n_running = 0;
+  int n_slots = 0;          // statistic slots; slot s: acc at s*kSlot doubles, stat at s*kSlot floats
+  char* ws = nullptr;       // single workspace allocation
+  size_t ws_bytes = 0;
+  // carved pointers
+  double* acc = nullptr; size_t acc_bytes = 0;      // zeroed every step (together with the counters)
+  unsigned* counters = nullptr;
+  float* stat = nullptr;
+  __nv_bfloat16* xin_p = nullptr;                  // level-0 norm0 output planes [Rp][2 inpad]
+  __nv_bfloat16* xin_pt = nullptr;                 // transposed
+  float* U[kMaxLevels][kMaxFc] = {};               // pre-BN Linear outputs [R][Hp]
+  __nv_bfloat16* A_p[kMaxLevels][kMaxFc] = {};     // post-activation planes (input of the next Linear / fcv)
+  __nv_bfloat16* A_pt[kMaxLevels][kMaxFc] = {};
+  float* E[kMaxLevels] = {};                       // fp32 embeddings of each level (input of the next level's norm0)
+  __nv_bfloat16* N_p[kMaxLevels] = {};             // norm0 output planes of levels >= 1
+  __nv_bfloat16* N_pt[kMaxLevels] = {};
+  float* Z[kMaxLevels] = {};                       // fcv outputs
+  float* row_stats[kMaxLevels] = {};
+  float *Y = nullptr, *dY = nullptr;               // [B][ycols]
+  __nv_bfloat16 *Y_p = nullptr, *Y_pt = nullptr;
+  float *O = nullptr, *dO = nullptr, *lse = nullptr;
+  __nv_bfloat16 *G_p = nullptr, *G_pt = nullptr;   // gradient planes (reused)
+  float *GV = nullptr, *GF = nullptr;              // attention branch gradients / general fp32 scratch [R][Hp]
+  float *dA = nullptr, *dB = nullptr, *dEnext = nullptr;  // fp32 gradient buffers [R][Hp]
+  float* dWtmp = nullptr;                          // padded dW GEMM output
+  int Hp, Kp, inpad, ycols, ycols_pad;
+};
+
+namespace {
+constexpr int kSlot = 1024;  // channels per statistic slot (>= max(T, K padded))
+
+struct Carver {
+  char* base; size_t off = 0;
+  template <class T> T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += up(n * sizeof(T));
+    return p;
+  }
+};
+
+void carve(vmb_mla_trainer* h, char* base) {
+  Carver c{base};
+  const long long B = h->max_batch, R = B * h->T, Rp = pad64(R), Bp = pad64(B);
+  const int Hp = h->Hp, inpad = h->inpad;
+  h->acc = c.take<double>(size_t(h->n_slots) * kSlot * 2);
+  h->counters = c.take<unsigned>(size_t(h->n_slots));
+  h->acc_bytes = c.off;
+  h->stat = c.take<float>(size_t(h->n_slots) * kSlot * 2);
+  h->xin_p = c.take<__nv_bfloat16>(size_t(Rp) * 2 * inpad);
+  h->xin_pt = c.take<__nv_bfloat16>(size_t(inpad) * 2 * Rp);
+  for (int l = 0; l < h->n_levels; ++l) {
+    for (int j = 0; j < h->lvl[l].n_fc; ++j) {
+      h->U[l][j] = c.take<float>(size_t(R) * Hp);
+      h->A_p[l][j] = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
+      h->A_pt[l][j] = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+    }
+    h->E[l] = c.take<float>(size_t(R) * Hp);
+    if (l > 0) {
+      h->N_p[l] = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
+      h->N_pt[l] = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+    }
+    h->Z[l] = c.take<float>(size_t(R) * Hp);
+    h->row_stats[l] = c.take<float>(size_t(R) * 2);
+  }
+  h->Y = c.take<float>(size_t(B) * h->ycols_pad);
+  h->dY = c.take<float>(size_t(B) * h->ycols_pad);
+  h->Y_p = c.take<__nv_bfloat16>(size_t(Bp) * 2 * h->ycols_pad);
+  h->Y_pt = c.take<__nv_bfloat16>(size_t(h->ycols_pad) * 2 * Bp);
+  h->O = c.take<float>(size_t(B) * Hp);
+  h->dO = c.take<float>(size_t(B) * Hp);
+  h->lse = c.take<float>(size_t(B));
+  h->G_p = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
+  h->G_pt = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+  h->GV = c.take<float>(size_t(R) * Hp);
+  h->GF = c.take<float>(size_t(R) * Hp);
+  h->dA = c.take<float>(size_t(R) * Hp);
+  h->dB = c.take<float>(size_t(R) * Hp);
+  h->dEnext = c.take<float>(size_t(R) * Hp);
+  const int widest = std::max(h->ycols_pad, std::max(Hp, inpad));
+  h->dWtmp = c.take<float>(size_t(Hp) * widest);
+  auto planes_for = [&](FcRef& f) {
+    f.bias_pad = c.take<float>(size_t(f.n_out_pad));
+    f.wp = c.take<__nv_bfloat16>(size_t(f.n_out_pad) * 2 * f.n_in_pad);
+    f.wtp = c.take<__nv_bfloat16>(size_t(f.n_in_pad) * 2 * f.n_out_pad);
+  };
+  for (int l = 0; l < h->n_levels; ++l) {
+    for (int j = 0; j < h->lvl[l].n_fc; ++j) planes_for(h->lvl[l].fc[j]);
+    planes_for(h->lvl[l].fcv);
+  }
+  planes_for(h->fc_out);
+  h->ws_bytes = c.off;
+}
+
+// the flat layout: named_parameters() order of the reference module with fcf left out (model.py:200-256)
+void build_layout(vmb_mla_trainer* h, const int* n_fc) {
+  long long p = 0, r = 0;
+  int slot = 0;
+  auto bn = [&](int n) {
+    BnRef b{p, p + n, r, n, slot, slot + 1};
+    slot += 2;
+    p += 2 * n;
+    r += 2 * n;
+    return b;
+  };
+  auto fc = [&](int n_out, int n_in) {
+    FcRef f{};
+    f.w = p; f.b = p + 1LL * n_out * n_in;
+    f.n_out = n_out; f.n_in = n_in; f.n_out_pad = pad128(n_out); f.n_in_pad = pad128(n_in);
+    p += 1LL * n_out * n_in + n_out;
+    return f;
+  };
+  for (int l = 0; l < h->n_levels; ++l) {
+    LevelRef& L = h->lvl[l];
+    L.n_fc = n_fc[l];
+    L.norm0 = bn(h->T);
+    for (int j = 0; j < L.n_fc; ++j) L.fc[j] = fc(h->H, (l == 0 && j == 0) ? h->emb_in : h->H);
+    for (int j = 0; j < L.n_fc; ++j) L.norms[j] = bn(h->T);
+  }
+  for (int l = 0; l < h->n_levels; ++l) {
+    LevelRef& L = h->lvl[l];
+    L.fcv = fc(h->K, h->H);
+    L.normv = bn(h->T);
+    L.normf = bn(h->T);
+  }
+  h->fc_out = fc(h->K, h->n_levels * h->K);
+  h->norm_out = bn(h->K);
+  h->n_params = p;
+  h->n_running = r;
+  h->n_slots = slot;
+}
+
+dim3 tile_grid(long long rows_pad, int cols_pad) {
+  return dim3(static_cast<unsigned>((cols_pad + 31) / 32), static_cast<unsigned>((rows_pad + 31) / 32));
+}
+
+template <class F>
+int run_tile(F f, TileOut o, cudaStream_t st, const char* what) {
+  tile_split_kernel<F><<<tile_grid(o.rows_pad, o.cols_pad), 256, 0, st>>>(f, o);
+  vmb::count_launch();
+  return vmb::check_launch(what);
+}
+
+int gemm(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo, long long M, int N,
+         int K, cudaStream_t st) {
+  if (vmb::igemm_linear_split(a_planes, w_planes, bias, out, ldo, 0, int(M), N, K, st)) {
+    vmb::set_kernel_error("%s", vmb::igemm_last_error());
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long vmb_mla_train_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps,
+                                    long long* n_running_out) {
+  if (n_levels < 1 || n_levels > kMaxLevels || !n_fc) return -1;
+  vmb_mla_trainer tmp{};
+  tmp.n_levels = n_levels; tmp.emb_in = emb_in; tmp.H = hidden; tmp.K = n_classes; tmp.T = t_steps;
+  build_layout(&tmp, n_fc);
+  if (n_running_out) *n_running_out = tmp.n_running;
+  return tmp.n_params;
+}
+
+int vmb_mla_trainer_create(vmb_mla_trainer_t** handle, int n_levels, const int* n_fc, int emb_in, int hidden,
+                           int n_classes, int t_steps, long long max_batch, void* stream) {
+  if (!handle || !n_fc) return fail("vmb_mla_trainer_create: null argument");
+  if (n_levels < 1 || n_levels > kMaxLevels) return fail("vmb_mla_trainer_create: 1..4 levels supported");
+  for (int l = 0; l < n_levels; ++l)
+    if (n_fc[l] < 1 || n_fc[l] > kMaxFc) return fail("vmb_mla_trainer_create: 1..4 fully connected layers per level");
+  if (t_steps < 1 || t_steps > 16) return fail("vmb_mla_trainer_create: 1 <= T <= 16");
+  if (emb_in < 1 || emb_in > 16384 || hidden < 1 || hidden > 1024 || n_classes < 1 || n_classes > 1024)
+    return fail("vmb_mla_trainer_create: hidden and n_classes must be in 1..1024, emb_in in 1..16384");
+  if (pad128(emb_in) > std::max(pad128(hidden), pad128(n_classes)))
+    return fail("vmb_mla_trainer_create: emb_in wider than the hidden width is not supported by the trainer yet");
+  if (max_batch < 2 || max_batch * t_steps > 0x7fffffffLL / 2048) return fail("vmb_mla_trainer_create: bad max_batch");
+  vmb_mla_trainer* h = new vmb_mla_trainer();
+  h->n_levels = n_levels; h->emb_in = emb_in; h->H = hidden; h->K = n_classes; h->T = t_steps;
+  h->max_batch = max_batch;
+  h->Hp = std::max(pad128(hidden), pad128(n_classes));
+  h->Kp = h->Hp;
+  h->inpad = pad128(emb_in);
+  h->ycols = n_levels * n_classes;
+  h->ycols_pad = pad128(h->ycols);
+  build_layout(h, n_fc);
+  carve(h, nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMalloc(reinterpret_cast<void**>(&h->ws), h->ws_bytes) != cudaSuccess) {
+    delete h;
+    return fail("vmb_mla_trainer_create: workspace allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  }
+  carve(h, h->ws);
+  // padding of every plane / fp32 buffer stays zero for the life of the handle
+  if (cudaMemsetAsync(h->ws, 0, h->ws_bytes, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    cudaFree(h->ws);
+    delete h;
+    return fail("vmb_mla_trainer_create: workspace clear failed");
+  }
+  *handle = h;
+  return 0;
+}
+
+void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
+  if (!h) return;
+  cudaFree(h->ws);
+  delete h;
+}
+
+}  // extern "C"
+
+namespace {
+enum { kPhaseForward = 1, kPhaseBackward = 2 };
+
+// One implementation for forward, backward and the fused step: the phases share the layout arithmetic.
+int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* running, const float* x,
+                 const long long* labels, const float* dscores, long long batch, float dropout_p,
+                 unsigned long long seed, float* grads, float* loss, float* scores, void* stream) {
+  if (!h) return fail("vmb_mla_train: null handle");
+  if (!params || !x) return fail("vmb_mla_train: null pointer");
+  if ((phases & kPhaseForward) && !running) return fail("vmb_mla_train: forward needs the running-statistics buffer");
+  if ((phases & kPhaseBackward) && (!grads || (!labels && !dscores)))
+    return fail("vmb_mla_train: backward needs grads and either labels or d(scores)");
+  if (labels && !loss) return fail("vmb_mla_train: labels given but no loss output");
+  if (batch < 2 || batch > h->max_batch) return fail("vmb_mla_train: batch must be in 2..max_batch");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail("vmb_mla_train: dropout_p must be in [0, 1)");
+  const bool do_fwd = phases & kPhaseForward, do_bwd = phases & kPhaseBackward;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = h->T, H = h->H, K = h->K, Hp = h->Hp, inpad = h->inpad;
+  const long long B = batch, R = B * T, Rp = pad64(R), Bp = pad64(B);
+  int rc = 0;
+#define TRY(expr) do { if (!rc && (expr)) rc = 1; } while (0)
+
+  // forward statistics live in even slots, backward reductions in odd slots: the forward clears everything, a
+  // separate backward call must not (it still needs the forward statistics) — backward slots are re-zeroed below
+  if (do_fwd && (cudaMemsetAsync(h->acc, 0, h->acc_bytes, st) != cudaSuccess ||
+                 (loss && cudaMemsetAsync(loss, 0, 4, st) != cudaSuccess)))
+    return fail("vmb_mla_train: memset failed");
+  if (do_bwd && cudaMemsetAsync(grads, 0, size_t(h->n_params) * 4, st) != cudaSuccess)
+    return fail("vmb_mla_train: memset failed");
+  if (do_bwd && !do_fwd)
+    for (int s = 1; s < h->n_slots; s += 2)
+      if (cudaMemsetAsync(h->acc + size_t(s) * kSlot * 2, 0, size_t(kSlot) * 2 * sizeof(double), st) != cudaSuccess)
+        return fail("vmb_mla_train: memset failed");
+  auto slotacc = [&](int s) { return h->acc + size_t(s) * kSlot * 2; };
+  auto slotstat = [&](int s) { return h->stat + size_t(s) * kSlot * 2; };
+  auto statjob = [&](const BnRef& bn, double count) {
+    return StatJob{slotacc(bn.slot), slotstat(bn.slot), h->counters + bn.slot, running + bn.rm, running + bn.rm + bn.n,
+                   count, bn.n};
+  };
+  auto time_stats = [&](const float* src, long long ld, int F, const BnRef& bn, bool update_running) {
+    StatJob j = statjob(bn, double(B) * F);
+    if (!update_running) j.run_mean = j.run_var = nullptr;
+    const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F + 256 * 8 - 1) / (256 * 8), 64));
+    bn_time_stats_kernel<<<dim3(chunks, T), 256, 0, st>>>(src, ld, B, F, T, j);
+    vmb::count_launch();
+    return vmb::check_launch("bn_time_stats_kernel");
+  };
+  auto weights = [&](const FcRef& f) {
+    TileOut o{f.wp, f.wtp, nullptr, 0, nullptr, f.n_out, f.n_out_pad, f.n_in, f.n_in_pad};
+    return run_tile(FIdentity{params + f.w, f.n_in, params + f.b, f.bias_pad, f.n_out}, o, st, "weight split");
+  };
+
+  if (do_fwd) {
+  // ---- weights -> hi|lo planes, row-major and transposed (they changed in the last optimiser step)
+  for (int l = 0; l < h->n_levels; ++l) {
+    for (int j = 0; j < h->lvl[l].n_fc; ++j) TRY(weights(h->lvl[l].fc[j]));
+    TRY(weights(h->lvl[l].fcv));
+  }
+  TRY(weights(h->fc_out));
+
+  // =============================================================================== forward
+  for (int l = 0; l < h->n_levels && !rc; ++l) {
+    const LevelRef& L = h->lvl[l];
+    const float* in = l == 0 ? x : h->E[l - 1];
+    const long long ld_in = l == 0 ? h->emb_in : Hp;
+    const int F_in = l == 0 ? h->emb_in : H;
+    const int in_pad = l == 0 ? inpad : Hp;
+    __nv_bfloat16* np = l == 0 ? h->xin_p : h->N_p[l];
+    __nv_bfloat16* npt = l == 0 ? h->xin_pt : h->N_pt[l];
+    TRY(time_stats(in, ld_in, F_in, L.norm0, true));
+    {
+      FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, seed, 0};
+      TileOut o{np, npt, nullptr, 0, nullptr, R, Rp, F_in, in_pad};
+      TRY(run_tile(f, o, st, "norm0 forward"));
+    }
+    const __nv_bfloat16* a = np;
+    for (int j = 0; j < L.n_fc && !rc; ++j) {
+      const FcRef& fc = L.fc[j];
+      TRY(gemm(a, fc.wp, fc.bias_pad, h->U[l][j], Hp, R, Hp, fc.n_in_pad, st));
+      TRY(time_stats(h->U[l][j], Hp, H, L.norms[j], true));
+      const bool last = j == L.n_fc - 1;
+      FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
+               dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
+      TileOut o{h->A_p[l][j], h->A_pt[l][j], last ? h->E[l] : nullptr, Hp, nullptr, R, Rp, H, Hp};
+      TRY(run_tile(f, o, st, "fc forward activation"));
+      a = h->A_p[l][j];
+    }
+    // attention branch of this level
+    TRY(gemm(a, L.fcv.wp, L.fcv.bias_pad, h->Z[l], Hp, R, Hp, Hp, st));
+    TRY(time_stats(h->Z[l], Hp, K, L.normv, true));
+    if (!rc) {
+      // normf shares the batch statistics but keeps its own running buffers
+      StatJob j = statjob(L.normf, double(B) * K);
+      j.acc = slotacc(L.normv.slot);
+      j.stat = slotstat(L.normf.slot);
+      bn_running_only_kernel<<<1, 32, 0, st>>>(j);
+      vmb::count_launch();
+      TRY(vmb::check_launch("bn_running_only_kernel"));
+      AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
+                   params + L.normf.g, params + L.normf.b};
+      att_forward_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(ap, h->Y, h->ycols_pad, l * K, h->row_stats[l]);
+      vmb::count_launch();
+      TRY(vmb::check_launch("att_forward_kernel"));
+    }
+  }
+  // output layer
+  {
+    TileOut o{h->Y_p, h->Y_pt, nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
+    TRY(run_tile(FIdentity{h->Y, h->ycols_pad}, o, st, "y split"));
+  }
+  TRY(gemm(h->Y_p, h->fc_out.wp, h->fc_out.bias_pad, h->O, Hp, B, Hp, h->ycols_pad, st));
+  if (!rc) {
+    StatJob j = statjob(h->norm_out, double(B));
+    bn_col_stats_kernel<<<(K + 31) / 32, 256, 0, st>>>(h->O, Hp, B, K, j);
+    vmb::count_launch();
+    TRY(vmb::check_launch("bn_col_stats_kernel"));
+    const float* stat = slotstat(h->norm_out.slot);
+    out_loss_rows_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(h->O, Hp, K, stat, params + h->norm_out.g,
+                                                                   params + h->norm_out.b, labels, B, scores, h->lse, loss);
+    vmb::count_launch();
+    TRY(vmb::check_launch("out_loss_rows_kernel"));
+  }
+  }  // do_fwd
+  if (do_bwd) {
+  // =============================================================================== backward
+  if (!rc) {
+    const float* stat = slotstat(h->norm_out.slot);
+    out_bn_backward_kernel<<<(K + 31) / 32, 256, 0, st>>>(h->O, Hp, K, stat, params + h->norm_out.g, params + h->norm_out.b,
+                                                          labels, h->lse, dscores, B, h->dO, Hp, grads + h->norm_out.g,
+                                                          grads + h->norm_out.b);
+    vmb::count_launch();
+    TRY(vmb::check_launch("out_bn_backward_kernel"));
+  }
+  {
+    // dO planes (+ transposed) and d(bias) = column sums
+    TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + h->fc_out.b, B, Bp, K, Hp};
+    TRY(run_tile(FIdentity{h->dO, Hp}, o, st, "dO split"));
+    // dW_fc [K][L*K] = dO^T [K x B] * Y^T [L*K x B]^T
+    TRY(gemm(h->G_pt, h->Y_pt, nullptr, h->dWtmp, h->ycols_pad, Hp, h->ycols_pad, int(Bp), st));
+    if (!rc && cudaMemcpy2DAsync(grads + h->fc_out.w, size_t(h->ycols) * 4, h->dWtmp, size_t(h->ycols_pad) * 4,
+                                 size_t(h->ycols) * 4, K, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      rc = 1;
+    // dY [B][L*K] = dO [B x K] * W_fc [K x L*K]
+    TRY(gemm(h->G_p, h->fc_out.wtp, nullptr, h->dY, h->ycols_pad, B, h->ycols_pad, Hp, st));
+  }
+  // levels in reverse
+  for (int l = h->n_levels - 1; l >= 0 && !rc; --l) {
+    const LevelRef& L = h->lvl[l];
+    const __nv_bfloat16* e_pt = h->A_pt[l][L.n_fc - 1];
+    AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
+                 params + L.normf.g, params + L.normf.b};
+    double* acc_v = slotacc(L.normv.bslot);
+    double* acc_f = slotacc(L.normf.bslot);
+    att_backward_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(ap, h->Y, h->dY, h->ycols_pad, l * K, h->row_stats[l],
+                                                                  h->GV, h->GF, Hp, acc_v, acc_f);
+    vmb::count_launch();
+    TRY(vmb::check_launch("att_backward_kernel"));
+    {
+      FAttCombine f{ap, h->GV, h->GF, Hp, acc_v, acc_f, double(B) * K, grads + L.normv.g, grads + L.normv.b,
+                    grads + L.normf.g, grads + L.normf.b};
+      TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
+      TRY(run_tile(f, o, st, "attention BN backward"));
+    }
+    // dWv [K][H] = dZ^T * E^T ; dE_att [R][H] = dZ * Wv
+    TRY(gemm(h->G_pt, e_pt, nullptr, h->dWtmp, Hp, Hp, Hp, int(Rp), st));
+    if (!rc && cudaMemcpy2DAsync(grads + L.fcv.w, size_t(H) * 4, h->dWtmp, size_t(Hp) * 4, size_t(H) * 4, K,
+                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      rc = 1;
+    TRY(gemm(h->G_p, L.fcv.wtp, nullptr, h->dA, Hp, R, Hp, Hp, st));
+    // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
+    const float* da1 = h->dA;
+    const float* da2 = (l + 1 < h->n_levels) ? h->dEnext : nullptr;
+    for (int j = L.n_fc - 1; j >= 0 && !rc; --j) {
+      const FcRef& fc = L.fc[j];
+      GradIn gi{da1, Hp, da2, Hp, h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g,
+                params + L.norms[j].b, 1, dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
+      double* acc = slotacc(L.norms[j].bslot);
+      const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * H + 256 * 8 - 1) / (256 * 8), 64));
+      bn_time_backward_reduce_kernel<<<dim3(chunks, T), 256, 0, st>>>(gi, B, acc);
+      vmb::count_launch();
+      TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
+      TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + fc.b, R, Rp, H, Hp};
+      TRY(run_tile(f, o, st, "fc BN backward"));
+      // dW [H][n_in] = dU^T * A_prev^T ; dA_prev [R][n_in] = dU * W
+      const __nv_bfloat16* prev_pt = j > 0 ? h->A_pt[l][j - 1] : (l == 0 ? h->xin_pt : h->N_pt[l]);
+      TRY(gemm(h->G_pt, prev_pt, nullptr, h->dWtmp, fc.n_in_pad, Hp, fc.n_in_pad, int(Rp), st));
+      if (!rc && cudaMemcpy2DAsync(grads + fc.w, size_t(fc.n_in) * 4, h->dWtmp, size_t(fc.n_in_pad) * 4,
+                                   size_t(fc.n_in) * 4, H, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = 1;
+      float* dprev = (da1 == h->dA) ? h->dB : h->dA;
+      TRY(gemm(h->G_p, fc.wtp, nullptr, dprev, Hp, R, fc.n_in_pad, Hp, st));
+      da1 = dprev;
+      da2 = nullptr;
+    }
+    // norm0 of this level: gradient wrt its input (= E_{l-1} for l > 0) and its affine parameters
+    {
+      const float* in = l == 0 ? x : h->E[l - 1];
+      const long long ld_in = l == 0 ? h->emb_in : Hp;
+      const int F_in = l == 0 ? h->emb_in : H;
+      GradIn gi{da1, Hp, nullptr, 0, in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g,
+                params + L.norm0.b, 0, 0.f, seed, 0};
+      double* acc = slotacc(L.norm0.bslot);
+      const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F_in + 256 * 8 - 1) / (256 * 8), 64));
+      bn_time_backward_reduce_kernel<<<dim3(chunks, T), 256, 0, st>>>(gi, B, acc);
+      vmb::count_launch();
+      TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      FBnBackward f{gi, acc, double(B) * F_in, grads + L.norm0.g, grads + L.norm0.b};
+      // level 0: only the parameter gradients are needed (written by the prologue); still run one tile row so
+      // the prologue executes.  level > 0: fp32 gradient wrt E_{l-1}
+      TileOut o{nullptr, nullptr, l > 0 ? h->dEnext : nullptr, Hp, nullptr, l > 0 ? R : 1, l > 0 ? R : 1, F_in,
+                l > 0 ? Hp : 32};
+      TRY(run_tile(f, o, st, "norm0 backward"));
+    }
+  }
+  }  // do_bwd
+#undef TRY
+  if (rc) return fail("vmb_mla_train: %s", vmb::kernels_last_error());
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int vmb_mla_train_step(vmb_mla_trainer_t* h, const float* params, float* running, const float* x,
+                       const long long* labels, long long batch, float dropout_p, unsigned long long seed,
+                       float* grads, float* loss, float* scores, void* stream) {
+  if (!labels) return fail("vmb_mla_train_step: labels are required");
+  return train_phases(kPhaseForward | kPhaseBackward, h, params, running, x, labels, nullptr, batch, dropout_p, seed,
+                      grads, loss, scores, stream);
+}
+
+int vmb_mla_train_forward(vmb_mla_trainer_t* h, const float* params, float* running, const float* x, long long batch,
+                          float dropout_p, unsigned long long seed, float* scores, void* stream) {
+  if (!scores) return fail("vmb_mla_train_forward: null scores");
+  return train_phases(kPhaseForward, h, params, running, x, nullptr, nullptr, batch, dropout_p, seed, nullptr, nullptr,
+                      scores, stream);
+}
+
+int vmb_mla_train_backward(vmb_mla_trainer_t* h, const float* params, const float* x, const float* dscores,
+                           long long batch, float dropout_p, unsigned long long seed, float* grads, void* stream) {
+  if (!dscores) return fail("vmb_mla_train_backward: null d(scores)");
+  return train_phases(kPhaseBackward, h, params, nullptr, x, nullptr, dscores, batch, dropout_p, seed, grads, nullptr,
+                      nullptr, stream);
+}
+
+int vmb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
+                  void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("vmb_adam_step: null pointer");
+  if (n <= 0) return 0;
+  if (step < 1) return fail("vmb_adam_step: step counts from 1");
+  const float bc1 = 1.f - std::pow(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - std::pow(beta2, static_cast<float>(step));
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148LL * 8));
+  adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                   eps, weight_decay, bc1, std::sqrt(bc2), grad_scale);
+  vmb::count_launch();
+  if (vmb::check_launch("adam_kernel")) return fail("vmb_adam_step: %s", vmb::kernels_last_error());
+  return 0;
+}
+
+}  // extern "C"

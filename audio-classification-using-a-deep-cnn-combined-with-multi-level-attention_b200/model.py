@@ -177,6 +177,37 @@ class MultiLevelAttention(nn.Module):
             self._handle_key = key
         return self._handle
 
+    def _b200_train_state(self):
+        """Lazily built bridge to the library trainer: flat parameter buffers mirrored from / to this module."""
+        dev = self.fc.weight.device
+        if dev.type != "cuda":
+            raise B200Error("head parameters are on %s: move the module to a CUDA device; this build has no CPU "
+                            "path" % dev)
+        st = getattr(self, "_train_state", None)
+        if st is not None and st["trainer"].device == dev:
+            return st
+        from b200 import training as _training
+        tr = _training.HeadTrainer(list(self.model), self.emb_input_size, self._h, self._k, self._t, max_batch=4096,
+                                   device=dev, dropout_p=self._dr)
+        names = [n for n, _ in self.named_parameters()]
+        pmap = dict(self.named_parameters())
+        bmap = dict(self.named_buffers())
+
+        def sync_in():        # module -> flat (parameters may have been changed by the optimiser or load_state_dict)
+            for key, shape, off in tr.p_layout:
+                tr.view(tr.params, key).copy_(pmap[key].detach())
+            for key, shape, off in tr.r_layout:
+                tr.running[off:off + shape[0]].copy_(bmap[key])
+
+        def sync_out():       # flat -> module: BatchNorm running statistics updated by the forward pass
+            for key, shape, off in tr.r_layout:
+                bmap[key].copy_(tr.running[off:off + shape[0]])
+                if key.endswith("running_var"):
+                    bmap[key[:-len("running_var")] + "num_batches_tracked"].add_(1)
+
+        self._train_state = dict(trainer=tr, param_names=names, sync_in=sync_in, sync_out=sync_out)
+        return self._train_state
+
     def forward(self, x):
         if self.training:
             from b200 import training as _training

@@ -21,6 +21,7 @@ extern "C" {
 
 typedef struct vmb_vggish vmb_vggish_t;
 typedef struct vmb_mla vmb_mla_t;
+typedef struct vmb_mla_trainer vmb_mla_trainer_t;
 
 /* ------------------------------------------------------------------------------------------ misc */
 const char* vmb_last_error(void);
@@ -130,6 +131,42 @@ int vmb_mla_forward(vmb_mla_t* handle, const float* emb_dev, long long batch, fl
 /* The same head as ONE fused CUDA-core fp32 kernel (the first implementation; emb_in <= 608).  Diagnostic: the
  * on-device cross-check for vmb_mla_forward; vmb_pipeline_forward never uses it.                         */
 int vmb_mla_forward_fp32(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------ MLA head training
+ * One optimisation step of the head as the reference's train loop runs it (train.py:119-138, :369-372) with the CNN
+ * frozen (model.py:159-160): forward in train mode — BatchNorm with batch statistics per time step,
+ * Dropout(p) after each ReLU (model.py:212,220), nn.CrossEntropyLoss on the sigmoid outputs — and backward.
+ * Flat layouts (fp32):
+ *   params / grads: named_parameters() order of MultiLevelAttention with fcf left out (it never gets a gradient, F3):
+ *     for each level l: norm0.{weight,bias}[T]; fc.{j}.{weight[H][in],bias[H]} for all j; norms.{j}.{weight,bias}[T];
+ *     for each level l: fcv.{weight[K][H],bias[K]}; normv.{weight,bias}[T]; normf.{weight,bias}[T];
+ *     fc.{weight[K][L*K],bias[K]}; norm.{weight,bias}[K]
+ *   running: for every BatchNorm in the same order {running_mean[n], running_var[n]} — updated in place like
+ *     nn.BatchNorm1d does (momentum 0.1, unbiased variance).
+ * vmb_mla_train_step zeroes `grads` and `loss`, then writes d(loss)/d(params) of THIS rank's batch into grads (ready
+ * for one flat NCCL all-reduce across data-parallel ranks) and the mean loss into *loss_dev.  scores_dev (optional)
+ * receives the train-mode outputs [batch][K].  Dropout uses a counter-based generator keyed by (seed, layer, element). */
+long long vmb_mla_train_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps,
+                                    long long* n_running_out);
+int vmb_mla_trainer_create(vmb_mla_trainer_t** handle, int n_levels, const int* n_fc, int emb_in, int hidden,
+                           int n_classes, int t_steps, long long max_batch, void* stream);
+void vmb_mla_trainer_destroy(vmb_mla_trainer_t* handle);
+int vmb_mla_train_step(vmb_mla_trainer_t* handle, const float* params_dev, float* running_dev, const float* emb_dev,
+                       const long long* labels_dev, long long batch, float dropout_p, unsigned long long seed,
+                       float* grads_dev, float* loss_dev, float* scores_dev, void* stream);
+/* The same step in two calls, for callers that compute the loss themselves (the reference's `criterion(outputs,
+ * labels); loss.backward()`, train.py:130-136): forward leaves its state in the handle, backward takes
+ * d(loss)/d(scores) [batch][K].  One step in flight per handle.                                              */
+int vmb_mla_train_forward(vmb_mla_trainer_t* handle, const float* params_dev, float* running_dev, const float* emb_dev,
+                          long long batch, float dropout_p, unsigned long long seed, float* scores_dev, void* stream);
+int vmb_mla_train_backward(vmb_mla_trainer_t* handle, const float* params_dev, const float* emb_dev,
+                           const float* dscores_dev, long long batch, float dropout_p, unsigned long long seed,
+                           float* grads_dev, void* stream);
+/* torch.optim.Adam (amsgrad = False) on flat buffers (train.py:369): step counts from 1; grads are multiplied by
+ * grad_scale first (1/world_size after a SUM all-reduce).                                                 */
+int vmb_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, long long n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------ whole path
  * Ensemble.forward for cnn_type == "vggish" (model.py:58-62) fed from raw audio:

@@ -1,0 +1,184 @@
+"""GPU parity of the head training step through the C-ABI:
+   * one step vs the reference's own module (golden vectors): loss, outputs, gradients, Adam update, running stats
+   * data parallel semantics: per-shard BatchNorm statistics, gradients averaged over shards == oracle per shard
+   * dropout: deterministic per seed, keep rate ~ 1 - p, inverted scaling
+   * the reference-named module in train mode under the reference's loop (criterion / backward / torch Adam)
+Tolerances: split-bf16 GEMMs carry ~16 mantissa bits, so gradients are checked to 2e-3 relative of each tensor's
+max-abs (measured ~1e-4), the loss to 1e-4, parameters after one Adam step (lr 1e-3) to 5e-5 absolute."""
+import numpy as np
+import pytest
+import torch
+
+from b200 import synth, training
+from oracle import train_torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+CONF = (2, 1)
+
+
+def _trainer(K=527, max_batch=64, dropout_p=0.0, conf=CONF, seed_sd=2):
+    tr = training.HeadTrainer(conf, 128, 600, K, 10, max_batch, DEV, dropout_p=dropout_p)
+    sd = synth.mla_state_dict(conf, 128, 600, K, 10, seed=seed_sd)
+    tr.load_state_dict(sd)
+    return tr, sd
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_one_step_vs_reference_golden(golden_head):
+    tr, sd = _trainer()
+    x = torch.from_numpy(golden_head["train_x"])
+    labels = torch.from_numpy(golden_head["train_labels"])
+    loss, scores = tr.forward_backward(x, labels, want_scores=True)
+    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-4
+    assert np.abs(scores.cpu().numpy() - golden_head["train_y"]).max() < 2e-5
+    worst = 0.0
+    for key in golden_head.files:
+        if key.startswith("grad::"):
+            name = key[len("grad::"):]
+            g = tr.view(tr.grads, name).cpu().numpy()
+            ref = golden_head[key]
+            g = g[:ref.shape[0]] if g.shape != ref.shape else g
+            worst = max(worst, _rel(g, ref))
+            assert _rel(g, ref) < 2e-3, name
+    norms = dict(zip(golden_head["grad_names"], golden_head["grad_norms"]))
+    for key, shape, off in tr.p_layout:
+        got = tr.view(tr.grads, key).norm().item()
+        assert abs(got - norms[key]) <= 2e-3 * norms[key] + 1e-9, key
+    print(f"head training step vs reference: worst gradient rel-max-err {worst:.2e}")
+    # Adam update (train.py:369: lr 1e-3) and running statistics
+    tr.adam(1)
+    for key in golden_head.files:
+        if key.startswith("after::"):
+            name = key[len("after::"):]
+            p = tr.view(tr.params, name).cpu().numpy()
+            ref = golden_head[key]
+            p = p[:ref.shape[0]] if p.shape != ref.shape else p
+            assert np.abs(p - ref).max() < 5e-5, name
+    out = tr.state_dict()
+    np.testing.assert_allclose(out["embedded_mappings.0.norm0.running_mean"].cpu().numpy(),
+                               golden_head["running_mean_after::embedded_mappings.0.norm0"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out["norm.running_var"].cpu().numpy(), golden_head["running_var_after::norm"],
+                               rtol=1e-3, atol=1e-7)
+    assert int(out["norm.num_batches_tracked"]) == 1
+    assert "attention_modules.0.fcf.weight" in out                      # fcf carried through untouched (F3)
+    assert torch.equal(out["attention_modules.0.fcf.weight"], sd["attention_modules.0.fcf.weight"])
+    tr.close()
+
+
+@pytest.mark.parametrize("K,conf,batch", [(10, (2, 1), 33), (10, (1, 2, 1), 8), (527, (2, 1), 96)])
+def test_gradients_vs_oracle(K, conf, batch):
+    tr = training.HeadTrainer(conf, 128, 600, K, 10, 128, DEV, dropout_p=0.0)
+    sd = synth.mla_state_dict(conf, 128, 600, K, 10, seed=7)
+    tr.load_state_dict(sd)
+    g = torch.Generator().manual_seed(batch)
+    x = torch.randn(batch, 10, 128, generator=g)
+    labels = torch.randint(0, K, (batch,), generator=g)
+    loss, scores = tr.forward_backward(x, labels, want_scores=True)
+    ref_loss, ref_scores, ref_grads = train_torch.head_step(sd, x, labels, conf)
+    assert abs(loss.item() - ref_loss.item()) < 1e-4
+    assert (scores.cpu() - ref_scores).abs().max() < 2e-5
+    for key, shape, off in tr.p_layout:
+        got = tr.view(tr.grads, key).cpu().numpy()
+        assert _rel(got, ref_grads[key].numpy()) < 2e-3, key
+    # a second, smaller batch on the same handle (padded planes must not leak rows of the previous step)
+    x2, l2 = x[:5], labels[:5]
+    tr.forward_backward(x2, l2)
+    _, _, ref2 = train_torch.head_step(sd, x2, l2, conf)
+    for key in ("fc.weight", "embedded_mappings.0.fc.0.weight", "attention_modules.0.fcv.weight"):
+        assert _rel(tr.view(tr.grads, key).cpu().numpy(), ref2[key].numpy()) < 2e-3, key
+    tr.close()
+
+
+def test_data_parallel_semantics_two_shards():
+    """What the 8-GPU step computes, emulated on one GPU: each shard runs with ITS OWN BatchNorm statistics, the flat
+    gradient buckets are summed and scaled by 1/world (the all-reduce), every rank applies the same Adam update."""
+    world, per = 2, 24
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(world * per, 10, 128, generator=g)
+    labels = torch.randint(0, 527, (world * per,), generator=g)
+    trs = [_trainer(max_batch=per)[0] for _ in range(world)]
+    sd = synth.mla_state_dict(CONF, 128, 600, 527, 10, seed=2)
+    bucket = torch.zeros_like(trs[0].grads)
+    ref_avg = None
+    for r, tr in enumerate(trs):
+        sl = slice(r * per, (r + 1) * per)
+        tr.forward_backward(x[sl], labels[sl])
+        bucket += tr.grads
+        _, _, gr = train_torch.head_step(sd, x[sl], labels[sl], CONF)
+        ref_avg = gr if ref_avg is None else {k: (None if v is None else v + gr[k]) for k, v in ref_avg.items()}
+    for tr in trs:
+        tr.grads.copy_(bucket)
+        tr.adam(world)
+    for key, shape, off in trs[0].p_layout:
+        got = trs[0].view(bucket, key).cpu().numpy() / world
+        assert _rel(got, (ref_avg[key] / world).numpy()) < 2e-3, key
+        want = train_torch.adam_update(sd[key], ref_avg[key] / world)
+        assert (trs[0].view(trs[0].params, key).cpu() - want).abs().max() < 5e-5, key
+    assert torch.equal(trs[0].params, trs[1].params)                       # replicas stay bit-identical
+    for tr in trs:
+        tr.close()
+
+
+def test_dropout_is_seeded_and_inverted():
+    tr, sd = _trainer(K=10, max_batch=64, dropout_p=0.4)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 10, 128, generator=g)
+    labels = torch.randint(0, 10, (64,), generator=g)
+    tr.seed = 5
+    l1, s1 = tr.forward_backward(x, labels, want_scores=True)
+    g1 = tr.grads.clone()
+    l1 = l1.item()
+    l2, s2 = tr.forward_backward(x, labels, want_scores=True)
+    assert torch.equal(s1, s2) and torch.equal(g1, tr.grads)                # same seed + step -> same mask
+    tr.seed = 6
+    _, s3 = tr.forward_backward(x, labels, want_scores=True)
+    assert not torch.equal(s1, s3)
+    assert torch.isfinite(tr.grads).all() and torch.isfinite(s3).all()
+    # with p = 0 the same batch gives the oracle's loss; with p = 0.4 the loss moves but stays in a sane band
+    tr0, _ = _trainer(K=10, max_batch=64, dropout_p=0.0)
+    l0 = tr0.forward_backward(x, labels)[0].item()
+    assert l0 != l1 and abs(l0 - l1) < 0.5
+    tr.close()
+    tr0.close()
+
+
+def test_reference_loop_on_the_module(golden_head):
+    """model.MultiLevelAttention in train mode driven exactly like train.py:124-138."""
+    import model
+    old_k, old_dr = model.K, model.DR
+    try:
+        model.K, model.DR = 527, 0.0
+        m = model.MultiLevelAttention([2, 1], 128)
+    finally:
+        model.K, model.DR = old_k, old_dr
+    m.load_state_dict(synth.mla_state_dict(CONF, 128, 600, 527, 10, seed=2))
+    m = m.to(DEV).train()
+    x = torch.from_numpy(golden_head["train_x"]).to(DEV)
+    labels = torch.from_numpy(golden_head["train_labels"]).to(DEV)
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=0.001)
+    opt.zero_grad()
+    out = m(x)
+    loss = torch.nn.CrossEntropyLoss()(out, labels)
+    loss.backward()
+    opt.step()
+    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-4
+    assert sorted(n for n, p in m.named_parameters() if p.grad is None) == list(golden_head["train_no_grad_params"])
+    params = dict(m.named_parameters())
+    for key in golden_head.files:
+        if key.startswith("after::"):
+            name = key[len("after::"):]
+            p = params[name].detach().cpu().numpy()
+            ref = golden_head[key]
+            p = p[:ref.shape[0]] if p.shape != ref.shape else p
+            assert np.abs(p - ref).max() < 5e-5, name
+    np.testing.assert_allclose(m.norm.running_var.cpu().numpy(), golden_head["running_var_after::norm"], rtol=1e-3,
+                               atol=1e-7)
+    assert int(m.norm.num_batches_tracked) == 1
+    # back to eval: the inference kernels see the updated parameters
+    m.eval()
+    y = m(x)
+    assert y.shape == (16, 527) and torch.isfinite(y).all()

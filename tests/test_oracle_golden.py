@@ -97,3 +97,36 @@ def test_ensemble(golden_ensemble, vgg_sd, head_sd):
     with torch.no_grad():
         scores = model_torch.ensemble_forward(vgg_sd, head_sd, torch.from_numpy(ex)[:, :, None], (2, 1))
     np.testing.assert_allclose(scores.numpy(), golden_ensemble["scores"], rtol=0, atol=1e-4)
+
+
+def test_head_training_step(golden_head):
+    """One reference training step (train.py:124-138 semantics, dropout off): loss, outputs, gradients, Adam update
+    and BatchNorm running statistics of the oracle against the reference module's."""
+    from oracle import train_torch
+    sd = synth.mla_state_dict((2, 1), 128, 600, 527, 10, seed=2)
+    x = torch.from_numpy(golden_head["train_x"])
+    labels = torch.from_numpy(golden_head["train_labels"])
+    loss, scores, grads = train_torch.head_step(sd, x, labels, (2, 1))
+    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-5
+    np.testing.assert_allclose(scores.numpy(), golden_head["train_y"], rtol=0, atol=2e-6)
+    assert sorted(k for k, g in grads.items() if g is None) == list(golden_head["train_no_grad_params"])
+    for key in golden_head.files:
+        if key.startswith("grad::"):
+            name = key[len("grad::"):]
+            g = grads[name].numpy()
+            ref = golden_head[key]
+            g = g[:ref.shape[0]] if g.shape != ref.shape else g
+            np.testing.assert_allclose(g, ref, rtol=1e-3, atol=1e-7 + 1e-4 * np.abs(ref).max())
+            after = train_torch.adam_update(sd[name], grads[name]).numpy()
+            ref_after = golden_head["after::" + name]
+            after = after[:ref_after.shape[0]] if after.shape != ref_after.shape else after
+            np.testing.assert_allclose(after, ref_after, rtol=0, atol=2e-5)     # lr = 1e-3: sign errors would show as 2e-3
+    names = list(golden_head["grad_names"])
+    for name, ref_norm in zip(names, golden_head["grad_norms"]):
+        got = 0.0 if grads[name] is None else grads[name].norm().item()
+        assert abs(got - ref_norm) <= 1e-3 * ref_norm + 1e-9, name
+    run = train_torch.updated_running_stats(sd, x, (2, 1))
+    np.testing.assert_allclose(run["embedded_mappings.0.norm0.running_mean"].numpy(),
+                               golden_head["running_mean_after::embedded_mappings.0.norm0"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(run["norm.running_var"].numpy(), golden_head["running_var_after::norm"], rtol=1e-4,
+                               atol=1e-7)
