@@ -103,12 +103,23 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                           by[q] + dh, bn[q]);
             if (++cb == p.cblks) { cb = 0; ++tap; }
           } else {
-            // split mode (p.split_nkb > 0): A and B are stored as [hi | lo] column blocks and the K loop runs over
-            // the three products hi*hi, lo*hi, hi*lo (see igemm_linear_split)
-            const int a_kb = (p.split_nkb && kb >= 2 * p.split_nkb) ? kb - 2 * p.split_nkb : kb;
+            // split mode (p.split_nkb > 0): A and B are stored as column blocks of 2 (hi | lo) or 3 (hi | mid | lo)
+            // bf16 planes and the K loop runs over the products with plane index sum <= planes - 1, smallest first
+            // (see igemm_linear_split)
+            int a_kb = kb;
+            if (p.split_nkb) {
+              const int q = kb / p.split_nkb;
+              const int pa = p.split_planes == 3 ? ((0x210100 >> (4 * (5 - q))) & 0xF) : (q == 1 ? 1 : 0);
+              a_kb = pa * p.split_nkb + (kb - q * p.split_nkb);
+            }
             tma_load_2d(a_dst, &tmap_a, &full_bar[stage], a_kb * kBlockK, m_tile * kBlockM);
           }
-          const int b_kb = (p.split_nkb && kb >= p.split_nkb) ? kb - p.split_nkb : kb;
+          int b_kb = kb;
+          if (p.split_nkb) {
+            const int q = kb / p.split_nkb;
+            const int pb = p.split_planes == 3 ? ((0x012010 >> (4 * (5 - q))) & 0xF) : (q == 2 ? 1 : 0);
+            b_kb = pb * p.split_nkb + (kb - q * p.split_nkb);
+          }
           tma_load_2d(b_dst, &tmap_b, &full_bar[stage], b_kb * kBlockK, n_tile * BLOCK_N);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -370,8 +381,12 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
 }
 
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
-                       int relu, int M, int N, int K, cudaStream_t stream) {
+                       int relu, int M, int N, int K, cudaStream_t stream, int planes) {
   if (M <= 0) return 0;
+  if (planes != 2 && planes != 3) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split: planes must be 2 or 3");
+    return 1;
+  }
   if (K % kBlockK != 0 || N % 128 != 0) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
     return 1;
@@ -379,14 +394,14 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
   const int block_n = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   {
-    uint64_t dims[2] = {uint64_t(2 * K), uint64_t(M)};
-    uint64_t str[1] = {uint64_t(2 * K) * 2};
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(M)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
     uint32_t box[2] = {kBlockK, kBlockM};
     if (make_tmap_bf16(&ta, a_planes, 2, dims, str, box)) return 1;
   }
   {
-    uint64_t dims[2] = {uint64_t(2 * K), uint64_t(N)};
-    uint64_t str[1] = {uint64_t(2 * K) * 2};
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(N)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
     uint32_t box[2] = {kBlockK, uint32_t(block_n)};
     if (make_tmap_bf16(&tb, w_planes, 2, dims, str, box)) return 1;
   }
@@ -394,7 +409,8 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
   p.M = M;
   p.N = N;
   p.split_nkb = K / kBlockK;
-  p.num_kb = 3 * p.split_nkb;
+  p.split_planes = planes;
+  p.num_kb = (planes == 3 ? 6 : 3) * p.split_nkb;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
   p.num_n_tiles = N / block_n;
   p.relu = relu;

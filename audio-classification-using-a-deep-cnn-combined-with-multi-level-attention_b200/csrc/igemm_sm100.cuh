@@ -35,6 +35,7 @@ struct IgemmParams {
   int num_n_tiles;
   int relu;
   int split_nkb;     // PLAIN split mode: K / 64 of one plane (0 = ordinary GEMM)
+  int split_planes;  // 2 (hi | lo: 3 products) or 3 (hi | mid | lo: 6 products)
   long long ldo;     // PLAIN: output row stride (elements)
   const float* bias; // [N]
   void* out;         // bf16 (or fp32 when OUT_F32)
@@ -44,11 +45,13 @@ struct IgemmParams {
 // PLAIN: out[M][N] (+ldo) = act(A[M][K] B[N][K]^T + bias).  K % 64 == 0, N % block_n == 0.
 int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int out_f32, int relu,
                  int M, int N, int K, cudaStream_t stream);
-// PLAIN, split-bf16: A = [A_hi | A_lo] as bf16 [M][2K], W = [W_hi | W_lo] as bf16 [N][2K];
+// PLAIN, split-bf16.  planes = 2: A = [A_hi | A_lo] as bf16 [M][2K], W likewise [N][2K];
 // out fp32 [M][ldo] = act(A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T + bias): ~16 mantissa bits per operand (the
-// attention head, where plain bf16 would move the ranking metric).  K % 64 == 0, N % 128 == 0.
+// eval-mode attention head, where plain bf16 would move the ranking metric).  planes = 3: [hi | mid | lo] as
+// [M][3K], the six products with plane-index sum <= 2: fp32-equivalent operands (head training, where ReLU masks
+// must not flip against the fp32 reference).  bias may be null.  K % 64 == 0, N % 128 == 0.
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
-                       int relu, int M, int N, int K, cudaStream_t stream);
+                       int relu, int M, int N, int K, cudaStream_t stream, int planes = 2);
 // CONV 3x3 pad 1 (+bias, ReLU, optional 2x2 maxpool): act NHWC bf16 [n][H][W][C_in], weights [C_out][9*C_in]
 // ((kh,kw,c) order), out NHWC bf16 [n][H or H/2][W or W/2][C_out].  C_in % 64 == 0, C_out % 128 == 0.
 int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,

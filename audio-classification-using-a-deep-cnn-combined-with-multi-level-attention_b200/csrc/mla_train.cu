@@ -5,7 +5,9 @@
 // nn.CrossEntropyLoss applied to the sigmoid outputs (train.py:131,372).  Running statistics are updated like
 // nn.BatchNorm1d does (momentum 0.1, unbiased variance).
 //
-// Every Linear (forward, dX and dW) is a split-bf16 tcgen05 GEMM (igemm_linear_split); everything between GEMMs
+// Every Linear (forward, dX and dW) is a 3-plane split-bf16 tcgen05 GEMM (igemm_linear_split with hi | mid | lo
+// operands = fp32-equivalent: with 2 planes the 4e-5 error on pre-activations flipped a few ReLU masks per step against
+// the fp32 reference, which moves whole gradient elements); everything between GEMMs
 // is fp32 CUDA-core work in a handful of kernels:
 //   bn_time_stats / bn_col_stats   sum and sum-of-squares per time step (or per class), finalised by the last block
 //   tile_split<Functor>            32x32 tiles: evaluate an element-wise functor (BN + ReLU + dropout, BN backward, ...),
@@ -21,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,6 +40,7 @@ namespace {
 constexpr int kMaxLevels = 4, kMaxFc = 4, kMaxBn = kMaxLevels * (1 + kMaxFc) + 2 * kMaxLevels + 1;
 constexpr float kBnEps = 1e-5f;
 constexpr float kBnMomentum = 0.1f;
+constexpr int kPl = 3;   // bf16 planes per GEMM operand: hi | mid | lo (fp32-equivalent, see igemm_linear_split)
 
 int fail(const char* fmt, const char* detail = "") {
   char buf[640];
@@ -157,8 +161,8 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned
 
 // ------------------------------------------------------------------ 32x32 tile kernel with element functor
 struct TileOut {
-  __nv_bfloat16* planes;    // [rows_pad][2 * cols_pad] hi | lo   (may be null)
-  __nv_bfloat16* planes_t;  // [cols_pad][2 * rows_pad] hi | lo   (may be null)
+  __nv_bfloat16* planes;    // [rows_pad][3 * cols_pad] hi | mid | lo   (may be null)
+  __nv_bfloat16* planes_t;  // [cols_pad][3 * rows_pad] hi | mid | lo   (may be null)
   float* f32;               // [rows][ld_f32]                     (may be null)
   long long ld_f32;
   float* col_sum;           // [cols] += sum over rows (atomic)   (may be null)
@@ -166,9 +170,11 @@ struct TileOut {
   int cols, cols_pad;
 };
 
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const float r1 = v - __bfloat162float(hi);      // exact
+  mid = __float2bfloat16_rn(r1);
+  lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
 
 template <class F>
@@ -186,10 +192,12 @@ __global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
     tile[ty + 8 * i][tx] = v;
     if (r < o.rows_pad && c < o.cols_pad) {
       if (o.planes) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
-        o.planes[r * (2LL * o.cols_pad) + c] = hi;
-        o.planes[r * (2LL * o.cols_pad) + o.cols_pad + c] = lo;
+        __nv_bfloat16 hi, mid, lo;
+        split_bf16(v, hi, mid, lo);
+        __nv_bfloat16* row = o.planes + r * (static_cast<long long>(kPl) * o.cols_pad);
+        row[c] = hi;
+        row[o.cols_pad + c] = mid;
+        row[2 * o.cols_pad + c] = lo;
       }
       if (o.f32 && r < o.rows) o.f32[r * o.ld_f32 + c] = v;
     }
@@ -201,10 +209,12 @@ __global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
       const int c = c0 + ty + 8 * i;
       const long long r = r0 + tx;
       if (c < o.cols_pad && r < o.rows_pad) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(tile[tx][ty + 8 * i], hi, lo);
-        o.planes_t[c * (2LL * o.rows_pad) + r] = hi;
-        o.planes_t[c * (2LL * o.rows_pad) + o.rows_pad + r] = lo;
+        __nv_bfloat16 hi, mid, lo;
+        split_bf16(tile[tx][ty + 8 * i], hi, mid, lo);
+        __nv_bfloat16* row = o.planes_t + c * (static_cast<long long>(kPl) * o.rows_pad);
+        row[r] = hi;
+        row[o.rows_pad + r] = mid;
+        row[2 * o.rows_pad + r] = lo;
       }
     }
   }
@@ -645,31 +655,31 @@ void carve(vmb_mla_trainer* h, char* base) {
   h->counters = c.take<unsigned>(size_t(h->n_slots));
   h->acc_bytes = c.off;
   h->stat = c.take<float>(size_t(h->n_slots) * kSlot * 2);
-  h->xin_p = c.take<__nv_bfloat16>(size_t(Rp) * 2 * inpad);
-  h->xin_pt = c.take<__nv_bfloat16>(size_t(inpad) * 2 * Rp);
+  h->xin_p = c.take<__nv_bfloat16>(size_t(Rp) * kPl * inpad);
+  h->xin_pt = c.take<__nv_bfloat16>(size_t(inpad) * kPl * Rp);
   for (int l = 0; l < h->n_levels; ++l) {
     for (int j = 0; j < h->lvl[l].n_fc; ++j) {
       h->U[l][j] = c.take<float>(size_t(R) * Hp);
-      h->A_p[l][j] = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
-      h->A_pt[l][j] = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+      h->A_p[l][j] = c.take<__nv_bfloat16>(size_t(Rp) * kPl * Hp);
+      h->A_pt[l][j] = c.take<__nv_bfloat16>(size_t(Hp) * kPl * Rp);
     }
     h->E[l] = c.take<float>(size_t(R) * Hp);
     if (l > 0) {
-      h->N_p[l] = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
-      h->N_pt[l] = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+      h->N_p[l] = c.take<__nv_bfloat16>(size_t(Rp) * kPl * Hp);
+      h->N_pt[l] = c.take<__nv_bfloat16>(size_t(Hp) * kPl * Rp);
     }
     h->Z[l] = c.take<float>(size_t(R) * Hp);
     h->row_stats[l] = c.take<float>(size_t(R) * 2);
   }
   h->Y = c.take<float>(size_t(B) * h->ycols_pad);
   h->dY = c.take<float>(size_t(B) * h->ycols_pad);
-  h->Y_p = c.take<__nv_bfloat16>(size_t(Bp) * 2 * h->ycols_pad);
-  h->Y_pt = c.take<__nv_bfloat16>(size_t(h->ycols_pad) * 2 * Bp);
+  h->Y_p = c.take<__nv_bfloat16>(size_t(Bp) * kPl * h->ycols_pad);
+  h->Y_pt = c.take<__nv_bfloat16>(size_t(h->ycols_pad) * kPl * Bp);
   h->O = c.take<float>(size_t(B) * Hp);
   h->dO = c.take<float>(size_t(B) * Hp);
   h->lse = c.take<float>(size_t(B));
-  h->G_p = c.take<__nv_bfloat16>(size_t(Rp) * 2 * Hp);
-  h->G_pt = c.take<__nv_bfloat16>(size_t(Hp) * 2 * Rp);
+  h->G_p = c.take<__nv_bfloat16>(size_t(Rp) * kPl * Hp);
+  h->G_pt = c.take<__nv_bfloat16>(size_t(Hp) * kPl * Rp);
   h->GV = c.take<float>(size_t(R) * Hp);
   h->GF = c.take<float>(size_t(R) * Hp);
   h->dA = c.take<float>(size_t(R) * Hp);
@@ -679,8 +689,8 @@ void carve(vmb_mla_trainer* h, char* base) {
   h->dWtmp = c.take<float>(size_t(Hp) * widest);
   auto planes_for = [&](FcRef& f) {
     f.bias_pad = c.take<float>(size_t(f.n_out_pad));
-    f.wp = c.take<__nv_bfloat16>(size_t(f.n_out_pad) * 2 * f.n_in_pad);
-    f.wtp = c.take<__nv_bfloat16>(size_t(f.n_in_pad) * 2 * f.n_out_pad);
+    f.wp = c.take<__nv_bfloat16>(size_t(f.n_out_pad) * kPl * f.n_in_pad);
+    f.wtp = c.take<__nv_bfloat16>(size_t(f.n_in_pad) * kPl * f.n_out_pad);
   };
   for (int l = 0; l < h->n_levels; ++l) {
     for (int j = 0; j < h->lvl[l].n_fc; ++j) planes_for(h->lvl[l].fc[j]);
@@ -701,10 +711,12 @@ void build_layout(vmb_mla_trainer* h, const int* n_fc) {
     r += 2 * n;
     return b;
   };
-  auto fc = [&](int n_out, int n_in) {
+  // every hidden / class dimension is padded to the common width Hp, the embedding input to inpad and the
+  // concatenated attention outputs to ycols_pad, so that a plane written for one GEMM can feed the next
+  auto fc = [&](int n_out, int n_in, int n_in_pad) {
     FcRef f{};
     f.w = p; f.b = p + 1LL * n_out * n_in;
-    f.n_out = n_out; f.n_in = n_in; f.n_out_pad = pad128(n_out); f.n_in_pad = pad128(n_in);
+    f.n_out = n_out; f.n_in = n_in; f.n_out_pad = h->Hp; f.n_in_pad = n_in_pad;
     p += 1LL * n_out * n_in + n_out;
     return f;
   };
@@ -712,16 +724,19 @@ void build_layout(vmb_mla_trainer* h, const int* n_fc) {
     LevelRef& L = h->lvl[l];
     L.n_fc = n_fc[l];
     L.norm0 = bn(h->T);
-    for (int j = 0; j < L.n_fc; ++j) L.fc[j] = fc(h->H, (l == 0 && j == 0) ? h->emb_in : h->H);
+    for (int j = 0; j < L.n_fc; ++j) {
+      const bool first = l == 0 && j == 0;
+      L.fc[j] = fc(h->H, first ? h->emb_in : h->H, first ? h->inpad : h->Hp);
+    }
     for (int j = 0; j < L.n_fc; ++j) L.norms[j] = bn(h->T);
   }
   for (int l = 0; l < h->n_levels; ++l) {
     LevelRef& L = h->lvl[l];
-    L.fcv = fc(h->K, h->H);
+    L.fcv = fc(h->K, h->H, h->Hp);
     L.normv = bn(h->T);
     L.normf = bn(h->T);
   }
-  h->fc_out = fc(h->K, h->n_levels * h->K);
+  h->fc_out = fc(h->K, h->n_levels * h->K, h->ycols_pad);
   h->norm_out = bn(h->K);
   h->n_params = p;
   h->n_running = r;
@@ -741,7 +756,7 @@ int run_tile(F f, TileOut o, cudaStream_t st, const char* what) {
 
 int gemm(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo, long long M, int N,
          int K, cudaStream_t st) {
-  if (vmb::igemm_linear_split(a_planes, w_planes, bias, out, ldo, 0, int(M), N, K, st)) {
+  if (vmb::igemm_linear_split(a_planes, w_planes, bias, out, ldo, 0, int(M), N, K, st, kPl)) {
     vmb::set_kernel_error("%s", vmb::igemm_last_error());
     return 1;
   }
@@ -757,6 +772,9 @@ long long vmb_mla_train_param_count(int n_levels, const int* n_fc, int emb_in, i
   if (n_levels < 1 || n_levels > kMaxLevels || !n_fc) return -1;
   vmb_mla_trainer tmp{};
   tmp.n_levels = n_levels; tmp.emb_in = emb_in; tmp.H = hidden; tmp.K = n_classes; tmp.T = t_steps;
+  tmp.Hp = std::max(pad128(hidden), pad128(n_classes));
+  tmp.inpad = pad128(emb_in);
+  tmp.ycols_pad = pad128(n_levels * n_classes);
   build_layout(&tmp, n_fc);
   if (n_running_out) *n_running_out = tmp.n_running;
   return tmp.n_params;
@@ -990,7 +1008,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       vmb::count_launch();
       TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
       FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
-      TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + fc.b, R, Rp, H, Hp};
+      TileOut o{h->G_p, h->G_pt, nullptr, Hp, grads + fc.b, R, Rp, H, Hp};
       TRY(run_tile(f, o, st, "fc BN backward"));
       // dW [H][n_in] = dU^T * A_prev^T ; dA_prev [R][n_in] = dU * W
       const __nv_bfloat16* prev_pt = j > 0 ? h->A_pt[l][j - 1] : (l == 0 ? h->xin_pt : h->N_pt[l]);

@@ -3,8 +3,11 @@
    * data parallel semantics: per-shard BatchNorm statistics, gradients averaged over shards == oracle per shard
    * dropout: deterministic per seed, keep rate ~ 1 - p, inverted scaling
    * the reference-named module in train mode under the reference's loop (criterion / backward / torch Adam)
-Tolerances: split-bf16 GEMMs carry ~16 mantissa bits, so gradients are checked to 2e-3 relative of each tensor's
-max-abs (measured ~1e-4), the loss to 1e-4, parameters after one Adam step (lr 1e-3) to 5e-5 absolute."""
+Tolerances: the training GEMMs use 3-plane split-bf16 operands (fp32-equivalent; with 2 planes a few ReLU masks
+per step flipped against the fp32 reference, moving whole gradient elements by ~1e-2 relative), so every gradient
+tensor is checked to |err| <= 3e-4 * max|ref| + 5e-7 (measured 7e-6 .. 6e-5 relative; the absolute floor covers gradients
+that are zero by symmetry — fc.bias before BatchNorm1d(K), normv.bias before the softmax — where the reference itself
+holds only rounding noise), the loss to 1e-5, parameters after one Adam step (lr 1e-3) to 2e-5 absolute."""
 import numpy as np
 import pytest
 import torch
@@ -28,12 +31,16 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
+def _ok(a, b):
+    return float(np.abs(a - b).max()) <= 3e-4 * float(np.abs(b).max()) + 5e-7
+
+
 def test_one_step_vs_reference_golden(golden_head):
     tr, sd = _trainer()
     x = torch.from_numpy(golden_head["train_x"])
     labels = torch.from_numpy(golden_head["train_labels"])
     loss, scores = tr.forward_backward(x, labels, want_scores=True)
-    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-4
+    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-5
     assert np.abs(scores.cpu().numpy() - golden_head["train_y"]).max() < 2e-5
     worst = 0.0
     for key in golden_head.files:
@@ -43,11 +50,11 @@ def test_one_step_vs_reference_golden(golden_head):
             ref = golden_head[key]
             g = g[:ref.shape[0]] if g.shape != ref.shape else g
             worst = max(worst, _rel(g, ref))
-            assert _rel(g, ref) < 2e-3, name
+            assert _ok(g, ref), name
     norms = dict(zip(golden_head["grad_names"], golden_head["grad_norms"]))
     for key, shape, off in tr.p_layout:
         got = tr.view(tr.grads, key).norm().item()
-        assert abs(got - norms[key]) <= 2e-3 * norms[key] + 1e-9, key
+        assert abs(got - norms[key]) <= 2e-4 * norms[key] + 1e-6, key
     print(f"head training step vs reference: worst gradient rel-max-err {worst:.2e}")
     # Adam update (train.py:369: lr 1e-3) and running statistics
     tr.adam(1)
@@ -57,7 +64,7 @@ def test_one_step_vs_reference_golden(golden_head):
             p = tr.view(tr.params, name).cpu().numpy()
             ref = golden_head[key]
             p = p[:ref.shape[0]] if p.shape != ref.shape else p
-            assert np.abs(p - ref).max() < 5e-5, name
+            assert np.abs(p - ref).max() < 2e-5, name
     out = tr.state_dict()
     np.testing.assert_allclose(out["embedded_mappings.0.norm0.running_mean"].cpu().numpy(),
                                golden_head["running_mean_after::embedded_mappings.0.norm0"], rtol=1e-4, atol=1e-6)
@@ -79,17 +86,20 @@ def test_gradients_vs_oracle(K, conf, batch):
     labels = torch.randint(0, K, (batch,), generator=g)
     loss, scores = tr.forward_backward(x, labels, want_scores=True)
     ref_loss, ref_scores, ref_grads = train_torch.head_step(sd, x, labels, conf)
-    assert abs(loss.item() - ref_loss.item()) < 1e-4
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
     assert (scores.cpu() - ref_scores).abs().max() < 2e-5
-    for key, shape, off in tr.p_layout:
-        got = tr.view(tr.grads, key).cpu().numpy()
-        assert _rel(got, ref_grads[key].numpy()) < 2e-3, key
+    bad = [key for key, _, _ in tr.p_layout
+           if not _ok(tr.view(tr.grads, key).cpu().numpy(), ref_grads[key].numpy())]
+    worst = max(_rel(tr.view(tr.grads, key).cpu().numpy(), ref_grads[key].numpy()) for key, _, _ in tr.p_layout
+                if ref_grads[key].abs().max() > 1e-6)
+    print(f"K={K} conf={conf} batch={batch}: worst gradient rel-max-err {worst:.2e}")
+    assert not bad, bad
     # a second, smaller batch on the same handle (padded planes must not leak rows of the previous step)
     x2, l2 = x[:5], labels[:5]
     tr.forward_backward(x2, l2)
     _, _, ref2 = train_torch.head_step(sd, x2, l2, conf)
     for key in ("fc.weight", "embedded_mappings.0.fc.0.weight", "attention_modules.0.fcv.weight"):
-        assert _rel(tr.view(tr.grads, key).cpu().numpy(), ref2[key].numpy()) < 2e-3, key
+        assert _ok(tr.view(tr.grads, key).cpu().numpy(), ref2[key].numpy()), key
     tr.close()
 
 
@@ -115,9 +125,10 @@ def test_data_parallel_semantics_two_shards():
         tr.adam(world)
     for key, shape, off in trs[0].p_layout:
         got = trs[0].view(bucket, key).cpu().numpy() / world
-        assert _rel(got, (ref_avg[key] / world).numpy()) < 2e-3, key
+        assert _ok(got, (ref_avg[key] / world).numpy()), key
         want = train_torch.adam_update(sd[key], ref_avg[key] / world)
-        assert (trs[0].view(trs[0].params, key).cpu() - want).abs().max() < 5e-5, key
+        if ref_avg[key].abs().max() > 1e-5:        # Adam normalises: a gradient that is pure rounding noise moves by lr
+            assert (trs[0].view(trs[0].params, key).cpu() - want).abs().max() < 2e-5, key
     assert torch.equal(trs[0].params, trs[1].params)                       # replicas stay bit-identical
     for tr in trs:
         tr.close()
@@ -133,7 +144,8 @@ def test_dropout_is_seeded_and_inverted():
     g1 = tr.grads.clone()
     l1 = l1.item()
     l2, s2 = tr.forward_backward(x, labels, want_scores=True)
-    assert torch.equal(s1, s2) and torch.equal(g1, tr.grads)                # same seed + step -> same mask
+    # same seed + step -> same mask; gradients agree up to the order of the atomic bias / BatchNorm reductions
+    assert torch.equal(s1, s2) and torch.allclose(g1, tr.grads, rtol=1e-4, atol=1e-7)
     tr.seed = 6
     _, s3 = tr.forward_backward(x, labels, want_scores=True)
     assert not torch.equal(s1, s3)
@@ -165,7 +177,7 @@ def test_reference_loop_on_the_module(golden_head):
     loss = torch.nn.CrossEntropyLoss()(out, labels)
     loss.backward()
     opt.step()
-    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-4
+    assert abs(loss.item() - float(golden_head["train_loss"])) < 1e-5
     assert sorted(n for n, p in m.named_parameters() if p.grad is None) == list(golden_head["train_no_grad_params"])
     params = dict(m.named_parameters())
     for key in golden_head.files:
@@ -174,7 +186,7 @@ def test_reference_loop_on_the_module(golden_head):
             p = params[name].detach().cpu().numpy()
             ref = golden_head[key]
             p = p[:ref.shape[0]] if p.shape != ref.shape else p
-            assert np.abs(p - ref).max() < 5e-5, name
+            assert np.abs(p - ref).max() < 2e-5, name
     np.testing.assert_allclose(m.norm.running_var.cpu().numpy(), golden_head["running_var_after::norm"], rtol=1e-3,
                                atol=1e-7)
     assert int(m.norm.num_batches_tracked) == 1
