@@ -14,16 +14,23 @@ namespace vmb {
 void set_api_error(const char* msg);
 }
 
-// Cached staging of vmb_pipeline_forward_host (grown on demand, freed with the handle).
+// Cached staging of the host-buffer entry points (grown on demand, freed with the handle).  Two device wave buffers
+// alternate between micro-batches — across calls too — so the H2D copy of the next micro-batch (or of the next
+// submitted call) overlaps the compute of the current one; two result slots let one call be in flight while the
+// previous one is being collected.
 struct HostStage {
   cudaStream_t copy_st = nullptr;
-  cudaEvent_t fence = nullptr, wave_ready[2] = {}, wave_free[2] = {};
+  cudaEvent_t wave_ready[2] = {}, wave_free[2] = {};
   float* d_wave[2] = {};
   size_t wave_cap[2] = {};
-  float* d_scores = nullptr;
-  size_t scores_cap = 0;
+  unsigned long long batches = 0;   // micro-batches issued so far (selects the wave buffer)
   void* d_ws = nullptr;
   size_t ws_cap = 0;
+  float* d_scores[2] = {};
+  size_t scores_cap[2] = {};
+  cudaEvent_t done[2] = {};
+  bool busy[2] = {false, false};
+  unsigned long long calls = 0;
 };
 
 struct vmb_vggish {
@@ -118,12 +125,12 @@ void vmb_vggish_destroy(vmb_vggish_t* h) {
   HostStage& hs = h->stage;
   for (int i = 0; i < 2; ++i) {
     cudaFree(hs.d_wave[i]);
+    cudaFree(hs.d_scores[i]);
     if (hs.wave_ready[i]) cudaEventDestroy(hs.wave_ready[i]);
     if (hs.wave_free[i]) cudaEventDestroy(hs.wave_free[i]);
+    if (hs.done[i]) cudaEventDestroy(hs.done[i]);
   }
-  cudaFree(hs.d_scores);
   cudaFree(hs.d_ws);
-  if (hs.fence) cudaEventDestroy(hs.fence);
   if (hs.copy_st) cudaStreamDestroy(hs.copy_st);
   delete h;
 }
@@ -227,33 +234,33 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   return vmb_mla_forward(mla, emb, n_clips, scores, stream);
 }
 
-int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
-                              long long samples_per_clip, float* scores_host, long long clips_per_batch,
-                              void* stream) {
-  if (!vggish || !mla) return fail("vmb_pipeline_forward_host: null handle");
-  if (n_clips < 0 || clips_per_batch <= 0) return fail("vmb_pipeline_forward_host: bad sizes");
-  if (n_clips == 0) return 0;
-  if (!wave_host || !scores_host) return fail("vmb_pipeline_forward_host: null pointer");
+int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                             long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream) {
+  if (!vggish || !mla) return -fail("vmb_pipeline_submit_host: null handle");
+  if (n_clips <= 0 || clips_per_batch <= 0) return -fail("vmb_pipeline_submit_host: bad sizes");
+  if (!wave_host || !scores_host) return -fail("vmb_pipeline_submit_host: null pointer");
   if (vmb_num_examples(samples_per_clip) != 10)
-    return fail("vmb_pipeline_forward_host: samples_per_clip must yield exactly T = 10 examples (params.py:26)");
+    return -fail("vmb_pipeline_submit_host: samples_per_clip must yield exactly T = 10 examples (params.py:26)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (clips_per_batch > n_clips) clips_per_batch = n_clips;
   const int n_classes = vmb_mla_num_classes(mla);
   HostStage& hs = vggish->stage;
-  // (re)size the cached staging buffers: two wave buffers so the H2D copy of batch i+1 overlaps compute of batch i
+  const int slot = static_cast<int>(hs.calls & 1);
+  if (hs.busy[slot]) return -fail("vmb_pipeline_submit_host: two calls are already in flight; wait for the oldest first");
   const size_t wave_bytes = size_t(clips_per_batch) * samples_per_clip * 4;
   const size_t ws_bytes = vmb_pipeline_workspace_bytes(clips_per_batch, samples_per_clip);
   const size_t score_bytes = size_t(n_clips) * n_classes * 4;
   bool ok = true;
   if (!hs.copy_st) {
-    ok = cudaStreamCreateWithFlags(&hs.copy_st, cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&hs.fence, cudaEventDisableTiming) == cudaSuccess;
+    ok = cudaStreamCreateWithFlags(&hs.copy_st, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
       ok = cudaEventCreateWithFlags(&hs.wave_ready[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&hs.wave_free[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&hs.wave_free[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&hs.done[i], cudaEventDisableTiming) == cudaSuccess;
   }
   auto grow = [&](void** p, size_t* cap, size_t need) {
     if (!ok || *cap >= need) return;
+    cudaStreamSynchronize(hs.copy_st);   // growing is rare: drain both streams before replacing a buffer
     cudaStreamSynchronize(st);
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -264,35 +271,56 @@ int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float*
   grow(reinterpret_cast<void**>(&hs.d_wave[0]), &hs.wave_cap[0], wave_bytes);
   grow(reinterpret_cast<void**>(&hs.d_wave[1]), &hs.wave_cap[1], wave_bytes);
   grow(&hs.d_ws, &hs.ws_cap, ws_bytes);
-  grow(reinterpret_cast<void**>(&hs.d_scores), &hs.scores_cap, score_bytes);
-  if (!ok) return fail("vmb_pipeline_forward_host: staging allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  grow(reinterpret_cast<void**>(&hs.d_scores[slot]), &hs.scores_cap[slot], score_bytes);
+  if (!ok) return -fail("vmb_pipeline_submit_host: staging allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
 
-  // the copy stream must not run ahead of work already queued on `stream`
-  cudaEventRecord(hs.fence, st);
-  cudaStreamWaitEvent(hs.copy_st, hs.fence, 0);
   int rc = 0;
-  long long b = 0;
-  for (long long c0 = 0; c0 < n_clips && rc == 0; c0 += clips_per_batch, ++b) {
-    const int s = int(b & 1);
+  for (long long c0 = 0; c0 < n_clips && rc == 0; c0 += clips_per_batch, ++hs.batches) {
+    const int s = static_cast<int>(hs.batches & 1);
     const long long nc = n_clips - c0 < clips_per_batch ? n_clips - c0 : clips_per_batch;
-    if (b >= 2) cudaStreamWaitEvent(hs.copy_st, hs.wave_free[s], 0);
+    // the buffer is free once the compute that read it two micro-batches ago has finished
+    if (hs.batches >= 2) cudaStreamWaitEvent(hs.copy_st, hs.wave_free[s], 0);
     if (cudaMemcpyAsync(hs.d_wave[s], wave_host + c0 * samples_per_clip, size_t(nc) * samples_per_clip * 4,
                         cudaMemcpyHostToDevice, hs.copy_st) != cudaSuccess) {
-      rc = fail("vmb_pipeline_forward_host: H2D copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+      rc = fail("vmb_pipeline_submit_host: H2D copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
       break;
     }
     cudaEventRecord(hs.wave_ready[s], hs.copy_st);
     cudaStreamWaitEvent(st, hs.wave_ready[s], 0);
-    rc = vmb_pipeline_forward(vggish, mla, hs.d_wave[s], nc, samples_per_clip, hs.d_scores + c0 * n_classes, nullptr,
-                              hs.d_ws, hs.ws_cap, stream);
+    rc = vmb_pipeline_forward(vggish, mla, hs.d_wave[s], nc, samples_per_clip, hs.d_scores[slot] + c0 * n_classes,
+                              nullptr, hs.d_ws, hs.ws_cap, stream);
     cudaEventRecord(hs.wave_free[s], st);
   }
-  if (rc == 0 && cudaMemcpyAsync(scores_host, hs.d_scores, score_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
-    rc = fail("vmb_pipeline_forward_host: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
-  cudaStreamSynchronize(hs.copy_st);
-  if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0)
-    rc = fail("vmb_pipeline_forward_host: %s", cudaGetErrorString(cudaGetLastError()));
-  return rc;
+  if (rc == 0 && cudaMemcpyAsync(scores_host, hs.d_scores[slot], score_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    rc = fail("vmb_pipeline_submit_host: D2H copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
+  cudaEventRecord(hs.done[slot], st);
+  if (rc) {
+    cudaStreamSynchronize(hs.copy_st);
+    cudaStreamSynchronize(st);
+    return -1;
+  }
+  hs.busy[slot] = true;
+  ++hs.calls;
+  return slot;
+}
+
+int vmb_pipeline_wait_host(vmb_vggish_t* vggish, int ticket) {
+  if (!vggish) return fail("vmb_pipeline_wait_host: null handle");
+  if (ticket < 0 || ticket > 1 || !vggish->stage.busy[ticket]) return fail("vmb_pipeline_wait_host: unknown ticket");
+  vggish->stage.busy[ticket] = false;
+  if (cudaEventSynchronize(vggish->stage.done[ticket]) != cudaSuccess)
+    return fail("vmb_pipeline_wait_host: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                              long long samples_per_clip, float* scores_host, long long clips_per_batch,
+                              void* stream) {
+  if (n_clips == 0) return 0;
+  const int ticket = vmb_pipeline_submit_host(vggish, mla, wave_host, n_clips, samples_per_clip, scores_host,
+                                              clips_per_batch, stream);
+  if (ticket < 0) return 1;
+  return vmb_pipeline_wait_host(vggish, ticket);
 }
 
 }  // extern "C"

@@ -257,20 +257,37 @@ def run_b200(args, rank, local_rank, world):
     sampler.join(timeout=1.0)
     finite = bool(torch.isfinite(scores).all().item())
 
-    # ---- end to end through the host-buffer C-ABI entry point (pinned host in, pinned host out)
+    # ---- end to end through the host-buffer C-ABI entry points (pinned host in, pinned host out).  Every step's
+    # H2D copy of its inputs, its compute and its D2H copy of the scores happen inside the timed region; two steps
+    # are kept in flight (submit i+1 before collecting i, as a DataLoader-fed loop would), so the copy of step i+1
+    # overlaps the compute of step i.  The strictly serial variant (one blocking call per step) is timed as well.
+    if args.e2e_microbatch <= 0:
+        args.e2e_microbatch = args.clips
+    scores_host2 = torch.empty(args.clips, N_CLASSES).pin_memory()
+    outs = (scores_host, scores_host2)
     for _ in range(max(3, args.warmup)):
         pipe.forward_host(wave_host, scores_host, clips_per_batch=args.e2e_microbatch)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        pipe.forward_host(wave_host, scores_host, clips_per_batch=args.e2e_microbatch)
+    pending = pipe.submit_host(wave_host, outs[0], clips_per_batch=args.e2e_microbatch)
+    for i in range(1, args.steps):
+        nxt = pipe.submit_host(wave_host, outs[i & 1], clips_per_batch=args.e2e_microbatch)
+        pipe.wait_host(pending)
+        pending = nxt
+    pipe.wait_host(pending)
     e1.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
-    e2e_equal = bool(torch.equal(scores_host, scores.cpu()))
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    e2e_equal = bool(torch.equal(outs[(args.steps - 1) & 1], scores.cpu()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.forward_host(wave_host, scores_host, clips_per_batch=args.serial_microbatch)
+    barrier()
+    serial_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
 
     if rank != 0:
         if world > 1:
@@ -295,8 +312,11 @@ def run_b200(args, rank, local_rank, world):
         "e2e": {"value": args.clips * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": args.clips * CLIP_SAMPLES * 4, "d2h_bytes_per_step": args.clips * N_CLASSES * 4,
                 "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                "microbatch_clips": args.e2e_microbatch, "matches_device_path": e2e_equal,
-                "api": "vmb_pipeline_forward_host via b200.engine.Pipeline.forward_host"},
+                "microbatch_clips": args.e2e_microbatch, "matches_device_path": e2e_equal, "steps_in_flight": 2,
+                "serial_value": args.clips * world / (serial_ms / args.steps * 1e-3),
+                "serial_ms_per_step": serial_ms / args.steps, "serial_microbatch_clips": args.serial_microbatch,
+                "api": "vmb_pipeline_submit_host / vmb_pipeline_wait_host via b200.engine.Pipeline (serial_*: one "
+                       "blocking vmb_pipeline_forward_host call per step)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -327,7 +347,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
-    ap.add_argument("--e2e-microbatch", type=int, default=64, help="clips per H2D/compute micro-batch in the e2e leg")
+    ap.add_argument("--e2e-microbatch", type=int, default=0,
+                    help="clips per H2D/compute micro-batch in the pipelined e2e leg (0 = the whole step)")
+    ap.add_argument("--serial-microbatch", type=int, default=64,
+                    help="clips per micro-batch in the serial (one blocking call per step) e2e variant")
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -178,10 +178,18 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
                          void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Host-buffer variant (the end-to-end number of bench.py): wave_host / scores_host are HOST pointers
  * (pinned for full speed); the call copies H2D, runs the path on `stream` in micro-batches of
- * `clips_per_batch`, copies the scores D2H and synchronises the stream before returning.               */
+ * `clips_per_batch` (the copy of micro-batch i+1 overlaps the compute of micro-batch i), copies the scores D2H
+ * and synchronises before returning.                                                                    */
 int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
                               long long samples_per_clip, float* scores_host, long long clips_per_batch,
                               void* stream);
+/* The same call split in two so that a caller can keep the device busy across calls (a DataLoader-style loop):
+ * submit enqueues the H2D copies, the compute and the D2H copy and returns a ticket (0 or 1) at once, or a
+ * negative value on error; wait blocks until that call's scores are in scores_host.  At most two calls in flight;
+ * wave_host must stay valid until wait returns.  Tickets must be waited in submission order.                 */
+int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                             long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream);
+int vmb_pipeline_wait_host(vmb_vggish_t* vggish, int ticket);
 
 #ifdef __cplusplus
 }

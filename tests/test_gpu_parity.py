@@ -363,3 +363,22 @@ def test_stream_embeddings_chunking_is_exact(vgg_handle):
     emb = torch.cat(parts)
     assert torch.equal(emb, whole)
     assert torch.equal(engine.postprocess(emb, eig.to(DEV), means.to(DEV), want_u8=True)[1], q_whole)
+
+
+def test_async_host_pipeline_matches_blocking_call(vgg_handle, head_handle):
+    """submit/wait with two calls in flight returns the same bits as the blocking call, in submission order."""
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    a = torch.from_numpy(synth.make_clips(300, 5)).pin_memory()
+    b = torch.from_numpy(synth.make_clips(305, 3)).pin_memory()
+    ra = torch.empty(5, 527).pin_memory()
+    rb = torch.empty(3, 527).pin_memory()
+    ta = pipe.submit_host(a, ra, clips_per_batch=2)
+    tb = pipe.submit_host(b, rb, clips_per_batch=2)
+    with pytest.raises(engine.B200Error):
+        pipe.submit_host(a, ra, clips_per_batch=2)                       # only two calls may be in flight
+    pipe.wait_host(ta)
+    pipe.wait_host(tb)
+    assert torch.equal(ra, pipe.forward_host(a, clips_per_batch=5))
+    assert torch.equal(rb, pipe.forward(b.to(DEV)).cpu())
+    with pytest.raises(engine.B200Error):
+        pipe.wait_host(ta)                                               # ticket already collected
