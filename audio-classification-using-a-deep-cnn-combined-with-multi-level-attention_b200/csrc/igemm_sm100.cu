@@ -19,22 +19,25 @@ constexpr int kQuarterBytes = 32 * kBlockK * 2;      // one 32-row quarter of A 
 constexpr int kNumThreads = 192;
 constexpr int kEpiThreads = 128;
 
-template <int BLOCK_N>
+// MT = number of 128-row sub-tiles per CTA tile that share one B stage (MT = 2 doubles the smem reuse of the
+// weights when BLOCK_N is only 128: a 256 x 128 tile moves as many bytes per FLOP as a 128 x 256 one).
+template <int BLOCK_N, int MT>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kStages = (kStageBytes >= 48 * 1024) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * MT * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
+  static_assert(kTmemCols <= 512, "TMEM holds 512 columns");
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBiasBytes + kBarBytes;
 };
 
-template <int BLOCK_N, bool CONV, bool POOL, bool OUT_F32>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, bool OUT_F32>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -76,11 +79,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
-        int bx[4], by[4], bn[4];
+        int bx[4 * MT], by[4 * MT], bn[4 * MT];
         if (CONV) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int g = m_tile * 4 + q;
+          for (int q = 0; q < 4 * MT; ++q) {
+            const int g = m_tile * 4 * MT + q;
             const int n_img = g / p.boxes_per_img;
             const int r = g - n_img * p.boxes_per_img;
             const int yy = r / p.boxes_per_row;
@@ -93,12 +96,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = stage_base + stage * C::kStageBytes;
-          uint8_t* b_dst = a_dst + kABytes;
+          uint8_t* b_dst = a_dst + MT * kABytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           if (CONV) {
             const int dh = tap / 3 - 1, dw = tap % 3 - 1;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4 * MT; ++q)
               tma_load_4d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[q] + dw,
                           by[q] + dh, bn[q]);
             if (++cb == p.cblks) { cb = 0; ++tap; }
@@ -112,7 +115,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const int pa = p.split_planes == 3 ? ((0x210100 >> (4 * (5 - q))) & 0xF) : (q == 1 ? 1 : 0);
               a_kb = pa * p.split_nkb + (kb - q * p.split_nkb);
             }
-            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], a_kb * kBlockK, m_tile * kBlockM);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_2d(a_dst + sub * kABytes, &tmap_a, &full_bar[stage], a_kb * kBlockK,
+                          (m_tile * MT + sub) * kBlockM);
           }
           int b_kb = kb;
           if (p.split_nkb) {
@@ -133,17 +139,20 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(stage_base + stage * C::kStageBytes);
-          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + kABytes);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + MT * kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr + sub * kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+              umma_bf16_ss(d_tmem + sub * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);
           if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
         }
@@ -165,12 +174,16 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads) bias_t[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
       // Where does this thread's accumulator row go?
       bool valid;
       size_t out_off;  // element offset of column n0 for this thread's output row / pooled pixel
       int sub = 0;
       if (CONV) {
-        const int g = m_tile * 4 + q;
+        const int g = (m_tile * MT + mt) * 4 + q;
         const int n_img = g / p.boxes_per_img;
         const int r = g - n_img * p.boxes_per_img;
         const int yy = r / p.boxes_per_row;
@@ -185,14 +198,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           out_off = ((static_cast<size_t>(n_img) * p.H + h) * p.W + w) * p.N + n0;
         }
       } else {
-        const int row = m_tile * kBlockM + q * 32 + lane;
+        const int row = (m_tile * MT + mt) * kBlockM + q * 32 + lane;
         valid = row < p.M;
         out_off = static_cast<size_t>(row) * p.ldo + n0;
       }
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + mt * BLOCK_N;
 
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
@@ -244,6 +255,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
+      }  // mt
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -313,11 +325,11 @@ int num_sms() {
 
 namespace {
 
-template <int BLOCK_N, bool CONV, bool POOL, bool OUT_F32>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, bool OUT_F32>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  auto kern = igemm_bf16_kernel<BLOCK_N, CONV, POOL, OUT_F32>;
+  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT_F32>;
   static bool attr_set = false;
-  constexpr int smem = Cfg<BLOCK_N>::kSmemBytes;
+  constexpr int smem = Cfg<BLOCK_N, MT>::kSmemBytes;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -374,10 +386,10 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
   p.bias = bias;
   p.out = out;
   if (block_n == 256)
-    return out_f32 ? launch<256, false, false, true>(ta, tb, p, stream)
-                   : launch<256, false, false, false>(ta, tb, p, stream);
-  return out_f32 ? launch<128, false, false, true>(ta, tb, p, stream)
-                 : launch<128, false, false, false>(ta, tb, p, stream);
+    return out_f32 ? launch<256, 1, false, false, true>(ta, tb, p, stream)
+                   : launch<256, 1, false, false, false>(ta, tb, p, stream);
+  return out_f32 ? launch<128, 1, false, false, true>(ta, tb, p, stream)
+                 : launch<128, 1, false, false, false>(ta, tb, p, stream);
 }
 
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
@@ -417,8 +429,8 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
   p.ldo = ldo;
   p.bias = bias;
   p.out = out;
-  return block_n == 256 ? launch<256, false, false, true>(ta, tb, p, stream)
-                        : launch<128, false, false, true>(ta, tb, p, stream);
+  return block_n == 256 ? launch<256, 1, false, false, true>(ta, tb, p, stream)
+                        : launch<128, 1, false, false, true>(ta, tb, p, stream);
 }
 
 int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
@@ -464,8 +476,15 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   p.bias = bias;
   p.out = out;
   if (block_n == 256)
-    return pool ? launch<256, true, true, false>(ta, tb, p, stream) : launch<256, true, false, false>(ta, tb, p, stream);
-  return pool ? launch<128, true, true, false>(ta, tb, p, stream) : launch<128, true, false, false>(ta, tb, p, stream);
+    return pool ? launch<256, 1, true, true, false>(ta, tb, p, stream) : launch<256, 1, true, false, false>(ta, tb, p, stream);
+  // C_out = 128: pair two 128-pixel sub-tiles per CTA tile when there are enough tiles to keep every SM busy
+  if (p.num_m_tiles >= 4 * num_sms()) {
+    p.num_m_tiles = (p.total_boxes + 7) / 8;
+    return pool ? launch<128, 2, true, true, false>(ta, tb, p, stream)
+                : launch<128, 2, true, false, false>(ta, tb, p, stream);
+  }
+  return pool ? launch<128, 1, true, true, false>(ta, tb, p, stream)
+              : launch<128, 1, true, false, false>(ta, tb, p, stream);
 }
 
 }  // namespace vmb
