@@ -29,6 +29,7 @@ SIGNATURES = {
     "vmb_logmel_cudacore": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
+    "vmb_conv1_relu_pool_cudacore": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_conv3x3_relu": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _int, _int, _int, _int, _c_p]),
     "vmb_linear": (_int, [_c_p, _c_p, _c_p, _c_p, _int, _int, _ll, _int, _int, _c_p]),
     "vmb_postprocess": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, _c_p]),

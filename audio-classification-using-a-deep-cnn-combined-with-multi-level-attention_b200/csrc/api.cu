@@ -91,13 +91,24 @@ int vmb_front_end_tables(double* hann400, double* mel257x64) {
   return 0;
 }
 
-int vmb_conv1_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n, void* stream) {
-  if (n < 0) return fail("vmb_conv1_relu_pool: negative n");
+static int conv1_common(const char* who, bool tensor_core, const float* examples, const float* w, const float* b,
+                        void* out, long long n, void* stream) {
+  if (n < 0) return fail("%s: negative n", who);
   if (n == 0) return 0;
-  if (!examples || !w || !b || !out) return fail("vmb_conv1_relu_pool: null pointer");
-  if (vmb::conv1_relu_pool(examples, w, b, out, n, S(stream)))
-    return fail_from("vmb_conv1_relu_pool", vmb::kernels_last_error());
+  if (!examples || !w || !b || !out) return fail("%s: null pointer", who);
+  const int rc = tensor_core ? vmb::conv1_tc_relu_pool(examples, w, b, out, n, S(stream))
+                             : vmb::conv1_relu_pool(examples, w, b, out, n, S(stream));
+  if (rc) return fail_from(who, vmb::kernels_last_error());
   return 0;
+}
+
+int vmb_conv1_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n, void* stream) {
+  return conv1_common("vmb_conv1_relu_pool", true, examples, w, b, out, n, stream);
+}
+
+int vmb_conv1_relu_pool_cudacore(const float* examples, const float* w, const float* b, void* out, long long n,
+                                 void* stream) {
+  return conv1_common("vmb_conv1_relu_pool_cudacore", false, examples, w, b, out, n, stream);
 }
 
 int vmb_conv3x3_relu(const void* act, const void* w, const float* bias, void* out, long long n, int H, int W, int C_in,

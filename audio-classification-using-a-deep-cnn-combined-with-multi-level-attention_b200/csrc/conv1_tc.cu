@@ -1,0 +1,272 @@
+// VGGish first layer on the tensor cores: Conv2d(1, 64, 3, padding=1) + ReLU + MaxPool2d(2, 2)
+// (reference torchvggish/vggish.py:108-118, features.0/1/2): examples fp32 [n][96][64] -> NHWC bf16 [n][48][32][64].
+//
+// With C_in = 1 the GEMM K is only 9, so the tile is built by hand instead of by TMA: one CTA tile = 128 POOLED
+// pixels (4 pooled rows x 32 columns of one example).  For each of the four positions of the 2x2 pooling window the
+// 128 threads write one im2col row each into shared memory,
+//     A_pos[pixel] = [ x_hi(9 taps) | x_lo(9 taps) | 1 | 1 | 0 ... ]   (32 bf16, K-major, no-swizzle core-matrix layout)
+//     B[channel]   = [ w(9 taps)    | w(9 taps)    | b_hi | b_lo | 0 ... ]
+// so one elected thread issues 4 x 2 tcgen05.mma (M = 128, N = 64, K = 16) and TMEM column block `pos` receives
+// conv + bias of that window position for all 64 channels (the input keeps 16 mantissa bits through the hi/lo split,
+// the bias is added in the fp32 accumulator).  In the epilogue thread = pooled pixel = TMEM lane: the max over the
+// four column blocks is the max-pool (no shuffles), then ReLU, bf16, one 128-byte store per thread.
+// Warp-specialised and persistent (one CTA per SM): warps 0-3 build tiles (the next tile's input patch is already in
+// flight in registers), warp 4 issues the MMAs, warps 5-8 run the epilogue; the A tiles and the TMEM accumulators are
+// two-deep rings, so tile i+1 is being built while tile i is multiplied and tile i-1 is written out.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vmb {
+
+namespace {
+
+constexpr int kH = 96, kW = 64, kC = 64;
+constexpr int kPH = kH / 2, kPW = kW / 2;        // 48 x 32 pooled
+constexpr int kRowsPerTile = 4;                  // pooled rows per CTA tile (x 32 columns = 128 pooled pixels)
+constexpr int kTilesPerExample = kPH / kRowsPerTile;  // 12
+constexpr int kPatchH = 2 * kRowsPerTile + 2;    // 10 input rows incl. halo
+constexpr int kPatchW = kW + 2;                  // 66
+constexpr int kPatchPitch = 68;
+constexpr int kLbo = 128;                        // bytes between the 16-byte K chunks of one 8-row group
+constexpr int kSbo = 512;                        // bytes between 8-row groups (4 chunks x 128 B)
+constexpr int kATile = 128 / 8 * kSbo;           // 8192 bytes per window position
+constexpr int kBTile = kC / 8 * kSbo;            // 4096
+constexpr int kProducerThreads = 128;            // warps 0-3 build the im2col tiles
+constexpr int kMmaWarp = 4;                      // warp 4 issues the MMAs
+constexpr int kThreads = 288;                    // warps 5-8: epilogue
+constexpr int kStages = 2;                       // A-tile ring and TMEM accumulator ring
+constexpr int kTmemCols = 512;                   // 2 buffers x 4 positions x 64 channels
+constexpr int kSmemBytes = 1024 + kStages * 4 * kATile + kBTile;
+
+// K-major, no swizzle: element (row r, 16-byte chunk j) at (r / 8) * SBO + j * LBO + (r % 8) * 16
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(kLbo >> 4) << 16;
+  d |= static_cast<uint64_t>(kSbo >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+constexpr int kPatchElems = kPatchH * kPatchW;                               // 660
+constexpr int kPatchPerThread = (kPatchElems + kProducerThreads - 1) / kProducerThreads;  // 6
+
+// Global loads of one tile's input patch (with zero halo) into registers: issued one tile ahead of their use.
+__device__ __forceinline__ void load_patch(const float* __restrict__ x, long long tile, int tid, float (&v)[kPatchPerThread]) {
+  const long long n = tile / kTilesPerExample;
+  const int tr = static_cast<int>(tile - n * kTilesPerExample);
+  const int row0 = 2 * kRowsPerTile * tr - 1;
+  const float* src = x + n * (kH * kW);
+#pragma unroll
+  for (int u = 0; u < kPatchPerThread; ++u) {
+    const int i = tid + u * kProducerThreads;
+    const int r = i / kPatchW, c = i - r * kPatchW;
+    const int gr = row0 + r, gc = c - 1;
+    v[u] = (i < kPatchElems && gr >= 0 && gr < kH && gc >= 0 && gc < kW) ? __ldg(src + gr * kW + gc) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                __nv_bfloat16* __restrict__ out, long long n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;                                   // [kStages][4 positions][kATile]
+  uint8_t* b_smem = smem + kStages * 4 * kATile;
+  __shared__ float patch[kPatchH][kPatchPitch];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[kStages], tmem_empty[kStages];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- one-time setup: B tile, constant chunk of the A tiles, barriers, TMEM
+  if (tid < kC) {
+    uint32_t k[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) k[i] = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      k[t] = bf16_bits(__ldg(w + tid * 9 + t));
+      k[9 + t] = k[t];
+    }
+    const float bias = __ldg(b + tid);
+    const __nv_bfloat16 bh = __float2bfloat16_rn(bias);
+    k[18] = __bfloat16_as_ushort(bh);
+    k[19] = bf16_bits(bias - __bfloat162float(bh));
+    uint8_t* row = b_smem + (tid / 8) * kSbo + (tid % 8) * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(row + j * kLbo) =
+          make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
+                     k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
+  }
+  if (tid < kProducerThreads) {
+#pragma unroll
+    for (int sp = 0; sp < kStages * 4; ++sp)   // chunk 3 (k = 24..31) of every A row stays zero for the life of the CTA
+      *reinterpret_cast<uint4*>(a_smem + sp * kATile + (tid / 8) * kSbo + 3 * kLbo + (tid % 8) * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers: patch -> four im2col tiles
+    const uint32_t one = 0x3F80u;   // bf16 1.0
+    const int pr = tid >> 5, pc = tid & 31;   // pooled row within the tile, pooled column
+    float pre[kPatchPerThread];
+    if (blockIdx.x < n_tiles) load_patch(x, blockIdx.x, tid, pre);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1, ph = (it >> 1) & 1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's patch reads are done
+#pragma unroll
+      for (int u = 0; u < kPatchPerThread; ++u) {
+        const int i = tid + u * kProducerThreads;
+        if (i < kPatchElems) patch[i / kPatchW][i % kPatchW] = pre[u];
+      }
+      if (tile + gridDim.x < n_tiles) load_patch(x, tile + gridDim.x, tid, pre);   // in flight during the build
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = patch[2 * pr + i][2 * pc + j];
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          hi[i][j] = __bfloat16_as_ushort(h);
+          lo[i][j] = bf16_bits(v - __bfloat162float(h));
+        }
+      mbar_wait(&empty_bar[stage], ph ^ 1);               // the MMAs that read this stage two tiles ago are done
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        const int dy = pos >> 1, dx = pos & 1;
+        uint32_t k[24];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            k[ky * 3 + kx] = hi[dy + ky][dx + kx];
+            k[9 + ky * 3 + kx] = lo[dy + ky][dx + kx];
+          }
+        k[18] = one; k[19] = one; k[20] = 0; k[21] = 0; k[22] = 0; k[23] = 0;
+        uint8_t* row = a_smem + (stage * 4 + pos) * kATile + (tid / 8) * kSbo + (tid % 8) * 16;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          *reinterpret_cast<uint4*>(row + j * kLbo) =
+              make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
+                         k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
+      }
+      fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kC);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[stage], ph ^ 1);
+      mbar_wait(&full_bar[stage], ph);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint64_t b_desc = umma_desc_kmajor_noswizzle(smem_u32(b_smem));
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) {
+          const uint64_t a_desc = umma_desc_kmajor_noswizzle(smem_u32(a_smem + (stage * 4 + pos) * kATile));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)   // K step 16 = two chunks = 2 * LBO = 256 bytes (>> 4 = 16)
+            umma_bf16_ss(tmem_base + stage * 256 + pos * kC, a_desc + ks * (2 * kLbo >> 4), b_desc + ks * (2 * kLbo >> 4),
+                         idesc, ks);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[stage]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: pool = max over 4 column blocks
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // pooled pixel within the tile
+    const int pr = row >> 5, pc = row & 31;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t stage = it & 1, ph = (it >> 1) & 1;
+      const long long n = tile / kTilesPerExample;
+      const int tr = static_cast<int>(tile - n * kTilesPerExample);
+      __nv_bfloat16* dst = out + ((n * kPH + tr * kRowsPerTile + pr) * kPW + pc) * kC;
+      mbar_wait(&tmem_full[stage], ph);
+      tc_fence_after_sync();
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * 256;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32(t_lane + 0 * kC + ch * 32, v0);
+        tmem_ld_32x32(t_lane + 1 * kC + ch * 32, v1);
+        tmem_ld_32x32(t_lane + 2 * kC + ch * 32, v2);
+        tmem_ld_32x32(t_lane + 3 * kC + ch * 32, v3);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j]), __uint_as_float(v1[2 * j])),
+                                      fmaxf(__uint_as_float(v2[2 * j]), __uint_as_float(v3[2 * j]))), 0.f);
+          const float c = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v1[2 * j + 1])),
+                                      fmaxf(__uint_as_float(v2[2 * j + 1]), __uint_as_float(v3[2 * j + 1]))), 0.f);
+          pk[j] = pack_bf16x2(a, c);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[stage]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n,
+                       cudaStream_t stream) {
+  const long long tiles = n * kTilesPerExample;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      set_kernel_error("conv1: cannot set the dynamic shared memory size");
+      return 1;
+    }
+    attr_set = true;
+  }
+  conv1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
+  count_launch();
+  return check_launch("conv1_tc_kernel");
+}
+
+}  // namespace vmb

@@ -40,6 +40,10 @@ int logmel_forward(const float* wave, long long n_clips, long long samples_per_c
                    long long frames_out, float* logmel, cudaStream_t stream);
 
 // ---- VGGish odd layers (layers.cu)
+// conv1 on the tensor cores (conv1_tc.cu): hand-built im2col tiles, pooling as a max over four TMEM column blocks.
+int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out_bf16, long long n,
+                       cudaStream_t stream);
+// conv1 on the CUDA cores in fp32 (layers.cu): the first implementation, kept as the on-device cross-check.
 int conv1_relu_pool(const float* examples, const float* w, const float* b, void* out_bf16, long long n,
                     cudaStream_t stream);
 int postprocess(const float* emb, const float* eigen, const float* means, float* out_f32, uint8_t* out_u8,

@@ -155,7 +155,7 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
 
   {
     vmb::StageTimer t(VMB_STAGE_CONV1, st);
-    if (vmb::conv1_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
+    if (vmb::conv1_tc_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
       return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
   }
   char* src = A;

@@ -79,6 +79,9 @@ int vmb_front_end_tables(double* hann400, double* mel257x64);
  * NHWC bf16 [n][48][32][64].  w_dev fp32 [64][9] (OIHW with I = 1), b_dev fp32 [64].                 */
 int vmb_conv1_relu_pool(const float* examples_dev, const float* w_dev, const float* b_dev, void* out_bf16_dev,
                         long long n, void* stream);
+/* The same layer on the CUDA cores in plain fp32 (the first implementation).  Diagnostic cross-check only. */
+int vmb_conv1_relu_pool_cudacore(const float* examples_dev, const float* w_dev, const float* b_dev,
+                                 void* out_bf16_dev, long long n, void* stream);
 
 /* Conv2d(3x3, padding=1) + ReLU (+ MaxPool2d(2,2) when pool != 0) as a tcgen05 implicit GEMM.
  *   act_bf16_dev NHWC bf16 [n][H][W][C_in]; w_bf16_dev bf16 [C_out][9*C_in] in (kh, kw, c_in) order;

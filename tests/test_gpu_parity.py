@@ -179,7 +179,20 @@ def test_conv1_layer(vgg_sd):
     engine.check(_lib.lib().vmb_conv1_relu_pool(x.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(), out.data_ptr(), 7,
                                                 engine.stream_ptr()), "vmb_conv1_relu_pool")
     ref = F.max_pool2d(F.relu(F.conv2d(x[:, None], w, b, padding=1)), 2, 2)
-    _layer_check(out.permute(0, 3, 1, 2), ref, "conv1", rel_tol=0.005)
+    _layer_check(out.permute(0, 3, 1, 2), ref, "conv1 (tensor cores)", rel_tol=0.005)
+    out2 = torch.empty_like(out)
+    engine.check(_lib.lib().vmb_conv1_relu_pool_cudacore(x.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(),
+                                                         out2.data_ptr(), 7, engine.stream_ptr()), "conv1 cudacore")
+    _layer_check(out2.permute(0, 3, 1, 2), ref, "conv1 (CUDA-core cross-check)", rel_tol=0.005)
+    # large batch: the two kernels agree to bf16 rounding (weights are bf16 on the tensor-core path)
+    xb = (torch.randn(300, 96, 64, generator=g) * 3).to(DEV)
+    o1 = torch.empty(300, 48, 32, 64, device=DEV, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    engine.check(_lib.lib().vmb_conv1_relu_pool(xb.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(), o1.data_ptr(), 300,
+                                                engine.stream_ptr()), "conv1")
+    engine.check(_lib.lib().vmb_conv1_relu_pool_cudacore(xb.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(),
+                                                         o2.data_ptr(), 300, engine.stream_ptr()), "conv1 cudacore")
+    _layer_check(o1, o2, "conv1 tensor cores vs CUDA cores, 300 examples", rel_tol=0.01)
 
 
 def test_vggish_embeddings_vs_golden_and_oracle(golden_front, golden_vggish, vgg_handle, vgg_sd):
