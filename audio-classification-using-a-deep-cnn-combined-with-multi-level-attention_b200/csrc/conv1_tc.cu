@@ -4,11 +4,12 @@
 // With C_in = 1 the GEMM K is only 9, so the tile is built by hand instead of by TMA: one CTA tile = 128 POOLED
 // pixels (4 pooled rows x 32 columns of one example).  For each of the four positions of the 2x2 pooling window the
 // 128 threads write one im2col row each into shared memory,
-//     A_pos[pixel] = [ x_hi(9 taps) | x_lo(9 taps) | 1 | 1 | 0 ... ]   (32 bf16, K-major, no-swizzle core-matrix layout)
-//     B[channel]   = [ w(9 taps)    | w(9 taps)    | b_hi | b_lo | 0 ... ]
+//     A_pos[pixel] = [ x_hi(9 taps) | x_lo(9 taps) | x_hi(9 taps) | 1 | 1 | 0 0 0 ]   (32 bf16, K-major, no-swizzle
+//     B[channel]   = [ w_hi(9 taps) | w_hi(9 taps) | w_lo(9 taps) | b_hi | b_lo | 0 0 0 ]    core-matrix layout)
 // so one elected thread issues 4 x 2 tcgen05.mma (M = 128, N = 64, K = 16) and TMEM column block `pos` receives
-// conv + bias of that window position for all 64 channels (the input keeps 16 mantissa bits through the hi/lo split,
-// the bias is added in the fp32 accumulator).  In the epilogue thread = pooled pixel = TMEM lane: the max over the
+// conv + bias of that window position for all 64 channels (input AND weights keep 16 mantissa bits through the hi/lo
+// splits — K = 29 of 32 slots — and the bias is added in the fp32 accumulator).  Output: bf16, or hi | lo planes for
+// the accuracy mode of the body.  In the epilogue thread = pooled pixel = TMEM lane: the max over the
 // four column blocks is the max-pool (no shuffles), then ReLU, bf16, one 128-byte store per thread.
 // Warp-specialised and persistent (one CTA per SM): warps 0-3 build tiles (the next tile's input patch is already in
 // flight in registers), warp 4 issues the MMAs, warps 5-8 run the epilogue; the A tiles and the TMEM accumulators are
@@ -74,6 +75,7 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ x, long lon
   }
 }
 
+template <bool SPLIT_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                 __nv_bfloat16* __restrict__ out, long long n_tiles) {
@@ -93,24 +95,22 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     for (int i = 0; i < 32; ++i) k[i] = 0;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      k[t] = bf16_bits(__ldg(w + tid * 9 + t));
-      k[9 + t] = k[t];
+      const float wv = __ldg(w + tid * 9 + t);
+      const __nv_bfloat16 wh = __float2bfloat16_rn(wv);
+      k[t] = __bfloat16_as_ushort(wh);          // pairs with x_hi
+      k[9 + t] = k[t];                          // pairs with x_lo
+      k[18 + t] = bf16_bits(wv - __bfloat162float(wh));   // w_lo pairs with x_hi
     }
     const float bias = __ldg(b + tid);
     const __nv_bfloat16 bh = __float2bfloat16_rn(bias);
-    k[18] = __bfloat16_as_ushort(bh);
-    k[19] = bf16_bits(bias - __bfloat162float(bh));
+    k[27] = __bfloat16_as_ushort(bh);
+    k[28] = bf16_bits(bias - __bfloat162float(bh));
     uint8_t* row = b_smem + (tid / 8) * kSbo + (tid % 8) * 16;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<uint4*>(row + j * kLbo) =
           make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
                      k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
-  }
-  if (tid < kProducerThreads) {
-#pragma unroll
-    for (int sp = 0; sp < kStages * 4; ++sp)   // chunk 3 (k = 24..31) of every A row stays zero for the life of the CTA
-      *reinterpret_cast<uint4*>(a_smem + sp * kATile + (tid / 8) * kSbo + 3 * kLbo + (tid % 8) * 16) = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -159,18 +159,19 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 #pragma unroll
       for (int pos = 0; pos < 4; ++pos) {
         const int dy = pos >> 1, dx = pos & 1;
-        uint32_t k[24];
+        uint32_t k[32];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             k[ky * 3 + kx] = hi[dy + ky][dx + kx];
             k[9 + ky * 3 + kx] = lo[dy + ky][dx + kx];
+            k[18 + ky * 3 + kx] = hi[dy + ky][dx + kx];
           }
-        k[18] = one; k[19] = one; k[20] = 0; k[21] = 0; k[22] = 0; k[23] = 0;
+        k[27] = one; k[28] = one; k[29] = 0; k[30] = 0; k[31] = 0;
         uint8_t* row = a_smem + (stage * 4 + pos) * kATile + (tid / 8) * kSbo + (tid % 8) * 16;
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(row + j * kLbo) =
               make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
                          k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
@@ -212,7 +213,10 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       const uint32_t stage = it & 1, ph = (it >> 1) & 1;
       const long long n = tile / kTilesPerExample;
       const int tr = static_cast<int>(tile - n * kTilesPerExample);
-      __nv_bfloat16* dst = out + ((n * kPH + tr * kRowsPerTile + pr) * kPW + pc) * kC;
+      // bf16 NHWC [n][48][32][64], or hi | lo planes [n][2][48][32][64]
+      constexpr long long kPlane = static_cast<long long>(kPH) * kPW * kC;
+      __nv_bfloat16* dst = out + n * (SPLIT_OUT ? 2 : 1) * kPlane +
+                           (static_cast<long long>(tr * kRowsPerTile + pr) * kPW + pc) * kC;
       mbar_wait(&tmem_full[stage], ph);
       tc_fence_after_sync();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * 256;
@@ -224,18 +228,25 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
         tmem_ld_32x32(t_lane + 2 * kC + ch * 32, v2);
         tmem_ld_32x32(t_lane + 3 * kC + ch * 32, v3);
         tmem_ld_wait();
-        uint32_t pk[16];
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float a = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j]), __uint_as_float(v1[2 * j])),
                                       fmaxf(__uint_as_float(v2[2 * j]), __uint_as_float(v3[2 * j]))), 0.f);
           const float c = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v1[2 * j + 1])),
                                       fmaxf(__uint_as_float(v2[2 * j + 1]), __uint_as_float(v3[2 * j + 1]))), 0.f);
-          pk[j] = pack_bf16x2(a, c);
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
         }
         uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
 #pragma unroll
         for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        if (SPLIT_OUT) {
+          uint4* l4 = reinterpret_cast<uint4*>(dst + kPlane + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) l4[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -253,18 +264,22 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 }  // namespace
 
 int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool split_out) {
   const long long tiles = n * kTilesPerExample;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
       set_kernel_error("conv1: cannot set the dynamic shared memory size");
       return 1;
     }
     attr_set = true;
   }
-  conv1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
+  if (split_out)
+    conv1_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
+  else
+    conv1_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
   count_launch();
   return check_launch("conv1_tc_kernel");
 }

@@ -33,7 +33,9 @@ struct Cfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBiasBytes + kBarBytes;
 };
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, bool OUT_F32>
+constexpr int kOutBf16 = 0, kOutF32 = 1, kOutSplit = 2;   // epilogue output: bf16, fp32, or hi | lo bf16 planes
+
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
@@ -98,6 +100,21 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* a_dst = stage_base + stage * C::kStageBytes;
           uint8_t* b_dst = a_dst + MT * kABytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (CONV && p.conv_split) {
+            // activations [n][2][H][W][C] (hi | lo planes per image), weights [C_out][hi(9 C_in) | lo(9 C_in)]:
+            // the K loop runs over the products hi*hi, lo*hi, hi*lo, each over (tap, c_in block)
+            const int per = 9 * p.cblks;
+            const int prod = kb / per, kk = kb - prod * per;
+            const int tp = kk / p.cblks, cbb = kk - tp * p.cblks;
+            const int dh = tp / 3 - 1, dw = tp % 3 - 1;
+#pragma unroll
+            for (int q = 0; q < 4 * MT; ++q)
+              tma_load_5d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cbb * kBlockK, bx[q] + dw, by[q] + dh,
+                          prod == 1 ? 1 : 0, bn[q]);
+            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], ((prod == 2 ? per : 0) + kk) * kBlockK, n_tile * BLOCK_N);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (CONV) {
             const int dh = tap / 3 - 1, dw = tap % 3 - 1;
 #pragma unroll
@@ -193,9 +210,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         valid = n_img < p.M;
         if (POOL) {
           sub = (ww & 1) | ((hh & 1) << 1);
-          out_off = ((static_cast<size_t>(n_img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.N + n0;
+          out_off = static_cast<size_t>(n_img) * p.out_img_stride +
+                    (static_cast<size_t>(h >> 1) * (p.W >> 1) + (w >> 1)) * p.N + n0;
         } else {
-          out_off = ((static_cast<size_t>(n_img) * p.H + h) * p.W + w) * p.N + n0;
+          out_off = static_cast<size_t>(n_img) * p.out_img_stride + (static_cast<size_t>(h) * p.W + w) * p.N + n0;
         }
       } else {
         const int row = (m_tile * MT + mt) * kBlockM + q * 32 + lane;
@@ -223,7 +241,47 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (OUT_F32) {
+        if (OUT == kOutSplit) {
+          if (POOL) {
+            // pool on the fp32 values (the hi/lo split does not commute with max)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], p.Wb));
+            }
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[j] = pack_bf16x2(f[2 * j] - __low2float(h2), f[2 * j + 1] - __high2float(h2));
+          }
+          __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
+          if (POOL) {
+            uint4 oh, ol;
+            oh.x = sub == 0 ? hi[0] : sub == 1 ? hi[4] : sub == 2 ? hi[8] : hi[12];
+            oh.y = sub == 0 ? hi[1] : sub == 1 ? hi[5] : sub == 2 ? hi[9] : hi[13];
+            oh.z = sub == 0 ? hi[2] : sub == 1 ? hi[6] : sub == 2 ? hi[10] : hi[14];
+            oh.w = sub == 0 ? hi[3] : sub == 1 ? hi[7] : sub == 2 ? hi[11] : hi[15];
+            ol.x = sub == 0 ? lo[0] : sub == 1 ? lo[4] : sub == 2 ? lo[8] : lo[12];
+            ol.y = sub == 0 ? lo[1] : sub == 1 ? lo[5] : sub == 2 ? lo[9] : lo[13];
+            ol.z = sub == 0 ? lo[2] : sub == 1 ? lo[6] : sub == 2 ? lo[10] : lo[14];
+            ol.w = sub == 0 ? lo[3] : sub == 1 ? lo[7] : sub == 2 ? lo[11] : lo[15];
+            if (valid) {
+              *reinterpret_cast<uint4*>(outp + sub * 8) = oh;
+              *reinterpret_cast<uint4*>(outp + p.lo_off + sub * 8) = ol;
+            }
+          } else if (valid) {
+            uint4* dh4 = reinterpret_cast<uint4*>(outp);
+            uint4* dl4 = reinterpret_cast<uint4*>(outp + p.lo_off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              dl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        } else if (OUT == kOutF32) {
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + ch * 32);
 #pragma unroll
@@ -325,9 +383,9 @@ int num_sms() {
 
 namespace {
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, bool OUT_F32>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT_F32>;
+  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT>;
   static bool attr_set = false;
   constexpr int smem = Cfg<BLOCK_N, MT>::kSmemBytes;
   if (!attr_set) {
@@ -386,10 +444,10 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
   p.bias = bias;
   p.out = out;
   if (block_n == 256)
-    return out_f32 ? launch<256, 1, false, false, true>(ta, tb, p, stream)
-                   : launch<256, 1, false, false, false>(ta, tb, p, stream);
-  return out_f32 ? launch<128, 1, false, false, true>(ta, tb, p, stream)
-                 : launch<128, 1, false, false, false>(ta, tb, p, stream);
+    return out_f32 ? launch<256, 1, false, false, kOutF32>(ta, tb, p, stream)
+                   : launch<256, 1, false, false, kOutBf16>(ta, tb, p, stream);
+  return out_f32 ? launch<128, 1, false, false, kOutF32>(ta, tb, p, stream)
+                 : launch<128, 1, false, false, kOutBf16>(ta, tb, p, stream);
 }
 
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
@@ -429,8 +487,97 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
   p.ldo = ldo;
   p.bias = bias;
   p.out = out;
-  return block_n == 256 ? launch<256, 1, false, false, true>(ta, tb, p, stream)
-                        : launch<128, 1, false, false, true>(ta, tb, p, stream);
+  return block_n == 256 ? launch<256, 1, false, false, kOutF32>(ta, tb, p, stream)
+                        : launch<128, 1, false, false, kOutF32>(ta, tb, p, stream);
+}
+
+int igemm_linear_split_out(const void* a_planes, const void* w_planes, const float* bias, void* out_planes, int relu,
+                           int M, int N, int K, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBlockK != 0 || N % 256 != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split_out: need K %% 64 == 0 and N %% 256 == 0 (got K=%d N=%d)", K, N);
+    return 1;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {uint64_t(2) * K, uint64_t(M)};
+    uint64_t str[1] = {uint64_t(2) * K * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (make_tmap_bf16(&ta, a_planes, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(2) * K, uint64_t(N)};
+    uint64_t str[1] = {uint64_t(2) * K * 2};
+    uint32_t box[2] = {kBlockK, 256};
+    if (make_tmap_bf16(&tb, w_planes, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.split_nkb = K / kBlockK;
+  p.split_planes = 2;
+  p.num_kb = 3 * p.split_nkb;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.num_n_tiles = N / 256;
+  p.relu = relu;
+  p.ldo = 2LL * N;     // [M][hi(N) | lo(N)]
+  p.lo_off = N;
+  p.bias = bias;
+  p.out = out_planes;
+  return launch<256, 1, false, false, kOutSplit>(ta, tb, p, stream);
+}
+
+int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const float* bias, void* out_planes, int n_img,
+                        int H, int W, int C_in, int C_out, int pool, cudaStream_t stream) {
+  if (n_img <= 0) return 0;
+  const int Wb = (W % 16 == 0) ? 16 : 8;
+  const int Hb = 32 / Wb;
+  if (C_in % kBlockK != 0 || C_out % 128 != 0 || W % Wb != 0 || H % Hb != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_conv3x3_split: unsupported geometry H=%d W=%d C_in=%d C_out=%d", H, W, C_in, C_out);
+    return 1;
+  }
+  const int block_n = (C_out % 256 == 0) ? 256 : 128;
+  const int K = 9 * C_in;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[5] = {uint64_t(C_in), uint64_t(W), uint64_t(H), 2, uint64_t(n_img)};
+    uint64_t str[4] = {uint64_t(C_in) * 2, uint64_t(W) * C_in * 2, uint64_t(H) * W * C_in * 2, uint64_t(2) * H * W * C_in * 2};
+    uint32_t box[5] = {kBlockK, uint32_t(Wb), uint32_t(Hb), 1, 1};
+    if (make_tmap_bf16(&ta, act_planes, 5, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(2) * K, uint64_t(C_out)};
+    uint64_t str[1] = {uint64_t(2) * K * 2};
+    uint32_t box[2] = {kBlockK, uint32_t(block_n)};
+    if (make_tmap_bf16(&tb, w_planes, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = n_img;
+  p.N = C_out;
+  p.cblks = C_in / kBlockK;
+  p.num_kb = 3 * 9 * p.cblks;
+  p.conv_split = 1;
+  p.H = H;
+  p.W = W;
+  p.Hb = Hb;
+  p.Wb = Wb;
+  p.boxes_per_row = W / Wb;
+  p.boxes_per_img = (H / Hb) * (W / Wb);
+  p.total_boxes = n_img * p.boxes_per_img;
+  p.num_m_tiles = (p.total_boxes + 3) / 4;
+  p.num_n_tiles = C_out / block_n;
+  p.relu = 1;
+  p.ldo = C_out;
+  p.bias = bias;
+  p.out = out_planes;
+  const long long plane = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
+  p.out_img_stride = 2 * plane;
+  p.lo_off = plane;
+  if (block_n == 256)
+    return pool ? launch<256, 1, true, true, kOutSplit>(ta, tb, p, stream)
+                : launch<256, 1, true, false, kOutSplit>(ta, tb, p, stream);
+  return pool ? launch<128, 1, true, true, kOutSplit>(ta, tb, p, stream)
+              : launch<128, 1, true, false, kOutSplit>(ta, tb, p, stream);
 }
 
 int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
@@ -475,16 +622,17 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   p.ldo = C_out;
   p.bias = bias;
   p.out = out;
+  p.out_img_stride = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
   if (block_n == 256)
-    return pool ? launch<256, 1, true, true, false>(ta, tb, p, stream) : launch<256, 1, true, false, false>(ta, tb, p, stream);
+    return pool ? launch<256, 1, true, true, kOutBf16>(ta, tb, p, stream) : launch<256, 1, true, false, kOutBf16>(ta, tb, p, stream);
   // C_out = 128: pair two 128-pixel sub-tiles per CTA tile when there are enough tiles to keep every SM busy
   if (p.num_m_tiles >= 4 * num_sms()) {
     p.num_m_tiles = (p.total_boxes + 7) / 8;
-    return pool ? launch<128, 2, true, true, false>(ta, tb, p, stream)
-                : launch<128, 2, true, false, false>(ta, tb, p, stream);
+    return pool ? launch<128, 2, true, true, kOutBf16>(ta, tb, p, stream)
+                : launch<128, 2, true, false, kOutBf16>(ta, tb, p, stream);
   }
-  return pool ? launch<128, 1, true, true, false>(ta, tb, p, stream)
-              : launch<128, 1, true, false, false>(ta, tb, p, stream);
+  return pool ? launch<128, 1, true, true, kOutBf16>(ta, tb, p, stream)
+              : launch<128, 1, true, false, kOutBf16>(ta, tb, p, stream);
 }
 
 }  // namespace vmb

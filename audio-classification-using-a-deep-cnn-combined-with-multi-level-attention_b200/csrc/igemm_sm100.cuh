@@ -36,6 +36,9 @@ struct IgemmParams {
   int relu;
   int split_nkb;     // PLAIN split mode: K / 64 of one plane (0 = ordinary GEMM)
   int split_planes;  // 2 (hi | lo: 3 products) or 3 (hi | mid | lo: 6 products)
+  int conv_split;    // CONV: activations are [n][2][H][W][C] hi | lo planes, weights [C_out][2 * 9 C_in]
+  long long out_img_stride;  // CONV: output elements per image (2 planes when the output is split)
+  long long lo_off;          // split output: element offset of the lo plane relative to the hi element
   long long ldo;     // PLAIN: output row stride (elements)
   const float* bias; // [N]
   void* out;         // bf16 (or fp32 when OUT_F32)
@@ -52,6 +55,14 @@ int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void
 // must not flip against the fp32 reference).  bias may be null.  K % 64 == 0, N % 128 == 0.
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
                        int relu, int M, int N, int K, cudaStream_t stream, int planes = 2);
+// Split in, split out (the accuracy mode of the VGGish body): out planes bf16 [M][hi(N) | lo(N)] =
+// split(act(A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T + bias)).  K % 64 == 0, N % 256 == 0.
+int igemm_linear_split_out(const void* a_planes, const void* w_planes, const float* bias, void* out_planes, int relu,
+                           int M, int N, int K, cudaStream_t stream);
+// CONV 3x3 with hi | lo activations [n][2][H][W][C_in], hi | lo weights [C_out][2 * 9 C_in] and hi | lo output
+// [n][2][H(/2)][W(/2)][C_out] (pooling, when asked, on the fp32 accumulators).
+int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const float* bias, void* out_planes, int n_img,
+                        int H, int W, int C_in, int C_out, int pool, cudaStream_t stream);
 // CONV 3x3 pad 1 (+bias, ReLU, optional 2x2 maxpool): act NHWC bf16 [n][H][W][C_in], weights [C_out][9*C_in]
 // ((kh,kw,c) order), out NHWC bf16 [n][H or H/2][W or W/2][C_out].  C_in % 64 == 0, C_out % 128 == 0.
 int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,

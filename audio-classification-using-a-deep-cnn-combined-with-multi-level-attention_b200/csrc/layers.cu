@@ -124,6 +124,32 @@ __global__ void relayout_conv_kernel(const float* __restrict__ w, __nv_bfloat16*
   }
 }
 
+__global__ void relayout_conv_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int C_out, int C_in) {
+  const long long K = 9LL * C_in, total = static_cast<long long>(C_out) * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = int(i % C_in);
+    const int tap = int((i / C_in) % 9);
+    const long long oc = i / K;
+    const float v = __ldg(w + (oc * C_in + c) * 9 + tap);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    o[oc * 2 * K + (i - oc * K)] = h;
+    o[oc * 2 * K + K + (i - oc * K)] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long rows, long long cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    const float v = __ldg(s + i);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    d[r * 2 * cols + c] = h;
+    d[r * 2 * cols + cols + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -158,6 +184,18 @@ int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in,
   relayout_conv_kernel<<<1024, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(w_bf16), C_out, C_in);
   count_launch();
   return check_launch("relayout_conv_kernel");
+}
+
+int relayout_conv_weight_split(const float* w_oihw, void* planes, int C_out, int C_in, cudaStream_t stream) {
+  relayout_conv_split_kernel<<<1024, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(planes), C_out, C_in);
+  count_launch();
+  return check_launch("relayout_conv_split_kernel");
+}
+
+int split_f32_to_planes(const float* src, void* planes, long long rows, long long cols, cudaStream_t stream) {
+  split_planes_kernel<<<2048, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(planes), rows, cols);
+  count_launch();
+  return check_launch("split_planes_kernel");
 }
 
 int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
