@@ -35,6 +35,10 @@ SIGNATURES = {
     "vmb_postprocess": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_vggish_create": (_int, [C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p),
                                  C.POINTER(_c_p), _c_p]),
+    "vmb_vggish_create_ex": (_int, [C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p),
+                                    C.POINTER(_c_p), _int, _c_p]),
+    "vmb_vggish_precision": (_int, [_c_p]),
+    "vmb_vggish_handle_workspace_bytes": (_sz, [_c_p, _ll]),
     "vmb_vggish_destroy": (None, [_c_p]),
     "vmb_vggish_workspace_bytes": (_sz, [_ll]),
     "vmb_vggish_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),

@@ -122,9 +122,14 @@ def postprocess(emb: torch.Tensor, eigen: torch.Tensor, means: torch.Tensor, wan
 class VggishHandle:
     """Owns the library-side VGGish weights (bf16, implicit-GEMM layout) built from a reference state_dict."""
 
-    def __init__(self, state_dict: dict, device: torch.device):
+    def __init__(self, state_dict: dict, device: torch.device, precision: str = "bf16"):
+        """precision: "bf16" (throughput mode) or "split" (accuracy mode: hi + lo bf16 activations and weights, 3x the
+        tensor work, embeddings within ~1e-5 of fp32 — for 8-bit quantised long-form extraction)."""
         require_b200(device)
+        if precision not in ("bf16", "split"):
+            raise ValueError("precision must be 'bf16' or 'split'")
         self.device = device
+        self.precision = precision
         self._h = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
         with torch.cuda.device(device):
@@ -139,7 +144,8 @@ class VggishHandle:
             cb = (C.c_void_p * 6)(*[dev(f"features.{k}.bias") for k in CONV_KEYS])
             fw = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.weight") for k in FC_KEYS])
             fb = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.bias") for k in FC_KEYS])
-            check(_lib.lib().vmb_vggish_create(C.byref(self._h), cw, cb, fw, fb, stream_ptr()), "vmb_vggish_create")
+            check(_lib.lib().vmb_vggish_create_ex(C.byref(self._h), cw, cb, fw, fb, 1 if precision == "split" else 0,
+                                                  stream_ptr()), "vmb_vggish_create_ex")
             del keep
 
     @property
@@ -173,7 +179,7 @@ class VggishHandle:
         if n == 0:
             return (emb, bott) if want_bottleneck else emb
         with torch.cuda.device(self.device):
-            need = int(_lib.lib().vmb_vggish_workspace_bytes(n))
+            need = int(_lib.lib().vmb_vggish_handle_workspace_bytes(self._h, n))
             ws = self._workspace(need)
             base = (ws.data_ptr() + 1023) // 1024 * 1024
             check(_lib.lib().vmb_vggish_forward(self._h, ptr(examples), n, ptr(emb), ptr(bott), base, need, stream_ptr()),

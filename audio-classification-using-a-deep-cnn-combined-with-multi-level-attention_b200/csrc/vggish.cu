@@ -34,10 +34,11 @@ struct HostStage {
 };
 
 struct vmb_vggish {
+  int precision = 0;         // 0: bf16 activations and weights; 1: hi | lo split activations and weights (accuracy mode)
   float* conv1_w = nullptr;  // fp32 [64][9]
   float* conv_b[6] = {};     // fp32 biases (index 0 = conv1)
-  void* conv_w[6] = {};      // bf16 [C_out][9*C_in], index 1..5
-  void* fc_w[3] = {};        // bf16 [out][in]
+  void* conv_w[6] = {};      // bf16 [C_out][9*C_in] (precision 1: [C_out][2*9*C_in] hi | lo), index 1..5
+  void* fc_w[3] = {};        // bf16 [out][in]       (precision 1: [out][2*in] hi | lo)
   float* fc_b[3] = {};
   HostStage stage;
 };
@@ -68,13 +69,21 @@ extern "C" {
 
 int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w[6], const float* const conv_b[6],
                       const float* const fc_w[3], const float* const fc_b[3], void* stream) {
+  return vmb_vggish_create_ex(handle, conv_w, conv_b, fc_w, fc_b, 0, stream);
+}
+
+int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], const float* const conv_b[6],
+                         const float* const fc_w[3], const float* const fc_b[3], int precision, void* stream) {
   if (!handle || !conv_w || !conv_b || !fc_w || !fc_b) return fail("vmb_vggish_create: null argument");
+  if (precision != 0 && precision != 1) return fail("vmb_vggish_create: precision must be 0 (bf16) or 1 (split)");
   for (int i = 0; i < 6; ++i)
     if (!conv_w[i] || !conv_b[i]) return fail("vmb_vggish_create: null conv tensor");
   for (int i = 0; i < 3; ++i)
     if (!fc_w[i] || !fc_b[i]) return fail("vmb_vggish_create: null fc tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vmb_vggish* h = new vmb_vggish();
+  h->precision = precision;
+  const size_t wmul = precision ? 2 : 1;
   bool ok = true;
   auto dmalloc = [&](void** p, size_t bytes) { ok = ok && cudaMalloc(p, bytes) == cudaSuccess; };
   auto dcopy = [&](void* d, const void* s, size_t bytes) {
@@ -88,18 +97,20 @@ int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w[6], const
   }
   for (int i = 0; i < 5 && ok; ++i) {
     const ConvGeom& g = kConv[i];
-    dmalloc(&h->conv_w[i + 1], size_t(g.C_out) * 9 * g.C_in * 2);
+    dmalloc(&h->conv_w[i + 1], size_t(g.C_out) * 9 * g.C_in * 2 * wmul);
     dmalloc(reinterpret_cast<void**>(&h->conv_b[i + 1]), size_t(g.C_out) * 4);
     if (!ok) break;
     dcopy(h->conv_b[i + 1], conv_b[i + 1], size_t(g.C_out) * 4);
-    ok = ok && vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st) == 0;
+    ok = ok && (precision ? vmb::relayout_conv_weight_split(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)
+                          : vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)) == 0;
   }
   for (int i = 0; i < 3 && ok; ++i) {
-    dmalloc(&h->fc_w[i], size_t(kFcOut[i]) * kFcIn[i] * 2);
+    dmalloc(&h->fc_w[i], size_t(kFcOut[i]) * kFcIn[i] * 2 * wmul);
     dmalloc(reinterpret_cast<void**>(&h->fc_b[i]), size_t(kFcOut[i]) * 4);
     if (!ok) break;
     dcopy(h->fc_b[i], fc_b[i], size_t(kFcOut[i]) * 4);
-    ok = ok && vmb::cast_f32_to_bf16(fc_w[i], h->fc_w[i], static_cast<long long>(kFcOut[i]) * kFcIn[i], st) == 0;
+    ok = ok && (precision ? vmb::split_f32_to_planes(fc_w[i], h->fc_w[i], kFcOut[i], kFcIn[i], st)
+                          : vmb::cast_f32_to_bf16(fc_w[i], h->fc_w[i], static_cast<long long>(kFcOut[i]) * kFcIn[i], st)) == 0;
   }
   ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
   if (!ok) {
@@ -140,6 +151,14 @@ size_t vmb_vggish_workspace_bytes(long long n) {
   return align_up(size_t(n) * kBufA, 1024) + align_up(size_t(n) * kBufB, 1024);
 }
 
+size_t vmb_vggish_handle_workspace_bytes(const vmb_vggish_t* h, long long n) {
+  if (n <= 0 || !h) return 0;
+  const size_t mul = h->precision ? 2 : 1;   // split mode: every activation is a hi | lo pair
+  return align_up(size_t(n) * kBufA * mul, 1024) + align_up(size_t(n) * kBufB * mul, 1024);
+}
+
+int vmb_vggish_precision(const vmb_vggish_t* h) { return h ? h->precision : -1; }
+
 int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, float* emb, void* bottleneck,
                        void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return fail("vmb_vggish_forward: null handle");
@@ -147,15 +166,17 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
   if (n == 0) return 0;
   if (n > 1000000) return fail("vmb_vggish_forward: at most 1 000 000 examples per call (chunk on the host)");
   if (!examples || !emb || !workspace) return fail("vmb_vggish_forward: null pointer");
-  if (workspace_bytes < vmb_vggish_workspace_bytes(n)) return fail("vmb_vggish_forward: workspace too small");
+  if (workspace_bytes < vmb_vggish_handle_workspace_bytes(h, n)) return fail("vmb_vggish_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_vggish_forward: workspace must be 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool split = h->precision != 0;
+  const size_t mul = split ? 2 : 1;
   char* A = static_cast<char*>(workspace);
-  char* B = A + align_up(size_t(n) * kBufA, 1024);
+  char* B = A + align_up(size_t(n) * kBufA * mul, 1024);
 
   {
     vmb::StageTimer t(VMB_STAGE_CONV1, st);
-    if (vmb::conv1_tc_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st))
+    if (vmb::conv1_tc_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st, split))
       return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
   }
   char* src = A;
@@ -163,21 +184,35 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
   for (int i = 0; i < 5; ++i) {
     const ConvGeom& g = kConv[i];
     vmb::StageTimer t(VMB_STAGE_CONV2 + i, st);
-    if (vmb::igemm_conv3x3(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in, g.C_out, g.pool, st))
-      return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+    const int rc = split ? vmb::igemm_conv3x3_split(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in,
+                                                    g.C_out, g.pool, st)
+                         : vmb::igemm_conv3x3(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in,
+                                              g.C_out, g.pool, st);
+    if (rc) return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
     char* sw = src; src = dst; dst = sw;
   }
-  // src == B now holds the NHWC [n][6][4][512] features == the (h,w,c)-flattened [n][12288] matrix (vggish.py:26-29)
-  if (bottleneck &&
-      cudaMemcpyAsync(bottleneck, src, size_t(n) * 12288 * 2, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-    return fail("vmb_vggish_forward: bottleneck copy failed");
+  // src == B now holds the NHWC [n][6][4][512] features == the (h,w,c)-flattened [n][12288] matrix (vggish.py:26-29);
+  // in split mode [n][hi(12288) | lo(12288)]
+  if (bottleneck) {
+    const cudaError_t e = split
+        ? cudaMemcpy2DAsync(bottleneck, size_t(12288) * 2, src, size_t(2) * 12288 * 2, size_t(12288) * 2, size_t(n),
+                            cudaMemcpyDeviceToDevice, st)      // the hi plane
+        : cudaMemcpyAsync(bottleneck, src, size_t(n) * 12288 * 2, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail("vmb_vggish_forward: bottleneck copy failed");
+  }
   // fc1: B -> A, fc2: A -> B, fc3: B -> emb (fp32)
   const void* fc_in[3] = {src, dst, src};
   void* fc_out[3] = {dst, src, emb};
   for (int i = 0; i < 3; ++i) {
     vmb::StageTimer t(VMB_STAGE_FC1 + i, st);
-    if (vmb::igemm_linear(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], i == 2, 1, int(n), kFcOut[i], kFcIn[i], st))
-      return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
+    int rc;
+    if (!split)
+      rc = vmb::igemm_linear(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], i == 2, 1, int(n), kFcOut[i], kFcIn[i], st);
+    else if (i < 2)
+      rc = vmb::igemm_linear_split_out(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], 1, int(n), kFcOut[i], kFcIn[i], st);
+    else
+      rc = vmb::igemm_linear_split(fc_in[i], h->fc_w[i], h->fc_b[i], emb, kFcOut[i], 1, int(n), kFcOut[i], kFcIn[i], st);
+    if (rc) return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
   }
   return 0;
 }
@@ -185,14 +220,14 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
 // ------------------------------------------------------------------------------------------ whole path
 namespace {
 struct PipeLayout { size_t examples, emb, vgg, total; long long n_ex; };
-PipeLayout pipe_layout(long long n_clips, long long samples_per_clip) {
+PipeLayout pipe_layout(long long n_clips, long long samples_per_clip, int precision = 1) {
   PipeLayout L{};
   const long long per = vmb_num_examples(samples_per_clip);
   L.n_ex = per > 0 ? per * n_clips : 0;
   L.examples = 0;
   L.emb = align_up(size_t(L.n_ex) * 96 * 64 * 4, 1024);
   L.vgg = L.emb + align_up(size_t(L.n_ex) * 128 * 4, 1024);
-  L.total = L.vgg + vmb_vggish_workspace_bytes(L.n_ex);
+  L.total = L.vgg + vmb_vggish_workspace_bytes(L.n_ex) * (precision ? 2 : 1);
   return L;
 }
 }  // namespace
@@ -212,7 +247,7 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   const long long per = vmb_num_examples(samples_per_clip);
   if (per != 10)
     return fail("vmb_pipeline_forward: samples_per_clip must yield exactly T = 10 examples (params.py:26)");
-  const PipeLayout L = pipe_layout(n_clips, samples_per_clip);
+  const PipeLayout L = pipe_layout(n_clips, samples_per_clip, vggish->precision);
   if (workspace_bytes < L.total) return fail("vmb_pipeline_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_pipeline_forward: workspace must be 1024-byte aligned");
   char* ws = static_cast<char*>(workspace);

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--chunk", type=int, default=2048, help="examples per chunk")
     ap.add_argument("--check", type=int, default=0, help="examples to verify against the CPU oracle")
+    ap.add_argument("--precision", choices=("bf16", "split"), default="bf16",
+                    help="bf16 = throughput mode; split = accuracy mode (hi + lo bf16, uint8 output matches fp32)")
     args = ap.parse_args()
     from b200 import engine, sharding, stream, synth
     dev = torch.device("cuda:0")
@@ -36,7 +38,7 @@ def main():
     wave = (0.3 * torch.sin(2 * np.pi * (110.0 + 40.0 * torch.sin(2 * np.pi * 0.05 * t)) * t)
             + 0.05 * torch.randn(n, generator=g)).pin_memory()
     sd = synth.vggish_state_dict(0)
-    vgg = engine.VggishHandle(sd, dev)
+    vgg = engine.VggishHandle(sd, dev, precision=args.precision)
     eig, means = synth.pca_params(1)
     n_ex = sharding.num_examples(n)
     for _ in range(2):
@@ -50,7 +52,7 @@ def main():
     line = {"metric": "long-form embedding extraction examples/sec (1-hour stream, PCA/uint8)", "value": n_ex / dt,
             "unit": "examples/s", "n_gpus": 1, "steps": args.steps, "seconds_per_stream": dt,
             "realtime_factor": args.seconds / dt, "n_examples": n_ex, "h2d_bytes": n * 4, "checksum": checksum,
-            "config": {"workload": f"{args.seconds} s stream, {n} samples, chunks of {args.chunk} examples", "dtype": "bf16"}}
+            "config": {"workload": f"{args.seconds} s stream, {n} samples, chunks of {args.chunk} examples", "dtype": "bf16" if args.precision == "bf16" else "split bf16 (hi + lo)"}}
     if args.check:
         from oracle import frontend_np, model_torch
         m = args.check

@@ -106,9 +106,18 @@ int vmb_postprocess(const float* emb_dev, const float* eigen_dev, const float* m
  * The handle owns bf16 re-laid-out copies; the caller's tensors are not referenced after create returns.   */
 int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w_dev[6], const float* const conv_b_dev[6],
                       const float* const fc_w_dev[3], const float* const fc_b_dev[3], void* stream);
+/* precision 0 = vmb_vggish_create (bf16 activations and weights, fp32 accumulation: the throughput mode);
+ * precision 1 = accuracy mode: every activation and weight is carried as a hi + lo bf16 pair (16 mantissa bits) and
+ * every conv / FC runs the three products hi*hi, lo*hi, hi*lo on the same tcgen05 kernels — 3x the tensor work, for
+ * the long-form embedding extraction where the 8-bit quantised output must match the fp32 reference. */
+int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w_dev[6], const float* const conv_b_dev[6],
+                         const float* const fc_w_dev[3], const float* const fc_b_dev[3], int precision, void* stream);
+int vmb_vggish_precision(const vmb_vggish_t* handle);
 void vmb_vggish_destroy(vmb_vggish_t* handle);
 /* Scratch bytes vmb_vggish_forward needs for n examples (caller allocates, 1024-byte aligned). */
 size_t vmb_vggish_workspace_bytes(long long n_examples);
+/* Same for a given handle (the accuracy mode needs twice as much). */
+size_t vmb_vggish_handle_workspace_bytes(const vmb_vggish_t* handle, long long n_examples);
 /* examples_dev fp32 [n][96][64] -> emb_dev fp32 [n][128] (post-ReLU embeddings, vggish.py:31).
  * If bottleneck_bf16_dev != NULL the (h,w,c)-flattened conv features [n][12288] bf16 (vggish.py:26-29) are
  * copied there as well (the reference's just_bottlenecks variant, model.py:162-167).                      */
@@ -175,6 +184,7 @@ int vmb_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev,
  * Ensemble.forward for cnn_type == "vggish" (model.py:58-62) fed from raw audio:
  * wave [n_clips][samples_per_clip] fp32 16 kHz -> scores [n_clips][K].  samples_per_clip must yield exactly
  * T examples (10 s -> 10).  Device-resident variant: everything already in HBM.                         */
+/* (sized for the accuracy mode, i.e. enough for either precision) */
 size_t vmb_pipeline_workspace_bytes(long long n_clips, long long samples_per_clip);
 int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_dev, long long n_clips,
                          long long samples_per_clip, float* scores_dev, float* emb_dev_or_null,

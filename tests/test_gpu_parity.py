@@ -395,3 +395,41 @@ def test_async_host_pipeline_matches_blocking_call(vgg_handle, head_handle):
     assert torch.equal(rb, pipe.forward(b.to(DEV)).cpu())
     with pytest.raises(engine.B200Error):
         pipe.wait_host(ta)                                               # ticket already collected
+
+
+# ------------------------------------------------------------------------------------------------ accuracy mode
+@pytest.fixture(scope="module")
+def vgg_split(vgg_sd):
+    h = engine.VggishHandle(vgg_sd, DEV, precision="split")
+    yield h
+    h.close()
+
+
+def test_accuracy_mode_embeddings_and_uint8(golden_front, golden_vggish, vgg_split, vgg_sd):
+    """precision='split' (hi + lo bf16 activations and weights): embeddings within 5e-4 (relative to the max) of the fp32 reference and the
+    8-bit quantised output bit-exact except where rounding straddles a quantisation boundary (north_star)."""
+    x = torch.from_numpy(golden_front["examples_f64"][:, 0]).float().to(DEV)
+    emb, bott = vgg_split.forward(x, want_bottleneck=True)
+    ref = torch.from_numpy(golden_vggish["embeddings"])
+    rel = ((emb.cpu() - ref).abs().max() / ref.abs().max()).item()
+    print(f"accuracy mode: embeddings rel-max-err {rel:.3e}")
+    assert rel < 5e-4
+    eig, means = synth.pca_params(1)
+    q = engine.postprocess(emb, eig.to(DEV), means.to(DEV)).cpu().numpy()
+    d = np.abs(q - golden_vggish["postprocessed"]).astype(np.int64)
+    print("accuracy mode: uint8 LSB histogram vs reference:", np.bincount(d.ravel()).tolist())
+    assert d.max() <= 1 and (d > 0).mean() <= 0.02
+    # larger sample against the oracle: 3 clips = 30 examples
+    waves = synth.make_clips(0, 3)
+    ex = engine.examples_from_wave(torch.from_numpy(waves).to(DEV))
+    got = vgg_split.forward(ex)
+    exo = np.concatenate([frontend_np.waveform_to_examples(w.astype(np.float64)) for w in waves]).astype(np.float32)
+    with torch.no_grad():
+        want = model_torch.vgg_forward(vgg_sd, torch.from_numpy(exo)[:, None])
+    rel = ((got.cpu() - want).abs().max() / want.abs().max()).item()
+    qd = (engine.postprocess(got, eig.to(DEV), means.to(DEV)).cpu() - model_torch.postprocess(eig, means, want)).abs()
+    print(f"accuracy mode, 30 examples: embeddings rel-max-err {rel:.3e}; uint8 LSB histogram "
+          f"{np.bincount(qd.numpy().astype(np.int64).ravel()).tolist()}")
+    assert rel < 1e-3 and qd.max() <= 1 and (qd > 0).float().mean() <= 0.02
+    # batch invariance holds in this mode too
+    assert torch.equal(vgg_split.forward(ex[7:19]), got[7:19])
