@@ -29,6 +29,13 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU measurement on rank 0 alone and must
+    # use every host core it can (set before numpy / torch load their thread pools)
+    _ncpu = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_k] = _ncpu
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -115,6 +122,7 @@ def time_cpu(vsd, msd, steps, warmup, budget_s):
 def run_reference(args, rank):
     if rank != 0:
         return
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     synth, _, _ = _oracle_modules()
     vsd = synth.vggish_state_dict(0)
     msd = synth.mla_state_dict(MODEL_CONF, 128, 600, N_CLASSES, 10, seed=2)
