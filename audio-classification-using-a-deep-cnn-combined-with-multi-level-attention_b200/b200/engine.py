@@ -153,7 +153,7 @@ class VggishHandle:
         return self._h
 
     def close(self) -> None:
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:     # _lib is None at interpreter exit
             _lib.lib().vmb_vggish_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -242,7 +242,7 @@ class MlaHandle:
         return self._h
 
     def close(self) -> None:
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:     # _lib is None at interpreter exit
             _lib.lib().vmb_mla_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -102,7 +102,7 @@ class HeadTrainer:
         self.fcf: Dict[str, torch.Tensor] = {}      # carried through state_dict round trips untouched
 
     def close(self) -> None:
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:     # _lib is None at interpreter exit
             _lib.lib().vmb_mla_trainer_destroy(self._h)
             self._h = C.c_void_p()
 

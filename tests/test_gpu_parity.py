@@ -433,3 +433,32 @@ def test_accuracy_mode_embeddings_and_uint8(golden_front, golden_vggish, vgg_spl
     assert rel < 1e-3 and qd.max() <= 1 and (qd > 0).float().mean() <= 0.02
     # batch invariance holds in this mode too
     assert torch.equal(vgg_split.forward(ex[7:19]), got[7:19])
+
+
+def test_just_bottlenecks_variant(vgg_sd):
+    """Ensemble(just_bottlenecks=True) feeds the 12 288-d conv features straight into the head
+    (model.py:43-44, :162-167): the tensor-core head takes emb_in = 12288."""
+    import model
+    old = model.K
+    try:
+        model.K = 10
+        conf = dict(cnn_type="vggish", num_classes=10, use_pretrained=False, just_bottlenecks=True,
+                    cnn_trainable=False, first_cnn_layer_trainable=False, in_channels=1)
+        ens = model.Ensemble("repeat", conf, [1], DEV)
+    finally:
+        model.K = old
+    assert ens.emb_input_size == 12288
+    head_sd = synth.mla_state_dict((1,), 12288, 600, 10, 10, seed=4)
+    ens.cnn.cnn_model.load_state_dict(vgg_sd)
+    ens.mla.load_state_dict(head_sd)
+    ens = ens.to(DEV).eval()
+    waves = synth.make_clips(8, 2)
+    ex = np.stack([frontend_np.waveform_to_examples(w.astype(np.float64)) for w in waves]).astype(np.float32)
+    x = torch.from_numpy(ex)[:, :, None]                                   # (2, 10, 1, 96, 64)
+    y = ens(x.to(DEV))
+    with torch.no_grad():
+        feats = model_torch.vgg_flatten(model_torch.vgg_features(vgg_sd, x.reshape(-1, 1, 96, 64)))
+        want = model_torch.mla_forward(head_sd, feats.reshape(2, 10, 12288), (1,))
+    d = (y.cpu() - want).abs().max().item()
+    print(f"just_bottlenecks: scores max-abs-err {d:.3e}")
+    assert tuple(y.shape) == (2, 10) and d < 2e-2
