@@ -33,7 +33,8 @@ struct Cfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBiasBytes + kBarBytes;
 };
 
-constexpr int kOutBf16 = 0, kOutF32 = 1, kOutSplit = 2;   // epilogue output: bf16, fp32, or hi | lo bf16 planes
+constexpr int kOutBf16 = 0, kOutF32 = 1, kOutSplit = 2, kOutF32Atomic = 3;   // epilogue output: bf16, fp32, hi | lo bf16
+                                                                              // planes, or fp32 atomicAdd (split-K)
 
 template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -53,7 +54,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // split-K (PLAIN, kOutF32Atomic): tile index = (k slice, m tile, n tile); every slice adds into the zeroed output
+  const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_tiles = mn_tiles * ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -79,8 +83,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
+        const int kb0 = static_cast<int>(static_cast<long long>(p.num_kb) * ks / ksplit);
+        const int kb1 = static_cast<int>(static_cast<long long>(p.num_kb) * (ks + 1) / ksplit);
         int bx[4 * MT], by[4 * MT], bn[4 * MT];
         if (CONV) {
 #pragma unroll
@@ -95,7 +102,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = stage_base + stage * C::kStageBytes;
           uint8_t* b_dst = a_dst + MT * kABytes;
@@ -154,10 +161,13 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int ks = tile / mn_tiles;
+      const int kb0 = static_cast<int>(static_cast<long long>(p.num_kb) * ks / ksplit);
+      const int kb1 = static_cast<int>(static_cast<long long>(p.num_kb) * (ks + 1) / ksplit);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (lane == 0) {
@@ -168,10 +178,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr + sub * kABytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-              umma_bf16_ss(d_tmem + sub * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              umma_bf16_ss(d_tmem + sub * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -183,12 +193,14 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int ep_tid = threadIdx.x - 64;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      const int m_tile = mn / p.num_n_tiles;
+      const int n_tile = mn - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BLOCK_N;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       float* bias_t = bias_s + acc * BLOCK_N;
-      for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads) bias_t[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads)
+        bias_t[i] = (p.bias && ks == 0) ? __ldg(p.bias + n0 + i) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -280,6 +292,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               dh4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
               dl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
+          }
+        } else if (OUT == kOutF32Atomic) {
+          if (valid) {
+            float* dst = static_cast<float*>(p.out) + out_off + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, f[j]);
           }
         } else if (OUT == kOutF32) {
           if (valid) {
@@ -396,7 +414,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, c
     }
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);
   count_launch();
@@ -489,6 +507,46 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
   p.out = out;
   return block_n == 256 ? launch<256, 1, false, false, kOutF32>(ta, tb, p, stream)
                         : launch<128, 1, false, false, kOutF32>(ta, tb, p, stream);
+}
+
+int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float* out_zeroed, long long ldo, int M, int N,
+                              int K, cudaStream_t stream, int planes) {
+  if (M <= 0) return 0;
+  if (K % kBlockK != 0 || N % 128 != 0 || (planes != 2 && planes != 3)) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split_ksplit: need K %% 64 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d)", K, N);
+    return 1;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(M)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (make_tmap_bf16(&ta, a_planes, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(N)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
+    uint32_t box[2] = {kBlockK, 128};
+    if (make_tmap_bf16(&tb, w_planes, 2, dims, str, box)) return 1;
+  }
+  IgemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.split_nkb = K / kBlockK;
+  p.split_planes = planes;
+  p.num_kb = (planes == 3 ? 6 : 3) * p.split_nkb;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.num_n_tiles = N / 128;
+  // enough K slices to give every SM a tile, each slice at least 8 K-blocks long
+  const int mn = p.num_m_tiles * p.num_n_tiles;
+  int ks = (num_sms() + mn - 1) / mn;
+  if (ks > p.num_kb / 8) ks = p.num_kb / 8;
+  p.ksplit = ks < 1 ? 1 : ks;
+  p.relu = 0;
+  p.ldo = ldo;
+  p.bias = nullptr;
+  p.out = out_zeroed;
+  return launch<128, 1, false, false, kOutF32Atomic>(ta, tb, p, stream);
 }
 
 int igemm_linear_split_out(const void* a_planes, const void* w_planes, const float* bias, void* out_planes, int relu,

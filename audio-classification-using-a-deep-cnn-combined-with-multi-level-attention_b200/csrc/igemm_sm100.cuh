@@ -36,6 +36,7 @@ struct IgemmParams {
   int relu;
   int split_nkb;     // PLAIN split mode: K / 64 of one plane (0 = ordinary GEMM)
   int split_planes;  // 2 (hi | lo: 3 products) or 3 (hi | mid | lo: 6 products)
+  int ksplit;        // PLAIN + atomic fp32 output: number of K slices (<= 1: none)
   int conv_split;    // CONV: activations are [n][2][H][W][C] hi | lo planes, weights [C_out][2 * 9 C_in]
   long long out_img_stride;  // CONV: output elements per image (2 planes when the output is split)
   long long lo_off;          // split output: element offset of the lo plane relative to the hi element
@@ -55,6 +56,10 @@ int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void
 // must not flip against the fp32 reference).  bias may be null.  K % 64 == 0, N % 128 == 0.
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
                        int relu, int M, int N, int K, cudaStream_t stream, int planes = 2);
+// Split-K variant for tall contractions (the dW GEMMs of head training: K = batch * T rows, only a few output tiles):
+// the K loop is cut into slices that run on different SMs and atomically add into out, which must be zero on entry.
+int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float* out_zeroed, long long ldo, int M, int N,
+                              int K, cudaStream_t stream, int planes);
 // Split in, split out (the accuracy mode of the VGGish body): out planes bf16 [M][hi(N) | lo(N)] =
 // split(act(A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T + bias)).  K % 64 == 0, N % 256 == 0.
 int igemm_linear_split_out(const void* a_planes, const void* w_planes, const float* bias, void* out_planes, int relu,

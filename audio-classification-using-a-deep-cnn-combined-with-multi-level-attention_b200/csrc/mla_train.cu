@@ -305,18 +305,27 @@ bn_time_backward_reduce_kernel(GradIn in, long long batch, double* __restrict__ 
 // phase B: du = gamma_t * rstd_t * (g - S1_t / n - xhat * S2_t / n); block (0,0) also writes dgamma = S2, dbeta = S1
 struct FBnBackward {
   GradIn in; const double* acc; double n; float* dgamma; float* dbeta;
+  float* coef;   // shared memory [T][3]: gamma * rstd, S1 / n, S2 / n   (set by prologue)
   __device__ void prologue() {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < in.T) {
-      dbeta[threadIdx.x] = static_cast<float>(acc[2 * threadIdx.x]);
-      dgamma[threadIdx.x] = static_cast<float>(acc[2 * threadIdx.x + 1]);
+    __shared__ float coef_s[16 * 3];
+    coef = coef_s;
+    if (threadIdx.x < in.T) {
+      const int t = threadIdx.x;
+      coef_s[3 * t] = in.gamma[t] * in.stat[2 * t + 1];
+      coef_s[3 * t + 1] = static_cast<float>(acc[2 * t] / n);
+      coef_s[3 * t + 2] = static_cast<float>(acc[2 * t + 1] / n);
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        dbeta[t] = static_cast<float>(acc[2 * t]);
+        dgamma[t] = static_cast<float>(acc[2 * t + 1]);
+      }
     }
+    __syncthreads();
   }
   __device__ float operator()(long long r, int c) const {
     const int t = static_cast<int>(r % in.T);
     const float xh = in.xhat(r, c);
     const float g = in.g(r, c, xh);
-    const float m1 = static_cast<float>(acc[2 * t] / n), m2 = static_cast<float>(acc[2 * t + 1] / n);
-    return __ldg(in.gamma + t) * __ldg(in.stat + 2 * t + 1) * (g - m1 - xh * m2);
+    return coef[3 * t] * (g - coef[3 * t + 1] - xh * coef[3 * t + 2]);
   }
 };
 
@@ -380,11 +389,16 @@ att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int co
 }
 
 // Backward of the pooling for one clip: writes gv = d(BN^v output), gf = d(BN^f output) as fp32 [rows][ldg] and adds
-// the four BatchNorm reductions (sum g, sum g * zhat for both branches) to acc_v / acc_f.
+// the four BatchNorm reductions (sum g, sum g * zhat for both branches) to acc_v / acc_f.  att and cla of the clip
+// (T x K each) are computed once into shared memory.
 __global__ void __launch_bounds__(256)
 att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __restrict__ dy, long long ystride, int col0,
                     const float* __restrict__ row_stats, float* __restrict__ gv, float* __restrict__ gf, long long ldg,
                     double* __restrict__ acc_v, double* __restrict__ acc_f) {
+  extern __shared__ float att_sm[];
+  float* att = att_sm;                 // [T][K]
+  float* cla = att + a.T * a.K;        // [T][K]
+  float* sinv = cla + a.T * a.K;       // [K]  1 / sum_t att
   __shared__ float sa_v[16], sb_v[16], sa_f[16], sb_f[16], dot[16];
   __shared__ double red[8][4];
   const long long clip = blockIdx.x;
@@ -398,47 +412,49 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
     dot[t] = 0.f;
   }
   __syncthreads();
-  // s[k] = sum_t att; datt = dy (cla - y) / s; dot[t] = sum_k datt * att  (the softmax backward needs it per row)
-  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < a.T; ++t) {
-      const float* rs2 = row_stats + 2 * (clip * a.T + t);
-      s += expf(fmaf(sa_v[t], __ldg(zc + t * a.ldz + k), sb_v[t]) - rs2[0]) / rs2[1];
-    }
-    const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
-    for (int t = 0; t < a.T; ++t) {
-      const float* rs2 = row_stats + 2 * (clip * a.T + t);
-      const float zz = __ldg(zc + t * a.ldz + k);
-      const float att = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
-      const float cla = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
-      atomicAdd(&dot[t], d * (cla - yy) / s * att);
-    }
+  for (int i = threadIdx.x; i < a.T * a.K; i += blockDim.x) {
+    const int t = i / a.K, k = i - t * a.K;
+    const float zz = __ldg(zc + t * a.ldz + k);
+    const float* rs2 = row_stats + 2 * (clip * a.T + t);
+    att[i] = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
+    cla[i] = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
   }
   __syncthreads();
-  double s1v = 0, s2v = 0, s1f = 0, s2f = 0;
+  // s[k] = sum_t att; datt = dy (cla - y) / s; dot[t] = sum_k datt * att  (the softmax backward needs it per row)
+  float pdot[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) pdot[t] = 0.f;
+  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < a.T; ++t) s += att[t * a.K + k];
+    const float si = 1.f / s;
+    sinv[k] = si;
+    const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (t < a.T) pdot[t] = fmaf(d * (cla[t * a.K + k] - yy) * si, att[t * a.K + k], pdot[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    float v = pdot[t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && t < a.T) atomicAdd(&dot[t], v);
+  }
+  __syncthreads();
   // second pass, one time step per iteration so the BatchNorm reductions stay per t
   for (int t = 0; t < a.T; ++t) {
-    const float* rs2 = row_stats + 2 * (clip * a.T + t);
     const float mu = a.stat[2 * t], rstd = a.stat[2 * t + 1];
     double p1v = 0, p2v = 0, p1f = 0, p2f = 0;
     for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-      float s = 0.f;
-      for (int tt = 0; tt < a.T; ++tt) {
-        const float* r3 = row_stats + 2 * (clip * a.T + tt);
-        s += expf(fmaf(sa_v[tt], __ldg(zc + tt * a.ldz + k), sb_v[tt]) - r3[0]) / r3[1];
-      }
-      const float zz = __ldg(zc + t * a.ldz + k);
-      const float att = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
-      const float cla = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
+      const float at = att[t * a.K + k], cl = cla[t * a.K + k], si = sinv[k];
       const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
-      const float dcla = d * att / s;
-      const float datt = d * (cla - yy) / s;
-      const float g_f = dcla * cla * (1.f - cla);
-      const float g_v = att * (datt - dot[t]);
+      const float g_f = d * at * si * cl * (1.f - cl);
+      const float g_v = at * (d * (cl - yy) * si - dot[t]);
       const long long r = clip * a.T + t;
       gv[r * ldg + k] = g_v;
       gf[r * ldg + k] = g_f;
-      const float zh = (zz - mu) * rstd;
+      const float zh = (__ldg(zc + t * a.ldz + k) - mu) * rstd;
       p1v += g_v; p2v += double(g_v) * zh;
       p1f += g_f; p2f += double(g_f) * zh;
     }
@@ -452,7 +468,7 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
     if (lane == 0) { red[warp][0] = p1v; red[warp][1] = p2v; red[warp][2] = p1f; red[warp][3] = p2f; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      s1v = s2v = s1f = s2f = 0;
+      double s1v = 0, s2v = 0, s1f = 0, s2f = 0;
       for (int w = 0; w < 8; ++w) { s1v += red[w][0]; s2v += red[w][1]; s1f += red[w][2]; s2f += red[w][3]; }
       atomicAdd(acc_v + 2 * t, s1v);
       atomicAdd(acc_v + 2 * t + 1, s2v);
@@ -754,6 +770,20 @@ int run_tile(F f, TileOut o, cudaStream_t st, const char* what) {
   return vmb::check_launch(what);
 }
 
+// dW = A^T B over the rows: tall contraction, few output tiles -> split-K with atomic accumulation into a zeroed buffer
+int gemm_dw(const void* at_planes, const void* bt_planes, float* out, long long ldo, int M, int N, long long K,
+            cudaStream_t st) {
+  if (cudaMemsetAsync(out, 0, size_t(M) * ldo * sizeof(float), st) != cudaSuccess) {
+    vmb::set_kernel_error("dW buffer clear failed");
+    return 1;
+  }
+  if (vmb::igemm_linear_split_ksplit(at_planes, bt_planes, out, ldo, M, N, int(K), st, kPl)) {
+    vmb::set_kernel_error("%s", vmb::igemm_last_error());
+    return 1;
+  }
+  return 0;
+}
+
 int gemm(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo, long long M, int N,
          int K, cudaStream_t st) {
   if (vmb::igemm_linear_split(a_planes, w_planes, bias, out, ldo, 0, int(M), N, K, st, kPl)) {
@@ -964,7 +994,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + h->fc_out.b, B, Bp, K, Hp};
     TRY(run_tile(FIdentity{h->dO, Hp}, o, st, "dO split"));
     // dW_fc [K][L*K] = dO^T [K x B] * Y^T [L*K x B]^T
-    TRY(gemm(h->G_pt, h->Y_pt, nullptr, h->dWtmp, h->ycols_pad, Hp, h->ycols_pad, int(Bp), st));
+    TRY(gemm_dw(h->G_pt, h->Y_pt, h->dWtmp, h->ycols_pad, Hp, h->ycols_pad, Bp, st));
     if (!rc && cudaMemcpy2DAsync(grads + h->fc_out.w, size_t(h->ycols) * 4, h->dWtmp, size_t(h->ycols_pad) * 4,
                                  size_t(h->ycols) * 4, K, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       rc = 1;
@@ -979,8 +1009,14 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
                  params + L.normf.g, params + L.normf.b};
     double* acc_v = slotacc(L.normv.bslot);
     double* acc_f = slotacc(L.normf.bslot);
-    att_backward_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(ap, h->Y, h->dY, h->ycols_pad, l * K, h->row_stats[l],
-                                                                  h->GV, h->GF, Hp, acc_v, acc_f);
+    const size_t att_smem = (size_t(2) * T * K + K) * sizeof(float);
+    static bool att_attr = false;
+    if (!att_attr) {
+      cudaFuncSetAttribute(att_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      att_attr = true;
+    }
+    att_backward_kernel<<<static_cast<unsigned>(B), 256, att_smem, st>>>(ap, h->Y, h->dY, h->ycols_pad, l * K,
+                                                                         h->row_stats[l], h->GV, h->GF, Hp, acc_v, acc_f);
     vmb::count_launch();
     TRY(vmb::check_launch("att_backward_kernel"));
     {
@@ -990,7 +1026,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(run_tile(f, o, st, "attention BN backward"));
     }
     // dWv [K][H] = dZ^T * E^T ; dE_att [R][H] = dZ * Wv
-    TRY(gemm(h->G_pt, e_pt, nullptr, h->dWtmp, Hp, Hp, Hp, int(Rp), st));
+    TRY(gemm_dw(h->G_pt, e_pt, h->dWtmp, Hp, Hp, Hp, Rp, st));
     if (!rc && cudaMemcpy2DAsync(grads + L.fcv.w, size_t(H) * 4, h->dWtmp, size_t(Hp) * 4, size_t(H) * 4, K,
                                  cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       rc = 1;
@@ -1012,7 +1048,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(run_tile(f, o, st, "fc BN backward"));
       // dW [H][n_in] = dU^T * A_prev^T ; dA_prev [R][n_in] = dU * W
       const __nv_bfloat16* prev_pt = j > 0 ? h->A_pt[l][j - 1] : (l == 0 ? h->xin_pt : h->N_pt[l]);
-      TRY(gemm(h->G_pt, prev_pt, nullptr, h->dWtmp, fc.n_in_pad, Hp, fc.n_in_pad, int(Rp), st));
+      TRY(gemm_dw(h->G_pt, prev_pt, h->dWtmp, fc.n_in_pad, Hp, fc.n_in_pad, Rp, st));
       if (!rc && cudaMemcpy2DAsync(grads + fc.w, size_t(fc.n_in) * 4, h->dWtmp, size_t(fc.n_in_pad) * 4,
                                    size_t(fc.n_in) * 4, H, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         rc = 1;

@@ -134,8 +134,11 @@ def test_data_parallel_semantics_two_shards():
         ref = (ref_avg[key] / world).numpy()
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 5e-7, key
         want = train_torch.adam_update(sd[key], ref_avg[key] / world)
-        if ref_avg[key].abs().max() > 1e-5:        # Adam normalises: a gradient that is pure rounding noise moves by lr
-            assert (trs[0].view(trs[0].params, key).cpu() - want).abs().max() < 2e-5, key
+        # Adam normalises each element by its own magnitude: where the gradient is rounding noise the step is +-lr
+        # whatever the sign of the noise, so compare the update only where the gradient is resolved
+        big = (ref_avg[key] / world).abs() > 1e-5
+        if big.any():
+            assert (trs[0].view(trs[0].params, key).cpu() - want)[big].abs().max() < 2e-5, key
     assert torch.equal(trs[0].params, trs[1].params)                       # replicas stay bit-identical
     for tr in trs:
         tr.close()
