@@ -297,6 +297,16 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     serial_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
 
+    # ---- latency of BASELINE.json configs[0]: ONE 10 s clip, host buffer in -> scores on the host (blocking call)
+    one_host = wave_host[:1].clone().pin_memory()
+    one_out = torch.empty(1, N_CLASSES).pin_memory()
+    for _ in range(5):
+        pipe.forward_host(one_host, one_out, clips_per_batch=1)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        pipe.forward_host(one_host, one_out, clips_per_batch=1)
+    b1_ms = 1e3 * (time.perf_counter() - t0) / 50
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,6 +346,7 @@ def run_b200(args, rank, local_rank, world):
                      "whole_step_tflops": FLOP_PER_CLIP * args.clips / (ms_step * 1e-3) / 1e12,
                      "whole_step_frac": FLOP_PER_CLIP * args.clips / (ms_step * 1e-3) / 1e12 / peaks["tflops"]},
         "stage_ms_per_step": per_stage, "stage_tflops": stage_tflops,
+        "single_clip_latency_ms": b1_ms,
         "scores_finite": finite,
     }
     if world == 1 and not args.no_cpu_baseline:
