@@ -26,6 +26,7 @@ SIGNATURES = {
     "vmb_num_frames": (_ll, [_ll]),
     "vmb_num_examples": (_ll, [_ll]),
     "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
+    "vmb_logmel_pcm16": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_logmel_cudacore": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),

@@ -68,6 +68,27 @@ def logmel(wave: torch.Tensor, frames_out: Optional[int] = None) -> torch.Tensor
     return out
 
 
+def logmel_pcm16(pcm: torch.Tensor, frames_out: Optional[int] = None) -> torch.Tensor:
+    """pcm (n_clips, n_samples) or (n_samples,) int16 CUDA -> (n_clips, frames_out, 64) fp32 log-mel of pcm / 32768
+    (the int16 WAV convention of vggish_input.py:96-98), without a float copy of the waveform."""
+    pcm = _need_cuda(pcm, "pcm", torch.int16)
+    if pcm.dim() == 1:
+        pcm = pcm[None]
+    n_clips, n_samples = pcm.shape
+    nf = num_frames(n_samples)
+    if nf < 0:
+        raise ValueError("negative dimensions are not allowed")
+    if frames_out is None:
+        frames_out = nf
+    out = torch.empty((n_clips, frames_out, MEL), device=pcm.device, dtype=torch.float32)
+    with torch.cuda.device(pcm.device):
+        for c0 in range(0, n_clips, 32768):
+            nc = min(32768, n_clips - c0)
+            check(_lib.lib().vmb_logmel_pcm16(ptr(pcm[c0:]), nc, n_samples, pcm.stride(0), frames_out, ptr(out[c0:]),
+                                              stream_ptr()), "vmb_logmel_pcm16")
+    return out
+
+
 def logmel_cudacore(wave: torch.Tensor) -> torch.Tensor:
     """Diagnostic: the fp32 CUDA-core log-mel kernel (vmb_logmel_cudacore), same contract as logmel()."""
     wave = _need_cuda(wave, "wave")

@@ -80,6 +80,21 @@ int vmb_logmel(const float* wave, long long n_clips, long long samples_per_clip,
   return logmel_common("vmb_logmel", true, wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, stream);
 }
 
+int vmb_logmel_pcm16(const int16_t* pcm, long long n_clips, long long samples_per_clip, long long clip_stride,
+                     long long frames_out, float* logmel, void* stream) {
+  const char* who = "vmb_logmel_pcm16";
+  if (n_clips < 0 || frames_out < 0) return fail("%s: negative size", who);
+  const long long nf = vmb_num_frames(samples_per_clip);
+  if (nf < 1) return fail("%s: %lld samples is shorter than one 400-sample window", who, samples_per_clip);
+  if (frames_out > nf) return fail("%s: frames_out %lld > available frames %lld", who, frames_out, nf);
+  if (clip_stride < samples_per_clip) return fail("%s: clip_stride < samples_per_clip", who);
+  if (n_clips == 0 || frames_out == 0) return 0;
+  if (!pcm || !logmel) return fail("%s: null pointer", who);
+  if (vmb::logmel_tc_forward_pcm16(pcm, n_clips, samples_per_clip, clip_stride, frames_out, logmel, S(stream)))
+    return fail_from(who, vmb::kernels_last_error());
+  return 0;
+}
+
 int vmb_logmel_cudacore(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                         long long frames_out, float* logmel, void* stream) {
   return logmel_common("vmb_logmel_cudacore", false, wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel,

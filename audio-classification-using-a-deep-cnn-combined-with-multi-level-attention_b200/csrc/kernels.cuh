@@ -35,6 +35,9 @@ void front_end_tables_host(double* hann400, double* mel257x64);
 // Tensor-core front end (logmel_tc.cu): split-bf16 tcgen05 DFT GEMM with the magnitude / mel / log epilogue.
 int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                       long long frames_out, float* logmel, cudaStream_t stream);
+// Same for 16-bit PCM input scaled by 1/32768 (vggish_input.py:96-98): two A planes are exact, five products.
+int logmel_tc_forward_pcm16(const int16_t* pcm, long long n_clips, long long samples_per_clip, long long clip_stride,
+                            long long frames_out, float* logmel, cudaStream_t stream);
 // CUDA-core fp32 version of the same computation (frontend.cu); kept as an on-device cross-check, not on the path.
 int logmel_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                    long long frames_out, float* logmel, cudaStream_t stream);

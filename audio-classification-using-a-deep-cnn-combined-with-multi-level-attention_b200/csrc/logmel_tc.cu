@@ -64,8 +64,17 @@ __constant__ float c_wrise[kEvalBins];
 
 // ------------------------------------------------------------------ waveform -> three bf16 planes
 // planes[p][clip][pitch]; samples >= n_samples are written as zero so that K padding never meets garbage.
+// IN = float (waveform in [-1, 1]) or int16_t (PCM, scaled by 1/32768 like vggish_input.py:98 — exact in fp32).
+template <class IN>
+__device__ __forceinline__ float load_sample(const IN* p);
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_sample<int16_t>(const int16_t* p) { return static_cast<float>(__ldg(p)) * (1.0f / 32768.0f); }
+
+template <class IN>
 __global__ void __launch_bounds__(256)
-split_wave_kernel(const float* __restrict__ wave, long long n_samples, long long clip_stride, long long pitch,
+split_wave_kernel(const IN* __restrict__ wave, long long n_samples, long long clip_stride, long long pitch,
                   long long n_clips, __nv_bfloat16* __restrict__ planes) {
   const long long groups_per_clip = pitch / 8;
   const long long total = groups_per_clip * n_clips;
@@ -74,13 +83,13 @@ split_wave_kernel(const float* __restrict__ wave, long long n_samples, long long
        g += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long clip = g / groups_per_clip;
     const long long s0 = (g - clip * groups_per_clip) * 8;
-    const float* src = wave + clip * clip_stride + s0;
+    const IN* src = wave + clip * clip_stride + s0;
     uint32_t h0[4], h1[4], h2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float x[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) x[u] = (s0 + 2 * i + u < n_samples) ? __ldg(src + 2 * i + u) : 0.f;
+      for (int u = 0; u < 2; ++u) x[u] = (s0 + 2 * i + u < n_samples) ? load_sample<IN>(src + 2 * i + u) : 0.f;
       __nv_bfloat16 a[2], b[2], c[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -103,6 +112,8 @@ split_wave_kernel(const float* __restrict__ wave, long long n_samples, long long
 
 // ------------------------------------------------------------------ the GEMM + mel/log epilogue
 struct LogmelParams {
+  int a_planes;             // 3 for fp32 input; 2 for 16-bit PCM (x = m / 32768 splits exactly into two bf16 terms,
+                            // the third plane is identically zero and its product A2*B0 is skipped)
   long long frames_out;     // frames written per clip
   int tiles_per_clip;       // ceil(frames_out / 128)
   int n_clips;
@@ -193,10 +204,11 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int kb = 0; kb < kKB; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* base = smem + stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
+            mbar_expect_tx(&full_bar[stage], p.a_planes * kATile + 3 * kBTile);
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) {
-              tma_load_3d(base + pl * kATile, &tmap_a, &full_bar[stage], kb * kBK, row0, pl * p.n_clips + clip);
+              if (pl < p.a_planes)
+                tma_load_3d(base + pl * kATile, &tmap_a, &full_bar[stage], kb * kBK, row0, pl * p.n_clips + clip);
               tma_load_2d(base + 3 * kATile + pl * kBTile, &tmap_b, &full_bar[stage], kb * kBK,
                           pl * kEvalBins * 2 + nt * kTN);
             }
@@ -224,13 +236,15 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // products (a plane, b plane), smallest magnitude first
             constexpr int prod_a[6] = {2, 1, 0, 1, 0, 0};
             constexpr int prod_b[6] = {0, 1, 2, 0, 1, 0};
+            const int q0 = p.a_planes == 3 ? 0 : 1;   // two A planes: skip the A2*B0 product
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
+              if (q < q0) continue;
               const uint64_t a_desc = umma_desc_kmajor_sw64(a0 + prod_a[q] * kATile);
               const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + prod_b[q] * kBTile);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (>>4 = 2) per 16-element K step
-                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | q | k) != 0);
+                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | (q - q0) | k) != 0);
             }
             umma_commit(&empty_bar[stage]);
             if (kb == kKB - 1) umma_commit(&tmem_full[acc]);
@@ -402,22 +416,20 @@ int get_tables(TcTables** out) {
   return 0;
 }
 
-}  // namespace
+// last frame reads up to sample 160 (frames - 1) + 415 <= samples + 15; rows of the A tensor map must stay inside the
+// plane; a multiple of 160 keeps every stride a multiple of the 320-byte frame stride
+long long logmel_tc_pitch(long long samples_per_clip) { return (samples_per_clip + 16 + kHop - 1) / kHop * kHop; }
 
-long long logmel_tc_pitch(long long samples_per_clip) {
-  // last frame reads up to sample 160 (frames - 1) + 415 <= samples + 15; rows of the A tensor map must stay inside
-  // the plane; a multiple of 160 keeps every stride a multiple of the 320-byte frame stride
-  return (samples_per_clip + 16 + kHop - 1) / kHop * kHop;
-}
-
-int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
-                      long long frames_out, float* logmel, cudaStream_t stream) {
+template <class IN>
+int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                           long long frames_out, float* logmel, cudaStream_t stream) {
   TcTables* t = nullptr;
   if (get_tables(&t)) return 1;
   if (3 * n_clips > 0x7fffffffLL || frames_out > 0x7fffffffLL) {
     set_kernel_error("logmel: too many clips / frames for one launch");
     return 1;
   }
+  constexpr int a_planes = sizeof(IN) == 2 ? 2 : 3;
   const long long pitch = logmel_tc_pitch(samples_per_clip);
   const size_t plane_bytes = size_t(n_clips) * pitch * 2;
   void* planes = nullptr;
@@ -429,8 +441,8 @@ int logmel_tc_forward(const float* wave, long long n_clips, long long samples_pe
   {
     const long long groups = pitch / 8 * n_clips;
     const unsigned grid = static_cast<unsigned>(std::min<long long>((groups + 255) / 256, 148LL * 16));
-    split_wave_kernel<<<grid, 256, 0, stream>>>(wave, samples_per_clip, clip_stride, pitch, n_clips,
-                                                static_cast<__nv_bfloat16*>(planes));
+    split_wave_kernel<IN><<<grid, 256, 0, stream>>>(wave, samples_per_clip, clip_stride, pitch, n_clips,
+                                                    static_cast<__nv_bfloat16*>(planes));
     count_launch();
     if (check_launch("split_wave_kernel")) return 1;
   }
@@ -454,6 +466,7 @@ int logmel_tc_forward(const float* wave, long long n_clips, long long samples_pe
     }
   }
   LogmelParams p{};
+  p.a_planes = a_planes;
   p.frames_out = frames_out;
   p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
   p.n_clips = static_cast<int>(n_clips);
@@ -468,6 +481,18 @@ int logmel_tc_forward(const float* wave, long long n_clips, long long samples_pe
     return 1;
   }
   return 0;
+}
+
+}  // namespace
+
+int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
+                      long long frames_out, float* logmel, cudaStream_t stream) {
+  return logmel_tc_forward_impl<float>(wave, n_clips, samples_per_clip, clip_stride, frames_out, logmel, stream);
+}
+
+int logmel_tc_forward_pcm16(const int16_t* pcm, long long n_clips, long long samples_per_clip, long long clip_stride,
+                            long long frames_out, float* logmel, cudaStream_t stream) {
+  return logmel_tc_forward_impl<int16_t>(pcm, n_clips, samples_per_clip, clip_stride, frames_out, logmel, stream);
 }
 
 }  // namespace vmb

@@ -63,6 +63,12 @@ long long vmb_num_examples(long long n_samples);
 int vmb_logmel(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                long long frames_out, float* logmel_dev, void* stream);
 
+/* The same for 16-bit PCM (what wavfile_to_examples reads, vggish_input.py:96-98): samples are scaled by 1/32768
+ * on the device, which is exact in fp32, so the result is bit-identical to vmb_logmel on pcm / 32768.0f; half the
+ * input bytes, and one of the six split products drops out because a 16-bit sample is exactly two bf16 terms.   */
+int vmb_logmel_pcm16(const int16_t* pcm_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
+                     long long frames_out, float* logmel_dev, void* stream);
+
 /* The same computation on the CUDA cores in plain fp32 (the first implementation).  Diagnostic only: an on-device
  * cross-check for the tensor-core kernel at sizes the CPU oracle cannot reach; vmb_pipeline_forward never uses it. */
 int vmb_logmel_cudacore(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
