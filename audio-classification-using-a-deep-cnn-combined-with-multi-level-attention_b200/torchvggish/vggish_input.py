@@ -45,5 +45,16 @@ def wavfile_to_examples(wav_file, return_tensor=True):
         pcm = np.frombuffer(wf.readframes(wf.getnframes()), dtype="<i2")
         if wf.getnchannels() > 1:
             pcm = pcm.reshape(-1, wf.getnchannels())
+    if pcm.ndim == 1 and sr == vggish_params.SAMPLE_RATE:
+        # mono 16 kHz: the int16 samples go to the device as they are and are scaled by 1/32768 there (exact in fp32,
+        # bit-identical to the float path); half the host-to-device bytes
+        dev_pcm = torch.from_numpy(np.ascontiguousarray(pcm)).to(device="cuda")
+        per = _engine.num_examples(dev_pcm.shape[0])
+        if per < 0:
+            raise ValueError("negative dimensions are not allowed")
+        examples = _engine.logmel_pcm16(dev_pcm, per * 96).view(per, 96, 64)
+        if return_tensor:
+            return examples[:, None, :, :]
+        return examples.cpu().numpy().astype(np.float64)
     samples = pcm / 32768.0
     return waveform_to_examples(samples, sr, return_tensor)

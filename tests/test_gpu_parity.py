@@ -482,3 +482,21 @@ def test_pcm16_ingestion_is_bit_identical():
     for i in (0, 2):
         ref = frontend_np.log_mel_spectrogram(pcm[i].numpy() / 32768.0)
         assert np.abs(a[i].cpu().numpy() - ref).max() <= 1e-4
+
+
+def test_wavfile_to_examples_pcm16(tmp_path):
+    """wavfile_to_examples (vggish_input.py:85-99) on a 16-bit mono WAV: int16 samples straight to the device."""
+    import wave as wav
+    from torchvggish import vggish_input
+    pcm = (np.random.default_rng(3).standard_normal(32000) * 3000).astype("<i2")
+    path = str(tmp_path / "clip.wav")
+    with wav.open(path, "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(16000)
+        f.writeframes(pcm.tobytes())
+    t = vggish_input.wavfile_to_examples(path)
+    assert tuple(t.shape) == (2, 1, 96, 64) and t.is_cuda
+    ref = frontend_np.waveform_to_examples(pcm / 32768.0)
+    assert np.abs(t[:, 0].cpu().numpy() - ref).max() <= 1e-4
+    assert vggish_input.wavfile_to_examples(path, return_tensor=False).shape == (2, 96, 64)
