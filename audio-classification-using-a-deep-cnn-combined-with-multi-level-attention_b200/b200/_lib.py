@@ -28,6 +28,7 @@ SIGNATURES = {
     "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_logmel_pcm16": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_logmel_cudacore": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
+    "vmb_spec_tiles": (_int, [_c_p, _ll, _int, _int, _int, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_conv1_relu_pool_cudacore": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),

@@ -101,6 +101,20 @@ int vmb_logmel_cudacore(const float* wave, long long n_clips, long long samples_
                        stream);
 }
 
+int vmb_spec_tiles(const float* examples, long long n_clips, int n_examples_per_clip, int n_frames, int overlap,
+                   float* out, void* stream) {
+  if (n_clips < 0) return fail("vmb_spec_tiles: negative n_clips");
+  if (n_examples_per_clip < 0 || n_examples_per_clip > 4) return fail("vmb_spec_tiles: 0..4 examples per clip (a 4 s clip)");
+  if (overlap ? n_frames < 4 : (n_frames < 1 || n_frames > 4))
+    return fail("vmb_spec_tiles: overlap needs >= 4 frames, contiguous tiling at most 4 (dataset.py:169-172)");
+  if (n_clips == 0) return 0;
+  if ((!examples && n_examples_per_clip) || !out) return fail("vmb_spec_tiles: null pointer");
+  const int step = overlap ? (384 - 96) / (n_frames - 1) : 96;   // dataset.py:356-359, :362-363
+  if (vmb::spec_tiles(examples, n_clips, n_examples_per_clip, n_frames, step, out, S(stream)))
+    return fail_from("vmb_spec_tiles", vmb::kernels_last_error());
+  return 0;
+}
+
 int vmb_front_end_tables(double* hann400, double* mel257x64) {
   vmb::front_end_tables_host(hann400, mel257x64);
   return 0;

@@ -51,6 +51,8 @@ int conv1_relu_pool(const float* examples, const float* w, const float* b, void*
                     cudaStream_t stream);
 int postprocess(const float* emb, const float* eigen, const float* means, float* out_f32, uint8_t* out_u8,
                 long long n, cudaStream_t stream);
+// dataset.create_spec + split tiling of <= 4 examples per clip into T windows of (64, 96)
+int spec_tiles(const float* examples, long long n_clips, int n_ex, int T, int step, float* out, cudaStream_t stream);
 // OIHW fp32 [C_out][C_in][3][3] -> bf16 [C_out][(kh*3+kw)*C_in + c]
 int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream);
 // OIHW fp32 -> bf16 [C_out][hi(9 C_in) | lo(9 C_in)], (kh, kw, c) order inside each plane

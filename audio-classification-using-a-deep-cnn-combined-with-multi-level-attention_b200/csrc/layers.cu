@@ -112,6 +112,25 @@ postprocess_kernel(const float* __restrict__ emb, const float* __restrict__ eig,
   }
 }
 
+// ------------------------------------------------------------------ UrbanSound8K tiling (dataset.py:318-326, :355-363)
+// create_spec (torchvggish branch): the <= 4 examples of a 4 s clip are laid side by side as a (64 mel, 384 time)
+// spectrogram, missing examples are zero; split(): T windows of 96 time steps, `step` apart.
+// out[clip][f][m][t] = spec[m][f * step + t],  spec[m][tau] = examples[clip][tau / 96][tau % 96][m].
+__global__ void __launch_bounds__(256)
+spec_tiles_kernel(const float* __restrict__ ex, long long n_clips, int n_ex, int T, int step, float* __restrict__ out) {
+  const long long total = n_clips * T * 64 * 96;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % 96);
+    const int m = static_cast<int>((i / 96) % 64);
+    const int f = static_cast<int>((i / (96 * 64)) % T);
+    const long long clip = i / (96LL * 64 * T);
+    const int tau = f * step + t;
+    const int e = tau / 96;
+    out[i] = (tau < 384 && e < n_ex) ? __ldg(ex + ((clip * n_ex + e) * 96 + (tau - e * 96)) * 64 + m) : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------ weight re-layout
 __global__ void relayout_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int C_out, int C_in) {
   const long long total = static_cast<long long>(C_out) * 9 * C_in;
@@ -178,6 +197,14 @@ int postprocess(const float* emb, const float* eigen, const float* means, float*
   postprocess_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(emb, eigen, means, out_f32, out_u8, n);
   count_launch();
   return check_launch("postprocess_kernel");
+}
+
+int spec_tiles(const float* examples, long long n_clips, int n_ex, int T, int step, float* out, cudaStream_t stream) {
+  const long long total = n_clips * T * 64 * 96;
+  const unsigned grid = static_cast<unsigned>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+  spec_tiles_kernel<<<grid, 256, 0, stream>>>(examples, n_clips, n_ex, T, step, out);
+  count_launch();
+  return check_launch("spec_tiles_kernel");
 }
 
 int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream) {

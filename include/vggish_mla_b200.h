@@ -74,6 +74,13 @@ int vmb_logmel_pcm16(const int16_t* pcm_dev, long long n_clips, long long sample
 int vmb_logmel_cudacore(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                         long long frames_out, float* logmel_dev, void* stream);
 
+/* dataset.create_spec (torchvggish branch, dataset.py:318-326) + dataset.split (dataset.py:329-363) for 4 s clips:
+ * the <= 4 examples of each clip [n_clips][n_examples_per_clip][96][64] are laid side by side as a (64 mel, 384 time)
+ * spectrogram (missing examples are zero) and cut into n_frames windows of (64, 96): overlapping with step
+ * 288 / (n_frames - 1), or contiguous.  out_dev fp32 [n_clips][n_frames][64][96].                         */
+int vmb_spec_tiles(const float* examples_dev, long long n_clips, int n_examples_per_clip, int n_frames, int overlap,
+                   float* out_dev, void* stream);
+
 /* The constant tables the kernel uses (host copies, for the parity tests against mel_features.py):
  * periodic Hann (400 doubles) and the 257x64 HTK mel matrix (row-major doubles).                      */
 int vmb_front_end_tables(double* hann400, double* mel257x64);

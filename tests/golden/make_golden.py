@@ -31,12 +31,15 @@ synth = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(synth)
 
 sys.path.insert(0, REF)
-for name in ("resampy", "soundfile"):
-    sys.modules.setdefault(name, types.ModuleType(name))
+for name in ("resampy", "soundfile", "librosa", "librosa.display", "h5py", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))     # imported at module top by the reference, never used here
+sys.modules["librosa"].display = sys.modules["librosa.display"]
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 from torchvggish import mel_features as ref_mel  # noqa: E402
 from torchvggish import vggish_input as ref_input  # noqa: E402
 from torchvggish import vggish as ref_vggish  # noqa: E402
 import model as ref_model  # noqa: E402
+import dataset as ref_dataset  # noqa: E402
 
 torch.manual_seed(0)
 torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -201,7 +204,23 @@ def ensemble(front):
                         keys=np.array(sorted(ens.state_dict().keys())))
 
 
+def dataset_tiling():
+    """dataset.create_spec (torchvggish branch) + dataset.split for a full 4 s clip and a 2.5 s one (2 examples)."""
+    out = {}
+    for tag, n in (("4s", 64000), ("2s5", 40000)):
+        w = synth.make_clips(20, 1, n, dtype=np.float32)[0]
+        spec = ref_dataset.create_spec(w.astype(np.float64), "vggish", 16000, 64000, 96, 64, False, True)
+        # inputs are synth.make_clips(20, 1, n) (reproducible, see test_synth_clips_reproduce_golden_inputs)
+        out[f"spec_checksum_{tag}"] = np.array([spec.sum(), np.abs(spec).sum()])
+        out[f"frames_{tag}"] = ref_dataset.split(spec, 10, 96, 64, True).astype(np.float32)
+    w = synth.make_clips(20, 1, 64000, dtype=np.float32)[0]
+    spec = ref_dataset.create_spec(w.astype(np.float64), "vggish", 16000, 64000, 96, 64, False, False)
+    out["frames_contig_4s"] = ref_dataset.split(spec, 4, 96, 64, False).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **out)
+
+
 if __name__ == "__main__":
+    dataset_tiling()
     f = front_end()
     vggish(f)
     head()

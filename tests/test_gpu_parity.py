@@ -500,3 +500,32 @@ def test_wavfile_to_examples_pcm16(tmp_path):
     ref = frontend_np.waveform_to_examples(pcm / 32768.0)
     assert np.abs(t[:, 0].cpu().numpy() - ref).max() <= 1e-4
     assert vggish_input.wavfile_to_examples(path, return_tensor=False).shape == (2, 96, 64)
+
+
+def test_dataset_tiling_vs_reference():
+    """dataset.create_spec (torchvggish branch) + dataset.split against the reference's own output
+    (tests/golden/dataset.npz), through the numpy-compatible drop-in functions and the batched device path."""
+    import dataset
+    from conftest import load_golden
+    g = load_golden("dataset.npz")
+    for tag, n in (("4s", 64000), ("2s5", 40000)):
+        w = synth.make_clips(20, 1, n)[0]
+        spec = dataset.create_spec(w.astype(np.float64), "vggish", 16000, 64000, 96, 64, False, True)
+        assert spec.shape == (64, 384)
+        frames = dataset.split(spec, 10, 96, 64, True)
+        assert frames.shape == (10, 64, 96)
+        assert np.abs(frames - g[f"frames_{tag}"]).max() <= 1e-4
+        dev = dataset.clips_to_frames(torch.from_numpy(w)[None].to(DEV))
+        assert tuple(dev.shape) == (1, 10, 1, 64, 96)
+        assert np.abs(dev[0, :, 0].cpu().numpy() - g[f"frames_{tag}"]).max() <= 1e-4
+        assert np.array_equal(dev[0, :, 0].cpu().numpy(), frames.astype(np.float32))      # same kernel output, tiled
+    w = synth.make_clips(20, 1, 64000)[0]
+    spec = dataset.create_spec(w.astype(np.float64), "vggish", 16000, 64000, 96, 64, False, False)
+    assert np.abs(dataset.split(spec, 4, 96, 64, False) - g["frames_contig_4s"]).max() <= 1e-4
+    dev = dataset.clips_to_frames(torch.from_numpy(w)[None].to(DEV), num_frames=4, overlap=False)
+    assert np.abs(dev[0, :, 0].cpu().numpy() - g["frames_contig_4s"]).max() <= 1e-4
+    with pytest.raises(NotImplementedError):
+        dataset.create_spec(w, "vggish", 16000, 64000, 96, 64, True, True)
+    # the frames feed Ensemble exactly like the reference's loader does: (B, T, 1, 64, 96) reshaped by Input
+    batch = dataset.clips_to_frames(torch.from_numpy(synth.make_clips(20, 3, 64000)).to(DEV))
+    assert tuple(batch.shape) == (3, 10, 1, 64, 96) and torch.isfinite(batch).all()

@@ -130,3 +130,20 @@ def test_head_training_step(golden_head):
                                golden_head["running_mean_after::embedded_mappings.0.norm0"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(run["norm.running_var"].numpy(), golden_head["running_var_after::norm"], rtol=1e-4,
                                atol=1e-7)
+
+
+def test_dataset_tiling_restatement():
+    """The (64, 384) spectrogram + 10 overlapping (64, 96) windows of dataset.py:318-326, :355-359, restated with the
+    oracle front end, against the reference's output."""
+    from conftest import load_golden
+    g = load_golden("dataset.npz")
+    for tag, n in (("4s", 64000), ("2s5", 40000)):
+        w = synth.make_clips(20, 1, n)[0].astype(np.float64)
+        slots = frontend_np.waveform_to_examples(w)
+        padded = np.zeros((4, 96, 64))
+        padded[:slots.shape[0]] = slots
+        spec = np.concatenate(np.swapaxes(padded, 1, 2), axis=1)
+        chk = g[f"spec_checksum_{tag}"]
+        assert abs(spec.sum() - chk[0]) < 1e-6 * chk[1]
+        frames = np.stack([spec[:, i:i + 96] for i in range(0, 384, 288 // 9)][:10])
+        np.testing.assert_allclose(frames, g[f"frames_{tag}"], rtol=0, atol=1e-5)
