@@ -529,3 +529,47 @@ def test_dataset_tiling_vs_reference():
     # the frames feed Ensemble exactly like the reference's loader does: (B, T, 1, 64, 96) reshaped by Input
     batch = dataset.clips_to_frames(torch.from_numpy(synth.make_clips(20, 3, 64000)).to(DEV))
     assert tuple(batch.shape) == (3, 10, 1, 64, 96) and torch.isfinite(batch).all()
+
+
+def test_reference_eval_loop_and_checkpoint_roundtrip(tmp_path, vgg_sd):
+    """the reference's test_model / save_model / load_model flow (train.py:182-240, :275-281) on the
+    drop-in Ensemble: state_dict round trip through torch.save, DataLoader batches, argmax accuracy == the oracle's."""
+    import dataset
+    import model
+    old = model.K
+    conf = dict(cnn_type="vggish", num_classes=10, use_pretrained=False, just_bottlenecks=False, cnn_trainable=False,
+                first_cnn_layer_trainable=False, in_channels=1)
+    args = dict(input_conf="repeat", cnn_conf=conf, model_conf=[2, 1], device=DEV)
+    try:
+        model.K = 10
+        clf = model.Ensemble(**args)
+        head_sd = synth.mla_state_dict((2, 1), 128, 600, 10, 10, seed=6)
+        clf.cnn.cnn_model.load_state_dict(vgg_sd)
+        clf.mla.load_state_dict(head_sd)
+        path = str(tmp_path / "wts.h5")
+        torch.save(clf.state_dict(), path)                                   # save_model, train.py:275-276
+        clf2 = model.Ensemble(**args)                                        # load_model, train.py:278-281
+        clf2.load_state_dict(torch.load(path, map_location=DEV))
+    finally:
+        model.K = old
+    clf2 = clf2.to(DEV).eval()
+    waves = synth.make_clips(40, 12, 64000)                                   # 4 s clips like UrbanSound8K
+    frames = dataset.clips_to_frames(torch.from_numpy(waves).to(DEV)).cpu()   # (12, 10, 1, 64, 96)
+    labels = torch.arange(12) % 10
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(frames, labels), batch_size=5)
+    criterion = torch.nn.CrossEntropyLoss()
+    preds, loss_sum = [], 0.0
+    for inputs, lab in loader:                                               # test_model, train.py:208-229
+        inputs, lab = inputs.to(DEV).float(), lab.to(DEV).long()
+        with torch.set_grad_enabled(False):
+            outputs = clf2(inputs)
+            loss_sum += criterion(outputs, lab).item() * inputs.size(0)
+            preds.append(torch.max(outputs, 1)[1])
+    preds = torch.cat(preds).cpu()
+    # oracle on the same frames (Input only reshapes (64, 96) -> (96, 64), model.py:98-99)
+    with torch.no_grad():
+        want = model_torch.ensemble_forward(vgg_sd, head_sd, frames.reshape(12, 10, 1, 96, 64), (2, 1))
+    agree = (preds == want.argmax(1)).float().mean().item()
+    print(f"eval loop: argmax agreement with the oracle {agree:.3f}, mean loss {loss_sum / 12:.4f}")
+    assert agree >= 11 / 12
+    assert abs(loss_sum / 12 - criterion(want, labels).item()) < 5e-3
