@@ -62,6 +62,8 @@ SIGNATURES = {
     "vmb_pipeline_forward": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_pipeline_forward_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),
     "vmb_pipeline_submit_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),
+    "vmb_pipeline_submit_host_pcm16": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),
+    "vmb_pipeline_forward_pcm16": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_pipeline_wait_host": (_int, [_c_p, _int]),
 }
 

@@ -331,14 +331,17 @@ class Pipeline:
     def submit_host(self, wave_host: torch.Tensor, scores_host: torch.Tensor, clips_per_batch: int = 64) -> int:
         """Asynchronous half of forward_host: enqueue copies + compute, return a ticket for wait_host().  Up to two
         calls may be in flight, so the H2D copy of call i+1 overlaps the compute of call i."""
-        if wave_host.is_cuda or wave_host.dtype != torch.float32 or wave_host.dim() != 2 or not wave_host.is_contiguous():
-            raise ValueError("wave_host must be a contiguous (n_clips, n_samples) fp32 CPU tensor")
+        if wave_host.is_cuda or wave_host.dtype not in (torch.float32, torch.int16) or wave_host.dim() != 2 \
+                or not wave_host.is_contiguous():
+            raise ValueError("wave_host must be a contiguous (n_clips, n_samples) fp32 or int16 (PCM) CPU tensor")
         n, ns = wave_host.shape
         if tuple(scores_host.shape) != (n, self.mla.n_classes) or scores_host.dtype != torch.float32:
             raise ValueError("scores_host must be (n_clips, n_classes) fp32 on the host")
         with torch.cuda.device(self.device):
-            ticket = _lib.lib().vmb_pipeline_submit_host(self.vggish.raw, self.mla.raw, wave_host.data_ptr(), n, ns,
-                                                         scores_host.data_ptr(), clips_per_batch, stream_ptr())
+            fn = (_lib.lib().vmb_pipeline_submit_host_pcm16 if wave_host.dtype == torch.int16
+                  else _lib.lib().vmb_pipeline_submit_host)
+            ticket = fn(self.vggish.raw, self.mla.raw, wave_host.data_ptr(), n, ns, scores_host.data_ptr(),
+                        clips_per_batch, stream_ptr())
         if ticket < 0:
             raise B200Error(f"vmb_pipeline_submit_host failed: {_lib.last_error()}")
         return ticket

@@ -21,7 +21,7 @@ void set_api_error(const char* msg);
 struct HostStage {
   cudaStream_t copy_st = nullptr;
   cudaEvent_t wave_ready[2] = {}, wave_free[2] = {};
-  float* d_wave[2] = {};
+  void* d_wave[2] = {};           // fp32 or int16 samples, whichever the call brings
   size_t wave_cap[2] = {};
   unsigned long long batches = 0;   // micro-batches issued so far (selects the wave buffer)
   void* d_ws = nullptr;
@@ -237,7 +237,11 @@ size_t vmb_pipeline_workspace_bytes(long long n_clips, long long samples_per_cli
   return pipe_layout(n_clips, samples_per_clip).total;
 }
 
-int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave, long long n_clips,
+}  // extern "C"
+
+namespace {
+// wave: fp32 samples in [-1, 1] (pcm16 == false) or int16 PCM (scaled by 1/32768 on the device)
+int pipeline_forward_any(vmb_vggish_t* vggish, vmb_mla_t* mla, const void* wave, bool pcm16, long long n_clips,
                          long long samples_per_clip, float* scores, float* emb_out, void* workspace,
                          size_t workspace_bytes, void* stream) {
   if (!vggish || !mla) return fail("vmb_pipeline_forward: null handle");
@@ -258,9 +262,12 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   for (long long c0 = 0; c0 < n_clips; c0 += 32768) {
     const long long nc = n_clips - c0 < 32768 ? n_clips - c0 : 32768;
     vmb::StageTimer t(VMB_STAGE_LOGMEL, st);
-    if (vmb_logmel(wave + c0 * samples_per_clip, nc, samples_per_clip, samples_per_clip, per * 96,
-                   examples + c0 * per * 96 * 64, stream))
-      return 1;
+    const int rc = pcm16 ? vmb_logmel_pcm16(static_cast<const int16_t*>(wave) + c0 * samples_per_clip, nc,
+                                            samples_per_clip, samples_per_clip, per * 96,
+                                            examples + c0 * per * 96 * 64, stream)
+                         : vmb_logmel(static_cast<const float*>(wave) + c0 * samples_per_clip, nc, samples_per_clip,
+                                      samples_per_clip, per * 96, examples + c0 * per * 96 * 64, stream);
+    if (rc) return 1;
   }
   if (vmb_vggish_forward(vggish, examples, L.n_ex, emb, nullptr, ws + L.vgg, workspace_bytes - L.vgg, stream)) return 1;
   if (emb_out && cudaMemcpyAsync(emb_out, emb, size_t(L.n_ex) * 128 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
@@ -268,9 +275,30 @@ int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave
   vmb::StageTimer t(VMB_STAGE_MLA, st);
   return vmb_mla_forward(mla, emb, n_clips, scores, stream);
 }
+}  // namespace
 
-int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
-                             long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream) {
+extern "C" {
+
+int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave, long long n_clips,
+                         long long samples_per_clip, float* scores, float* emb_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return pipeline_forward_any(vggish, mla, wave, false, n_clips, samples_per_clip, scores, emb_out, workspace,
+                              workspace_bytes, stream);
+}
+
+int vmb_pipeline_forward_pcm16(vmb_vggish_t* vggish, vmb_mla_t* mla, const int16_t* pcm, long long n_clips,
+                               long long samples_per_clip, float* scores, float* emb_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  return pipeline_forward_any(vggish, mla, pcm, true, n_clips, samples_per_clip, scores, emb_out, workspace,
+                              workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace {
+int submit_host_any(vmb_vggish_t* vggish, vmb_mla_t* mla, const void* wave_host, bool pcm16, long long n_clips,
+                    long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream) {
+  const size_t esz = pcm16 ? 2 : 4;
   if (!vggish || !mla) return -fail("vmb_pipeline_submit_host: null handle");
   if (n_clips <= 0 || clips_per_batch <= 0) return -fail("vmb_pipeline_submit_host: bad sizes");
   if (!wave_host || !scores_host) return -fail("vmb_pipeline_submit_host: null pointer");
@@ -282,7 +310,7 @@ int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* 
   HostStage& hs = vggish->stage;
   const int slot = static_cast<int>(hs.calls & 1);
   if (hs.busy[slot]) return -fail("vmb_pipeline_submit_host: two calls are already in flight; wait for the oldest first");
-  const size_t wave_bytes = size_t(clips_per_batch) * samples_per_clip * 4;
+  const size_t wave_bytes = size_t(clips_per_batch) * samples_per_clip * 4;   // sized for fp32 either way
   const size_t ws_bytes = vmb_pipeline_workspace_bytes(clips_per_batch, samples_per_clip);
   const size_t score_bytes = size_t(n_clips) * n_classes * 4;
   bool ok = true;
@@ -303,8 +331,8 @@ int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* 
     ok = cudaMalloc(p, need) == cudaSuccess;
     if (ok) *cap = need;
   };
-  grow(reinterpret_cast<void**>(&hs.d_wave[0]), &hs.wave_cap[0], wave_bytes);
-  grow(reinterpret_cast<void**>(&hs.d_wave[1]), &hs.wave_cap[1], wave_bytes);
+  grow(&hs.d_wave[0], &hs.wave_cap[0], wave_bytes);
+  grow(&hs.d_wave[1], &hs.wave_cap[1], wave_bytes);
   grow(&hs.d_ws, &hs.ws_cap, ws_bytes);
   grow(reinterpret_cast<void**>(&hs.d_scores[slot]), &hs.scores_cap[slot], score_bytes);
   if (!ok) return -fail("vmb_pipeline_submit_host: staging allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -315,14 +343,14 @@ int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* 
     const long long nc = n_clips - c0 < clips_per_batch ? n_clips - c0 : clips_per_batch;
     // the buffer is free once the compute that read it two micro-batches ago has finished
     if (hs.batches >= 2) cudaStreamWaitEvent(hs.copy_st, hs.wave_free[s], 0);
-    if (cudaMemcpyAsync(hs.d_wave[s], wave_host + c0 * samples_per_clip, size_t(nc) * samples_per_clip * 4,
-                        cudaMemcpyHostToDevice, hs.copy_st) != cudaSuccess) {
+    if (cudaMemcpyAsync(hs.d_wave[s], static_cast<const char*>(wave_host) + size_t(c0) * samples_per_clip * esz,
+                        size_t(nc) * samples_per_clip * esz, cudaMemcpyHostToDevice, hs.copy_st) != cudaSuccess) {
       rc = fail("vmb_pipeline_submit_host: H2D copy failed (%s)", cudaGetErrorString(cudaGetLastError()));
       break;
     }
     cudaEventRecord(hs.wave_ready[s], hs.copy_st);
     cudaStreamWaitEvent(st, hs.wave_ready[s], 0);
-    rc = vmb_pipeline_forward(vggish, mla, hs.d_wave[s], nc, samples_per_clip, hs.d_scores[slot] + c0 * n_classes,
+    rc = pipeline_forward_any(vggish, mla, hs.d_wave[s], pcm16, nc, samples_per_clip, hs.d_scores[slot] + c0 * n_classes,
                               nullptr, hs.d_ws, hs.ws_cap, stream);
     cudaEventRecord(hs.wave_free[s], st);
   }
@@ -337,6 +365,20 @@ int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* 
   hs.busy[slot] = true;
   ++hs.calls;
   return slot;
+}
+}  // namespace
+
+extern "C" {
+
+int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
+                             long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream) {
+  return submit_host_any(vggish, mla, wave_host, false, n_clips, samples_per_clip, scores_host, clips_per_batch, stream);
+}
+
+int vmb_pipeline_submit_host_pcm16(vmb_vggish_t* vggish, vmb_mla_t* mla, const int16_t* pcm_host, long long n_clips,
+                                   long long samples_per_clip, float* scores_host, long long clips_per_batch,
+                                   void* stream) {
+  return submit_host_any(vggish, mla, pcm_host, true, n_clips, samples_per_clip, scores_host, clips_per_batch, stream);
 }
 
 int vmb_pipeline_wait_host(vmb_vggish_t* vggish, int ticket) {

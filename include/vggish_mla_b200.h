@@ -202,6 +202,10 @@ size_t vmb_pipeline_workspace_bytes(long long n_clips, long long samples_per_cli
 int vmb_pipeline_forward(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_dev, long long n_clips,
                          long long samples_per_clip, float* scores_dev, float* emb_dev_or_null,
                          void* workspace_dev, size_t workspace_bytes, void* stream);
+/* The same fed with 16-bit PCM (pcm / 32768 on the device, exact; see vmb_logmel_pcm16): half the input bytes. */
+int vmb_pipeline_forward_pcm16(vmb_vggish_t* vggish, vmb_mla_t* mla, const int16_t* pcm_dev, long long n_clips,
+                               long long samples_per_clip, float* scores_dev, float* emb_dev_or_null,
+                               void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Host-buffer variant (the end-to-end number of bench.py): wave_host / scores_host are HOST pointers
  * (pinned for full speed); the call copies H2D, runs the path on `stream` in micro-batches of
  * `clips_per_batch` (the copy of micro-batch i+1 overlaps the compute of micro-batch i), copies the scores D2H
@@ -215,6 +219,9 @@ int vmb_pipeline_forward_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float*
  * wave_host must stay valid until wait returns.  Tickets must be waited in submission order.                 */
 int vmb_pipeline_submit_host(vmb_vggish_t* vggish, vmb_mla_t* mla, const float* wave_host, long long n_clips,
                              long long samples_per_clip, float* scores_host, long long clips_per_batch, void* stream);
+int vmb_pipeline_submit_host_pcm16(vmb_vggish_t* vggish, vmb_mla_t* mla, const int16_t* pcm_host, long long n_clips,
+                                   long long samples_per_clip, float* scores_host, long long clips_per_batch,
+                                   void* stream);
 int vmb_pipeline_wait_host(vmb_vggish_t* vggish, int ticket);
 
 #ifdef __cplusplus

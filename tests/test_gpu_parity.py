@@ -573,3 +573,14 @@ def test_reference_eval_loop_and_checkpoint_roundtrip(tmp_path, vgg_sd):
     print(f"eval loop: argmax agreement with the oracle {agree:.3f}, mean loss {loss_sum / 12:.4f}")
     assert agree >= 11 / 12
     assert abs(loss_sum / 12 - criterion(want, labels).item()) < 5e-3
+
+
+def test_pcm16_host_pipeline(vgg_handle, head_handle):
+    """int16 PCM host buffers through submit/wait == the float pipeline on pcm / 32768 (bit-identical)."""
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    w = torch.from_numpy(synth.make_clips(60, 3))
+    pcm = torch.clamp(torch.round(w * 32768.0), -32768, 32767).to(torch.int16).pin_memory()
+    out = torch.empty(3, 527).pin_memory()
+    pipe.wait_host(pipe.submit_host(pcm, out, clips_per_batch=2))
+    want = pipe.forward((pcm.float() / 32768.0).to(DEV)).cpu()
+    assert torch.equal(out, want)
