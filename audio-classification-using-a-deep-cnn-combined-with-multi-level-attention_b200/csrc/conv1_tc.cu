@@ -11,9 +11,9 @@
 // splits — K = 29 of 32 slots — and the bias is added in the fp32 accumulator).  Output: bf16, or hi | lo planes for
 // the accuracy mode of the body.  In the epilogue thread = pooled pixel = TMEM lane: the max over the
 // four column blocks is the max-pool (no shuffles), then ReLU, bf16, one 128-byte store per thread.
-// Warp-specialised and persistent (one CTA per SM): warps 0-3 build tiles (the next tile's input patch is already in
-// flight in registers), warp 4 issues the MMAs, warps 5-8 run the epilogue; the A tiles and the TMEM accumulators are
-// two-deep rings, so tile i+1 is being built while tile i is multiplied and tile i-1 is written out.
+// Warp-specialised and persistent (one CTA per SM): two producer groups of four warps build alternate tiles (each
+// thread reads its 4x4 input window straight from global / L1, one tile ahead), warp 8 issues the MMAs, warps 9-12
+// run the epilogue; the A tiles and the TMEM accumulators are two-deep rings.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -38,10 +38,11 @@ constexpr int kLbo = 128;                        // bytes between the 16-byte K 
 constexpr int kSbo = 512;                        // bytes between 8-row groups (4 chunks x 128 B)
 constexpr int kATile = 128 / 8 * kSbo;           // 8192 bytes per window position
 constexpr int kBTile = kC / 8 * kSbo;            // 4096
-constexpr int kProducerThreads = 128;            // warps 0-3 build the im2col tiles
-constexpr int kMmaWarp = 4;                      // warp 4 issues the MMAs
-constexpr int kThreads = 288;                    // warps 5-8: epilogue
-constexpr int kStages = 2;                       // A-tile ring and TMEM accumulator ring
+constexpr int kProducerThreads = 128;            // per producer group
+constexpr int kProducerGroups = 2;               // warps 0-3 and 4-7: group g builds the tiles with (iteration & 1) == g
+constexpr int kMmaWarp = 8;                      // warp 8 issues the MMAs
+constexpr int kThreads = 416;                    // warps 9-12: epilogue
+constexpr int kStages = 2;                       // A-tile ring (one stage per producer group) and TMEM accumulator ring
 constexpr int kTmemCols = 512;                   // 2 buffers x 4 positions x 64 channels
 constexpr int kSmemBytes = 1024 + kStages * 4 * kATile + kBTile;
 
@@ -57,21 +58,22 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_add
 
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
-constexpr int kPatchElems = kPatchH * kPatchW;                               // 660
-constexpr int kPatchPerThread = (kPatchElems + kProducerThreads - 1) / kProducerThreads;  // 6
-
-// Global loads of one tile's input patch (with zero halo) into registers: issued one tile ahead of their use.
-__device__ __forceinline__ void load_patch(const float* __restrict__ x, long long tile, int tid, float (&v)[kPatchPerThread]) {
+// The 4x4 input window of one pooled pixel (rows 2*prow-1 .. 2*prow+2, columns 2*pcol-1 .. 2*pcol+2), zero outside the
+// image: read straight from global / L1 (neighbouring threads overlap), issued one tile ahead of its use.
+__device__ __forceinline__ void load_window(const float* __restrict__ x, long long tile, int pr, int pc, float (&v)[16]) {
   const long long n = tile / kTilesPerExample;
   const int tr = static_cast<int>(tile - n * kTilesPerExample);
-  const int row0 = 2 * kRowsPerTile * tr - 1;
+  const int r0 = 2 * (tr * kRowsPerTile + pr) - 1, c0 = 2 * pc - 1;
   const float* src = x + n * (kH * kW);
 #pragma unroll
-  for (int u = 0; u < kPatchPerThread; ++u) {
-    const int i = tid + u * kProducerThreads;
-    const int r = i / kPatchW, c = i - r * kPatchW;
-    const int gr = row0 + r, gc = c - 1;
-    v[u] = (i < kPatchElems && gr >= 0 && gr < kH && gc >= 0 && gc < kW) ? __ldg(src + gr * kW + gc) : 0.f;
+  for (int i = 0; i < 4; ++i) {
+    const int gr = r0 + i;
+    const bool rok = gr >= 0 && gr < kH;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = c0 + j;
+      v[4 * i + j] = (rok && gc >= 0 && gc < kW) ? __ldg(src + gr * kW + gc) : 0.f;
+    }
   }
 }
 
@@ -83,12 +85,11 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;                                   // [kStages][4 positions][kATile]
   uint8_t* b_smem = smem + kStages * 4 * kATile;
-  __shared__ float patch[kPatchH][kPatchPitch];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[kStages], tmem_empty[kStages];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- one-time setup: B tile, constant chunk of the A tiles, barriers, TMEM
+  // ---- one-time setup: B tile, barriers, TMEM
   if (tid < kC) {
     uint32_t k[32];
 #pragma unroll
@@ -128,34 +129,30 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ producers: patch -> four im2col tiles
-    const uint32_t one = 0x3F80u;   // bf16 1.0
-    const int pr = tid >> 5, pc = tid & 31;   // pooled row within the tile, pooled column
-    float pre[kPatchPerThread];
-    if (blockIdx.x < n_tiles) load_patch(x, blockIdx.x, tid, pre);
-    uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t stage = it & 1, ph = (it >> 1) & 1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's patch reads are done
-#pragma unroll
-      for (int u = 0; u < kPatchPerThread; ++u) {
-        const int i = tid + u * kProducerThreads;
-        if (i < kPatchElems) patch[i / kPatchW][i % kPatchW] = pre[u];
-      }
-      if (tile + gridDim.x < n_tiles) load_patch(x, tile + gridDim.x, tid, pre);   // in flight during the build
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (warp < 4 * kProducerGroups) {
+    // ------------------------------------------------------------------ producers: 4x4 window -> four im2col rows
+    const int group = warp >> 2;                     // owns A stage `group`
+    const int row = tid & (kProducerThreads - 1);    // pooled pixel within the tile = A row = TMEM lane
+    const int pr = row >> 5, pc = row & 31;
+    const long long stride = static_cast<long long>(gridDim.x) * kProducerGroups;
+    long long tile = blockIdx.x + static_cast<long long>(group) * gridDim.x;
+    float win[16];
+    if (tile < n_tiles) load_window(x, tile, pr, pc, win);
+    uint32_t use = 0;
+    for (; tile < n_tiles; tile += stride, ++use) {
+      // hi / lo halves of the window, packed two per register: pair (i, jp) = columns 2jp, 2jp+1 of window row i
       uint32_t hi[4][4], lo[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v = patch[2 * pr + i][2 * pc + j];
+          const float v = win[4 * i + j];
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
           hi[i][j] = __bfloat16_as_ushort(h);
           lo[i][j] = bf16_bits(v - __bfloat162float(h));
         }
-      mbar_wait(&empty_bar[stage], ph ^ 1);               // the MMAs that read this stage two tiles ago are done
+      if (tile + stride < n_tiles) load_window(x, tile + stride, pr, pc, win);   // in flight during the stores
+      mbar_wait(&empty_bar[group], (use & 1) ^ 1);         // the MMAs that read this stage last time are done
 #pragma unroll
       for (int pos = 0; pos < 4; ++pos) {
         const int dy = pos >> 1, dx = pos & 1;
@@ -168,16 +165,16 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
             k[9 + ky * 3 + kx] = lo[dy + ky][dx + kx];
             k[18 + ky * 3 + kx] = hi[dy + ky][dx + kx];
           }
-        k[27] = one; k[28] = one; k[29] = 0; k[30] = 0; k[31] = 0;
-        uint8_t* row = a_smem + (stage * 4 + pos) * kATile + (tid / 8) * kSbo + (tid % 8) * 16;
+        k[27] = 0x3F80u; k[28] = 0x3F80u; k[29] = 0; k[30] = 0; k[31] = 0;    // bf16 1.0 twice: b_hi + b_lo
+        uint8_t* dst = a_smem + (group * 4 + pos) * kATile + (row / 8) * kSbo + (row % 8) * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(row + j * kLbo) =
+          *reinterpret_cast<uint4*>(dst + j * kLbo) =
               make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
                          k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
       }
       fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[stage]);
+      mbar_arrive(&full_bar[group]);
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
@@ -220,17 +217,17 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       mbar_wait(&tmem_full[stage], ph);
       tc_fence_after_sync();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * 256;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t v0[32], v1[32], v2[32], v3[32];
-        tmem_ld_32x32(t_lane + 0 * kC + ch * 32, v0);
-        tmem_ld_32x32(t_lane + 1 * kC + ch * 32, v1);
-        tmem_ld_32x32(t_lane + 2 * kC + ch * 32, v2);
-        tmem_ld_32x32(t_lane + 3 * kC + ch * 32, v3);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {            // 16 channels at a time keeps the register count low
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld_32x16(t_lane + 0 * kC + ch * 16, v0);
+        tmem_ld_32x16(t_lane + 1 * kC + ch * 16, v1);
+        tmem_ld_32x16(t_lane + 2 * kC + ch * 16, v2);
+        tmem_ld_32x16(t_lane + 3 * kC + ch * 16, v3);
         tmem_ld_wait();
-        uint32_t pk[16], pl[16];
+        uint32_t pk[8], pl[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float a = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j]), __uint_as_float(v1[2 * j])),
                                       fmaxf(__uint_as_float(v2[2 * j]), __uint_as_float(v3[2 * j]))), 0.f);
           const float c = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v1[2 * j + 1])),
@@ -239,13 +236,13 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
           if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 16);
+        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         if (SPLIT_OUT) {
-          uint4* l4 = reinterpret_cast<uint4*>(dst + kPlane + ch * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) l4[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+          uint4* l4 = reinterpret_cast<uint4*>(dst + kPlane + ch * 16);
+          l4[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          l4[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
       }
       tc_fence_before_sync();

@@ -83,11 +83,16 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+        // split-K is the rare case: keep the divisions out of the ordinary tile loop
+        int mn = tile, kb0 = 0, kb1 = p.num_kb;
+        if (ksplit > 1) {
+          const int ks = tile / mn_tiles;
+          mn = tile - ks * mn_tiles;
+          kb0 = p.num_kb * ks / ksplit;
+          kb1 = p.num_kb * (ks + 1) / ksplit;
+        }
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
-        const int kb0 = static_cast<int>(static_cast<long long>(p.num_kb) * ks / ksplit);
-        const int kb1 = static_cast<int>(static_cast<long long>(p.num_kb) * (ks + 1) / ksplit);
         int bx[4 * MT], by[4 * MT], bn[4 * MT];
         if (CONV) {
 #pragma unroll
@@ -161,9 +166,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int ks = tile / mn_tiles;
-      const int kb0 = static_cast<int>(static_cast<long long>(p.num_kb) * ks / ksplit);
-      const int kb1 = static_cast<int>(static_cast<long long>(p.num_kb) * (ks + 1) / ksplit);
+      int kb0 = 0, kb1 = p.num_kb;
+      if (ksplit > 1) {
+        const int ks = tile / mn_tiles;
+        kb0 = p.num_kb * ks / ksplit;
+        kb1 = p.num_kb * (ks + 1) / ksplit;
+      }
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
@@ -193,7 +201,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int ep_tid = threadIdx.x - 64;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int ks = tile / mn_tiles, mn = tile - ks * mn_tiles;
+      int mn = tile, ks = 0;
+      if (ksplit > 1) {
+        ks = tile / mn_tiles;
+        mn = tile - ks * mn_tiles;
+      }
       const int m_tile = mn / p.num_n_tiles;
       const int n_tile = mn - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BLOCK_N;
