@@ -134,11 +134,16 @@ def test_data_parallel_semantics_two_shards():
         ref = (ref_avg[key] / world).numpy()
         assert np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max() + 5e-7, key
         want = train_torch.adam_update(sd[key], ref_avg[key] / world)
-        # Adam normalises each element by its own magnitude: where the gradient is rounding noise the step is +-lr
-        # whatever the sign of the noise, so compare the update only where the gradient is resolved
-        big = (ref_avg[key] / world).abs() > 1e-5
-        if big.any():
-            assert (trs[0].view(trs[0].params, key).cpu() - want)[big].abs().max() < 2e-5, key
+        # Adam normalises each element by its own magnitude: where the gradient is rounding noise — or sits in the
+        # weight row of a unit whose ReLU flipped (see above) — the step is +-lr whatever the sign, so the update is
+        # compared where the gradient is resolved, and the unresolved elements must stay rare
+        g_ref = ref_avg[key] / world
+        g_got = trs[0].view(bucket, key).cpu() / world
+        ok = (g_ref.abs() > 1e-5) & ((g_got - g_ref).abs() < 0.05 * g_ref.abs())
+        if ok.any():
+            assert (trs[0].view(trs[0].params, key).cpu() - want)[ok].abs().max() < 2e-5, key
+        flipped = (g_ref.abs() > 1e-5) & ~ok
+        assert flipped.float().mean() < 0.01, key
     assert torch.equal(trs[0].params, trs[1].params)                       # replicas stay bit-identical
     for tr in trs:
         tr.close()
