@@ -18,7 +18,7 @@
 // * Epilogue: one thread owns one frame (TMEM lane); it walks the bins in order and, because every bin feeds at
 //   most the two adjacent mel bands, keeps just two running band sums, emitting log(band + 0.01) as bands complete.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.  Persistent over 128-frame
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 epilogue of N-tile 0 / 1.  Persistent over 128-frame
 // tiles; the two N-tiles of a frame tile use the two halves of TMEM so the epilogue of one overlaps the MMAs of the
 // next.  Smem: 3 stages x {A0,A1,A2 (128x32), B0,B1,B2 (240x32)} bf16, 64-byte swizzle = 207 KB.
 #include <cuda.h>
@@ -51,8 +51,9 @@ constexpr int kATile = kTM * kBK * 2;   // 8192
 constexpr int kBTile = kTN * kBK * 2;   // 15360
 constexpr int kStageBytes = 3 * (kATile + kBTile);  // 70656
 constexpr int kStages = 3;
-constexpr int kThreads = 192;
-constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+constexpr int kThreads = 320;          // producer, MMA issuer, 2 x 4 epilogue warps
+constexpr int kHandFloats = 6;          // per-row walk state handed from the N-tile-0 epilogue to the N-tile-1 one
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 512 + 2 * kTM * kHandFloats * 4;
 constexpr int kTmemCols = 512;          // accumulator t lives at column 256 t
 constexpr double kPi = 3.14159265358979323846;
 constexpr float kLogOffset = 0.01f;
@@ -152,7 +153,8 @@ __device__ __forceinline__ void walk_bins(BandWalk& w, const uint32_t* v, int bi
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
-    const float mag = sqrtf(fmaf(re, re, im * im));
+    float mag;   // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));
     const int e = c_band[bin0 + j];
     while (w.e < e) emit_band(w, row_out, valid);      // warp-uniform: depends on the bin index only
     w.lo = fmaf(c_wfall[bin0 + j], mag, w.lo);
@@ -169,7 +171,10 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* hand_full = tmem_empty + 2;       // [2 buffers][4 lane quarters]
+  uint64_t* hand_empty = hand_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hand_empty + 8);
+  float* hand = reinterpret_cast<float*>(smem + kStages * kStageBytes + 512);   // [2][kTM][kHandFloats]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,6 +189,10 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&hand_full[s], 1);
+      mbar_init(&hand_empty[s], 1);
     }
     mbar_fence_init();
   }
@@ -255,39 +264,61 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue
+    // Two sets of four warps: set 0 (warps 2-5) walks the bins of N-tile 0, set 1 (warps 6-9) those of N-tile 1, so
+    // the two halves of a frame tile are post-processed concurrently.  The band walk is sequential over the bins, so
+    // warp q of set 0 hands its per-row state (two running band sums + the partly filled group of four outputs) to
+    // warp q of set 1 through shared memory; the arithmetic and its order are exactly those of a single walk.
+    const int set = (warp - 2) >> 2;
     const int q = warp & 3;
-    uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int row = q * 32 + lane;
+    uint32_t mi = 0;   // frame-tile iteration of this CTA
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++mi) {
       const long long clip = tile / p.tiles_per_clip;
-      const long long frame = (tile - clip * p.tiles_per_clip) * kTM + q * 32 + lane;
+      const long long frame = (tile - clip * p.tiles_per_clip) * kTM + row;
       const bool valid = frame < p.frames_out;
       float* row_out = p.out + (clip * p.frames_out + (valid ? frame : 0)) * kMel;
+      const uint32_t hb = mi & 1, hphase = (mi >> 1) & 1;
+      float* hrow = hand + (hb * kTM + row) * kHandFloats;
       BandWalk w;
       w.pend = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int nt = 0; nt < kNTiles; ++nt, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after_sync();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-#pragma unroll 1
-        for (int ch = 0; ch < kTN / 32; ++ch) {     // 7 chunks of 32 columns = 16 bins
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + ch * 32, v);
-          tmem_ld_wait();
-          walk_bins<16>(w, v, nt * kTileBins + ch * 16, row_out, valid);
-        }
-        {                                            // last 16 columns = 8 bins
-          uint32_t v[16];
-          tmem_ld_32x16(t_addr + (kTN / 32) * 32, v);
-          tmem_ld_wait();
-          walk_bins<8>(w, v, nt * kTileBins + (kTN / 32) * 16, row_out, valid);
-        }
-        tc_fence_before_sync();
+      if (set == 1) {
+        mbar_wait(&hand_full[hb * 4 + q], hphase);
+        w.e = c_band[kTileBins - 1];            // where the walk over bins 0..119 stops (uniform)
+        w.lo = hrow[0]; w.hi = hrow[1];
+        w.pend = make_float4(hrow[2], hrow[3], hrow[4], 0.f);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
       }
-      while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+      const uint32_t acc = set, acc_phase = mi & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int ch = 0; ch < kTN / 32; ++ch) {     // 7 chunks of 32 columns = 16 bins
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + ch * 32, v);
+        tmem_ld_wait();
+        walk_bins<16>(w, v, set * kTileBins + ch * 16, row_out, valid);
+      }
+      {                                            // last 16 columns = 8 bins
+        uint32_t v[16];
+        tmem_ld_32x16(t_addr + (kTN / 32) * 32, v);
+        tmem_ld_wait();
+        walk_bins<8>(w, v, set * kTileBins + (kTN / 32) * 16, row_out, valid);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (set == 0) {
+        mbar_wait(&hand_empty[hb * 4 + q], hphase ^ 1);
+        hrow[0] = w.lo; hrow[1] = w.hi;
+        hrow[2] = w.pend.x; hrow[3] = w.pend.y; hrow[4] = w.pend.z;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hand_full[hb * 4 + q]);
+      } else {
+        while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+      }
     }
   }
 

@@ -13,6 +13,7 @@ for path in sys.argv[1:]:
     L.vmb_conv3x3_relu.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, ci, vp]
     L.vmb_linear.argtypes = [vp, vp, vp, vp, ci, ci, ll, ci, ci, vp]
     L.vmb_conv1_relu_pool.argtypes = [vp, vp, vp, vp, ll, vp]
+    L.vmb_logmel.argtypes = [vp, ll, ll, ll, ll, vp, vp]
     libs.append((path.split("/")[-1], L))
 n = 2560
 st = lambda: torch.cuda.current_stream().cuda_stream
@@ -37,6 +38,10 @@ ex = torch.randn(n, 96, 64, device=dev)
 w1, b1 = torch.randn(64, 9, device=dev), torch.randn(64, device=dev)
 o1 = torch.empty(n, 48, 32, 64, device=dev, dtype=torch.bfloat16)
 cases.append(("conv1", 2.0 * n * 96 * 64 * 64 * 9, lambda L: L.vmb_conv1_relu_pool(ex.data_ptr(), w1.data_ptr(), b1.data_ptr(), o1.data_ptr(), n, st())))
+wave = (torch.rand(256, 160000, device=dev) * 2 - 1)
+lm = torch.empty(256, 960, 64, device=dev)
+cases.append(("logmel 256 clips", 256 * (2.0 * 400 * 514 + 2.0 * 257 * 64) * 998,
+              lambda L: L.vmb_logmel(wave.data_ptr(), 256, 160000, 160000, 960, lm.data_ptr(), st())))
 for name, fl, fn in cases:
     res = {nm: [] for nm, _ in libs}
     for rep in range(4):                       # interleave the builds
