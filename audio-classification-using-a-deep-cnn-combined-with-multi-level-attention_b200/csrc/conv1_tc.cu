@@ -1,16 +1,17 @@
 // VGGish first layer on the tensor cores: Conv2d(1, 64, 3, padding=1) + ReLU + MaxPool2d(2, 2)
 // (reference torchvggish/vggish.py:108-118, features.0/1/2): examples fp32 [n][96][64] -> NHWC bf16 [n][48][32][64].
 //
-// With C_in = 1 the GEMM K is only 9, so the tile is built by hand instead of by TMA: one CTA tile = 128 POOLED
-// pixels (4 pooled rows x 32 columns of one example).  For each of the four positions of the 2x2 pooling window the
-// 128 threads write one im2col row each into shared memory,
-//     A_pos[pixel] = [ x_hi(9 taps) | x_lo(9 taps) | x_hi(9 taps) | 1 | 1 | 0 0 0 ]   (32 bf16, K-major, no-swizzle
-//     B[channel]   = [ w_hi(9 taps) | w_hi(9 taps) | w_lo(9 taps) | b_hi | b_lo | 0 0 0 ]    core-matrix layout)
-// so one elected thread issues 4 x 2 tcgen05.mma (M = 128, N = 64, K = 16) and TMEM column block `pos` receives
-// conv + bias of that window position for all 64 channels (input AND weights keep 16 mantissa bits through the hi/lo
-// splits — K = 29 of 32 slots — and the bias is added in the fp32 accumulator).  Output: bf16, or hi | lo planes for
-// the accuracy mode of the body.  In the epilogue thread = pooled pixel = TMEM lane: the max over the
-// four column blocks is the max-pool (no shuffles), then ReLU, bf16, one 128-byte store per thread.
+// With C_in = 1 the GEMM K is only 9, so the operand tiles are built by hand instead of by TMA.  One CTA tile = 128
+// POOLED pixels (4 pooled rows x 32 columns of one example).  Each producer thread writes ONE row: the 4x4 input
+// window of its pooled pixel, split into bf16 hi / lo halves,
+//     A[pixel]      = [ win_hi(16) | win_lo(16) | win_hi(16) | 1 | 1 | 0 ... ]          (64 bf16, K-major, no-swizzle
+// and the 3x3 kernel is scattered, once per CTA, into four weight tiles — one per position (dy, dx) of the 2x2    core-matrix
+// pooling window —                                                                                               layout)
+//     B_pos[ch][..] = w_hi at slots (dy+ky)*4 + dx+kx of the first two blocks, w_lo in the third, then b_hi, b_lo,
+// so 4 x 4 tcgen05.mma (M = 128, N = 64, K = 16) leave conv + bias of window position `pos` for all 64 channels in
+// TMEM column block `pos` (input AND weights keep 16 mantissa bits through the hi/lo splits; the bias is added in the
+// fp32 accumulator).  In the epilogue thread = pooled pixel = TMEM lane: the max over the four column blocks is the
+// max-pool (no shuffles), then ReLU, bf16 (or hi | lo planes for the accuracy mode), one 128-byte store per thread.
 // Warp-specialised and persistent (one CTA per SM): two producer groups of four warps build alternate tiles (each
 // thread reads its 4x4 input window straight from global / L1, one tile ahead), warp 8 issues the MMAs, warps 9-12
 // run the epilogue; the A tiles and the TMEM accumulators are two-deep rings.
@@ -34,17 +35,18 @@ constexpr int kTilesPerExample = kPH / kRowsPerTile;  // 12
 constexpr int kPatchH = 2 * kRowsPerTile + 2;    // 10 input rows incl. halo
 constexpr int kPatchW = kW + 2;                  // 66
 constexpr int kPatchPitch = 68;
+constexpr int kK = 64;                           // GEMM K: [win_hi(16) | win_lo(16) | win_hi(16) | 1 | 1 | 0 ...]
 constexpr int kLbo = 128;                        // bytes between the 16-byte K chunks of one 8-row group
-constexpr int kSbo = 512;                        // bytes between 8-row groups (4 chunks x 128 B)
-constexpr int kATile = 128 / 8 * kSbo;           // 8192 bytes per window position
-constexpr int kBTile = kC / 8 * kSbo;            // 4096
+constexpr int kSbo = kK / 8 * kLbo;              // 1024 bytes between 8-row groups (8 chunks x 128 B)
+constexpr int kATile = 128 / 8 * kSbo;           // 16 KiB: one im2col-free tile (the 4x4 windows of 128 pooled pixels)
+constexpr int kBTile = kC / 8 * kSbo;            // 8 KiB per pooling-window position
 constexpr int kProducerThreads = 128;            // per producer group
 constexpr int kProducerGroups = 2;               // warps 0-3 and 4-7: group g builds the tiles with (iteration & 1) == g
 constexpr int kMmaWarp = 8;                      // warp 8 issues the MMAs
 constexpr int kThreads = 416;                    // warps 9-12: epilogue
 constexpr int kStages = 2;                       // A-tile ring (one stage per producer group) and TMEM accumulator ring
 constexpr int kTmemCols = 512;                   // 2 buffers x 4 positions x 64 channels
-constexpr int kSmemBytes = 1024 + kStages * 4 * kATile + kBTile;
+constexpr int kSmemBytes = 1024 + kStages * kATile + 4 * kBTile;
 
 // K-major, no swizzle: element (row r, 16-byte chunk j) at (r / 8) * SBO + j * LBO + (r % 8) * 16
 __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr) {
@@ -83,35 +85,47 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                 __nv_bfloat16* __restrict__ out, long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_smem = smem;                                   // [kStages][4 positions][kATile]
-  uint8_t* b_smem = smem + kStages * 4 * kATile;
+  uint8_t* a_smem = smem;                                   // [kStages][kATile]
+  uint8_t* b_smem = smem + kStages * kATile;                // [4 positions][kBTile]
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[kStages], tmem_empty[kStages];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- one-time setup: B tile, barriers, TMEM
-  if (tid < kC) {
-    uint32_t k[32];
+  // ---- one-time setup: the four B tiles (one per pooling-window position), the constant chunks of A, barriers, TMEM
+  // B_pos[channel][k]: the 3x3 kernel scattered to the window slots (dy+ky, dx+kx) it touches for position (dy, dx):
+  // w_hi against win_hi, w_hi against win_lo, w_lo against win_hi, then b_hi, b_lo against the two ones.
+  if (tid < 4 * kC) {
+    const int pos = tid / kC, c = tid % kC, dy = pos >> 1, dx = pos & 1;
+    uint32_t k[kK];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) k[i] = 0;
+    for (int i = 0; i < kK; ++i) k[i] = 0;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float wv = __ldg(w + tid * 9 + t);
-      const __nv_bfloat16 wh = __float2bfloat16_rn(wv);
-      k[t] = __bfloat16_as_ushort(wh);          // pairs with x_hi
-      k[9 + t] = k[t];                          // pairs with x_lo
-      k[18 + t] = bf16_bits(wv - __bfloat162float(wh));   // w_lo pairs with x_hi
-    }
-    const float bias = __ldg(b + tid);
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float wv = __ldg(w + c * 9 + ky * 3 + kx);
+        const __nv_bfloat16 wh = __float2bfloat16_rn(wv);
+        const int slot = (dy + ky) * 4 + dx + kx;
+        k[slot] = __bfloat16_as_ushort(wh);
+        k[16 + slot] = k[slot];
+        k[32 + slot] = bf16_bits(wv - __bfloat162float(wh));
+      }
+    const float bias = __ldg(b + c);
     const __nv_bfloat16 bh = __float2bfloat16_rn(bias);
-    k[27] = __bfloat16_as_ushort(bh);
-    k[28] = bf16_bits(bias - __bfloat162float(bh));
-    uint8_t* row = b_smem + (tid / 8) * kSbo + (tid % 8) * 16;
+    k[48] = __bfloat16_as_ushort(bh);
+    k[49] = bf16_bits(bias - __bfloat162float(bh));
+    uint8_t* row = b_smem + pos * kBTile + (c / 8) * kSbo + (c % 8) * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < kK / 8; ++j)
       *reinterpret_cast<uint4*>(row + j * kLbo) =
           make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
                      k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
+  }
+  if (tid < kProducerThreads * kStages) {   // chunks 6 (1, 1, 0 ...) and 7 (zeros) of every A row never change
+    const int stg = tid / kProducerThreads, r = tid % kProducerThreads;
+    uint8_t* row = a_smem + stg * kATile + (r / 8) * kSbo + (r % 8) * 16;
+    *reinterpret_cast<uint4*>(row + 6 * kLbo) = make_uint4(0x3F803F80u, 0, 0, 0);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(row + 7 * kLbo) = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -140,39 +154,24 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     if (tile < n_tiles) load_window(x, tile, pr, pc, win);
     uint32_t use = 0;
     for (; tile < n_tiles; tile += stride, ++use) {
-      // hi / lo halves of the window, packed two per register: pair (i, jp) = columns 2jp, 2jp+1 of window row i
-      uint32_t hi[4][4], lo[4][4];
+      // hi / lo halves of the window, two per register in window order (the GEMM K order)
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v = win[4 * i + j];
-          const __nv_bfloat16 h = __float2bfloat16_rn(v);
-          hi[i][j] = __bfloat16_as_ushort(h);
-          lo[i][j] = bf16_bits(v - __bfloat162float(h));
-        }
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(win[2 * j], win[2 * j + 1]);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[j] = pack_bf16x2(win[2 * j] - __low2float(h2), win[2 * j + 1] - __high2float(h2));
+      }
       if (tile + stride < n_tiles) load_window(x, tile + stride, pr, pc, win);   // in flight during the stores
       mbar_wait(&empty_bar[group], (use & 1) ^ 1);         // the MMAs that read this stage last time are done
-#pragma unroll
-      for (int pos = 0; pos < 4; ++pos) {
-        const int dy = pos >> 1, dx = pos & 1;
-        uint32_t k[32];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            k[ky * 3 + kx] = hi[dy + ky][dx + kx];
-            k[9 + ky * 3 + kx] = lo[dy + ky][dx + kx];
-            k[18 + ky * 3 + kx] = hi[dy + ky][dx + kx];
-          }
-        k[27] = 0x3F80u; k[28] = 0x3F80u; k[29] = 0; k[30] = 0; k[31] = 0;    // bf16 1.0 twice: b_hi + b_lo
-        uint8_t* dst = a_smem + (group * 4 + pos) * kATile + (row / 8) * kSbo + (row % 8) * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(dst + j * kLbo) =
-              make_uint4(k[8 * j] | (k[8 * j + 1] << 16), k[8 * j + 2] | (k[8 * j + 3] << 16),
-                         k[8 * j + 4] | (k[8 * j + 5] << 16), k[8 * j + 6] | (k[8 * j + 7] << 16));
-      }
+      uint8_t* dst = a_smem + group * kATile + (row / 8) * kSbo + (row % 8) * 16;
+      const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(dst + 0 * kLbo) = h0;
+      *reinterpret_cast<uint4*>(dst + 1 * kLbo) = h1;
+      *reinterpret_cast<uint4*>(dst + 2 * kLbo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(dst + 3 * kLbo) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      *reinterpret_cast<uint4*>(dst + 4 * kLbo) = h0;
+      *reinterpret_cast<uint4*>(dst + 5 * kLbo) = h1;
       fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&full_bar[group]);
     }
@@ -186,12 +185,12 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       mbar_wait(&full_bar[stage], ph);
       tc_fence_after_sync();
       if (lane == 0) {
-        const uint64_t b_desc = umma_desc_kmajor_noswizzle(smem_u32(b_smem));
+        const uint64_t a_desc = umma_desc_kmajor_noswizzle(smem_u32(a_smem + stage * kATile));
 #pragma unroll
         for (int pos = 0; pos < 4; ++pos) {
-          const uint64_t a_desc = umma_desc_kmajor_noswizzle(smem_u32(a_smem + (stage * 4 + pos) * kATile));
+          const uint64_t b_desc = umma_desc_kmajor_noswizzle(smem_u32(b_smem + pos * kBTile));
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)   // K step 16 = two chunks = 2 * LBO = 256 bytes (>> 4 = 16)
+          for (int ks = 0; ks < kK / 16; ++ks)   // K step 16 = two chunks = 2 * LBO = 256 bytes (>> 4 = 16)
             umma_bf16_ss(tmem_base + stage * 256 + pos * kC, a_desc + ks * (2 * kLbo >> 4), b_desc + ks * (2 * kLbo >> 4),
                          idesc, ks);
         }
