@@ -646,6 +646,11 @@ int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const floa
   if (block_n == 256)
     return pool ? launch<256, 1, true, true, kOutSplit>(ta, tb, p, stream)
                 : launch<256, 1, true, false, kOutSplit>(ta, tb, p, stream);
+  if (p.num_m_tiles >= 4 * num_sms()) {   // C_out = 128: 256-row CTA tiles, as in igemm_conv3x3
+    p.num_m_tiles = (p.total_boxes + 7) / 8;
+    return pool ? launch<128, 2, true, true, kOutSplit>(ta, tb, p, stream)
+                : launch<128, 2, true, false, kOutSplit>(ta, tb, p, stream);
+  }
   return pool ? launch<128, 1, true, true, kOutSplit>(ta, tb, p, stream)
               : launch<128, 1, true, false, kOutSplit>(ta, tb, p, stream);
 }
