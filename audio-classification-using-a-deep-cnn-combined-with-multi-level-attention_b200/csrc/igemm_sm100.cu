@@ -36,7 +36,7 @@ struct Cfg {
 constexpr int kOutBf16 = 0, kOutF32 = 1, kOutSplit = 2, kOutF32Atomic = 3;   // epilogue output: bf16, fp32, hi | lo bf16
                                                                               // planes, or fp32 atomicAdd (split-K)
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
@@ -94,7 +94,19 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
         int bx[4 * MT], by[4 * MT], bn[4 * MT];
-        if (CONV) {
+        if (CONV && BIG) {
+          // one TMA box per 128-pixel sub-tile: Wb columns x 4*Hb rows (its four 32-pixel quarters stacked vertically)
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            const int g = m_tile * MT + sub;
+            const int n_img = g / p.boxes_per_img;
+            const int r = g - n_img * p.boxes_per_img;
+            const int yy = r / p.boxes_per_row;
+            bn[sub] = n_img;
+            by[sub] = yy * 4 * p.Hb;
+            bx[sub] = (r - yy * p.boxes_per_row) * p.Wb;
+          }
+        } else if (CONV) {
 #pragma unroll
           for (int q = 0; q < 4 * MT; ++q) {
             const int g = m_tile * 4 * MT + q;
@@ -129,10 +141,17 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           if (CONV) {
             const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            if (BIG) {
 #pragma unroll
-            for (int q = 0; q < 4 * MT; ++q)
-              tma_load_4d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[q] + dw,
-                          by[q] + dh, bn[q]);
+              for (int sub = 0; sub < MT; ++sub)
+                tma_load_4d(a_dst + sub * kABytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[sub] + dw,
+                            by[sub] + dh, bn[sub]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4 * MT; ++q)
+                tma_load_4d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[q] + dw,
+                            by[q] + dh, bn[q]);
+            }
             if (++cb == p.cblks) { cb = 0; ++tap; }
           } else {
             // split mode (p.split_nkb > 0): A and B are stored as column blocks of 2 (hi | lo) or 3 (hi | mid | lo)
@@ -224,12 +243,13 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       size_t out_off;  // element offset of column n0 for this thread's output row / pooled pixel
       int sub = 0;
       if (CONV) {
-        const int g = (m_tile * MT + mt) * 4 + q;
+        // quarter q of this sub-tile: its own 32-pixel box, or rows [q*Hb, (q+1)*Hb) of one 128-pixel box
+        const int g = BIG ? (m_tile * MT + mt) : (m_tile * MT + mt) * 4 + q;
         const int n_img = g / p.boxes_per_img;
         const int r = g - n_img * p.boxes_per_img;
         const int yy = r / p.boxes_per_row;
         const int hh = lane / p.Wb, ww = lane - hh * p.Wb;
-        const int h = yy * p.Hb + hh;
+        const int h = BIG ? yy * 4 * p.Hb + q * p.Hb + hh : yy * p.Hb + hh;
         const int w = (r - yy * p.boxes_per_row) * p.Wb + ww;
         valid = n_img < p.M;
         if (POOL) {
@@ -413,9 +433,9 @@ int num_sms() {
 
 namespace {
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT>;
+  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT, BIG>;
   static bool attr_set = false;
   constexpr int smem = Cfg<BLOCK_N, MT>::kSmemBytes;
   if (!attr_set) {
@@ -666,11 +686,14 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   }
   const int block_n = (C_out % 256 == 0) ? 256 : 128;
   const int K = 9 * C_in;
+  // when the image height allows it, one TMA box brings a whole 128-pixel sub-tile (Wb x 4*Hb pixels) instead of four
+  // 32-pixel quarters: the single producer thread issues 2-3 copies per K block instead of 5-9
+  const bool big = H % (4 * Hb) == 0;
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {uint64_t(C_in), uint64_t(W), uint64_t(H), uint64_t(n_img)};
     uint64_t str[3] = {uint64_t(C_in) * 2, uint64_t(W) * C_in * 2, uint64_t(H) * W * C_in * 2};
-    uint32_t box[4] = {kBlockK, uint32_t(Wb), uint32_t(Hb), 1};
+    uint32_t box[4] = {kBlockK, uint32_t(Wb), uint32_t(big ? 4 * Hb : Hb), 1};
     if (make_tmap_bf16(&ta, act, 4, dims, str, box)) return 1;
   }
   {
@@ -689,23 +712,37 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   p.Hb = Hb;
   p.Wb = Wb;
   p.boxes_per_row = W / Wb;
-  p.boxes_per_img = (H / Hb) * (W / Wb);
+  p.big_box = big ? 1 : 0;
+  // "box" = the unit the tile index counts: a 32-pixel quarter, or a whole 128-pixel sub-tile in big-box mode
+  p.boxes_per_img = big ? (H / (4 * Hb)) * (W / Wb) : (H / Hb) * (W / Wb);
   p.total_boxes = n_img * p.boxes_per_img;
-  p.num_m_tiles = (p.total_boxes + 3) / 4;
+  const int sub_tiles = big ? p.total_boxes : (p.total_boxes + 3) / 4;   // 128-pixel sub-tiles
+  p.num_m_tiles = sub_tiles;
   p.num_n_tiles = C_out / block_n;
   p.relu = 1;
   p.ldo = C_out;
   p.bias = bias;
   p.out = out;
   p.out_img_stride = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
-  if (block_n == 256)
-    return pool ? launch<256, 1, true, true, kOutBf16>(ta, tb, p, stream) : launch<256, 1, true, false, kOutBf16>(ta, tb, p, stream);
+  if (block_n == 256) {
+    if (big)
+      return pool ? launch<256, 1, true, true, kOutBf16, true>(ta, tb, p, stream)
+                  : launch<256, 1, true, false, kOutBf16, true>(ta, tb, p, stream);
+    return pool ? launch<256, 1, true, true, kOutBf16>(ta, tb, p, stream)
+                : launch<256, 1, true, false, kOutBf16>(ta, tb, p, stream);
+  }
   // C_out = 128: pair two 128-pixel sub-tiles per CTA tile when there are enough tiles to keep every SM busy
   if (p.num_m_tiles >= 4 * num_sms()) {
-    p.num_m_tiles = (p.total_boxes + 7) / 8;
+    p.num_m_tiles = (sub_tiles + 1) / 2;
+    if (big)
+      return pool ? launch<128, 2, true, true, kOutBf16, true>(ta, tb, p, stream)
+                  : launch<128, 2, true, false, kOutBf16, true>(ta, tb, p, stream);
     return pool ? launch<128, 2, true, true, kOutBf16>(ta, tb, p, stream)
                 : launch<128, 2, true, false, kOutBf16>(ta, tb, p, stream);
   }
+  if (big)
+    return pool ? launch<128, 1, true, true, kOutBf16, true>(ta, tb, p, stream)
+                : launch<128, 1, true, false, kOutBf16, true>(ta, tb, p, stream);
   return pool ? launch<128, 1, true, true, kOutBf16>(ta, tb, p, stream)
               : launch<128, 1, true, false, kOutBf16>(ta, tb, p, stream);
 }

@@ -27,7 +27,8 @@ struct IgemmParams {
   int num_kb;        // K / 64
   int cblks;         // CONV: C_in / 64
   int H, W;          // CONV: input (= conv output) spatial size
-  int Hb, Wb;        // CONV: box = Hb x Wb pixels, Hb*Wb == 32, both even
+  int Hb, Wb;        // CONV: quarter = Hb x Wb pixels, Hb*Wb == 32, both even
+  int big_box;       // CONV: one TMA box per 128-pixel sub-tile (Wb x 4*Hb) instead of four quarter boxes
   int boxes_per_row; // W / Wb
   int boxes_per_img; // (H / Hb) * (W / Wb)
   int total_boxes;   // M * boxes_per_img
