@@ -141,7 +141,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform by construction
 
   if (warp < 4 * kProducerGroups) {
     // ------------------------------------------------------------------ producers: 4x4 window -> four im2col rows
@@ -184,7 +184,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       mbar_wait(&tmem_empty[stage], ph ^ 1);
       mbar_wait(&full_bar[stage], ph);
       tc_fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t a_desc = umma_desc_kmajor_noswizzle(smem_u32(a_smem + stage * kATile));
 #pragma unroll
         for (int pos = 0; pos < 4; ++pos) {

@@ -76,11 +76,11 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         // split-K is the rare case: keep the divisions out of the ordinary tile loop
@@ -197,7 +197,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(stage_base + stage * C::kStageBytes);
           const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + MT * kABytes);
 #pragma unroll

@@ -200,11 +200,11 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int clip = static_cast<int>(tile / p.tiles_per_clip);
@@ -239,7 +239,7 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < kKB; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a0 = smem_u32(smem + stage * kStageBytes);
             const uint32_t b0 = a0 + 3 * kATile;
             // products (a plane, b plane), smallest magnitude first

@@ -17,6 +17,19 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of the (converged) warp, chosen by the hardware.  Unlike `lane == 0`, the compiler knows that exactly
+// one thread runs the guarded code, so warp-uniform operands of tcgen05 / TMA instructions stay in uniform registers
+// instead of going through a per-instruction ELECT / R2UR "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
