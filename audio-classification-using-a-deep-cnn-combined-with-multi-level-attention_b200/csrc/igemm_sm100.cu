@@ -2,6 +2,7 @@
 #include "igemm_sm100.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -303,27 +304,23 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
           if (POOL) {
-            uint4 oh, ol;
-            oh.x = sub == 0 ? hi[0] : sub == 1 ? hi[4] : sub == 2 ? hi[8] : hi[12];
-            oh.y = sub == 0 ? hi[1] : sub == 1 ? hi[5] : sub == 2 ? hi[9] : hi[13];
-            oh.z = sub == 0 ? hi[2] : sub == 1 ? hi[6] : sub == 2 ? hi[10] : hi[14];
-            oh.w = sub == 0 ? hi[3] : sub == 1 ? hi[7] : sub == 2 ? hi[11] : hi[15];
-            ol.x = sub == 0 ? lo[0] : sub == 1 ? lo[4] : sub == 2 ? lo[8] : lo[12];
-            ol.y = sub == 0 ? lo[1] : sub == 1 ? lo[5] : sub == 2 ? lo[9] : lo[13];
-            ol.z = sub == 0 ? lo[2] : sub == 1 ? lo[6] : sub == 2 ? lo[10] : lo[14];
-            ol.w = sub == 0 ? lo[3] : sub == 1 ? lo[7] : sub == 2 ? lo[11] : lo[15];
+            // the four lanes of a window share the 32 results: each stores one full 32-byte sector (hi: sub 0/1, lo: sub 2/3)
+            const bool up = sub & 1;
             if (valid) {
-              *reinterpret_cast<uint4*>(outp + sub * 8) = oh;
-              *reinterpret_cast<uint4*>(outp + p.lo_off + sub * 8) = ol;
+              if (!(sub & 2))
+                st_global_256(outp + (up ? 16 : 0), up ? hi[8] : hi[0], up ? hi[9] : hi[1], up ? hi[10] : hi[2],
+                              up ? hi[11] : hi[3], up ? hi[12] : hi[4], up ? hi[13] : hi[5], up ? hi[14] : hi[6],
+                              up ? hi[15] : hi[7]);
+              else
+                st_global_256(outp + p.lo_off + (up ? 16 : 0), up ? lo[8] : lo[0], up ? lo[9] : lo[1],
+                              up ? lo[10] : lo[2], up ? lo[11] : lo[3], up ? lo[12] : lo[4], up ? lo[13] : lo[5],
+                              up ? lo[14] : lo[6], up ? lo[15] : lo[7]);
             }
           } else if (valid) {
-            uint4* dh4 = reinterpret_cast<uint4*>(outp);
-            uint4* dl4 = reinterpret_cast<uint4*>(outp + p.lo_off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dh4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              dl4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
+            st_global_256(outp, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+            st_global_256(outp + 16, hi[8], hi[9], hi[10], hi[11], hi[12], hi[13], hi[14], hi[15]);
+            st_global_256(outp + p.lo_off, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
+            st_global_256(outp + p.lo_off + 16, lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]);
           }
         } else if (OUT == kOutF32Atomic) {
           if (valid) {
@@ -333,9 +330,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         } else if (OUT == kOutF32) {
           if (valid) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + ch * 32);
+            float* dst = static_cast<float*>(p.out) + out_off + ch * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 32; j += 8)
+              st_global_256(dst + j, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]),
+                            __float_as_uint(f[j + 3]), __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]),
+                            __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
           }
         } else {
           uint32_t pk[16];
@@ -350,16 +350,15 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], p.Wb));
             }
             // the four lanes of a window each store a different 8-channel (16 B) slice
-            uint4 o;
-            o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
-            o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
-            o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
-            o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
-            if (valid) *reinterpret_cast<uint4*>(outp + sub * 8) = o;
+            // two lanes of the window (sub 0, 1) each store one full 32-byte sector (16 channels)
+            const bool up = sub & 1;
+            if (valid && !(sub & 2))
+              st_global_256(outp + (up ? 16 : 0), up ? pk[8] : pk[0], up ? pk[9] : pk[1], up ? pk[10] : pk[2],
+                            up ? pk[11] : pk[3], up ? pk[12] : pk[4], up ? pk[13] : pk[5], up ? pk[14] : pk[6],
+                            up ? pk[15] : pk[7]);
           } else if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(outp);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            st_global_256(outp + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
           }
         }
       }
@@ -462,6 +461,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, c
 
 const char* igemm_last_error() { return g_err; }
 
+#ifndef VMB_PAIR_DEFAULT
+#define VMB_PAIR_DEFAULT 1
+#endif
+bool igemm_use_pair() {
+  static const bool on = [] {
+    const char* e = getenv("VMB_IGEMM_PAIR");
+    return e ? (e[0] != '0') : (VMB_PAIR_DEFAULT != 0);
+  }();
+  return on;
+}
+
+namespace {
+int pair_result(int rc) {
+  if (rc) snprintf(g_err, sizeof g_err, "%s", igemm_pair_last_error());
+  return rc ? 1 : 0;
+}
+}  // namespace
+
 int igemm_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, int M, int N,
                  int K, cudaStream_t stream) {
   if (M <= 0) return 0;
@@ -469,6 +486,8 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
     snprintf(g_err, sizeof g_err, "igemm_linear: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
     return 1;
   }
+  if (!out_f32 && N % 256 == 0 && M >= 256 && igemm_use_pair())
+    return pair_result(igemm_pair_linear(a, w, bias, out, relu, M, N, K, stream));
   const int block_n = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   {
@@ -684,6 +703,10 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
     snprintf(g_err, sizeof g_err, "igemm_conv3x3: unsupported geometry H=%d W=%d C_in=%d C_out=%d", H, W, C_in, C_out);
     return 1;
   }
+  // C_out = 128 (conv2) stays on the single-CTA 256 x 128 tiles: at N = 128 the MMA's operand fetch saturates shared
+  // memory either way and the pair kernel measured no faster
+  if (igemm_use_pair() && C_out % 256 == 0)
+    return pair_result(igemm_pair_conv3x3(act, w, bias, out, n_img, H, W, C_in, C_out, pool, stream));
   const int block_n = (C_out % 256 == 0) ? 256 : 128;
   const int K = 9 * C_in;
   // when the image height allows it, one TMA box brings a whole 128-pixel sub-tile (Wb x 4*Hb pixels) instead of four

@@ -74,6 +74,15 @@ int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const floa
 int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
                   int W, int C_in, int C_out, int pool, cudaStream_t stream);
 
+// CTA-pair (cta_group::2) kernels for the bf16 layers with C_out / N a multiple of 256 (igemm_pair_sm100.cu);
+// igemm_conv3x3 / igemm_linear route to them when igemm_use_pair() (env VMB_IGEMM_PAIR=0/1 overrides the default).
+int igemm_pair_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, int relu, int M, int N,
+                      int K, cudaStream_t stream);
+int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
+                       int W, int C_in, int C_out, int pool, cudaStream_t stream);
+const char* igemm_pair_last_error();
+bool igemm_use_pair();
+
 const char* igemm_last_error();
 
 // Shared host helpers (igemm_sm100.cu): bf16 tensor map with 128- or 64-byte swizzle (error text goes to
