@@ -43,7 +43,11 @@ constexpr int kBTile = kC / 8 * kSbo;            // 8 KiB per pooling-window pos
 constexpr int kProducerThreads = 128;            // per producer group
 constexpr int kProducerGroups = 2;               // warps 0-3 and 4-7: group g builds the tiles with (iteration & 1) == g
 constexpr int kMmaWarp = 8;                      // warp 8 issues the MMAs
-constexpr int kThreads = 416;                    // warps 9-12: epilogue
+#ifndef VMB_CONV1_EPI_WARPS
+#define VMB_CONV1_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = VMB_CONV1_EPI_WARPS;                     // warps 9-16: epilogue, two per TMEM lane quarter (read-out paced)
+constexpr int kThreads = (kMmaWarp + 1 + kEpiWarps) * 32;
 constexpr int kStages = 2;                       // A-tile ring (one stage per producer group) and TMEM accumulator ring
 constexpr int kTmemCols = 512;                   // 2 buffers x 4 positions x 64 channels
 constexpr int kSmemBytes = 1024 + kStages * kATile + 4 * kBTile;
@@ -132,7 +136,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       mbar_init(&full_bar[s], kProducerThreads);
       mbar_init(&empty_bar[s], 1);
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -202,6 +206,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   } else {
     // ------------------------------------------------------------------ epilogue: pool = max over 4 column blocks
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - kMmaWarp - 1) >> 2;  // the two warps of a quarter alternate over the 16-channel chunks
     const int row = q * 32 + lane;                // pooled pixel within the tile
     const int pr = row >> 5, pc = row & 31;
     uint32_t it = 0;
@@ -217,7 +222,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       tc_fence_after_sync();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * 256;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {            // 16 channels at a time keeps the register count low
+      for (int ch = half; ch < 4; ch += kEpiWarps / 4) {      // 16 channels at a time keeps the register count low
         uint32_t v0[16], v1[16], v2[16], v3[16];
         tmem_ld_32x16(t_lane + 0 * kC + ch * 16, v0);
         tmem_ld_32x16(t_lane + 1 * kC + ch * 16, v1);
@@ -235,14 +240,9 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
           if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 16);
-        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (SPLIT_OUT) {
-          uint4* l4 = reinterpret_cast<uint4*>(dst + kPlane + ch * 16);
-          l4[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          l4[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-        }
+        st_global_256(dst + ch * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);   // one full sector
+        if (SPLIT_OUT)
+          st_global_256(dst + kPlane + ch * 16, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
       }
       tc_fence_before_sync();
       __syncwarp();
