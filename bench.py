@@ -378,7 +378,9 @@ def run_b200(args, rank, local_rank, world):
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": igemm_traffic(),
-                     "kernel": "igemm_bf16_kernel (tcgen05 implicit GEMM: conv2..conv4_2, fc1..fc3)",
+                     "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if achieved else None,
+                     "kernel": "igemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM: conv3_1..conv4_2, fc1, fc2) + "
+                               "igemm_bf16_kernel (cta_group::1: conv2, fc3)",
                      "launches_per_step": ig_launches_per_step, "algorithmic_flop_per_launch":
                          ig_flop_per_step / max(1, ig_launches_per_step),
                      "avg_launch_ms": ig_ms_per_step / max(1, ig_launches_per_step), "peak_source": peaks["source"],
