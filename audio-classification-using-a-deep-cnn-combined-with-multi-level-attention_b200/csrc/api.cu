@@ -44,6 +44,8 @@ int vmb_device_arch(int device) {
   return major * 10 + minor;
 }
 
+int vmb_igemm_pair_enable(int on) { return vmb::igemm_set_pair(on); }
+
 long long vmb_num_frames(long long n_samples) {
   // mel_features.py:42  1 + int(floor((num_samples - window_length) / hop_length)), floor division
   const long long d = n_samples - 400;

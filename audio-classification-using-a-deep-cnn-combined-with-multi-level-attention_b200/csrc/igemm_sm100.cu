@@ -1,6 +1,7 @@
 // tcgen05 implicit-GEMM kernel + host launchers.  See igemm_sm100.cuh for the design notes.
 #include "igemm_sm100.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -380,6 +381,13 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ---------------------------------------------------------------------------------------- host side
 thread_local char g_err[512] = "";
 
+// the epilogues write one full 32-byte sector per lane (STG.256)
+bool misaligned32(const void* out, const char* who) {
+  if (reinterpret_cast<uintptr_t>(out) % 32 == 0) return false;
+  snprintf(g_err, sizeof g_err, "%s: the output buffer must be 32-byte aligned", who);
+  return true;
+}
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -464,12 +472,22 @@ const char* igemm_last_error() { return g_err; }
 #ifndef VMB_PAIR_DEFAULT
 #define VMB_PAIR_DEFAULT 1
 #endif
+namespace {
+std::atomic<int> g_pair_override{-1};   // -1: follow the environment / build default
+}
 bool igemm_use_pair() {
+  const int o = g_pair_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o != 0;
   static const bool on = [] {
     const char* e = getenv("VMB_IGEMM_PAIR");
     return e ? (e[0] != '0') : (VMB_PAIR_DEFAULT != 0);
   }();
   return on;
+}
+int igemm_set_pair(int on) {
+  const int prev = igemm_use_pair() ? 1 : 0;
+  g_pair_override.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
+  return prev;
 }
 
 namespace {
@@ -482,6 +500,7 @@ int pair_result(int rc) {
 int igemm_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, int M, int N,
                  int K, cudaStream_t stream) {
   if (M <= 0) return 0;
+  if (misaligned32(out, "igemm_linear")) return 1;
   if (K % kBlockK != 0 || N % 128 != 0) {
     snprintf(g_err, sizeof g_err, "igemm_linear: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
     return 1;
@@ -522,6 +541,11 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,
                        int relu, int M, int N, int K, cudaStream_t stream, int planes) {
   if (M <= 0) return 0;
+  if (misaligned32(out, "igemm_linear_split")) return 1;
+  if (ldo % 8 != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split: ldo must be a multiple of 8 floats (32-byte rows), got %lld", ldo);
+    return 1;
+  }
   if (planes != 2 && planes != 3) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split: planes must be 2 or 3");
     return 1;
@@ -563,6 +587,7 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
 int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float* out_zeroed, long long ldo, int M, int N,
                               int K, cudaStream_t stream, int planes) {
   if (M <= 0) return 0;
+  if (misaligned32(out_zeroed, "igemm_linear_split_ksplit")) return 1;
   if (K % kBlockK != 0 || N % 128 != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split_ksplit: need K %% 64 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d)", K, N);
     return 1;
@@ -603,6 +628,7 @@ int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float*
 int igemm_linear_split_out(const void* a_planes, const void* w_planes, const float* bias, void* out_planes, int relu,
                            int M, int N, int K, cudaStream_t stream) {
   if (M <= 0) return 0;
+  if (misaligned32(out_planes, "igemm_linear_split_out")) return 1;
   if (K % kBlockK != 0 || N % 256 != 0) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split_out: need K %% 64 == 0 and N %% 256 == 0 (got K=%d N=%d)", K, N);
     return 1;
@@ -639,6 +665,7 @@ int igemm_linear_split_out(const void* a_planes, const void* w_planes, const flo
 int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const float* bias, void* out_planes, int n_img,
                         int H, int W, int C_in, int C_out, int pool, cudaStream_t stream) {
   if (n_img <= 0) return 0;
+  if (misaligned32(out_planes, "igemm_conv3x3_split")) return 1;
   const int Wb = (W % 16 == 0) ? 16 : 8;
   const int Hb = 32 / Wb;
   if (C_in % kBlockK != 0 || C_out % 128 != 0 || W % Wb != 0 || H % Hb != 0) {
@@ -697,6 +724,7 @@ int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const floa
 int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
                   int C_out, int pool, cudaStream_t stream) {
   if (n_img <= 0) return 0;
+  if (misaligned32(out, "igemm_conv3x3")) return 1;
   const int Wb = (W % 16 == 0) ? 16 : 8;
   const int Hb = 32 / Wb;
   if (C_in % kBlockK != 0 || C_out % 128 != 0 || W % Wb != 0 || H % Hb != 0) {

@@ -82,6 +82,7 @@ int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bi
                        int W, int C_in, int C_out, int pool, cudaStream_t stream);
 const char* igemm_pair_last_error();
 bool igemm_use_pair();
+int igemm_set_pair(int on);   // 1 / 0 force the choice, -1 returns to the default; returns the previous setting
 
 const char* igemm_last_error();
 

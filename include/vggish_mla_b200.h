@@ -33,6 +33,11 @@ int vmb_device_arch(int device);
  * (no reference counterpart: the reference only wall-clocks whole epochs, train.py:71,164-165)
  * Number of CUDA kernels this library has launched in this process.                                   */
 long long vmb_launch_count(void);
+/* Kernel selection for the bf16 conv3x3 / FC layers with C_out (N) a multiple of 256: 1 = the CTA-pair kernel
+ * (tcgen05 cta_group::2, the default), 0 = the single-CTA kernel (kept as the A/B baseline; results are bit-identical),
+ * -1 = back to the default (environment VMB_IGEMM_PAIR, else 1).  Returns the previous setting (0/1).  Diagnostics only:
+ * the reference has no counterpart (vggish.py:13-19, :108-118 are the layers both kernels implement). */
+int vmb_igemm_pair_enable(int on);
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each stage of
  * vmb_vggish_forward / vmb_pipeline_forward.  Stage ids: */
 enum {

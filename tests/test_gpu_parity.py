@@ -158,6 +158,48 @@ def test_conv3x3_layer(n, H, W, Cin, Cout, pool):
     _layer_check(out.permute(0, 3, 1, 2), ref, f"conv {H}x{W} {Cin}->{Cout} pool={pool}", rel_tol=0.005)
 
 
+@pytest.mark.parametrize("n", [1, 3, 77])
+def test_pair_kernel_bit_identical_to_single_cta(n):
+    """The CTA-pair (tcgen05 cta_group::2) kernel and the single-CTA kernel run the same K order into fp32 TMEM
+    accumulators: their outputs must be bit-identical, including odd tile counts (the partner CTA of the last pair then
+    works on an out-of-range tile that TMA zero-fills and the epilogue masks)."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n)
+    cases = []
+    for (H, W, Cin, Cout, pool) in [(24, 16, 128, 256, 0), (24, 16, 256, 256, 1), (12, 8, 256, 512, 0), (12, 8, 512, 512, 1)]:
+        x = torch.randn(n, H, W, Cin, generator=g).to(DEV).bfloat16()
+        w = (torch.randn(Cout, 9 * Cin, generator=g) * 0.03).to(DEV).bfloat16()
+        b = torch.randn(Cout, generator=g).to(DEV)
+        shape = (n, H // 2, W // 2, Cout) if pool else (n, H, W, Cout)
+        cases.append((f"conv {H}x{W} {Cin}->{Cout} p{pool}", shape,
+                      lambda o, x=x, w=w, b=b, H=H, W=W, Cin=Cin, Cout=Cout, pool=pool: L.vmb_conv3x3_relu(
+                          x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), n, H, W, Cin, Cout, pool,
+                          engine.stream_ptr())))
+    for (M, N, K) in [(n, 4096, 4096), (256 + n, 256, 12288), (130 * n, 512, 128)]:
+        a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+        w = (torch.randn(N, K, generator=g) * 0.02).to(DEV).bfloat16()
+        b = torch.randn(N, generator=g).to(DEV)
+        cases.append((f"linear {M}x{N}x{K}", (M, N),
+                      lambda o, a=a, w=w, b=b, M=M, N=N, K=K: L.vmb_linear(a.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                                                           o.data_ptr(), 0, 1, M, N, K,
+                                                                           engine.stream_ptr())))
+    prev = L.vmb_igemm_pair_enable(1)
+    try:
+        for name, shape, fn in cases:
+            outs = []
+            for pair in (1, 0):
+                L.vmb_igemm_pair_enable(pair)
+                o = torch.full(shape, float("nan"), device=DEV, dtype=torch.bfloat16)
+                engine.check(fn(o), name)
+                torch.cuda.synchronize()
+                outs.append(o)
+            assert not torch.isnan(outs[0].float()).any(), name
+            assert torch.equal(outs[0], outs[1]), name
+    finally:
+        L.vmb_igemm_pair_enable(-1)
+    assert prev in (0, 1)
+
+
 @pytest.mark.parametrize("M,N,K,f32", [(1, 128, 64, 1), (10, 4096, 12288, 0), (130, 256, 512, 0), (257, 128, 4096, 1)])
 def test_linear_layer(M, N, K, f32):
     g = torch.Generator().manual_seed(M + N + K)
