@@ -254,7 +254,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (p.relu) {
+        if (p.relu && !POOL) {   // the pooled path applies ReLU after the pooling (fewer values)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
@@ -263,17 +263,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
         __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
         if (POOL) {
-          // 2x2 window = lanes {l, l^1, l^Wb, l^1^Wb}; max commutes with the monotone bf16 rounding
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-            pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], p.Wb));
-          }
-          const bool up = sub & 1;   // two lanes of the window store one full 32-byte sector each
-          if (valid && !(sub & 2))
-            st_global_256(outp + (up ? 16 : 0), up ? pk[8] : pk[0], up ? pk[9] : pk[1], up ? pk[10] : pk[2],
-                          up ? pk[11] : pk[3], up ? pk[12] : pk[4], up ? pk[13] : pk[5], up ? pk[14] : pk[6],
-                          up ? pk[15] : pk[7]);
+          pool2x2_relu_store_bf16(pk, sub, p.Wb, p.relu != 0, valid, outp);
         } else if (valid) {
           st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
           st_global_256(outp + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);

@@ -18,8 +18,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                          // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KiB
 constexpr int kQuarterBytes = 32 * kBlockK * 2;      // one 32-row quarter of A (one TMA box in CONV mode)
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter (the short-K layers are epilogue-paced)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = 64 + kEpiThreads;
 
 // MT = number of 128-row sub-tiles per CTA tile that share one B stage (MT = 2 doubles the smem reuse of the
 // weights when BLOCK_N is only 128: a 256 x 128 tile moves as many bytes per FLOP as a 128 x 256 one).
@@ -70,7 +71,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[s], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -218,7 +219,10 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // warp w may read TMEM lanes 32*(w%4)..+31; the two warps of a quarter split the tile's sub-tiles (MT = 2) or
+    // alternate over its 32-column chunks (MT = 1)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int ep_tid = threadIdx.x - 64;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -234,12 +238,12 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       float* bias_t = bias_s + acc * BLOCK_N;
       for (int i = ep_tid; i < BLOCK_N; i += kEpiThreads)
         bias_t[i] = (p.bias && ks == 0) ? __ldg(p.bias + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = (MT == 2 ? half : 0); mt < (MT == 2 ? half + 1 : 1); ++mt) {
       // Where does this thread's accumulator row go?
       bool valid;
       size_t out_off;  // element offset of column n0 for this thread's output row / pooled pixel
@@ -270,7 +274,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + mt * BLOCK_N;
 
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ch = (MT == 2 ? 0 : half); ch < BLOCK_N / 32; ch += (MT == 2 ? 1 : 2)) {
         uint32_t v[32];
         tmem_ld_32x32(t_addr + ch * 32, v);
         tmem_ld_wait();
@@ -283,7 +287,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (p.relu) {
+        if (p.relu && !(OUT == kOutBf16 && POOL)) {   // the pooled bf16 path applies ReLU after the pooling (fewer values)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
@@ -344,19 +348,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
           __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
           if (POOL) {
-            // 2x2 window = lanes {l, l^1, l^Wb, l^1^Wb}; max commutes with the monotone bf16 rounding.
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-              pk[j] = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], p.Wb));
-            }
-            // the four lanes of a window each store a different 8-channel (16 B) slice
-            // two lanes of the window (sub 0, 1) each store one full 32-byte sector (16 channels)
-            const bool up = sub & 1;
-            if (valid && !(sub & 2))
-              st_global_256(outp + (up ? 16 : 0), up ? pk[8] : pk[0], up ? pk[9] : pk[1], up ? pk[10] : pk[2],
-                            up ? pk[11] : pk[3], up ? pk[12] : pk[4], up ? pk[13] : pk[5], up ? pk[14] : pk[6],
-                            up ? pk[15] : pk[7]);
+            pool2x2_relu_store_bf16(pk, sub, p.Wb, p.relu != 0, valid, outp);
           } else if (valid) {
             st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             st_global_256(outp + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);

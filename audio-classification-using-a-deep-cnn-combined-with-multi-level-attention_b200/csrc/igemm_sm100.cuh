@@ -11,8 +11,8 @@
 //             one 32-row quarter of the 128-row UMMA tile, so one epilogue warp owns whole 2x2 pooling
 //             windows and MaxPool2d(2,2) (vggish.py:111) is a pair of warp shuffles.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-5 = epilogue (TMEM -> regs -> bias/ReLU/pool -> global).  Persistent over tiles, accumulators
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-9 = epilogue, two per TMEM lane quarter (TMEM -> regs -> bias/ReLU/pool -> global).  Persistent over tiles, accumulators
 // double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>

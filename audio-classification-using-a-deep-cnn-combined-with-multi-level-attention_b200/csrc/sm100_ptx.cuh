@@ -286,4 +286,31 @@ __device__ __forceinline__ void st_global_256(void* ptr, uint32_t a0, uint32_t a
                : "memory");
 }
 
+// 2x2 max-pool of 32 channels held as 16 packed bf16 pairs per lane, across the four lanes {l, l^1, l^wb} of a pooling
+// window, followed by ReLU and ONE full-sector store: a transposing exchange with the horizontal neighbour (each lane
+// sends the half it will not keep: 8 shuffles), then a plain exchange with the vertical neighbour (8 shuffles) — half the
+// shuffles of reducing all 16 registers twice.  Afterwards lanes with sub = 0 / 1 hold channels 0-15 / 16-31 of the
+// pooled pixel and store them; sub = (w & 1) | ((h & 1) << 1).  max commutes with the monotone bf16 rounding and with
+// ReLU, so the result equals pooling the fp32 values.
+__device__ __forceinline__ void pool2x2_relu_store_bf16(const uint32_t (&pk)[16], int sub, int wb, bool relu, bool valid,
+                                                        void* out_pixel_chunk) {
+  const bool up = sub & 1;
+  uint32_t keep[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t send = up ? pk[j] : pk[8 + j];
+    const uint32_t own = up ? pk[8 + j] : pk[j];
+    keep[j] = max_bf16x2(own, __shfl_xor_sync(0xffffffffu, send, 1));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) keep[j] = max_bf16x2(keep[j], __shfl_xor_sync(0xffffffffu, keep[j], wb));
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = max_bf16x2(keep[j], 0u);
+  }
+  if (valid && !(sub & 2))
+    st_global_256(static_cast<uint8_t*>(out_pixel_chunk) + (up ? 32 : 0), keep[0], keep[1], keep[2], keep[3], keep[4],
+                  keep[5], keep[6], keep[7]);
+}
+
 }  // namespace vmb
