@@ -69,6 +69,16 @@ def igemm_traffic():
         return None
 
 
+def tensor_pipe_util():
+    """Tensor-pipe utilisation per layer from the committed ncu capture (BASELINE.json's second metric); a profiler
+    figure, copied from profiles/, never measured inside the timed run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "igemm_traffic.json")) as fh:
+            return json.load(fh)["tensor_pipe_active_pct"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -379,6 +389,7 @@ def run_b200(args, rank, local_rank, world):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": igemm_traffic(),
                      "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if achieved else None,
+                     "tensor_pipe_active_pct_ncu": tensor_pipe_util(),
                      "kernel": "igemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM: conv3_1..conv4_2, fc1, fc2) + "
                                "igemm_bf16_kernel (cta_group::1: conv2, fc3)",
                      "launches_per_step": ig_launches_per_step, "algorithmic_flop_per_launch":
