@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                 __nv_bfloat16* __restrict__ out, long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;                                   // [kStages][kATile]
   uint8_t* b_smem = smem + kStages * kATile;                // [4 positions][kBTile]
@@ -146,6 +147,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform by construction
+  pdl_wait();   // the set-up above read only the layer's constant weights; the examples are read below
 
   if (warp < 4 * kProducerGroups) {
     // ------------------------------------------------------------------ producers: 4x4 window -> four im2col rows
@@ -272,11 +274,13 @@ int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, vo
     }
     attr_set = true;
   }
-  if (split_out)
-    conv1_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
-  else
-    conv1_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
+  const cudaError_t e = launch_pdl(split_out ? conv1_tc_kernel<true> : conv1_tc_kernel<false>, dim3(grid), dim3(kThreads),
+                                   kSmemBytes, stream, examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
   count_launch();
+  if (e != cudaSuccess) {
+    set_kernel_error("conv1_tc_kernel: %s", cudaGetErrorString(e));
+    return 1;
+  }
   return check_launch("conv1_tc_kernel");
 }
 

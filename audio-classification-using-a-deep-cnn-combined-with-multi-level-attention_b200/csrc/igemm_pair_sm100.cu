@@ -75,6 +75,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_m_pairs = (p.num_m_tiles + 2 * MT - 1) / (2 * MT);
   const int num_tiles = num_m_pairs * p.num_n_tiles;     // pair tiles (2 * MT * 128 rows x BLOCK_N)
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -95,6 +96,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -305,9 +307,10 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams&
   const int pair_tiles = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * p.num_n_tiles;
   const int max_pairs = num_sms() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
-  kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);   // cluster shape comes from __cluster_dims__
+  // cluster shape comes from __cluster_dims__
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, ta, tb, p);
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_pair_err, sizeof g_pair_err, "igemm pair launch failed: %s", cudaGetErrorString(e));
     return 1;

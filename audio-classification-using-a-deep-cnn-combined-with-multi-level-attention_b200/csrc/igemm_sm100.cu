@@ -62,6 +62,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
   const int num_tiles = mn_tiles * ksplit;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -80,6 +81,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -447,9 +449,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, c
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kNumThreads, smem, stream>>>(ta, tb, p);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, ta, tb, p);
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof g_err, "igemm launch failed: %s", cudaGetErrorString(e));
     return 1;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <utility>
 
 namespace vmb {
 
@@ -10,6 +11,24 @@ const char* kernels_last_error();
 void set_kernel_error(const char* fmt, ...);
 // cudaGetLastError() -> 0 / 1 with the message recorded.
 int check_launch(const char* what);
+
+// Launch `kern` so that it may overlap the tail of the previous kernel in the stream (programmatic dependent launch).
+// Only for kernels that call pdl_wait() (sm100_ptx.cuh) before their first access to global memory.
+bool pdl_enabled();   // environment VMB_PDL=0 turns the overlap off (A/B timing); profile.cu
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- accounting (profile.cu)
 // Every kernel launcher calls count_launch(); StageTimer brackets one stage with CUDA events when profiling is on.

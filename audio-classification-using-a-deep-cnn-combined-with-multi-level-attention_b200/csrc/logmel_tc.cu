@@ -77,6 +77,7 @@ template <class IN>
 __global__ void __launch_bounds__(256)
 split_wave_kernel(const IN* __restrict__ wave, long long n_samples, long long clip_stride, long long pitch,
                   long long n_clips, __nv_bfloat16* __restrict__ planes) {
+  pdl_launch_dependents();   // logmel_tc_kernel's prologue may start while the last blocks here still run
   const long long groups_per_clip = pitch / 8;
   const long long total = groups_per_clip * n_clips;
   const long long plane_elems = n_clips * pitch;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const LogmelParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
@@ -201,6 +203,7 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
+  pdl_wait();   // the sample planes (split_wave_kernel's output) are read below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -504,8 +507,13 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
-  logmel_tc_kernel<<<static_cast<unsigned>(grid), kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  const cudaError_t le = launch_pdl(logmel_tc_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads), kSmemBytes,
+                                    stream, ta, tb, p);
   count_launch();
+  if (le != cudaSuccess) {
+    set_kernel_error("logmel_tc_kernel: %s", cudaGetErrorString(le));
+    return 1;
+  }
   if (check_launch("logmel_tc_kernel")) return 1;
   if (cudaFreeAsync(planes, stream) != cudaSuccess) {
     set_kernel_error("logmel: cudaFreeAsync failed");

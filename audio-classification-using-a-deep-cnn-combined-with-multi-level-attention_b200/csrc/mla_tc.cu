@@ -16,6 +16,7 @@
 #include "igemm_sm100.cuh"
 #include "kernels.cuh"
 #include "mla_internal.cuh"
+#include "sm100_ptx.cuh"
 
 namespace vmb_head {
 
@@ -39,6 +40,8 @@ rows_affine_split_kernel(const float* __restrict__ src, long long lds, long long
                          const float* __restrict__ a1, const float* __restrict__ b1, int relu,
                          const float* __restrict__ a2, const float* __restrict__ b2,
                          __nv_bfloat16* __restrict__ dst) {
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
   const int quads = cpad / 4;
   const long long total = rows * quads;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -81,6 +84,8 @@ attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, 
                       const float* __restrict__ bv, const float* __restrict__ af, const float* __restrict__ bf,
                       float* __restrict__ y, long long ystride, int col0) {
   __shared__ float rmax[16], rsum[16];
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
   const long long clip = blockIdx.x;
   const float* zc = z + clip * T * ldz;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -112,6 +117,8 @@ attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, 
 __global__ void __launch_bounds__(256)
 sigmoid_affine_kernel(const float* __restrict__ u, long long ldu, long long batch, int K, const float* __restrict__ oa,
                       const float* __restrict__ ob, float* __restrict__ out) {
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
   const long long total = batch * K;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -127,8 +134,11 @@ unsigned grid_for(long long items, int per_block) {
 
 int split_rows(const float* src, long long lds, long long rows, int cols, int cpad, int T, const float* a1,
                const float* b1, int relu, const float* a2, const float* b2, void* dst, cudaStream_t st) {
-  rows_affine_split_kernel<<<grid_for(rows * (cpad / 4), 256), 256, 0, st>>>(
-      src, lds, rows, cols, cpad, T, a1, b1, relu, a2, b2, static_cast<__nv_bfloat16*>(dst));
+  if (vmb::launch_pdl(rows_affine_split_kernel, dim3(grid_for(rows * (cpad / 4), 256)), dim3(256), 0, st, src, lds, rows,
+                      cols, cpad, T, a1, b1, relu, a2, b2, static_cast<__nv_bfloat16*>(dst)) != cudaSuccess) {
+    vmb::set_kernel_error("rows_affine_split_kernel: launch failed");
+    return 1;
+  }
   vmb::count_launch();
   return vmb::check_launch("rows_affine_split_kernel");
 }
@@ -189,8 +199,8 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
     }
     gemm(cur, L.fcv);   // z = fcv(emb_l) -> U
     if (!rc) {
-      attention_pool_kernel<<<static_cast<unsigned>(batch), 256, 0, st>>>(U, hpad, d.K, d.T, L.av, L.bv, L.af, L.bf, Y,
-                                                                          ystride, l * d.K);
+      vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U, hpad, d.K, d.T, L.av,
+                      L.bv, L.af, L.bf, Y, ystride, l * d.K);
       vmb::count_launch();
       rc = vmb::check_launch("attention_pool_kernel");
     }
@@ -203,7 +213,8 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
     rc = 1;
   }
   if (!rc) {
-    sigmoid_affine_kernel<<<grid_for(batch * d.K, 256), 256, 0, st>>>(U, hpad, batch, d.K, d.out_a, d.out_b, scores);
+    vmb::launch_pdl(sigmoid_affine_kernel, dim3(grid_for(batch * d.K, 256)), dim3(256), 0, st, U, hpad, batch, d.K, d.out_a,
+                    d.out_b, scores);
     vmb::count_launch();
     rc = vmb::check_launch("sigmoid_affine_kernel");
   }

@@ -30,6 +30,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: its CTAs become resident as the predecessor's CTAs exit and run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch); pdl_wait() then blocks until the predecessor has completed and its
+// writes are visible.  Nothing before pdl_wait() may touch global memory written by earlier kernels, and nothing
+// before it may write global memory at all.  Both are no-ops under an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
