@@ -389,6 +389,20 @@ def test_map_identical_to_three_decimals(vgg_handle, head_handle, vgg_sd, head_s
     a, b = synth.mean_average_precision(labels, got), synth.mean_average_precision(labels, want)
     print(f"mAP B200 {a:.5f} oracle {b:.5f}; scores max-abs-err {np.abs(got - want).max():.3e}")
     assert abs(a - b) < 5e-4
+    # the same with the accuracy mode of the VGGish body (hi + lo bf16 planes): the ranking metric agrees to 4 decimals,
+    # and on labels that follow the oracle's own ranking (what a trained classifier looks like) both modes do
+    hs = engine.VggishHandle(vgg_sd, DEV, precision="split")
+    try:
+        got_s = engine.Pipeline(hs, head_handle).forward(torch.from_numpy(waves).to(DEV)).cpu().numpy()
+    finally:
+        hs.close()
+    c = synth.mean_average_precision(labels, got_s)
+    thr = np.quantile(want, 0.8, axis=0, keepdims=True)
+    ranked = (want >= thr).astype(labels.dtype)                       # top 20 % of the oracle's scores per class
+    a2, b2, c2 = (synth.mean_average_precision(ranked, x) for x in (got, want, got_s))
+    print(f"mAP accuracy mode {c:.5f} (oracle {b:.5f}); oracle-ranked labels: bf16 {a2:.5f} accuracy mode {c2:.5f} "
+          f"oracle {b2:.5f}")
+    assert abs(c - b) < 5e-5 and abs(c2 - b2) < 5e-5 and abs(a2 - b2) < 5e-3
 
 
 def test_shard_invariance(vgg_handle, head_handle):
