@@ -45,6 +45,7 @@ int vmb_device_arch(int device) {
 }
 
 int vmb_igemm_pair_enable(int on) { return vmb::igemm_set_pair(on); }
+int vmb_igemm_halo_enable(int on) { return vmb::igemm_set_halo(on); }
 
 long long vmb_num_frames(long long n_samples) {
   // mel_features.py:42  1 + int(floor((num_samples - window_length) / hop_length)), floor division

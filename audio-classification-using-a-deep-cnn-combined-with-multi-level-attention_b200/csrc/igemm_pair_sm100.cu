@@ -132,7 +132,8 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
         const int b_row = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
-        int tap = 0, cb = 0;
+        int tap = 0, cb = 0;   // K order (channel block, dx, dy): see the single-CTA kernel; tap = dxi * 3 + dyi
+        int b_kb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = stage_base + stage * C::kStageBytes;
@@ -140,7 +141,9 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t full = full0 + stage * 8;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
           if (CONV) {
-            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            const int dxi = tap / 3, dyi = tap - dxi * 3;
+            const int dh = dyi - 1, dw = dxi - 1;
+            b_kb = (dyi * 3 + dxi) * p.cblks + cb;
             if (BIG) {
 #pragma unroll
               for (int sub = 0; sub < MT; ++sub)
@@ -151,13 +154,14 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int q = 0; q < 4 * MT; ++q)
                 tma_load_4d_pair(a_dst + q * kQuarterBytes, &tmap_a, full, cb * kBlockK, bx[q] + dw, by[q] + dh, bn[q]);
             }
-            if (++cb == p.cblks) { cb = 0; ++tap; }
+            if (++tap == 9) { tap = 0; ++cb; }
           } else {
+            b_kb = kb;
 #pragma unroll
             for (int sub = 0; sub < MT; ++sub)
               tma_load_2d_pair(a_dst + sub * kABytes, &tmap_a, full, kb * kBlockK, (m_tile + sub) * kBlockM);
           }
-          tma_load_2d_pair(b_dst, &tmap_b, full, kb * kBlockK, b_row);
+          tma_load_2d_pair(b_dst, &tmap_b, full, b_kb * kBlockK, b_row);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }

@@ -24,11 +24,19 @@ constexpr int kNumThreads = 64 + kEpiThreads;
 
 // MT = number of 128-row sub-tiles per CTA tile that share one B stage (MT = 2 doubles the smem reuse of the
 // weights when BLOCK_N is only 128: a 256 x 128 tile moves as many bytes per FLOP as a 128 x 256 one).
-template <int BLOCK_N, int MT>
+// HALO (CONV + BIG, Wb = 16, Hb = 2): a stage holds, per sub-tile, ONE activation box with a one-row halo above and below
+// (10 rows x 16 pixels x 64 channels = 20 KB, loaded at column offset dx) plus the three weight tiles of the taps
+// (dy = -1, 0, 1; dx).  The three MMAs groups of a stage read the same box at row offsets 0 / 16 / 32 (2 KB apart,
+// which keeps the 128-byte swizzle phase), so the activations cross L2 -> shared memory 3 times per tile instead of 9:
+// 59 instead of 96 B/clk/SM for conv2, i.e. the same bytes in flight now cover 3 000 cycles of load latency, not 2 000.
+constexpr int kHaloRows = 10, kHaloWb = 16;
+constexpr int kHaloBytes = kHaloRows * kHaloWb * kBlockK * 2;   // 20480
+template <int BLOCK_N, int MT, bool HALO = false>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kStages = (kStageBytes >= 48 * 1024) ? 4 : 6;
+  static constexpr int kStageBytes = HALO ? MT * kHaloBytes + 3 * kBBytes : MT * kABytes + kBBytes;
+  static constexpr int kStages = HALO ? (200 * 1024 / kStageBytes) : ((kStageBytes >= 48 * 1024) ? 4 : 6);
+  static_assert(kStages >= 2, "need a double-buffered stage ring");
   static constexpr int kTmemCols = 2 * MT * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
   static_assert(kTmemCols <= 512, "TMEM holds 512 columns");
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
@@ -39,11 +47,12 @@ struct Cfg {
 constexpr int kOutBf16 = 0, kOutF32 = 1, kOutSplit = 2, kOutF32Atomic = 3;   // epilogue output: bf16, fp32, hi | lo bf16
                                                                               // planes, or fp32 atomicAdd (split-K)
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false, bool HALO = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
-  using C = Cfg<BLOCK_N, MT>;
+  static_assert(!HALO || (CONV && BIG && OUT == kOutBf16), "HALO is a variant of the bf16 big-box conv");
+  using C = Cfg<BLOCK_N, MT, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -123,7 +132,30 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             bx[q] = (r - yy * p.boxes_per_row) * p.Wb;
           }
         }
-        int tap = 0, cb = 0;
+        if (HALO) {
+          for (int s = 0; s < 3 * p.cblks; ++s) {
+            const int cbh = s / 3, dxi = s - cbh * 3;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = stage_base + stage * C::kStageBytes;
+            uint8_t* b_dst = a_dst + MT * kHaloBytes;
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_4d(a_dst + sub * kHaloBytes, &tmap_a, &full_bar[stage], cbh * kBlockK, bx[sub] + dxi - 1,
+                          by[sub] - 1, bn[sub]);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_2d(b_dst + dyi * C::kBBytes, &tmap_b, &full_bar[stage], ((dyi * 3 + dxi) * p.cblks + cbh) * kBlockK,
+                          n_tile * BLOCK_N);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
+        // CONV K order: channel block outermost, then dx, then dy — the order the HALO variant needs (its stage is one
+        // (channel block, dx) and feeds the three dy taps), used by every bf16 conv kernel so that all of them add the
+        // same partial products in the same order (results are bit-identical whichever kernel a batch size selects)
+        int tap = 0, cb = 0;   // tap = dxi * 3 + dyi
+        int b_conv_kb = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = stage_base + stage * C::kStageBytes;
@@ -145,7 +177,9 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             continue;
           }
           if (CONV) {
-            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            const int dxi = tap / 3, dyi = tap - dxi * 3;
+            const int dh = dyi - 1, dw = dxi - 1;
+            b_conv_kb = (dyi * 3 + dxi) * p.cblks + cb;   // weights are stored [C_out][(kh, kw, c)]
             if (BIG) {
 #pragma unroll
               for (int sub = 0; sub < MT; ++sub)
@@ -157,7 +191,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 tma_load_4d(a_dst + q * kQuarterBytes, &tmap_a, &full_bar[stage], cb * kBlockK, bx[q] + dw,
                             by[q] + dh, bn[q]);
             }
-            if (++cb == p.cblks) { cb = 0; ++tap; }
+            if (++tap == 9) { tap = 0; ++cb; }
           } else {
             // split mode (p.split_nkb > 0): A and B are stored as column blocks of 2 (hi | lo) or 3 (hi | mid | lo)
             // bf16 planes and the K loop runs over the products with plane index sum <= planes - 1, smallest first
@@ -173,7 +207,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               tma_load_2d(a_dst + sub * kABytes, &tmap_a, &full_bar[stage], a_kb * kBlockK,
                           (m_tile * MT + sub) * kBlockM);
           }
-          int b_kb = kb;
+          int b_kb = CONV ? b_conv_kb : kb;
           if (p.split_nkb) {
             const int q = kb / p.split_nkb;
             const int pb = p.split_planes == 3 ? ((0x012010 >> (4 * (5 - q))) & 0xF) : (q == 2 ? 1 : 0);
@@ -199,6 +233,34 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
+      if (HALO) {
+        const int n_st = 3 * p.cblks;
+        for (int s = 0; s < n_st; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(stage_base + stage * C::kStageBytes);
+            const uint32_t b_addr = a_addr + MT * kHaloBytes;
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + dyi * C::kBBytes);
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub) {
+                // rows dyi*16 .. dyi*16+127 of the halo box = the 8 x 16 output pixels shifted by dy = dyi - 1
+                const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr + sub * kHaloBytes + dyi * (kHaloWb * kBlockK * 2));
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16_ss(d_tmem + sub * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (s | dyi | k) != 0);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (s == n_st - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
@@ -434,11 +496,11 @@ int num_sms() {
 
 namespace {
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false, bool HALO = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT, BIG>;
+  auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT, BIG, HALO>;
   static bool attr_set = false;
-  constexpr int smem = Cfg<BLOCK_N, MT>::kSmemBytes;
+  constexpr int smem = Cfg<BLOCK_N, MT, HALO>::kSmemBytes;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -477,6 +539,23 @@ bool igemm_use_pair() {
     return e ? (e[0] != '0') : (VMB_PAIR_DEFAULT != 0);
   }();
   return on;
+}
+namespace {
+std::atomic<int> g_halo_override{-1};
+}
+bool igemm_use_halo() {
+  const int o = g_halo_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o != 0;
+  static const bool on = [] {
+    const char* e = getenv("VMB_IGEMM_HALO");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+int igemm_set_halo(int on) {
+  const int prev = igemm_use_halo() ? 1 : 0;
+  g_halo_override.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
+  return prev;
 }
 int igemm_set_pair(int on) {
   const int prev = igemm_use_pair() ? 1 : 0;
@@ -779,6 +858,16 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   // C_out = 128: pair two 128-pixel sub-tiles per CTA tile when there are enough tiles to keep every SM busy
   if (p.num_m_tiles >= 4 * num_sms()) {
     p.num_m_tiles = (sub_tiles + 1) / 2;
+    if (big && Wb == kHaloWb && 4 * Hb + 2 == kHaloRows && igemm_use_halo()) {
+      // one haloed activation box per (channel block, dx) instead of one box per tap (see Cfg)
+      CUtensorMap th;
+      uint64_t dims[4] = {uint64_t(C_in), uint64_t(W), uint64_t(H), uint64_t(n_img)};
+      uint64_t str[3] = {uint64_t(C_in) * 2, uint64_t(W) * C_in * 2, uint64_t(H) * W * C_in * 2};
+      uint32_t box[4] = {kBlockK, uint32_t(kHaloWb), uint32_t(kHaloRows), 1};
+      if (make_tmap_bf16(&th, act, 4, dims, str, box)) return 1;
+      return pool ? launch<128, 2, true, true, kOutBf16, true, true>(th, tb, p, stream)
+                  : launch<128, 2, true, false, kOutBf16, true, true>(th, tb, p, stream);
+    }
     if (big)
       return pool ? launch<128, 2, true, true, kOutBf16, true>(ta, tb, p, stream)
                   : launch<128, 2, true, false, kOutBf16, true>(ta, tb, p, stream);

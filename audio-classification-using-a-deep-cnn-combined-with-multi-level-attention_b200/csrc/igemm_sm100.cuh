@@ -82,7 +82,10 @@ int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bi
                        int W, int C_in, int C_out, int pool, cudaStream_t stream);
 const char* igemm_pair_last_error();
 bool igemm_use_pair();
-int igemm_set_pair(int on);   // 1 / 0 force the choice, -1 returns to the default; returns the previous setting
+int igemm_set_pair(int on);
+// Haloed activation boxes for the C_out = 128 conv (conv2): same contract as igemm_set_pair.
+bool igemm_use_halo();
+int igemm_set_halo(int on);   // 1 / 0 force the choice, -1 returns to the default; returns the previous setting
 
 const char* igemm_last_error();
 

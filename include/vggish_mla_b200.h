@@ -38,6 +38,11 @@ long long vmb_launch_count(void);
  * -1 = back to the default (environment VMB_IGEMM_PAIR, else 1).  Returns the previous setting (0/1).  Diagnostics only:
  * the reference has no counterpart (vggish.py:13-19, :108-118 are the layers both kernels implement). */
 int vmb_igemm_pair_enable(int on);
+/* Same switch for the haloed-box variant of the C_out = 128 conv (conv2, vggish.py:113 with 64 -> 128 channels): one
+ * activation box with a one-row halo per (channel block, dx) feeds the three dy taps, instead of one box per tap.
+ * 1 (default) / 0 / -1 as above; every bf16 conv kernel adds its partial products in the same order, so the results are
+ * bit-identical either way. */
+int vmb_igemm_halo_enable(int on);
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each stage of
  * vmb_vggish_forward / vmb_pipeline_forward.  Stage ids: */
 enum {

@@ -200,6 +200,38 @@ def test_pair_kernel_bit_identical_to_single_cta(n):
     assert prev in (0, 1)
 
 
+def test_halo_conv2_bit_identical_to_per_tap_boxes():
+    """conv2 at batch sizes that take the 256 x 128 tiles: the haloed-box kernel (one activation box per dx, three dy
+    taps each) against the one-box-per-tap kernel, and against the small-batch 128 x 128 path on a slice of the batch —
+    all bf16 conv kernels add the partial products in the same (channel block, dx, dy) order."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    n, H, W, Cin, Cout = 77, 48, 32, 64, 128
+    x = torch.randn(n, H, W, Cin, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(Cout, 9 * Cin, generator=g) * 0.04).to(DEV).bfloat16()
+    b = torch.randn(Cout, generator=g).to(DEV)
+
+    def run(xx, pool):
+        m = xx.shape[0]
+        o = torch.full((m, H // 2, W // 2, Cout) if pool else (m, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+        engine.check(L.vmb_conv3x3_relu(xx.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), m, H, W, Cin, Cout, pool,
+                                        engine.stream_ptr()), "vmb_conv3x3_relu")
+        torch.cuda.synchronize()
+        return o
+
+    try:
+        for pool in (1, 0):
+            L.vmb_igemm_halo_enable(1)
+            a = run(x, pool)
+            L.vmb_igemm_halo_enable(0)
+            c = run(x, pool)
+            small = run(x[:5].contiguous(), pool)          # 5 images: the 128 x 128 tile path
+            assert not torch.isnan(a.float()).any()
+            assert torch.equal(a, c) and torch.equal(a[:5], small)
+    finally:
+        L.vmb_igemm_halo_enable(-1)
+
+
 @pytest.mark.parametrize("M,N,K,f32", [(1, 128, 64, 1), (10, 4096, 12288, 0), (130, 256, 512, 0), (257, 128, 4096, 1)])
 def test_linear_layer(M, N, K, f32):
     g = torch.Generator().manual_seed(M + N + K)
