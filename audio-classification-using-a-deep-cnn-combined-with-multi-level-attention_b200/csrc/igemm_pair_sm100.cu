@@ -37,11 +37,17 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumThreads = 64 + kEpiThreads;
 
 // MT = 128-row sub-tiles per CTA that share one B stage (MT = 2 for C_out = 128: a 512 x 128 pair tile)
-template <int BLOCK_N, int MT>
+// HALO: as in the single-CTA kernel (igemm_sm100.cu, Cfg) — a stage is one haloed activation box (10 rows x 16 pixels x
+// 64 channels, loaded at column offset dx) plus this CTA's halves of the three weight tiles (dy = -1, 0, 1; dx): 68 KB
+// for 12 MMAs (1536 tensor cycles), 44 instead of 64 B/clk/SM from L2.
+constexpr int kHaloRows = 10, kHaloWb = 16;
+constexpr int kHaloBytes = kHaloRows * kHaloWb * kBlockK * 2;   // 20480
+template <int BLOCK_N, int MT, bool HALO = false>
 struct PairCfg {
   static constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;   // this CTA's half of the B tile
-  static constexpr int kStageBytes = MT * kABytes + kBHalfBytes;
-  static constexpr int kStages = 200 * 1024 / kStageBytes;          // 6 x 32 KB (256, 1) or 5 x 40 KB (128, 2)
+  static constexpr int kStageBytes = HALO ? MT * kHaloBytes + 3 * kBHalfBytes : MT * kABytes + kBHalfBytes;
+  static constexpr int kStages = (HALO ? 208 : 200) * 1024 / kStageBytes;   // 6 x 32 KB, or 3 x 68 KB with HALO
+  static_assert(kStages >= 2, "need a double-buffered stage ring");
   static constexpr int kTmemCols = 2 * MT * BLOCK_N;                // two accumulator buffers
   static_assert(kTmemCols <= 512, "TMEM holds 512 columns");
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;
@@ -49,11 +55,12 @@ struct PairCfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes;
 };
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, bool BIG>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, bool BIG, bool HALO = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
-  using C = PairCfg<BLOCK_N, MT>;
+  static_assert(!HALO || (CONV && BIG), "HALO is a variant of the big-box conv");
+  using C = PairCfg<BLOCK_N, MT, HALO>;
   extern __shared__ uint8_t smem_raw[];
   // both CTAs of the pair must use identical shared-memory offsets (the MMA and the multicast commits address the
   // peer's memory by offset): the dynamic segment starts at the same offset in both, so the same rounding applies
@@ -132,6 +139,26 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
         const int b_row = n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        if (HALO) {
+          for (int s = 0; s < 3 * p.cblks; ++s) {
+            const int cbh = s / 3, dxi = s - cbh * 3;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = stage_base + stage * C::kStageBytes;
+            uint8_t* b_dst = a_dst + MT * kHaloBytes;
+            const uint32_t full = full0 + stage * 8;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_4d_pair(a_dst + sub * kHaloBytes, &tmap_a, full, cbh * kBlockK, bx[sub] + dxi - 1, by[sub] - 1,
+                               bn[sub]);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_2d_pair(b_dst + dyi * C::kBHalfBytes, &tmap_b, full, ((dyi * 3 + dxi) * p.cblks + cbh) * kBlockK,
+                               b_row);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         int tap = 0, cb = 0;   // K order (channel block, dx, dy): see the single-CTA kernel; tap = dxi * 3 + dyi
         int b_kb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -176,6 +203,34 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
+        if (HALO) {
+          const int n_st = 3 * p.cblks;
+          for (int s = 0; s < n_st; ++s) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t a_addr = smem_u32(stage_base + stage * C::kStageBytes);
+              const uint32_t b_addr = a_addr + MT * kHaloBytes;
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi) {
+                const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + dyi * C::kBHalfBytes);
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub) {
+                  const uint64_t a_desc =
+                      umma_desc_kmajor_sw128(a_addr + sub * kHaloBytes + dyi * (kHaloWb * kBlockK * 2));
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16_ss_pair(d_tmem + sub * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (s | dyi | k) != 0);
+                }
+              }
+              umma_commit_pair(&empty_bar[stage], 0b11);
+              if (s == n_st - 1) umma_commit_pair(&tmem_full[acc], 0b11);
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
@@ -295,11 +350,11 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 thread_local char g_pair_err[512] = "";
 
-template <int BLOCK_N, int MT, bool CONV, bool POOL, bool BIG>
+template <int BLOCK_N, int MT, bool CONV, bool POOL, bool BIG, bool HALO = false>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  auto kern = igemm_pair_kernel<BLOCK_N, MT, CONV, POOL, BIG>;
+  auto kern = igemm_pair_kernel<BLOCK_N, MT, CONV, POOL, BIG, HALO>;
   static bool attr_set = false;
-  constexpr int smem = PairCfg<BLOCK_N, MT>::kSmemBytes;
+  constexpr int smem = PairCfg<BLOCK_N, MT, HALO>::kSmemBytes;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -404,6 +459,15 @@ int igemm_pair_conv3x3(const void* act, const void* w, const float* bias, void* 
   p.bias = bias;
   p.out = out;
   p.out_img_stride = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
+  if (big && Wb == kHaloWb && 4 * Hb + 2 == kHaloRows && igemm_use_halo()) {
+    CUtensorMap th;
+    uint64_t dims[4] = {uint64_t(C_in), uint64_t(W), uint64_t(H), uint64_t(n_img)};
+    uint64_t str[3] = {uint64_t(C_in) * 2, uint64_t(W) * C_in * 2, uint64_t(H) * W * C_in * 2};
+    uint32_t box[4] = {kBlockK, uint32_t(kHaloWb), uint32_t(kHaloRows), 1};
+    if (make_tmap_bf16(&th, act, 4, dims, str, box)) return 2;
+    return pool ? launch_pair<256, 1, true, true, true, true>(th, tb, p, stream)
+                : launch_pair<256, 1, true, false, true, true>(th, tb, p, stream);
+  }
   if (big)
     return pool ? launch_pair<256, 1, true, true, true>(ta, tb, p, stream)
                 : launch_pair<256, 1, true, false, true>(ta, tb, p, stream);

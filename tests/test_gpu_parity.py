@@ -200,13 +200,14 @@ def test_pair_kernel_bit_identical_to_single_cta(n):
     assert prev in (0, 1)
 
 
-def test_halo_conv2_bit_identical_to_per_tap_boxes():
-    """conv2 at batch sizes that take the 256 x 128 tiles: the haloed-box kernel (one activation box per dx, three dy
-    taps each) against the one-box-per-tap kernel, and against the small-batch 128 x 128 path on a slice of the batch —
-    all bf16 conv kernels add the partial products in the same (channel block, dx, dy) order."""
+@pytest.mark.parametrize("H,W,Cin,Cout", [(48, 32, 64, 128), (24, 16, 128, 256), (24, 16, 256, 256)])
+def test_halo_boxes_bit_identical_to_per_tap_boxes(H, W, Cin, Cout):
+    """conv2 (256 x 128 single-CTA tiles) and conv3_x (CTA-pair tiles): the haloed-box kernels (one activation box per
+    dx feeding the three dy taps) against the one-box-per-tap kernels, and against the small-batch path on a slice of
+    the batch — every bf16 conv kernel adds the partial products in the same (channel block, dx, dy) order."""
     L = _lib.lib()
-    g = torch.Generator().manual_seed(11)
-    n, H, W, Cin, Cout = 77, 48, 32, 64, 128
+    g = torch.Generator().manual_seed(11 + Cin)
+    n = 77
     x = torch.randn(n, H, W, Cin, generator=g).to(DEV).bfloat16()
     w = (torch.randn(Cout, 9 * Cin, generator=g) * 0.04).to(DEV).bfloat16()
     b = torch.randn(Cout, generator=g).to(DEV)
@@ -223,13 +224,17 @@ def test_halo_conv2_bit_identical_to_per_tap_boxes():
         for pool in (1, 0):
             L.vmb_igemm_halo_enable(1)
             a = run(x, pool)
+            small = run(x[:5].contiguous(), pool)          # 5 images: for conv2 the 128 x 128 tile path
             L.vmb_igemm_halo_enable(0)
             c = run(x, pool)
-            small = run(x[:5].contiguous(), pool)          # 5 images: the 128 x 128 tile path
+            L.vmb_igemm_pair_enable(0)                     # and the single-CTA per-tap kernel
+            d = run(x, pool)
+            L.vmb_igemm_pair_enable(-1)
             assert not torch.isnan(a.float()).any()
-            assert torch.equal(a, c) and torch.equal(a[:5], small)
+            assert torch.equal(a, c) and torch.equal(a, d) and torch.equal(a[:5], small)
     finally:
         L.vmb_igemm_halo_enable(-1)
+        L.vmb_igemm_pair_enable(-1)
 
 
 @pytest.mark.parametrize("M,N,K,f32", [(1, 128, 64, 1), (10, 4096, 12288, 0), (130, 256, 512, 0), (257, 128, 4096, 1)])
