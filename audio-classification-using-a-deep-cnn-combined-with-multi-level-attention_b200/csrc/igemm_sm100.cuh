@@ -12,8 +12,14 @@
 //             windows and MaxPool2d(2,2) (vggish.py:111) is a pair of warp shuffles.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-9 = epilogue, two per TMEM lane quarter (TMEM -> regs -> bias/ReLU/pool -> global).  Persistent over tiles, accumulators
-// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// warps 2-9 = epilogue, two per TMEM lane quarter (TMEM -> regs -> bias/ReLU/pool -> global, one full 32-byte sector per
+// lane and store).  Persistent over tiles, accumulators double-buffered in TMEM so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+//
+// Variants: BIG (one 128-pixel TMA box per sub-tile when the image height allows), HALO (one haloed box per (channel
+// block, dx) feeding the three dy taps — conv2), MT = 2 (256 x 128 tiles for C_out = 128), and the CTA-pair kernel of
+// igemm_pair_sm100.cu (tcgen05 cta_group::2, 256 x 256 tiles) for C_out / N multiples of 256.  Every bf16 conv variant
+// walks K in the same (channel block, dx, dy) order, so their results are bit-identical.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
