@@ -29,6 +29,7 @@
 
 #include "../../include/vggish_mla_b200.h"
 #include "igemm_sm100.cuh"
+#include "sm100_ptx.cuh"
 #include "kernels.cuh"
 
 namespace vmb {
@@ -93,6 +94,8 @@ __device__ bool last_block_done(unsigned* counter, unsigned total) {
 // BatchNorm1d(T) on [rows = (b, t)][F]: channel = r % T.  grid = (chunks, T); block 256.
 __global__ void __launch_bounds__(256)
 bn_time_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int F, int T, StatJob job) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   const int t = blockIdx.y;
   const long long per_t = batch * F;
   double s1 = 0, s2 = 0;
@@ -127,6 +130,8 @@ __global__ void bn_running_only_kernel(StatJob job) { finalize_stats(job); }
 // BatchNorm1d(K) on [batch][K]: channel = column.  grid = ceil(K / 32); block (32, 8).
 __global__ void __launch_bounds__(256)
 bn_col_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int K, StatJob job) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x % 32, ty = threadIdx.x / 32;
   double s1 = 0, s2 = 0;
   if (c < K)
@@ -179,6 +184,8 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 
 template <class F>
 __global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   __shared__ float tile[32][33];
   f.prologue();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -273,6 +280,8 @@ struct GradIn {
 // phase A of BN backward: S1_t = sum g, S2_t = sum g * xhat  (double atomics), grid = (chunks, T)
 __global__ void __launch_bounds__(256)
 bn_time_backward_reduce_kernel(GradIn in, long long batch, double* __restrict__ acc) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   const int t = blockIdx.y;
   const long long per_t = batch * in.F;
   double s1 = 0, s2 = 0;
@@ -350,6 +359,8 @@ struct AttParams {
 // y[clip][col0 + k] = sum_t cla * att / sum_t att; row_stats[r] = {max, sum} of the class softmax of row r
 __global__ void __launch_bounds__(256)
 att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int col0, float* __restrict__ row_stats) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   __shared__ float rmax[16], rsum[16], sa_v[16], sb_v[16], sa_f[16], sb_f[16];
   const long long clip = blockIdx.x;
   const float* zc = a.z + clip * a.T * a.ldz;
@@ -395,6 +406,8 @@ __global__ void __launch_bounds__(256)
 att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __restrict__ dy, long long ystride, int col0,
                     const float* __restrict__ row_stats, float* __restrict__ gv, float* __restrict__ gf, long long ldg,
                     double* __restrict__ acc_v, double* __restrict__ acc_f) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   extern __shared__ float att_sm[];
   float* att = att_sm;                 // [T][K]
   float* cla = att + a.T * a.K;        // [T][K]
@@ -510,6 +523,8 @@ __global__ void __launch_bounds__(256)
 out_loss_rows_kernel(const float* __restrict__ o, long long ldo, int K, const float* __restrict__ stat,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const long long* __restrict__ labels,
                      long long batch, float* __restrict__ scores, float* __restrict__ lse, float* __restrict__ loss) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   const long long b = blockIdx.x;
   __shared__ float red[8];
   __shared__ float s_lab;
@@ -545,6 +560,8 @@ out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const 
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        const long long* __restrict__ labels, const float* __restrict__ lse,
                        const float* __restrict__ dscores, long long batch, float* __restrict__ d_o, long long ldd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + tx;
   __shared__ double r1[8][32], r2[8][32];
@@ -765,7 +782,7 @@ dim3 tile_grid(long long rows_pad, int cols_pad) {
 
 template <class F>
 int run_tile(F f, TileOut o, cudaStream_t st, const char* what) {
-  tile_split_kernel<F><<<tile_grid(o.rows_pad, o.cols_pad), 256, 0, st>>>(f, o);
+  vmb::launch_pdl(tile_split_kernel<F>, tile_grid(o.rows_pad, o.cols_pad), dim3(256), 0, st, f, o);
   vmb::count_launch();
   return vmb::check_launch(what);
 }
@@ -899,7 +916,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     StatJob j = statjob(bn, double(B) * F);
     if (!update_running) j.run_mean = j.run_var = nullptr;
     const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F + 256 * 8 - 1) / (256 * 8), 64));
-    bn_time_stats_kernel<<<dim3(chunks, T), 256, 0, st>>>(src, ld, B, F, T, j);
+    vmb::launch_pdl(bn_time_stats_kernel, dim3(chunks, T), dim3(256), 0, st, src, ld, B, F, T, j);
     vmb::count_launch();
     return vmb::check_launch("bn_time_stats_kernel");
   };
@@ -956,7 +973,8 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(vmb::check_launch("bn_running_only_kernel"));
       AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
                    params + L.normf.g, params + L.normf.b};
-      att_forward_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(ap, h->Y, h->ycols_pad, l * K, h->row_stats[l]);
+      vmb::launch_pdl(att_forward_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0, st, ap, h->Y, h->ycols_pad, l * K,
+                      h->row_stats[l]);
       vmb::count_launch();
       TRY(vmb::check_launch("att_forward_kernel"));
     }
@@ -969,7 +987,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   TRY(gemm(h->Y_p, h->fc_out.wp, h->fc_out.bias_pad, h->O, Hp, B, Hp, h->ycols_pad, st));
   if (!rc) {
     StatJob j = statjob(h->norm_out, double(B));
-    bn_col_stats_kernel<<<(K + 31) / 32, 256, 0, st>>>(h->O, Hp, B, K, j);
+    vmb::launch_pdl(bn_col_stats_kernel, dim3((K + 31) / 32), dim3(256), 0, st, h->O, Hp, B, K, j);
     vmb::count_launch();
     TRY(vmb::check_launch("bn_col_stats_kernel"));
     const float* stat = slotstat(h->norm_out.slot);
@@ -1040,7 +1058,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
                 params + L.norms[j].b, 1, dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
       double* acc = slotacc(L.norms[j].bslot);
       const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * H + 256 * 8 - 1) / (256 * 8), 64));
-      bn_time_backward_reduce_kernel<<<dim3(chunks, T), 256, 0, st>>>(gi, B, acc);
+      vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
       vmb::count_launch();
       TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
       FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
@@ -1066,7 +1084,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
                 params + L.norm0.b, 0, 0.f, seed, 0};
       double* acc = slotacc(L.norm0.bslot);
       const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F_in + 256 * 8 - 1) / (256 * 8), 64));
-      bn_time_backward_reduce_kernel<<<dim3(chunks, T), 256, 0, st>>>(gi, B, acc);
+      vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
       vmb::count_launch();
       TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
       FBnBackward f{gi, acc, double(B) * F_in, grads + L.norm0.g, grads + L.norm0.b};
