@@ -192,6 +192,12 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      // producer tail: every stage this CTA filled has been released, i.e. all of the leader's multicast commits to THIS
+      // CTA's empty barriers have landed before the CTA can reach the teardown barrier and exit
+      for (int i = 0; i < C::kStages; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
