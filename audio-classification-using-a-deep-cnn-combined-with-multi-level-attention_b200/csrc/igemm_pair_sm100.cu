@@ -80,7 +80,8 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int num_m_pairs = (p.num_m_tiles + 2 * MT - 1) / (2 * MT);
-  const int num_tiles = num_m_pairs * p.num_n_tiles;     // pair tiles (2 * MT * 128 rows x BLOCK_N)
+  const int all_tiles = num_m_pairs * p.num_n_tiles;     // pair tiles (2 * MT * 128 rows x BLOCK_N)
+  const int num_tiles = (p.tile_count > 0 && p.tile_count < all_tiles) ? p.tile_count : all_tiles;
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -369,7 +370,8 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams&
     }
     attr_set = true;
   }
-  const int pair_tiles = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * p.num_n_tiles;
+  const int all_pair_tiles = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * p.num_n_tiles;
+  const int pair_tiles = (p.tile_count > 0 && p.tile_count < all_pair_tiles) ? p.tile_count : all_pair_tiles;
   const int max_pairs = num_sms() / 2;
   const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
   // cluster shape comes from __cluster_dims__
@@ -417,7 +419,40 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   p.ldo = N;
   p.bias = bias;
   p.out = out;
-  return launch_pair<256, 1, false, false, false>(ta, tb, p, stream);
+  // Wave quantisation: T tiles on P SM pairs run as ceil(T / P) rounds.  When the last round would be less than half
+  // full (fc1 / fc2 at 2 560 rows: 160 tiles on 74 pairs = 2 full rounds + 12 tiles), the full rounds go to the pair
+  // kernel and the left-over tiles — one or two rectangles of the output — to the single-CTA kernel with 128 x 128
+  // tiles, which spreads them over all SMs at half the tile duration.  Same K order, so every output element is
+  // the same sum either way (bit-identical; tested).
+  const int P = num_sms() / 2;
+  const int nn = p.num_n_tiles, T = ((p.num_m_tiles + 1) / 2) * nn;
+  const int left = T > P ? T % P : 0;
+  if (left == 0 || 2 * left > P) return launch_pair<256, 1, false, false, false>(ta, tb, p, stream);
+  const int full = T - left;
+  p.tile_count = full;
+  if (launch_pair<256, 1, false, false, false>(ta, tb, p, stream)) return 1;
+  const char* a8 = static_cast<const char*>(a);
+  const char* w8 = static_cast<const char*>(w);
+  char* o8 = static_cast<char*>(out);
+  int r = full / nn;
+  const int c = full - r * nn;
+  if (c > 0) {   // the rest of the partly covered row of tiles
+    const int row0 = r * 256, rows = (M - row0 < 256) ? M - row0 : 256, col0 = c * 256;
+    if (igemm_linear_rect128(a8 + size_t(row0) * K * 2, w8 + size_t(col0) * K * 2, bias ? bias + col0 : nullptr,
+                             o8 + (size_t(row0) * N + col0) * 2, N, relu, rows, N - col0, K, stream)) {
+      snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
+      return 1;
+    }
+    ++r;
+  }
+  if (r * 256 < M) {   // whole rows of tiles below
+    const int row0 = r * 256;
+    if (igemm_linear_rect128(a8 + size_t(row0) * K * 2, w, bias, o8 + size_t(row0) * N * 2, N, relu, M - row0, N, K, stream)) {
+      snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
+      return 1;
+    }
+  }
+  return 0;
 }
 
 int igemm_pair_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,

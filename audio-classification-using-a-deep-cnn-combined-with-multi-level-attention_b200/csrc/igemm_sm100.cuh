@@ -44,6 +44,7 @@ struct IgemmParams {
   int split_nkb;     // PLAIN split mode: K / 64 of one plane (0 = ordinary GEMM)
   int split_planes;  // 2 (hi | lo: 3 products) or 3 (hi | mid | lo: 6 products)
   int ksplit;        // PLAIN + atomic fp32 output: number of K slices (<= 1: none)
+  int tile_count;    // pair kernel: process only the first tile_count tiles (0 = all); see igemm_pair_linear
   int conv_split;    // CONV: activations are [n][2][H][W][C] hi | lo planes, weights [C_out][2 * 9 C_in]
   long long out_img_stride;  // CONV: output elements per image (2 planes when the output is split)
   long long lo_off;          // split output: element offset of the lo plane relative to the hi element
@@ -87,6 +88,10 @@ int igemm_pair_linear(const void* a_bf16, const void* w_bf16, const float* bias,
 int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
                        int W, int C_in, int C_out, int pool, cudaStream_t stream);
 const char* igemm_pair_last_error();
+// A rectangle of a PLAIN bf16 GEMM on the single-CTA kernel with 128-wide tiles: out[M][N] (row stride ldo) =
+// act(A[M][K] W[N][K]^T + bias); used by igemm_pair_linear for the tiles of an incomplete last round.
+int igemm_linear_rect128(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, long long ldo, int relu,
+                         int M, int N, int K, cudaStream_t stream);
 bool igemm_use_pair();
 int igemm_set_pair(int on);
 // Haloed activation boxes for the C_out = 128 conv (conv2): same contract as igemm_set_pair.

@@ -175,7 +175,8 @@ def test_pair_kernel_bit_identical_to_single_cta(n):
                       lambda o, x=x, w=w, b=b, H=H, W=W, Cin=Cin, Cout=Cout, pool=pool: L.vmb_conv3x3_relu(
                           x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), n, H, W, Cin, Cout, pool,
                           engine.stream_ptr())))
-    for (M, N, K) in [(n, 4096, 4096), (256 + n, 256, 12288), (130 * n, 512, 128)]:
+    # the last shape leaves 12 of 160 pair tiles for an incomplete third round: they go to the single-CTA kernel
+    for (M, N, K) in [(n, 4096, 4096), (256 + n, 256, 12288), (130 * n, 512, 128), (2560 - n, 4096, 512)]:
         a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
         w = (torch.randn(N, K, generator=g) * 0.02).to(DEV).bfloat16()
         b = torch.randn(N, generator=g).to(DEV)
