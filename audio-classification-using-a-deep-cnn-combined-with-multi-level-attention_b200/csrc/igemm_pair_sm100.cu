@@ -438,7 +438,7 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   const int c = full - r * nn;
   if (c > 0) {   // the rest of the partly covered row of tiles
     const int row0 = r * 256, rows = (M - row0 < 256) ? M - row0 : 256, col0 = c * 256;
-    if (igemm_linear_rect128(a8 + size_t(row0) * K * 2, w8 + size_t(col0) * K * 2, bias ? bias + col0 : nullptr,
+    if (igemm_linear_rect(a8 + size_t(row0) * K * 2, w8 + size_t(col0) * K * 2, bias ? bias + col0 : nullptr,
                              o8 + (size_t(row0) * N + col0) * 2, N, relu, rows, N - col0, K, stream)) {
       snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
       return 1;
@@ -447,7 +447,7 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   }
   if (r * 256 < M) {   // whole rows of tiles below
     const int row0 = r * 256;
-    if (igemm_linear_rect128(a8 + size_t(row0) * K * 2, w, bias, o8 + size_t(row0) * N * 2, N, relu, M - row0, N, K, stream)) {
+    if (igemm_linear_rect(a8 + size_t(row0) * K * 2, w, bias, o8 + size_t(row0) * N * 2, N, relu, M - row0, N, K, stream)) {
       snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
       return 1;
     }

@@ -611,12 +611,12 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
                  : launch<128, 1, false, false, kOutBf16>(ta, tb, p, stream);
 }
 
-int igemm_linear_rect128(const void* a, const void* w, const float* bias, void* out, long long ldo, int relu, int M, int N,
+int igemm_linear_rect(const void* a, const void* w, const float* bias, void* out, long long ldo, int relu, int M, int N,
                          int K, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
-  if (misaligned32(out, "igemm_linear_rect128")) return 1;
+  if (misaligned32(out, "igemm_linear_rect")) return 1;
   if (K % kBlockK != 0 || N % 128 != 0 || ldo % 16 != 0) {
-    snprintf(g_err, sizeof g_err, "igemm_linear_rect128: need K %% 64 == 0, N %% 128 == 0, ldo %% 16 == 0");
+    snprintf(g_err, sizeof g_err, "igemm_linear_rect: need K %% 64 == 0, N %% 128 == 0, ldo %% 16 == 0");
     return 1;
   }
   CUtensorMap ta, tb;
@@ -626,23 +626,27 @@ int igemm_linear_rect128(const void* a, const void* w, const float* bias, void* 
     uint32_t box[2] = {kBlockK, kBlockM};
     if (make_tmap_bf16(&ta, a, 2, dims, str, box)) return 1;
   }
+  // 64-wide tiles when 128-wide ones would leave more than half of the SMs without a tile
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int block_n = (2 * m_tiles * (N / 128) <= num_sms()) ? 64 : 128;
   {
     uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
     uint64_t str[1] = {uint64_t(K) * 2};
-    uint32_t box[2] = {kBlockK, 128};
+    uint32_t box[2] = {kBlockK, uint32_t(block_n)};
     if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return 1;
   }
   IgemmParams p{};
   p.M = M;
   p.N = N;
   p.num_kb = K / kBlockK;
-  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
-  p.num_n_tiles = N / 128;
+  p.num_m_tiles = m_tiles;
+  p.num_n_tiles = N / block_n;
   p.relu = relu;
   p.ldo = ldo;
   p.bias = bias;
   p.out = out;
-  return launch<128, 1, false, false, kOutBf16>(ta, tb, p, stream);
+  return block_n == 64 ? launch<64, 1, false, false, kOutBf16>(ta, tb, p, stream)
+                       : launch<128, 1, false, false, kOutBf16>(ta, tb, p, stream);
 }
 
 int igemm_linear_split(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo,

@@ -88,9 +88,9 @@ int igemm_pair_linear(const void* a_bf16, const void* w_bf16, const float* bias,
 int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
                        int W, int C_in, int C_out, int pool, cudaStream_t stream);
 const char* igemm_pair_last_error();
-// A rectangle of a PLAIN bf16 GEMM on the single-CTA kernel with 128-wide tiles: out[M][N] (row stride ldo) =
+// A rectangle of a PLAIN bf16 GEMM on the single-CTA kernel with 128- or 64-wide tiles: out[M][N] (row stride ldo) =
 // act(A[M][K] W[N][K]^T + bias); used by igemm_pair_linear for the tiles of an incomplete last round.
-int igemm_linear_rect128(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, long long ldo, int relu,
+int igemm_linear_rect(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, long long ldo, int relu,
                          int M, int N, int K, cudaStream_t stream);
 bool igemm_use_pair();
 int igemm_set_pair(int on);
