@@ -32,9 +32,6 @@ constexpr int kH = 96, kW = 64, kC = 64;
 constexpr int kPH = kH / 2, kPW = kW / 2;        // 48 x 32 pooled
 constexpr int kRowsPerTile = 4;                  // pooled rows per CTA tile (x 32 columns = 128 pooled pixels)
 constexpr int kTilesPerExample = kPH / kRowsPerTile;  // 12
-constexpr int kPatchH = 2 * kRowsPerTile + 2;    // 10 input rows incl. halo
-constexpr int kPatchW = kW + 2;                  // 66
-constexpr int kPatchPitch = 68;
 constexpr int kK = 64;                           // GEMM K: [win_hi(16) | win_lo(16) | win_hi(16) | 1 | 1 | 0 ...]
 constexpr int kLbo = 128;                        // bytes between the 16-byte K chunks of one 8-row group
 constexpr int kSbo = kK / 8 * kLbo;              // 1024 bytes between 8-row groups (8 chunks x 128 B)
@@ -50,7 +47,10 @@ constexpr int kEpiWarps = VMB_CONV1_EPI_WARPS;                     // warps 9-16
 constexpr int kThreads = (kMmaWarp + 1 + kEpiWarps) * 32;
 constexpr int kStages = 2;                       // A-tile ring (one stage per producer group) and TMEM accumulator ring
 constexpr int kTmemCols = 512;                   // 2 buffers x 4 positions x 64 channels
-constexpr int kSmemBytes = 1024 + kStages * kATile + 4 * kBTile;
+constexpr int kOutTile = 128 * kC * 2;            // 16 KiB: the bf16 output of one tile = 128 pooled pixels x 64 channels,
+                                                 // one contiguous block of the NHWC tensor (4 full pooled rows)
+template <bool SPLIT_OUT>
+constexpr int conv1_smem_bytes() { return 1024 + kStages * kATile + 4 * kBTile + (SPLIT_OUT ? 4 : 2) * kOutTile; }
 
 // K-major, no swizzle: element (row r, 16-byte chunk j) at (r / 8) * SBO + j * LBO + (r % 8) * 16
 __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr) {
@@ -86,12 +86,13 @@ __device__ __forceinline__ void load_window(const float* __restrict__ x, long lo
 template <bool SPLIT_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                __nv_bfloat16* __restrict__ out, long long n_tiles) {
+                const __grid_constant__ CUtensorMap tmap_out, long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;                                   // [kStages][kATile]
   uint8_t* b_smem = smem + kStages * kATile;                // [4 positions][kBTile]
+  uint8_t* o_smem = b_smem + 4 * kBTile;                    // [2 buffers][hi (, lo)][kOutTile], 128-byte swizzle
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[kStages], tmem_empty[kStages];
   __shared__ uint32_t tmem_slot;
 
@@ -207,19 +208,21 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     }
   } else {
     // ------------------------------------------------------------------ epilogue: pool = max over 4 column blocks
+    // The results are staged in shared memory (row = pooled pixel = 128 bytes, 128-byte swizzle so that the lanes of a
+    // quarter-warp hit different banks) and leave as ONE TMA store per tile: the tile's output is a contiguous 16 KB
+    // block of the NHWC tensor, and 32-byte stores at a 128-byte stride were what throttled this kernel.
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - kMmaWarp - 1) >> 2;  // the two warps of a quarter alternate over the 16-channel chunks
     const int row = q * 32 + lane;                // pooled pixel within the tile
-    const int pr = row >> 5, pc = row & 31;
+    const bool store_thread = (warp == kMmaWarp + 1) && lane == 0;
+    constexpr int kBufBytes = (SPLIT_OUT ? 2 : 1) * kOutTile;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t stage = it & 1, ph = (it >> 1) & 1;
-      const long long n = tile / kTilesPerExample;
-      const int tr = static_cast<int>(tile - n * kTilesPerExample);
-      // bf16 NHWC [n][48][32][64], or hi | lo planes [n][2][48][32][64]
-      constexpr long long kPlane = static_cast<long long>(kPH) * kPW * kC;
-      __nv_bfloat16* dst = out + n * (SPLIT_OUT ? 2 : 1) * kPlane +
-                           (static_cast<long long>(tr * kRowsPerTile + pr) * kPW + pc) * kC;
+      uint8_t* obuf = o_smem + (it & 1) * kBufBytes;
+      // the store of two tiles ago has finished reading this buffer
+      if (store_thread) bulk_wait_group_read<1>();
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");
       mbar_wait(&tmem_full[stage], ph);
       tc_fence_after_sync();
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + stage * 256;
@@ -242,14 +245,36 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
           if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
         }
-        st_global_256(dst + ch * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);   // one full sector
-        if (SPLIT_OUT)
-          st_global_256(dst + kPlane + ch * 16, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
+        // 16-byte pieces 2*ch and 2*ch+1 of this pixel's 128-byte row, at the swizzled positions TMA expects
+        uint8_t* orow = obuf + row * 128;
+        const int s0 = ((2 * ch) ^ (row & 7)) * 16, s1 = ((2 * ch + 1) ^ (row & 7)) * 16;
+        *reinterpret_cast<uint4*>(orow + s0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(orow + s1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (SPLIT_OUT) {
+          *reinterpret_cast<uint4*>(orow + kOutTile + s0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(orow + kOutTile + s1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[stage]);
+      fence_proxy_async_smem();                   // the generic-proxy writes above, before the async-proxy (TMA) read
+      asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (store_thread) {
+        // output rows: bf16 NHWC [n][48*32][64], or hi | lo planes [n][2][48*32][64]; tile = 128 consecutive rows
+        const long long n = tile / kTilesPerExample;
+        const int tr = static_cast<int>(tile - n * kTilesPerExample);
+        constexpr int kRowsPerImg = kPH * kPW;
+        if (SPLIT_OUT) {
+          tma_store_2d(&tmap_out, obuf, 0, static_cast<int>((2 * n) * kRowsPerImg + tr * 128));
+          tma_store_2d(&tmap_out, obuf + kOutTile, 0, static_cast<int>((2 * n + 1) * kRowsPerImg + tr * 128));
+        } else {
+          tma_store_2d(&tmap_out, obuf, 0, static_cast<int>(n * kRowsPerImg + tr * 128));
+        }
+        bulk_commit_group();
+      }
     }
+    if (store_thread) bulk_wait_group<0>();       // shared memory stays valid until the last store has read it
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -264,18 +289,39 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n,
                        cudaStream_t stream, bool split_out) {
   const long long tiles = n * kTilesPerExample;
+  if (tiles <= 0) return 0;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             conv1_smem_bytes<false>()) != cudaSuccess ||
+        cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             conv1_smem_bytes<true>()) != cudaSuccess) {
       set_kernel_error("conv1: cannot set the dynamic shared memory size");
       return 1;
     }
     attr_set = true;
   }
-  const cudaError_t e = launch_pdl(split_out ? conv1_tc_kernel<true> : conv1_tc_kernel<false>, dim3(grid), dim3(kThreads),
-                                   kSmemBytes, stream, examples, w, b, static_cast<__nv_bfloat16*>(out), tiles);
+  // the output as [rows = n * (1 or 2 planes) * 48 * 32][64 channels]; one box = one tile = 128 rows
+  CUtensorMap to;
+  {
+    const long long rows = n * (split_out ? 2 : 1) * kPH * kPW;
+    if (rows > 0x7fffffffLL) {
+      set_kernel_error("conv1: too many output rows for one call");
+      return 1;
+    }
+    uint64_t dims[2] = {uint64_t(kC), uint64_t(rows)};
+    uint64_t str[1] = {uint64_t(kC) * 2};
+    uint32_t box[2] = {uint32_t(kC), 128};
+    if (make_tmap_bf16(&to, out, 2, dims, str, box)) {
+      set_kernel_error("conv1: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  const cudaError_t e = split_out ? launch_pdl(conv1_tc_kernel<true>, dim3(grid), dim3(kThreads), conv1_smem_bytes<true>(),
+                                               stream, examples, w, b, to, tiles)
+                                  : launch_pdl(conv1_tc_kernel<false>, dim3(grid), dim3(kThreads), conv1_smem_bytes<false>(),
+                                               stream, examples, w, b, to, tiles);
   count_launch();
   if (e != cudaSuccess) {
     set_kernel_error("conv1_tc_kernel: %s", cudaGetErrorString(e));

@@ -116,6 +116,25 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// TMA store of a shared-memory box (bulk async-group completion): whole 128-byte lines reach L2 without going through
+// the LSU.  The issuing thread commits a group and later waits for the group's reads of shared memory (wait_read<N>:
+// at most N groups still reading) before the staging buffer is rewritten.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05: TMEM allocation
 // Executed by one full warp.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
