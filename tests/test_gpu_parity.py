@@ -453,6 +453,19 @@ def test_shard_invariance(vgg_handle, head_handle):
         assert torch.equal(torch.cat(parts), whole)
 
 
+def test_batch_size_invariance_across_kernel_variants(vgg_handle, head_handle):
+    """Small and large batches select different kernels (128 x 128 or 256 x 128 tiles and haloed boxes for conv2, CTA
+    pairs, the single-CTA tail of fc1 / fc2): a 300-clip batch must still equal its pieces bit for bit."""
+    pipe = engine.Pipeline(vgg_handle, head_handle)
+    waves = synth.fast_clips(900, 300).to(DEV)
+    whole = pipe.forward(waves).clone()
+    parts, i = [], 0
+    for m in (1, 3, 5, 41, 250):
+        parts.append(pipe.forward(waves[i:i + m]).clone())
+        i += m
+    assert i == 300 and torch.equal(torch.cat(parts), whole)
+
+
 def test_stream_embeddings_chunking_is_exact(vgg_handle):
     """Long-stream path (config 4 shape, shortened): chunked at multiples of 15 360 samples == unchunked."""
     n_ex = 41
