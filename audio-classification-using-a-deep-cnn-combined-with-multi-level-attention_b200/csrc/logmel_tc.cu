@@ -23,9 +23,11 @@
 // next.  Smem: 3 stages x {A0,A1,A2 (128x32), B0,B1,B2 (240x32)} bf16, 64-byte swizzle = 207 KB.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -333,9 +335,425 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ================================================================== centred even / odd variant (the default path)
+// |X_k| does not change when the time origin of a frame moves to its centre sample (a phase factor of modulus 1).  About
+// that centre the periodic Hann window is even (g[m] = hann[200 + m] = g[-m], hann[0] = 0), so with
+//     E[m] = x[200 + m] + x[200 - m],   O[m] = x[200 + m] - x[200 - m],   m = 0 .. 199
+//     Re Y_k = sum_m E[m] g[m] cos(2 pi k m / 512) (the m = 0 weight halved),   Im Y_k = -sum_m O[m] g[m] sin(2 pi k m / 512)
+// the DFT is two GEMMs with K = 200 (13 steps of 16) and N = 120 bins each instead of one with K = 400 and N = 240: half
+// the tensor-core work.  The price: E and O are not strided views of the waveform, so the A tiles are built by hand —
+// eight producer warps read the samples straight from global memory (L1 / L2; no separate split pass over HBM), form
+// E and O in fp32, split them and write the planes in the no-swizzle core-matrix layout (8 rows x 16 bytes per core
+// matrix: one 16-byte store per lane, a quarter-warp fills one core matrix).  The basis tiles arrive by TMA (64-byte
+// swizzle).
+// Operand precision: both operands are split into TWO fp16 terms (v = hi + lo, 22 mantissa bits; fp16 rather than bf16
+// because 2 x 11 bits need three products where 3 x 8 bits need six) and the three products lo*hi, hi*lo, hi*hi are
+// accumulated in one fp32 TMEM accumulator, smallest first.  ncu on the six-product bf16 version of this kernel showed
+// the shared-memory pipe at 92 % with the tensor pipe at 41 %: every tcgen05.mma re-reads its A and B tiles from shared
+// memory (8 KB per 64 tensor cycles at N = 128), so the number of MMA instructions, not the flops, is what is paid for.
+// Per frame tile (128 frames) and N-tile (120 bins): TMEM columns [0, 128) = Re, [128, 256) = Im (columns 120..127 of
+// each are zero padding); 7 K-blocks of 32 (the last one issues a single K step), each 2 parts x 3 products.
+// 576 threads: warps 0-7 A producers, warp 8 TMA (basis), warp 9 MMA issuer, warps 10-13 / 14-17 epilogue of N-tile 0 / 1.
+constexpr int eoHalf = kWin / 2;                 // 200 centred lags
+constexpr int eoBK = 32;                         // K block (lags per stage)
+constexpr int eoKB = 7;                          // blocks 0..6 cover lags 0..223; block 6 issues one K step (192..207)
+constexpr int eoKPad = eoKB * eoBK;              // 224 columns in the basis table (zero from lag 200 on)
+constexpr int eoTN = 128;                        // accumulator columns per part: 120 bins + 8 zero columns
+constexpr int eoPlanes = 2;                      // fp16 hi, lo
+constexpr int eoLbo = 160;                       // bytes between the 16-byte K chunks of one 8-row group: 128 + 32, so that
+                                                 // the four chunks a half-warp writes at once fall into different banks
+constexpr int eoSbo = (eoBK / 8) * eoLbo;        // 640 bytes between 8-row groups
+constexpr int eoATile = (kTM / 8) * eoSbo;       // 10240 B: one fp16 plane of the 128 x 32 A tile (core-matrix layout)
+constexpr int eoBTile = kTM * eoBK * 2;          // 8192 B: one fp16 plane of the 128 x 32 basis tile (64-byte swizzle)
+constexpr int eoABytes = 2 * eoPlanes * eoATile; // E_hi E_lo O_hi O_lo
+constexpr int eoBBytes = 2 * eoPlanes * eoBTile; // C_hi C_lo S_hi S_lo
+constexpr int eoStageBytes = eoABytes + eoBBytes;      // 72 KB
+constexpr int eoStages = 3;
+constexpr float eoScaleA = 4096.f;               // E, O and the basis are scaled by powers of two so that the lo planes
+constexpr double eoScaleB = 1024.0;              // stay clear of the fp16 subnormal range; undone exactly in the epilogue
+constexpr float eoUnscale = 1.0f / (4096.f * 1024.f);
+constexpr int eoProdWarps = 8;
+constexpr int eoTmaWarp = eoProdWarps, eoMmaWarp = eoProdWarps + 1, eoEpiWarp0 = eoProdWarps + 2;
+constexpr int eoThreads = (eoEpiWarp0 + 8) * 32; // 576
+constexpr int eoTabBytes = 2 * kEvalBins * 4 + kEvalBins;   // mel walk tables copied to shared memory: wfall, wrise, band
+constexpr int eoSmemBytes = 1024 + eoStages * eoStageBytes + 512 + 2 * kTM * kHandFloats * 4 + ((eoTabBytes + 15) & ~15);
+
+// K-major, no swizzle: element (row r, 16-byte chunk j) at (r / 8) * SBO + j * LBO + (r % 8) * 16
+__device__ __forceinline__ uint64_t umma_desc_kmajor_cores(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(eoLbo >> 4) << 16;
+  d |= static_cast<uint64_t>(eoSbo >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
+// Raw samples for four consecutive lags m .. m + 3 of one frame, on both sides of the centre sample c: fetched one
+// whole stage ahead of their use and left untouched in registers until then (the L2 latency of these loads was what
+// the producers, and with them the whole kernel, waited for).  A quarter-warp (eight lanes, m = m0 + 4 * lane) reads 128
+// contiguous bytes (fp32) on either side.
+// vec: every (c + m) is 16-byte (fp32) / 8-byte (PCM) aligned (the launcher checks the base pointer and the clip stride).
+template <class IN> struct RawLags;
+template <> struct RawLags<float> {
+  float4 a;     // c[m .. m+3]
+  float4 d;     // c[-m-4 .. -m-1]  (lags m+4, m+3, m+2, m+1; the first is not used)
+  float s;      // c[-m]
+  __device__ __forceinline__ void zero() { a = d = make_float4(0.f, 0.f, 0.f, 0.f); s = 0.f; }
+  __device__ __forceinline__ void load(const float* __restrict__ c, int m, bool vec) {
+    if (vec) {
+      a = __ldg(reinterpret_cast<const float4*>(c + m));
+      d = __ldg(reinterpret_cast<const float4*>(c - m - 4));
+    } else {
+      a = make_float4(__ldg(c + m), __ldg(c + m + 1), __ldg(c + m + 2), __ldg(c + m + 3));
+      d = make_float4(0.f, __ldg(c - m - 3), __ldg(c - m - 2), __ldg(c - m - 1));
+    }
+    s = __ldg(c - m);
+  }
+  // xp keeps its scale factor for the fused multiply-add that forms E and O; xm is scaled here
+  __device__ __forceinline__ void unpack(float (&xp)[4], float (&xm)[4]) const {
+    xp[0] = a.x; xp[1] = a.y; xp[2] = a.z; xp[3] = a.w;
+    xm[0] = s * eoScaleA; xm[1] = d.w * eoScaleA; xm[2] = d.z * eoScaleA; xm[3] = d.y * eoScaleA;
+  }
+  static constexpr float xp_scale = eoScaleA;
+};
+constexpr float eoPcmScale = eoScaleA / 32768.0f;
+__device__ __forceinline__ float pcm_lo(uint32_t w) { return static_cast<float>(static_cast<int16_t>(w & 0xffffu)) * eoPcmScale; }
+__device__ __forceinline__ float pcm_hi(uint32_t w) { return static_cast<float>(static_cast<int32_t>(w) >> 16) * eoPcmScale; }
+template <> struct RawLags<int16_t> {
+  uint2 a, d;   // four 16-bit samples each, same ranges as above
+  int s;
+  __device__ __forceinline__ void zero() { a = d = make_uint2(0u, 0u); s = 0; }
+  __device__ __forceinline__ void load(const int16_t* __restrict__ c, int m, bool vec) {
+    if (vec) {
+      a = __ldg(reinterpret_cast<const uint2*>(c + m));
+      d = __ldg(reinterpret_cast<const uint2*>(c - m - 4));
+    } else {
+      const uint16_t* u = reinterpret_cast<const uint16_t*>(c);
+      a = make_uint2(uint32_t(__ldg(u + m)) | (uint32_t(__ldg(u + m + 1)) << 16),
+                     uint32_t(__ldg(u + m + 2)) | (uint32_t(__ldg(u + m + 3)) << 16));
+      d = make_uint2(uint32_t(__ldg(u - m - 3)) << 16, uint32_t(__ldg(u - m - 2)) | (uint32_t(__ldg(u - m - 1)) << 16));
+    }
+    s = __ldg(c - m);
+  }
+  __device__ __forceinline__ void unpack(float (&xp)[4], float (&xm)[4]) const {
+    xp[0] = pcm_lo(a.x); xp[1] = pcm_hi(a.x); xp[2] = pcm_lo(a.y); xp[3] = pcm_hi(a.y);
+    xm[0] = static_cast<float>(s) * eoPcmScale; xm[1] = pcm_hi(d.y); xm[2] = pcm_lo(d.y); xm[3] = pcm_hi(d.x);
+  }
+  static constexpr float xp_scale = 1.0f;
+};
+
+// v ~ hi + lo (two fp16 terms, 22 mantissa bits; the residual v - hi is exact in fp32), two values per register
+__device__ __forceinline__ void split2_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __half2 l = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+struct LogmelEoParams {
+  long long clip_stride;    // elements between clips of the input
+  long long frames_out;     // frames written per clip
+  int tiles_per_clip;       // ceil(frames_out / 128)
+  long long total_tiles;    // n_clips * tiles_per_clip
+  int vec;                  // aligned vector loads allowed
+  float* out;               // [n_clips][frames_out][64]
+};
+
+// NB bins starting at table index bin0 (a multiple of 8): the magnitudes first (independent, so the MUFU latencies
+// overlap), then the sequential band walk on registers.  The walk tables come from shared memory as vector loads: indexed
+// __constant__ loads inside the walk (one dependent LDC per table and bin, each behind a branch) cost ~300 cycles per bin
+// and made the epilogue, not the tensor pipe, the limiter of this kernel.
+template <int NB>
+__device__ __forceinline__ void walk_bins_eo(BandWalk& w, const uint32_t* re_v, const uint32_t* im_v,
+                                             const float (&wf)[16], const float (&wr)[16], const uint2 bd,
+                                             float* __restrict__ row_out, bool valid) {
+  float mag[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float re = __uint_as_float(re_v[j]), im = __uint_as_float(im_v[j]);
+    float m;     // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(re, re, im * im)));
+    mag[j] = m * eoUnscale;                              // exact: the operands carried 2^12 and 2^10
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int e = static_cast<int>(((j < 4 ? bd.x : bd.y) >> (8 * (j & 3))) & 0xffu);
+    while (w.e < e) emit_band(w, row_out, valid);      // warp-uniform: depends on the bin index only
+    w.lo = fmaf(wf[j], mag[j], w.lo);
+    w.hi = fmaf(wr[j], mag[j], w.hi);
+  }
+}
+
+template <class IN>
+__global__ void __launch_bounds__(eoThreads, 1)
+logmel_eo_kernel(const IN* __restrict__ wave, const __grid_constant__ CUtensorMap tmap_b, const LogmelEoParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + eoStages * eoStageBytes);
+  uint64_t* empty_bar = full_bar + eoStages;
+  uint64_t* tmem_full = empty_bar + eoStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* hand_full = tmem_empty + 2;       // [2 buffers][4 lane quarters]
+  uint64_t* hand_empty = hand_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hand_empty + 8);
+  float* hand = reinterpret_cast<float*>(smem + eoStages * eoStageBytes + 512);   // [2][kTM][kHandFloats]
+  float* s_wf = hand + 2 * kTM * kHandFloats;                                     // [kEvalBins] falling-side weights
+  float* s_wr = s_wf + kEvalBins;                                                 // [kEvalBins] rising-side weights
+  uint8_t* s_band = reinterpret_cast<uint8_t*>(s_wr + kEvalBins);                 // [kEvalBins] band interval per bin
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x < kEvalBins) {
+    s_wf[threadIdx.x] = c_wfall[threadIdx.x];
+    s_wr[threadIdx.x] = c_wrise[threadIdx.x];
+    s_band[threadIdx.x] = static_cast<uint8_t>(c_band[threadIdx.x]);
+  }
+  if (warp == eoTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < eoStages; ++s) {
+      mbar_init(&full_bar[s], eoProdWarps * 32 + 1);   // every producer thread + the TMA thread's expect_tx
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&hand_full[s], 1);
+      mbar_init(&hand_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == eoMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform by construction
+  pdl_wait();   // the waveform may have been written by the previous kernel in the stream
+
+  if (warp < eoProdWarps) {
+    // ------------------------------------------------------------------ A producers: E / O planes of 16 frames per warp
+    // lane = (row within a 4-row group, 4 lags): the eight lanes of a quarter-warp read 32 consecutive lags of one frame
+    // (128 contiguous bytes of fp32 on either side of the centre) and a half-warp's 8-byte stores cover all 32 banks.
+    // The loop runs over the flattened (tile, N-tile, K-block) sequence with the raw samples of the NEXT stage in flight
+    // while the current one is converted and stored.
+    const int rs = lane >> 3, c4 = lane & 7;
+    const uint32_t lane_off = warp * 2 * eoSbo + rs * 16 + (c4 >> 1) * eoLbo + (c4 & 1) * 8;
+    struct Cursor {
+      long long tile;
+      int step;                 // nt * eoKB + kb
+      const IN* centre0;        // centre sample of this lane's first frame in the tile
+      long long frame0;
+    };
+    auto place = [&](Cursor& cu) {
+      const long long clip = cu.tile / p.tiles_per_clip;
+      cu.frame0 = (cu.tile - clip * p.tiles_per_clip) * kTM + warp * 16 + rs;   // + 4 * it
+      cu.centre0 = wave + clip * p.clip_stride + cu.frame0 * kHop + eoHalf;
+    };
+    auto fetch = [&](const Cursor& cu, RawLags<IN> (&raw)[4]) {
+      const int kb = cu.step >= eoKB ? cu.step - eoKB : cu.step;
+      const int m = kb * eoBK + c4 * 4;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (cu.frame0 + 4 * it < p.frames_out && m < eoHalf) raw[it].load(cu.centre0 + it * 4 * kHop, m, p.vec != 0);
+        else raw[it].zero();
+      }
+    };
+    uint32_t stage = 0, phase = 0;
+    auto emit = [&](const Cursor& cu, const RawLags<IN> (&raw)[4]) {
+      const int kb = cu.step >= eoKB ? cu.step - eoKB : cu.step;
+      const int m = kb * eoBK + c4 * 4;
+      mbar_wait(&empty_bar[stage], phase ^ 1);        // the MMAs that read this stage last time are done
+      const uint32_t a_base = smem_u32(smem + stage * eoStageBytes) + lane_off;
+      if (m < eoHalf + 8) {                            // chunks from lag 208 on are never read by an MMA
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float xp[4], xm[4];
+          raw[it].unpack(xp, xm);
+          uint32_t eh[2], el[2], oh[2], ol[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            constexpr float sc = RawLags<IN>::xp_scale;
+            split2_pair(fmaf(xp[2 * t], sc, xm[2 * t]), fmaf(xp[2 * t + 1], sc, xm[2 * t + 1]), eh[t], el[t]);
+            split2_pair(fmaf(xp[2 * t], sc, -xm[2 * t]), fmaf(xp[2 * t + 1], sc, -xm[2 * t + 1]), oh[t], ol[t]);
+          }
+          // rows 16 * warp + 4 * it + rs: 8-row group 2 * warp + (it >> 1), row (it & 1) * 4 + rs within it
+          const uint32_t dst = a_base + (it >> 1) * eoSbo + (it & 1) * 64;
+          st_shared_v2(dst + 0 * eoATile, eh[0], eh[1]);
+          st_shared_v2(dst + 1 * eoATile, el[0], el[1]);
+          st_shared_v2(dst + 2 * eoATile, oh[0], oh[1]);
+          st_shared_v2(dst + 3 * eoATile, ol[0], ol[1]);
+        }
+      }
+      fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[stage]);
+      if (++stage == eoStages) { stage = 0; phase ^= 1; }
+    };
+    auto advance = [&](Cursor& cu) {      // false once the CTA's last stage has been passed
+      if (++cu.step == kNTiles * eoKB) {
+        cu.step = 0;
+        cu.tile += gridDim.x;
+        if (cu.tile >= p.total_tiles) return false;
+        place(cu);
+      }
+      return true;
+    };
+    Cursor cur{static_cast<long long>(blockIdx.x), 0, nullptr, 0};
+    if (cur.tile < p.total_tiles) {
+      place(cur);
+      RawLags<IN> buf0[4], buf1[4];
+      fetch(cur, buf0);
+      for (;;) {
+        Cursor nxt = cur;
+        const bool more1 = advance(nxt);
+        if (more1) fetch(nxt, buf1);
+        emit(cur, buf0);
+        if (!more1) break;
+        cur = nxt;
+        const bool more0 = advance(nxt);
+        if (more0) fetch(nxt, buf0);
+        emit(cur, buf1);
+        if (!more0) break;
+        cur = nxt;
+      }
+    }
+  } else if (warp == eoTmaWarp) {
+    // ------------------------------------------------------------------ basis tiles by TMA
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int nt = 0; nt < kNTiles; ++nt) {
+          for (int kb = 0; kb < eoKB; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* b_base = smem + stage * eoStageBytes + eoABytes;
+            mbar_expect_tx(&full_bar[stage], eoBBytes);
+#pragma unroll
+            for (int t = 0; t < 2 * eoPlanes; ++t)   // tile t = part * 2 + plane; table rows ((plane * 2 + part) * 2 + nt) * 128
+              tma_load_2d(b_base + t * eoBTile, &tmap_b, &full_bar[stage], kb * eoBK,
+                          (((t % eoPlanes) * 2 + t / eoPlanes) * kNTiles + nt) * eoTN);
+            if (++stage == eoStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == eoMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16_f32(kTM, eoTN);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < kNTiles; ++nt, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < eoKB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a0 = smem_u32(smem + stage * eoStageBytes);
+            const uint32_t b0 = a0 + eoABytes;
+            const int nks = (kb == eoKB - 1) ? 1 : 2;
+            // products (a plane, b plane), smallest magnitude first
+            constexpr int prod_a[3] = {1, 0, 0};
+            constexpr int prod_b[3] = {0, 1, 0};
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {       // E x C -> Re columns, O x S -> Im columns
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const uint64_t a_desc = umma_desc_kmajor_cores(a0 + (part * eoPlanes + prod_a[q]) * eoATile);
+                const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + (part * eoPlanes + prod_b[q]) * eoBTile);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)   // K step 16 lags: two chunks = 2 * LBO in A, 32 bytes in the swizzled B row
+                  if (k < nks)
+                    umma_bf16_ss(d_tmem + part * eoTN, a_desc + k * (2 * eoLbo >> 4), b_desc + 2 * k, idesc,
+                                 (kb | q | k) != 0);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == eoKB - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == eoStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (same walk and hand-off as above)
+    const int set = (warp - eoEpiWarp0) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t mi = 0;   // frame-tile iteration of this CTA
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++mi) {
+      const long long clip = tile / p.tiles_per_clip;
+      const long long frame = (tile - clip * p.tiles_per_clip) * kTM + row;
+      const bool valid = frame < p.frames_out;
+      float* row_out = p.out + (clip * p.frames_out + (valid ? frame : 0)) * kMel;
+      const uint32_t hb = mi & 1, hphase = (mi >> 1) & 1;
+      float* hrow = hand + (hb * kTM + row) * kHandFloats;
+      BandWalk w;
+      w.pend = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (set == 1) {
+        mbar_wait(&hand_full[hb * 4 + q], hphase);
+        w.e = c_band[kTileBins - 1];            // where the walk over bins 0..119 stops (uniform)
+        w.lo = hrow[0]; w.hi = hrow[1];
+        w.pend = make_float4(hrow[2], hrow[3], hrow[4], 0.f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
+      }
+      const uint32_t acc = set, acc_phase = mi & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int ch = 0; ch < 2 * (kTileBins / 16) + 1; ++ch) {   // 15 chunks of 8 bins
+        const int bin0 = set * kTileBins + ch * 8;
+        uint32_t re[8], im[8];
+        tmem_ld_32x8(t_addr + ch * 8, re);
+        tmem_ld_32x8(t_addr + eoTN + ch * 8, im);
+        float wf[16], wr[16];
+        {
+          const float4 a0 = *reinterpret_cast<const float4*>(s_wf + bin0), a1 = *reinterpret_cast<const float4*>(s_wf + bin0 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_wr + bin0), b1 = *reinterpret_cast<const float4*>(s_wr + bin0 + 4);
+          wf[0] = a0.x; wf[1] = a0.y; wf[2] = a0.z; wf[3] = a0.w; wf[4] = a1.x; wf[5] = a1.y; wf[6] = a1.z; wf[7] = a1.w;
+          wr[0] = b0.x; wr[1] = b0.y; wr[2] = b0.z; wr[3] = b0.w; wr[4] = b1.x; wr[5] = b1.y; wr[6] = b1.z; wr[7] = b1.w;
+        }
+        const uint2 bd = *reinterpret_cast<const uint2*>(s_band + bin0);
+        tmem_ld_wait();
+        walk_bins_eo<8>(w, re, im, wf, wr, bd, row_out, valid);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (set == 0) {
+        mbar_wait(&hand_empty[hb * 4 + q], hphase ^ 1);
+        hrow[0] = w.lo; hrow[1] = w.hi;
+        hrow[2] = w.pend.x; hrow[3] = w.pend.y; hrow[4] = w.pend.z;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hand_full[hb * 4 + q]);
+      } else {
+        while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == eoMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ per-device constant tables
 struct TcTables {
   __nv_bfloat16* basis = nullptr;  // [3][480][416] bf16: row = 2*bin_index + {cos, sin}, col = sample in frame
+  __half* basis_eo = nullptr;      // [2 planes: hi, lo][2 parts: cos, sin][2 N-tiles][128 bins (120 used)][224 lags (200 used)]
   bool ready = false;
 };
 std::mutex g_mu;
@@ -422,6 +840,32 @@ int build_tables(TcTables& t) {
     return 1;
   }
   t.basis = static_cast<__nv_bfloat16*>(d);
+  // centred basis of the even / odd kernel: g[m] cos / sin(2 pi k m / 512), g[m] = hann[200 + m]; the lag-0 cosine
+  // weight is halved because E[0] = 2 x[200]
+  const size_t rows_eo = size_t(eoPlanes) * 2 * kNTiles * eoTN;
+  std::vector<uint16_t> beo(rows_eo * eoKPad, 0);
+  for (int nt = 0; nt < kNTiles; ++nt)
+    for (int r = 0; r < kTileBins; ++r)
+      for (int m = 0; m < eoHalf; ++m) {
+        const int km = ((kBinLo + nt * kTileBins + r) * m) % kFft;       // exact argument reduction
+        const double ang = 2 * kPi * km / kFft, g = eoScaleB * hann[eoHalf + m] * (m == 0 ? 0.5 : 1.0);
+        const double val[2] = {g * std::cos(ang), g * std::sin(ang)};
+        for (int c = 0; c < 2; ++c) {
+          double rem = val[c];
+          for (int pl = 0; pl < eoPlanes; ++pl) {
+            const __half h = __float2half_rn(static_cast<float>(rem));
+            beo[(size_t((pl * 2 + c) * kNTiles + nt) * eoTN + r) * eoKPad + m] = __half_as_ushort(h);
+            rem -= static_cast<double>(__half2float(h));
+          }
+        }
+      }
+  void* de = nullptr;
+  if (cudaMalloc(&de, beo.size() * 2) != cudaSuccess ||
+      cudaMemcpy(de, beo.data(), beo.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_kernel_error("logmel: centred basis upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  t.basis_eo = static_cast<__half*>(de);
   t.ready = true;
   return 0;
 }
@@ -436,8 +880,10 @@ int get_tables(TcTables** out) {
   TcTables& t = g_tabs[dev];
   if (!t.ready) {
     if (build_tables(t)) return 1;
-    if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
-      set_kernel_error("logmel: cannot raise dynamic shared memory to %d bytes", kSmemBytes);
+    if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(logmel_eo_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, eoSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(logmel_eo_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, eoSmemBytes) != cudaSuccess) {
+      set_kernel_error("logmel: cannot raise dynamic shared memory to %d / %d bytes", kSmemBytes, eoSmemBytes);
       return 1;
     }
     cudaMemPool_t pool;
@@ -454,6 +900,49 @@ int get_tables(TcTables** out) {
 // plane; a multiple of 160 keeps every stride a multiple of the 320-byte frame stride
 long long logmel_tc_pitch(long long samples_per_clip) { return (samples_per_clip + 16 + kHop - 1) / kHop * kHop; }
 
+// VMB_LOGMEL_PLANES=1 selects the first tensor-core version (split_wave_kernel + logmel_tc_kernel: K = 400 straight DFT
+// over TMA-framed sample planes), kept for A/B timing and as an on-device cross-check of the centred kernel.
+bool logmel_use_planes() {
+  static const bool on = [] {
+    const char* e = std::getenv("VMB_LOGMEL_PLANES");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+template <class IN>
+int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long clip_stride, long long frames_out,
+                      float* logmel, cudaStream_t stream) {
+  CUtensorMap tb;
+  {
+    uint64_t dims[2] = {uint64_t(eoKPad), uint64_t(eoPlanes * 2 * kNTiles * eoTN)};
+    uint64_t str[1] = {uint64_t(eoKPad) * 2};
+    uint32_t box[2] = {eoBK, eoTN};
+    if (make_tmap_bf16(&tb, t->basis_eo, 2, dims, str, box, 64)) {   // 16-bit elements: the map only moves bytes
+      set_kernel_error("logmel: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  LogmelEoParams p{};
+  p.clip_stride = clip_stride;
+  p.frames_out = frames_out;
+  p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
+  p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
+  // vector loads need the centre sample of every frame (offset 160 f + 200 elements from the clip start) aligned
+  p.vec = (reinterpret_cast<uintptr_t>(wave) % 16 == 0) && ((clip_stride * static_cast<long long>(sizeof(IN))) % 16 == 0);
+  p.out = logmel;
+  if (p.total_tiles <= 0) return 0;
+  const long long grid = std::min<long long>(p.total_tiles, num_sms());
+  const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
+                                    stream, wave, tb, p);
+  count_launch();
+  if (le != cudaSuccess) {
+    set_kernel_error("logmel_eo_kernel: %s", cudaGetErrorString(le));
+    return 1;
+  }
+  return check_launch("logmel_eo_kernel");
+}
+
 template <class IN>
 int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                            long long frames_out, float* logmel, cudaStream_t stream) {
@@ -463,6 +952,7 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
     set_kernel_error("logmel: too many clips / frames for one launch");
     return 1;
   }
+  if (!logmel_use_planes()) return logmel_eo_forward<IN>(t, wave, n_clips, clip_stride, frames_out, logmel, stream);
   constexpr int a_planes = sizeof(IN) == 2 ? 2 : 3;
   const long long pitch = logmel_tc_pitch(samples_per_clip);
   const size_t plane_bytes = size_t(n_clips) * pitch * 2;

@@ -43,7 +43,7 @@ def test_library_is_the_thing_that_runs():
     before = _lib.lib().vmb_launch_count()
     engine.logmel(torch.zeros(1, 16000, device=DEV))
     torch.cuda.synchronize()
-    assert _lib.lib().vmb_launch_count() == before + 2          # split kernel + tcgen05 DFT/mel kernel
+    assert _lib.lib().vmb_launch_count() == before + 1          # one fused kernel: framing + tcgen05 DFT + mel + log
 
 
 # ------------------------------------------------------------------------------------------------ front end
