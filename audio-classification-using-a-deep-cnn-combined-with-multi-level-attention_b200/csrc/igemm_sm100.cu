@@ -483,6 +483,25 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   return 0;
 }
 
+int make_tmap_plain(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType ty = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  CUresult r = fn(m, ty, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled (plain, %d-byte elements) failed: CUresult %d (rank %d)",
+             elem_bytes, int(r), rank);
+    return 1;
+  }
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {

@@ -104,6 +104,9 @@ const char* igemm_last_error();
 // igemm_last_error()), and the SM count of the current device.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes = 128);
+// Unswizzled tensor map over 4-byte (fp32) or 2-byte (16-bit integer) elements; out-of-range box elements read as zero.
+int make_tmap_plain(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
 int num_sms();
 
 }  // namespace vmb

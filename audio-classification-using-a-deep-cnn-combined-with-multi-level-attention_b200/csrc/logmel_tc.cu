@@ -369,6 +369,9 @@ constexpr int eoABytes = 2 * eoPlanes * eoATile; // E_hi E_lo O_hi O_lo
 constexpr int eoBBytes = 2 * eoPlanes * eoBTile; // C_hi C_lo S_hi S_lo
 constexpr int eoStageBytes = eoABytes + eoBBytes;      // 72 KB
 constexpr int eoStages = 3;
+constexpr int eoRawTile = kTM * eoBK * 4;        // 16 KB: the forward raw fp32 sample tile; it and the backward one (18 KB) land
+                                                 // in the A region of a stage (4 x 10 KB) before the producers turn them
+                                                 // into the four planes
 constexpr float eoScaleA = 4096.f;               // E, O and the basis are scaled by powers of two so that the lo planes
 constexpr double eoScaleB = 1024.0;              // stay clear of the fp16 subnormal range; undone exactly in the epilogue
 constexpr float eoUnscale = 1.0f / (4096.f * 1024.f);
@@ -388,56 +391,62 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_cores(uint32_t smem_addr) {
   return d;
 }
 
-// Raw samples for four consecutive lags m .. m + 3 of one frame, on both sides of the centre sample c: fetched one
-// whole stage ahead of their use and left untouched in registers until then (the L2 latency of these loads was what
-// the producers, and with them the whole kernel, waited for).  A quarter-warp (eight lanes, m = m0 + 4 * lane) reads 128
-// contiguous bytes (fp32) on either side.
-// vec: every (c + m) is 16-byte (fp32) / 8-byte (PCM) aligned (the launcher checks the base pointer and the clip stride).
-template <class IN> struct RawLags;
-template <> struct RawLags<float> {
-  float4 a;     // c[m .. m+3]
-  float4 d;     // c[-m-4 .. -m-1]  (lags m+4, m+3, m+2, m+1; the first is not used)
-  float s;      // c[-m]
-  __device__ __forceinline__ void zero() { a = d = make_float4(0.f, 0.f, 0.f, 0.f); s = 0.f; }
-  __device__ __forceinline__ void load(const float* __restrict__ c, int m, bool vec) {
-    if (vec) {
-      a = __ldg(reinterpret_cast<const float4*>(c + m));
-      d = __ldg(reinterpret_cast<const float4*>(c - m - 4));
-    } else {
-      a = make_float4(__ldg(c + m), __ldg(c + m + 1), __ldg(c + m + 2), __ldg(c + m + 3));
-      d = make_float4(0.f, __ldg(c - m - 3), __ldg(c - m - 2), __ldg(c - m - 1));
-    }
-    s = __ldg(c - m);
-  }
-  // xp keeps its scale factor for the fused multiply-add that forms E and O; xm is scaled here
-  __device__ __forceinline__ void unpack(float (&xp)[4], float (&xm)[4]) const {
-    xp[0] = a.x; xp[1] = a.y; xp[2] = a.z; xp[3] = a.w;
-    xm[0] = s * eoScaleA; xm[1] = d.w * eoScaleA; xm[2] = d.z * eoScaleA; xm[3] = d.y * eoScaleA;
-  }
-  static constexpr float xp_scale = eoScaleA;
-};
+// Raw sample tiles of one stage, landed in shared memory by TMA (two boxes of the overlapping-rows view of the waveform:
+// row = frame, 160 samples apart): fwd[r][l] = x[lag 32 kb + l] to the right of the centre sample, bwd[r][l] = the
+// sample at lag 32 kb + 32 - l to its left (the box runs forwards in memory, so the lags run backwards in it).  Elements
+// outside the frame (lags >= 200 at either end) and frames past the end of the clip are zero-filled by TMA.
+// Each lane converts four consecutive lags of one frame: one 16-byte (fp32) or 8-byte (PCM) read from either tile.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 constexpr float eoPcmScale = eoScaleA / 32768.0f;
 __device__ __forceinline__ float pcm_lo(uint32_t w) { return static_cast<float>(static_cast<int16_t>(w & 0xffffu)) * eoPcmScale; }
 __device__ __forceinline__ float pcm_hi(uint32_t w) { return static_cast<float>(static_cast<int32_t>(w) >> 16) * eoPcmScale; }
+// TMA box starts must be 16-byte aligned in global memory, and a mirrored group of four lags starts one element off
+// a four-element boundary, so the backward box is 4 (fp32) / 8 (PCM) elements wider than it needs to be: column l of
+// it holds lag 32 kb + 32 - l, a lane reads columns 28 - 4 c4 .. 31 - 4 c4 (aligned) plus column 32 - 4 c4.
+template <class IN> struct RawLags;
+template <> struct RawLags<float> {
+  uint4 f, b;
+  uint32_t s;
+  static constexpr int kRowBytes = eoBK * 4, kBwdCols = eoBK + 4, kBwdRowBytes = kBwdCols * 4;
+  __device__ __forceinline__ void read(uint32_t fwd, uint32_t bwd, int row, int c4) {
+    f = lds128(fwd + row * kRowBytes + c4 * 16);
+    b = lds128(bwd + row * kBwdRowBytes + (7 - c4) * 16);       // lags m+4, m+3, m+2, m+1
+    s = lds32(bwd + row * kBwdRowBytes + (8 - c4) * 16);        // lag m
+  }
+  // xp keeps its scale factor for the fused multiply-add that forms E and O; xm is scaled here
+  __device__ __forceinline__ void unpack(float (&xp)[4], float (&xm)[4]) const {
+    xp[0] = __uint_as_float(f.x); xp[1] = __uint_as_float(f.y); xp[2] = __uint_as_float(f.z); xp[3] = __uint_as_float(f.w);
+    xm[0] = __uint_as_float(s) * eoScaleA; xm[1] = __uint_as_float(b.w) * eoScaleA;
+    xm[2] = __uint_as_float(b.z) * eoScaleA; xm[3] = __uint_as_float(b.y) * eoScaleA;
+  }
+  static constexpr float xp_scale = eoScaleA;
+};
 template <> struct RawLags<int16_t> {
-  uint2 a, d;   // four 16-bit samples each, same ranges as above
-  int s;
-  __device__ __forceinline__ void zero() { a = d = make_uint2(0u, 0u); s = 0; }
-  __device__ __forceinline__ void load(const int16_t* __restrict__ c, int m, bool vec) {
-    if (vec) {
-      a = __ldg(reinterpret_cast<const uint2*>(c + m));
-      d = __ldg(reinterpret_cast<const uint2*>(c - m - 4));
-    } else {
-      const uint16_t* u = reinterpret_cast<const uint16_t*>(c);
-      a = make_uint2(uint32_t(__ldg(u + m)) | (uint32_t(__ldg(u + m + 1)) << 16),
-                     uint32_t(__ldg(u + m + 2)) | (uint32_t(__ldg(u + m + 3)) << 16));
-      d = make_uint2(uint32_t(__ldg(u - m - 3)) << 16, uint32_t(__ldg(u - m - 2)) | (uint32_t(__ldg(u - m - 1)) << 16));
-    }
-    s = __ldg(c - m);
+  uint2 f, b;
+  uint32_t s;
+  static constexpr int kRowBytes = eoBK * 2, kBwdCols = eoBK + 8, kBwdRowBytes = kBwdCols * 2;
+  __device__ __forceinline__ void read(uint32_t fwd, uint32_t bwd, int row, int c4) {
+    f = lds64(fwd + row * kRowBytes + c4 * 8);
+    b = lds64(bwd + row * kBwdRowBytes + (7 - c4) * 8);         // lags m+4, m+3, m+2, m+1
+    s = lds32(bwd + row * kBwdRowBytes + (8 - c4) * 8);         // lag m in the low half
   }
   __device__ __forceinline__ void unpack(float (&xp)[4], float (&xm)[4]) const {
-    xp[0] = pcm_lo(a.x); xp[1] = pcm_hi(a.x); xp[2] = pcm_lo(a.y); xp[3] = pcm_hi(a.y);
-    xm[0] = static_cast<float>(s) * eoPcmScale; xm[1] = pcm_hi(d.y); xm[2] = pcm_lo(d.y); xm[3] = pcm_hi(d.x);
+    xp[0] = pcm_lo(f.x); xp[1] = pcm_hi(f.x); xp[2] = pcm_lo(f.y); xp[3] = pcm_hi(f.y);
+    xm[0] = pcm_lo(s); xm[1] = pcm_hi(b.y); xm[2] = pcm_lo(b.y); xm[3] = pcm_hi(b.x);
   }
   static constexpr float xp_scale = 1.0f;
 };
@@ -455,11 +464,9 @@ __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t
 }
 
 struct LogmelEoParams {
-  long long clip_stride;    // elements between clips of the input
   long long frames_out;     // frames written per clip
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
-  int vec;                  // aligned vector loads allowed
   float* out;               // [n_clips][frames_out][64]
 };
 
@@ -490,7 +497,8 @@ __device__ __forceinline__ void walk_bins_eo(BandWalk& w, const uint32_t* re_v, 
 
 template <class IN>
 __global__ void __launch_bounds__(eoThreads, 1)
-logmel_eo_kernel(const IN* __restrict__ wave, const __grid_constant__ CUtensorMap tmap_b, const LogmelEoParams p) {
+logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xb,
+                 const __grid_constant__ CUtensorMap tmap_b, const LogmelEoParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -500,7 +508,8 @@ logmel_eo_kernel(const IN* __restrict__ wave, const __grid_constant__ CUtensorMa
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* hand_full = tmem_empty + 2;       // [2 buffers][4 lane quarters]
   uint64_t* hand_empty = hand_full + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hand_empty + 8);
+  uint64_t* raw_full = hand_empty + 8;        // [eoStages]: the raw sample tiles of the stage have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + eoStages);
   float* hand = reinterpret_cast<float*>(smem + eoStages * eoStageBytes + 512);   // [2][kTM][kHandFloats]
   float* s_wf = hand + 2 * kTM * kHandFloats;                                     // [kEvalBins] falling-side weights
   float* s_wr = s_wf + kEvalBins;                                                 // [kEvalBins] rising-side weights
@@ -515,10 +524,13 @@ logmel_eo_kernel(const IN* __restrict__ wave, const __grid_constant__ CUtensorMa
     s_band[threadIdx.x] = static_cast<uint8_t>(c_band[threadIdx.x]);
   }
   if (warp == eoTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_xb);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < eoStages; ++s) {
       mbar_init(&full_bar[s], eoProdWarps * 32 + 1);   // every producer thread + the TMA thread's expect_tx
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&raw_full[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -539,99 +551,63 @@ logmel_eo_kernel(const IN* __restrict__ wave, const __grid_constant__ CUtensorMa
 
   if (warp < eoProdWarps) {
     // ------------------------------------------------------------------ A producers: E / O planes of 16 frames per warp
-    // lane = (row within a 4-row group, 4 lags): the eight lanes of a quarter-warp read 32 consecutive lags of one frame
-    // (128 contiguous bytes of fp32 on either side of the centre) and a half-warp's 8-byte stores cover all 32 banks.
-    // The loop runs over the flattened (tile, N-tile, K-block) sequence with the raw samples of the NEXT stage in flight
-    // while the current one is converted and stored.
+    // lane = (row within a 4-row group, 4 lags).  The raw sample tiles of the stage arrive by TMA in the very region
+    // the operand planes go to, so the conversion is: read (all producers) -> named barrier -> write.  A half-warp's
+    // 8-byte plane stores cover all 32 banks (LBO = 160), a quarter-warp's raw read is one contiguous row.
     const int rs = lane >> 3, c4 = lane & 7;
     const uint32_t lane_off = warp * 2 * eoSbo + rs * 16 + (c4 >> 1) * eoLbo + (c4 & 1) * 8;
-    struct Cursor {
-      long long tile;
-      int step;                 // nt * eoKB + kb
-      const IN* centre0;        // centre sample of this lane's first frame in the tile
-      long long frame0;
-    };
-    auto place = [&](Cursor& cu) {
-      const long long clip = cu.tile / p.tiles_per_clip;
-      cu.frame0 = (cu.tile - clip * p.tiles_per_clip) * kTM + warp * 16 + rs;   // + 4 * it
-      cu.centre0 = wave + clip * p.clip_stride + cu.frame0 * kHop + eoHalf;
-    };
-    auto fetch = [&](const Cursor& cu, RawLags<IN> (&raw)[4]) {
-      const int kb = cu.step >= eoKB ? cu.step - eoKB : cu.step;
-      const int m = kb * eoBK + c4 * 4;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (cu.frame0 + 4 * it < p.frames_out && m < eoHalf) raw[it].load(cu.centre0 + it * 4 * kHop, m, p.vec != 0);
-        else raw[it].zero();
-      }
-    };
     uint32_t stage = 0, phase = 0;
-    auto emit = [&](const Cursor& cu, const RawLags<IN> (&raw)[4]) {
-      const int kb = cu.step >= eoKB ? cu.step - eoKB : cu.step;
-      const int m = kb * eoBK + c4 * 4;
-      mbar_wait(&empty_bar[stage], phase ^ 1);        // the MMAs that read this stage last time are done
-      const uint32_t a_base = smem_u32(smem + stage * eoStageBytes) + lane_off;
-      if (m < eoHalf + 8) {                            // chunks from lag 208 on are never read by an MMA
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int nt = 0; nt < kNTiles; ++nt) {
+        for (int kb = 0; kb < eoKB; ++kb) {
+          const uint32_t a_base = smem_u32(smem + stage * eoStageBytes);
+          mbar_wait(&raw_full[stage], phase);
+          RawLags<IN> raw[4];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          float xp[4], xm[4];
-          raw[it].unpack(xp, xm);
-          uint32_t eh[2], el[2], oh[2], ol[2];
+          for (int it = 0; it < 4; ++it) raw[it].read(a_base, a_base + eoRawTile, warp * 16 + it * 4 + rs, c4);
+          asm volatile("bar.sync 1, %0;" ::"n"(eoProdWarps * 32) : "memory");   // every raw row has been read
+          if (kb < eoKB - 1 || c4 < 4) {                   // chunks from lag 208 on are never read by an MMA
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            constexpr float sc = RawLags<IN>::xp_scale;
-            split2_pair(fmaf(xp[2 * t], sc, xm[2 * t]), fmaf(xp[2 * t + 1], sc, xm[2 * t + 1]), eh[t], el[t]);
-            split2_pair(fmaf(xp[2 * t], sc, -xm[2 * t]), fmaf(xp[2 * t + 1], sc, -xm[2 * t + 1]), oh[t], ol[t]);
+            for (int it = 0; it < 4; ++it) {
+              float xp[4], xm[4];
+              raw[it].unpack(xp, xm);
+              uint32_t eh[2], el[2], oh[2], ol[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                constexpr float sc = RawLags<IN>::xp_scale;
+                split2_pair(fmaf(xp[2 * t], sc, xm[2 * t]), fmaf(xp[2 * t + 1], sc, xm[2 * t + 1]), eh[t], el[t]);
+                split2_pair(fmaf(xp[2 * t], sc, -xm[2 * t]), fmaf(xp[2 * t + 1], sc, -xm[2 * t + 1]), oh[t], ol[t]);
+              }
+              // rows 16 * warp + 4 * it + rs: 8-row group 2 * warp + (it >> 1), row (it & 1) * 4 + rs within it
+              const uint32_t dst = a_base + lane_off + (it >> 1) * eoSbo + (it & 1) * 64;
+              st_shared_v2(dst + 0 * eoATile, eh[0], eh[1]);
+              st_shared_v2(dst + 1 * eoATile, el[0], el[1]);
+              st_shared_v2(dst + 2 * eoATile, oh[0], oh[1]);
+              st_shared_v2(dst + 3 * eoATile, ol[0], ol[1]);
+            }
           }
-          // rows 16 * warp + 4 * it + rs: 8-row group 2 * warp + (it >> 1), row (it & 1) * 4 + rs within it
-          const uint32_t dst = a_base + (it >> 1) * eoSbo + (it & 1) * 64;
-          st_shared_v2(dst + 0 * eoATile, eh[0], eh[1]);
-          st_shared_v2(dst + 1 * eoATile, el[0], el[1]);
-          st_shared_v2(dst + 2 * eoATile, oh[0], oh[1]);
-          st_shared_v2(dst + 3 * eoATile, ol[0], ol[1]);
+          fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == eoStages) { stage = 0; phase ^= 1; }
         }
-      }
-      fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[stage]);
-      if (++stage == eoStages) { stage = 0; phase ^= 1; }
-    };
-    auto advance = [&](Cursor& cu) {      // false once the CTA's last stage has been passed
-      if (++cu.step == kNTiles * eoKB) {
-        cu.step = 0;
-        cu.tile += gridDim.x;
-        if (cu.tile >= p.total_tiles) return false;
-        place(cu);
-      }
-      return true;
-    };
-    Cursor cur{static_cast<long long>(blockIdx.x), 0, nullptr, 0};
-    if (cur.tile < p.total_tiles) {
-      place(cur);
-      RawLags<IN> buf0[4], buf1[4];
-      fetch(cur, buf0);
-      for (;;) {
-        Cursor nxt = cur;
-        const bool more1 = advance(nxt);
-        if (more1) fetch(nxt, buf1);
-        emit(cur, buf0);
-        if (!more1) break;
-        cur = nxt;
-        const bool more0 = advance(nxt);
-        if (more0) fetch(nxt, buf0);
-        emit(cur, buf1);
-        if (!more0) break;
-        cur = nxt;
       }
     }
   } else if (warp == eoTmaWarp) {
-    // ------------------------------------------------------------------ basis tiles by TMA
+    // ------------------------------------------------------------------ raw sample tiles and basis tiles by TMA
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int clip = static_cast<int>(tile / p.tiles_per_clip);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(clip) * p.tiles_per_clip) * kTM;
         for (int nt = 0; nt < kNTiles; ++nt) {
           for (int kb = 0; kb < eoKB; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* b_base = smem + stage * eoStageBytes + eoABytes;
+            uint8_t* a_base = smem + stage * eoStageBytes;
+            uint8_t* b_base = a_base + eoABytes;
+            // samples eoHalf + 32 kb .. + 31 of every frame, and eoHalf - 32 kb - 32 .. eoHalf - 32 kb (+ padding)
+            mbar_expect_tx(&raw_full[stage], kTM * (RawLags<IN>::kRowBytes + RawLags<IN>::kBwdRowBytes));
+            tma_load_3d(a_base, &tmap_x, &raw_full[stage], eoHalf + kb * eoBK, row0, clip);
+            tma_load_3d(a_base + eoRawTile, &tmap_xb, &raw_full[stage], eoHalf - kb * eoBK - eoBK, row0, clip);
             mbar_expect_tx(&full_bar[stage], eoBBytes);
 #pragma unroll
             for (int t = 0; t < 2 * eoPlanes; ++t)   // tile t = part * 2 + plane; table rows ((plane * 2 + part) * 2 + nt) * 128
@@ -910,10 +886,32 @@ bool logmel_use_planes() {
   return on;
 }
 
+// The raw sample tiles are TMA boxes, so the clip base and the clip stride must be 16-byte aligned; other inputs
+// take the plane kernel, which accepts any alignment.
+template <class IN>
+bool logmel_eo_accepts(const IN* wave, long long n_clips, long long clip_stride) {
+  return reinterpret_cast<uintptr_t>(wave) % 16 == 0 &&
+         (n_clips == 1 || (clip_stride * static_cast<long long>(sizeof(IN))) % 16 == 0);
+}
+
 template <class IN>
 int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long clip_stride, long long frames_out,
                       float* logmel, cudaStream_t stream) {
-  CUtensorMap tb;
+  CUtensorMap tx, txb, tb;
+  {
+    // frames as overlapping rows of the waveform: element (sample in frame, frame, clip)
+    uint64_t dims[3] = {uint64_t(kWin), uint64_t(frames_out), uint64_t(n_clips)};
+    // (a single clip never uses its stride: any legal value will do)
+    const uint64_t cs = n_clips == 1 ? uint64_t(frames_out + 3) * kHop : uint64_t(clip_stride);
+    uint64_t str[2] = {uint64_t(kHop) * sizeof(IN), cs * sizeof(IN)};
+    uint32_t box[3] = {eoBK, kTM, 1};
+    uint32_t boxb[3] = {uint32_t(RawLags<IN>::kBwdCols), kTM, 1};
+    if (make_tmap_plain(&tx, wave, sizeof(IN), 3, dims, str, box) ||
+        make_tmap_plain(&txb, wave, sizeof(IN), 3, dims, str, boxb)) {
+      set_kernel_error("logmel: %s", igemm_last_error());
+      return 1;
+    }
+  }
   {
     uint64_t dims[2] = {uint64_t(eoKPad), uint64_t(eoPlanes * 2 * kNTiles * eoTN)};
     uint64_t str[1] = {uint64_t(eoKPad) * 2};
@@ -924,17 +922,14 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
     }
   }
   LogmelEoParams p{};
-  p.clip_stride = clip_stride;
   p.frames_out = frames_out;
   p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
-  // vector loads need the centre sample of every frame (offset 160 f + 200 elements from the clip start) aligned
-  p.vec = (reinterpret_cast<uintptr_t>(wave) % 16 == 0) && ((clip_stride * static_cast<long long>(sizeof(IN))) % 16 == 0);
   p.out = logmel;
   if (p.total_tiles <= 0) return 0;
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
-                                    stream, wave, tb, p);
+                                    stream, tx, txb, tb, p);
   count_launch();
   if (le != cudaSuccess) {
     set_kernel_error("logmel_eo_kernel: %s", cudaGetErrorString(le));
@@ -952,7 +947,8 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
     set_kernel_error("logmel: too many clips / frames for one launch");
     return 1;
   }
-  if (!logmel_use_planes()) return logmel_eo_forward<IN>(t, wave, n_clips, clip_stride, frames_out, logmel, stream);
+  if (!logmel_use_planes() && logmel_eo_accepts(wave, n_clips, clip_stride))
+    return logmel_eo_forward<IN>(t, wave, n_clips, clip_stride, frames_out, logmel, stream);
   constexpr int a_planes = sizeof(IN) == 2 ? 2 : 3;
   const long long pitch = logmel_tc_pitch(samples_per_clip);
   const size_t plane_bytes = size_t(n_clips) * pitch * 2;
