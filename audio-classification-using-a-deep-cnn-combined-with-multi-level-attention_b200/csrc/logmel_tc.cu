@@ -378,8 +378,7 @@ constexpr float eoUnscale = 1.0f / (4096.f * 1024.f);
 constexpr int eoProdWarps = 8;
 constexpr int eoTmaWarp = eoProdWarps, eoMmaWarp = eoProdWarps + 1, eoEpiWarp0 = eoProdWarps + 2;
 constexpr int eoThreads = (eoEpiWarp0 + 8) * 32; // 576
-constexpr int eoTabBytes = 2 * kEvalBins * 4 + kEvalBins;   // mel walk tables copied to shared memory: wfall, wrise, band
-constexpr int eoSmemBytes = 1024 + eoStages * eoStageBytes + 512 + 2 * kTM * kHandFloats * 4 + ((eoTabBytes + 15) & ~15);
+constexpr int eoSmemBytes = 1024 + eoStages * eoStageBytes + 512 + 2 * kTM * kHandFloats * 4;
 
 // K-major, no swizzle: element (row r, 16-byte chunk j) at (r / 8) * SBO + j * LBO + (r % 8) * 16
 __device__ __forceinline__ uint64_t umma_desc_kmajor_cores(uint32_t smem_addr) {
@@ -468,31 +467,91 @@ struct LogmelEoParams {
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
+  int probe;                // timing probes (VMB_LOGMEL_PROBE, wrong results): 1 = half the basis tiles, 2 = none, 4 = no raw tiles
 };
 
-// NB bins starting at table index bin0 (a multiple of 8): the magnitudes first (independent, so the MUFU latencies
-// overlap), then the sequential band walk on registers.  The walk tables come from shared memory as vector loads: indexed
-// __constant__ loads inside the walk (one dependent LDC per table and bin, each behind a branch) cost ~300 cycles per bin
-// and made the epilogue, not the tensor pipe, the limiter of this kernel.
-template <int NB>
-__device__ __forceinline__ void walk_bins_eo(BandWalk& w, const uint32_t* re_v, const uint32_t* im_v,
-                                             const float (&wf)[16], const float (&wr)[16], const uint2 bd,
-                                             float* __restrict__ row_out, bool valid) {
-  float mag[NB];
+// The band walk of the epilogue with everything about the mel layout resolved at compile time.  kBandOfBin is the
+// interval index of every evaluated bin (bin kBinLo + i feeds band e - 1 on its falling side and band e on its rising
+// side) for the reference's fixed parameters (16 kHz, 512-point DFT, 64 HTK bands 125..7500 Hz); build_tables() compares
+// it with the layout derived from the float64 mel matrix and refuses to run on a mismatch.  With static bin indices the
+// weights are constant-bank operands of the FFMAs, the places where a band completes are known, and so is the slot of
+// the 16-byte output group it lands in: no loads, no branches, ~7 instructions per bin.  (The first version walked with
+// run-time tables: ~30 instructions and four branches per bin made the epilogue, not the tensor pipe, the limiter.)
+constexpr unsigned char kBandOfBin[kEvalBins] = {
+    0, 1, 2, 3, 3, 4, 5, 6, 7, 8, 9, 9, 10, 11, 12, 12, 13, 14, 14, 15, 15, 16, 17, 17, 18, 18, 19, 19, 20, 20,
+    21, 21, 22, 22, 23, 23, 24, 24, 25, 25, 26, 26, 26, 27, 27, 28, 28, 28, 29, 29, 30, 30, 30, 31, 31, 31, 32,
+    32, 32, 33, 33, 33, 34, 34, 34, 35, 35, 35, 36, 36, 36, 36, 37, 37, 37, 38, 38, 38, 38, 39, 39, 39, 39, 40,
+    40, 40, 41, 41, 41, 41, 41, 42, 42, 42, 42, 43, 43, 43, 43, 44, 44, 44, 44, 44, 45, 45, 45, 45, 46, 46, 46,
+    46, 46, 47, 47, 47, 47, 47, 48, 48, 48, 48, 48, 49, 49, 49, 49, 49, 49, 50, 50, 50, 50, 50, 51, 51, 51, 51,
+    51, 51, 52, 52, 52, 52, 52, 52, 53, 53, 53, 53, 53, 53, 54, 54, 54, 54, 54, 54, 55, 55, 55, 55, 55, 55, 55,
+    56, 56, 56, 56, 56, 56, 56, 57, 57, 57, 57, 57, 57, 57, 58, 58, 58, 58, 58, 58, 58, 59, 59, 59, 59, 59, 59,
+    59, 59, 60, 60, 60, 60, 60, 60, 60, 60, 61, 61, 61, 61, 61, 61, 61, 61, 62, 62, 62, 62, 62, 62, 62, 62, 62,
+    63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+struct WalkState {
+  float lo, hi;       // running sums of band e - 1 (complete after its falling side) and band e
+  float pend[4];      // finished bands of the current group of four, waiting for one 16-byte store
+};
+
+template <int E>   // close interval E: band E - 1 is complete
+__device__ __forceinline__ void emit_static(WalkState& w, float* __restrict__ row_out, bool valid) {
+  constexpr int band = E - 1;
+  if constexpr (band >= 0 && band < kMel) {
+    w.pend[band & 3] = __logf(w.lo + kLogOffset);
+    if constexpr ((band & 3) == 3) {
+      if (valid) *reinterpret_cast<float4*>(row_out + band - 3) = make_float4(w.pend[0], w.pend[1], w.pend[2], w.pend[3]);
+    }
+  }
+  w.lo = w.hi;
+  w.hi = 0.f;
+}
+
+template <int G0, int J, int NB, int E>   // bin J of the NB-bin chunk that starts at table index G0; current interval E
+__device__ __forceinline__ void walk_static(WalkState& w, const float (&mag)[NB], float* __restrict__ row_out, bool valid) {
+  if constexpr (J < NB) {
+    constexpr int g = G0 + J;
+    constexpr int e = kBandOfBin[g];
+    static_assert(e == E || e == E + 1, "a bin closes at most one band");
+    if constexpr (e > E) emit_static<E>(w, row_out, valid);
+    w.lo = fmaf(c_wfall[g], mag[J], w.lo);
+    w.hi = fmaf(c_wrise[g], mag[J], w.hi);
+    walk_static<G0, J + 1, NB, e>(w, mag, row_out, valid);
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void flush_static(WalkState& w, float* __restrict__ row_out, bool valid) {
+  if constexpr (E <= kMel) {
+    emit_static<E>(w, row_out, valid);
+    flush_static<E + 1>(w, row_out, valid);
+  }
+}
+
+constexpr int eoChunkBins = 8;
+constexpr int eoChunks = kTileBins / eoChunkBins;   // 15
+
+// Chunk CH of N-tile SET: on entry the TMEM loads of its 8 Re and 8 Im columns are in flight in re / im; the next
+// chunk's loads are issued as soon as the magnitudes have been formed, so they overlap the walk.
+template <int SET, int CH>
+__device__ __forceinline__ void epilogue_chunks(uint32_t t_addr, uint32_t (&re)[8], uint32_t (&im)[8], WalkState& w,
+                                                float* __restrict__ row_out, bool valid) {
+  tmem_ld_wait();
+  float mag[eoChunkBins];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const float re = __uint_as_float(re_v[j]), im = __uint_as_float(im_v[j]);
+  for (int j = 0; j < eoChunkBins; ++j) {
+    const float r = __uint_as_float(re[j]), i = __uint_as_float(im[j]);
     float m;     // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(re, re, im * im)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(r, r, i * i)));
     mag[j] = m * eoUnscale;                              // exact: the operands carried 2^12 and 2^10
   }
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const int e = static_cast<int>(((j < 4 ? bd.x : bd.y) >> (8 * (j & 3))) & 0xffu);
-    while (w.e < e) emit_band(w, row_out, valid);      // warp-uniform: depends on the bin index only
-    w.lo = fmaf(wf[j], mag[j], w.lo);
-    w.hi = fmaf(wr[j], mag[j], w.hi);
+  if constexpr (CH + 1 < eoChunks) {
+    tmem_ld_32x8(t_addr + (CH + 1) * eoChunkBins, re);
+    tmem_ld_32x8(t_addr + eoTN + (CH + 1) * eoChunkBins, im);
   }
+  constexpr int g0 = SET * kTileBins + CH * eoChunkBins;
+  constexpr int e0 = g0 == 0 ? 0 : kBandOfBin[g0 - 1];
+  walk_static<g0, 0, eoChunkBins, e0>(w, mag, row_out, valid);
+  if constexpr (CH + 1 < eoChunks) epilogue_chunks<SET, CH + 1>(t_addr, re, im, w, row_out, valid);
 }
 
 template <class IN>
@@ -511,18 +570,10 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t* raw_full = hand_empty + 8;        // [eoStages]: the raw sample tiles of the stage have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_full + eoStages);
   float* hand = reinterpret_cast<float*>(smem + eoStages * eoStageBytes + 512);   // [2][kTM][kHandFloats]
-  float* s_wf = hand + 2 * kTM * kHandFloats;                                     // [kEvalBins] falling-side weights
-  float* s_wr = s_wf + kEvalBins;                                                 // [kEvalBins] rising-side weights
-  uint8_t* s_band = reinterpret_cast<uint8_t*>(s_wr + kEvalBins);                 // [kEvalBins] band interval per bin
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (threadIdx.x < kEvalBins) {
-    s_wf[threadIdx.x] = c_wfall[threadIdx.x];
-    s_wr[threadIdx.x] = c_wrise[threadIdx.x];
-    s_band[threadIdx.x] = static_cast<uint8_t>(c_band[threadIdx.x]);
-  }
   if (warp == eoTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_xb);
@@ -605,14 +656,20 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint8_t* a_base = smem + stage * eoStageBytes;
             uint8_t* b_base = a_base + eoABytes;
             // samples eoHalf + 32 kb .. + 31 of every frame, and eoHalf - 32 kb - 32 .. eoHalf - 32 kb (+ padding)
-            mbar_expect_tx(&raw_full[stage], kTM * (RawLags<IN>::kRowBytes + RawLags<IN>::kBwdRowBytes));
-            tma_load_3d(a_base, &tmap_x, &raw_full[stage], eoHalf + kb * eoBK, row0, clip);
-            tma_load_3d(a_base + eoRawTile, &tmap_xb, &raw_full[stage], eoHalf - kb * eoBK - eoBK, row0, clip);
-            mbar_expect_tx(&full_bar[stage], eoBBytes);
+            if (p.probe & 4) {
+              mbar_expect_tx(&raw_full[stage], 0);
+            } else {
+              mbar_expect_tx(&raw_full[stage], kTM * (RawLags<IN>::kRowBytes + RawLags<IN>::kBwdRowBytes));
+              tma_load_3d(a_base, &tmap_x, &raw_full[stage], eoHalf + kb * eoBK, row0, clip);
+              tma_load_3d(a_base + eoRawTile, &tmap_xb, &raw_full[stage], eoHalf - kb * eoBK - eoBK, row0, clip);
+            }
+            const int nb = (p.probe & 2) ? 0 : (p.probe & 1) ? eoPlanes : 2 * eoPlanes;
+            mbar_expect_tx(&full_bar[stage], nb * eoBTile);
 #pragma unroll
             for (int t = 0; t < 2 * eoPlanes; ++t)   // tile t = part * 2 + plane; table rows ((plane * 2 + part) * 2 + nt) * 128
-              tma_load_2d(b_base + t * eoBTile, &tmap_b, &full_bar[stage], kb * eoBK,
-                          (((t % eoPlanes) * 2 + t / eoPlanes) * kNTiles + nt) * eoTN);
+              if (t < nb)
+                tma_load_2d(b_base + t * eoBTile, &tmap_b, &full_bar[stage], kb * eoBK,
+                            (((t % eoPlanes) * 2 + t / eoPlanes) * kNTiles + nt) * eoTN);
             if (++stage == eoStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -660,7 +717,10 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (same walk and hand-off as above)
+    // ------------------------------------------------------------------ epilogue
+    // Two sets of four warps: set 0 (warps 10-13) walks the bins of N-tile 0, set 1 (warps 14-17) those of N-tile 1.
+    // The band walk is sequential over the bins, so warp q of set 0 hands its per-row state to warp q of set 1 through
+    // shared memory; the arithmetic and its order are exactly those of a single walk.
     const int set = (warp - eoEpiWarp0) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -672,48 +732,41 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       float* row_out = p.out + (clip * p.frames_out + (valid ? frame : 0)) * kMel;
       const uint32_t hb = mi & 1, hphase = (mi >> 1) & 1;
       float* hrow = hand + (hb * kTM + row) * kHandFloats;
-      BandWalk w;
-      w.pend = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (set == 1) {
-        mbar_wait(&hand_full[hb * 4 + q], hphase);
-        w.e = c_band[kTileBins - 1];            // where the walk over bins 0..119 stops (uniform)
-        w.lo = hrow[0]; w.hi = hrow[1];
-        w.pend = make_float4(hrow[2], hrow[3], hrow[4], 0.f);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
-      }
       const uint32_t acc = set, acc_phase = mi & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-#pragma unroll 1
-      for (int ch = 0; ch < 2 * (kTileBins / 16) + 1; ++ch) {   // 15 chunks of 8 bins
-        const int bin0 = set * kTileBins + ch * 8;
-        uint32_t re[8], im[8];
-        tmem_ld_32x8(t_addr + ch * 8, re);
-        tmem_ld_32x8(t_addr + eoTN + ch * 8, im);
-        float wf[16], wr[16];
-        {
-          const float4 a0 = *reinterpret_cast<const float4*>(s_wf + bin0), a1 = *reinterpret_cast<const float4*>(s_wf + bin0 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(s_wr + bin0), b1 = *reinterpret_cast<const float4*>(s_wr + bin0 + 4);
-          wf[0] = a0.x; wf[1] = a0.y; wf[2] = a0.z; wf[3] = a0.w; wf[4] = a1.x; wf[5] = a1.y; wf[6] = a1.z; wf[7] = a1.w;
-          wr[0] = b0.x; wr[1] = b0.y; wr[2] = b0.z; wr[3] = b0.w; wr[4] = b1.x; wr[5] = b1.y; wr[6] = b1.z; wr[7] = b1.w;
-        }
-        const uint2 bd = *reinterpret_cast<const uint2*>(s_band + bin0);
-        tmem_ld_wait();
-        walk_bins_eo<8>(w, re, im, wf, wr, bd, row_out, valid);
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      WalkState w;
+      uint32_t re[8], im[8];
       if (set == 0) {
+        w.lo = w.hi = 0.f;
+        w.pend[0] = w.pend[1] = w.pend[2] = w.pend[3] = 0.f;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        tmem_ld_32x8(t_addr, re);
+        tmem_ld_32x8(t_addr + eoTN, im);
+        epilogue_chunks<0, 0>(t_addr, re, im, w, row_out, valid);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         mbar_wait(&hand_empty[hb * 4 + q], hphase ^ 1);
         hrow[0] = w.lo; hrow[1] = w.hi;
-        hrow[2] = w.pend.x; hrow[3] = w.pend.y; hrow[4] = w.pend.z;
+        hrow[2] = w.pend[0]; hrow[3] = w.pend[1]; hrow[4] = w.pend[2]; hrow[5] = w.pend[3];
         __syncwarp();
         if (lane == 0) mbar_arrive(&hand_full[hb * 4 + q]);
       } else {
-        while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        tmem_ld_32x8(t_addr, re);
+        tmem_ld_32x8(t_addr + eoTN, im);
+        mbar_wait(&hand_full[hb * 4 + q], hphase);
+        w.lo = hrow[0]; w.hi = hrow[1];
+        w.pend[0] = hrow[2]; w.pend[1] = hrow[3]; w.pend[2] = hrow[4]; w.pend[3] = hrow[5];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
+        epilogue_chunks<1, 0>(t_addr, re, im, w, row_out, valid);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        flush_static<kBandOfBin[kEvalBins - 1]>(w, row_out, valid);   // the remaining bands (up to band 63)
       }
     }
   }
@@ -788,6 +841,12 @@ int build_tables(TcTables& t) {
       }
     prev = e;
   }
+  for (int i = 0; i < kEvalBins; ++i)
+    if (band[i] != kBandOfBin[i]) {
+      set_kernel_error("logmel: compiled mel band layout differs from the float64 tables at bin %d (%d vs %d)", kBinLo + i,
+                       int(kBandOfBin[i]), band[i]);
+      return 1;
+    }
   if (cudaMemcpyToSymbol(c_band, band.data(), sizeof(int) * kEvalBins) != cudaSuccess ||
       cudaMemcpyToSymbol(c_wfall, wf.data(), sizeof(float) * kEvalBins) != cudaSuccess ||
       cudaMemcpyToSymbol(c_wrise, wr.data(), sizeof(float) * kEvalBins) != cudaSuccess) {
@@ -926,6 +985,10 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
   p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
+  {
+    static const int probe = [] { const char* e = std::getenv("VMB_LOGMEL_PROBE"); return e ? std::atoi(e) : 0; }();
+    p.probe = probe;
+  }
   if (p.total_tiles <= 0) return 0;
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
