@@ -51,10 +51,12 @@ class StageTimer {
 // Constant tables exactly as mel_features.py builds them (float64): periodic_hann(400) and
 // spectrogram_to_mel_matrix(64, 257, 16000, 125, 7500).
 void front_end_tables_host(double* hann400, double* mel257x64);
-// Tensor-core front end (logmel_tc.cu): split-bf16 tcgen05 DFT GEMM with the magnitude / mel / log epilogue.
+// Tensor-core front end (logmel_tc.cu): centred even / odd DFT as fp16-split tcgen05 GEMMs over TMA-framed raw samples
+// with the magnitude / mel / log epilogue; inputs that are not 16-byte aligned take the first version of the kernel
+// (bf16 planes of the waveform + straight K = 400 DFT).
 int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                       long long frames_out, float* logmel, cudaStream_t stream);
-// Same for 16-bit PCM input scaled by 1/32768 (vggish_input.py:96-98): two A planes are exact, five products.
+// Same for 16-bit PCM input scaled by 1/32768 (vggish_input.py:96-98): the same kernel with 16-bit TMA boxes.
 int logmel_tc_forward_pcm16(const int16_t* pcm, long long n_clips, long long samples_per_clip, long long clip_stride,
                             long long frames_out, float* logmel, cudaStream_t stream);
 // CUDA-core fp32 version of the same computation (frontend.cu); kept as an on-device cross-check, not on the path.

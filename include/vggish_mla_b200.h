@@ -69,13 +69,16 @@ long long vmb_num_examples(long long n_samples);
  *   wave_dev   [n_clips][clip_stride] fp32 (first samples_per_clip samples of each row are used)
  *   logmel_dev [n_clips][frames_out][64] fp32 where frames_out <= vmb_num_frames(samples_per_clip)
  * Only the first frames_out frames of each clip are produced (pass 96*vmb_num_examples(..) to get the
- * (n_examples, 96, 64) example tensor of waveform_to_examples, vggish_input.py:73-80).                 */
+ * (n_examples, 96, 64) example tensor of waveform_to_examples, vggish_input.py:73-80).
+ * The waveform is read in place through TMA; with wave_dev (and, for n_clips > 1, the clip stride in bytes) 16-byte
+ * aligned the centred even/odd kernel runs, any other alignment takes the plane kernel (same tolerance, different
+ * rounding, so results are bit-identical only between calls that take the same kernel).                   */
 int vmb_logmel(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                long long frames_out, float* logmel_dev, void* stream);
 
 /* The same for 16-bit PCM (what wavfile_to_examples reads, vggish_input.py:96-98): samples are scaled by 1/32768
- * on the device, which is exact in fp32, so the result is bit-identical to vmb_logmel on pcm / 32768.0f; half the
- * input bytes, and one of the six split products drops out because a 16-bit sample is exactly two bf16 terms.   */
+ * on the device, which is exact in fp32, so the result is bit-identical to vmb_logmel on pcm / 32768.0f (same
+ * alignment class); half the input bytes.                                                                        */
 int vmb_logmel_pcm16(const int16_t* pcm_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                      long long frames_out, float* logmel_dev, void* stream);
 
