@@ -1,26 +1,36 @@
-// Tensor-core log-mel front end (sm_100a): framing + periodic Hann + 512-point real DFT as a split-bf16 tcgen05 GEMM,
-// magnitude + HTK mel projection + log fused into the epilogue.
+// Tensor-core log-mel front end (sm_100a): framing + periodic Hann + 512-point real DFT as split-precision tcgen05
+// GEMMs, magnitude + HTK mel projection + log fused into the epilogue.
 // Replaces torchvggish/mel_features.py:21-45 (frame), :48-68 (periodic_hann), :71-92 (stft_magnitude),
 // :114-189 (spectrogram_to_mel_matrix), :192-223 (log_mel_spectrogram).
+//
+// Two kernels live here:
+//  * logmel_eo_kernel (second half of the file, the default): centred even / odd form of the DFT (K = 200), raw samples
+//    framed by TMA straight from the caller's waveform, fp16 hi + lo operand planes built in shared memory, three
+//    products.  Its header comment has the algebra and the data flow.
+//  * split_wave_kernel + logmel_tc_kernel (first half, the first tensor-core version): the waveform is split into three
+//    bf16 planes in HBM, A tiles are TMA boxes of an overlapping-rows view of those planes, straight K = 400 DFT, six
+//    products.  Serves inputs that are not 16-byte aligned; VMB_LOGMEL_PLANES=1 selects it for A/B runs.
 //
 //   S[f][c] = sum_n x[160 f + n] * W[n][c],   W[n][2j] = hann[n] cos(2 pi k_j n / 512), W[n][2j+1] = hann[n] sin(..)
 //   |X_j| = sqrt(S[f][2j]^2 + S[f][2j+1]^2);  mel[f][m] = sum_j |X_j| M[k_j][m];  out = log(mel + 0.01)
 //
+// Shared by both:
+// * Only DFT bins 4..243 are evaluated (2 N-tiles of 120 bins): the HTK mel matrix is exactly zero outside bins
+//   5..239 (checked when the tables are built).
+// * Epilogue: one thread owns one frame (TMEM lane); it walks the bins in order and, because every bin feeds at
+//   most the two adjacent mel bands, keeps just two running band sums, emitting log(band + 0.01) as bands complete.
+//
+// The plane kernel in detail:
 // * Precision.  log(mel + 0.01) has slope up to 100, so the DFT needs fp32-class accuracy: plain
-//   bf16/tf32 operands miss the 1e-4 bound by orders of magnitude.  Both operands are therefore split exactly into
+//   bf16/tf32 operands miss the 1e-4 bound by orders of magnitude.  Both operands are split exactly into
 //   three bf16 terms (x = x0 + x1 + x2, 24 mantissa bits) and the six products with i + j <= 2 are accumulated
 //   in the same fp32 TMEM accumulator, smallest first: A2B0, A1B1, A0B2, A1B0, A0B1, A0B0.
 // * Framing is never materialised: the A operand is a 3-D TMA tensor map over the split waveform planes with
 //   dims {416 (sample in frame), frames (stride 160 samples), plane*clip}; rows overlap in memory.  The Hann window
 //   is folded into W; columns 400..415 of W are zero (K padded to 13 blocks of 32).
-// * Only DFT bins 4..243 are evaluated (2 N-tiles of 240 columns): the HTK mel matrix is exactly zero outside bins
-//   5..239 (checked when the tables are built).
-// * Epilogue: one thread owns one frame (TMEM lane); it walks the bins in order and, because every bin feeds at
-//   most the two adjacent mel bands, keeps just two running band sums, emitting log(band + 0.01) as bands complete.
-//
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 epilogue of N-tile 0 / 1.  Persistent over 128-frame
-// tiles; the two N-tiles of a frame tile use the two halves of TMEM so the epilogue of one overlaps the MMAs of the
-// next.  Smem: 3 stages x {A0,A1,A2 (128x32), B0,B1,B2 (240x32)} bf16, 64-byte swizzle = 207 KB.
+// * Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 epilogue of N-tile 0 / 1.
+//   Persistent over 128-frame tiles; the two N-tiles of a frame tile use the two halves of TMEM so the epilogue of one
+//   overlaps the MMAs of the next.  Smem: 3 stages x {A0,A1,A2 (128x32), B0,B1,B2 (240x32)} bf16, 64-byte swizzle = 207 KB.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -467,7 +477,6 @@ struct LogmelEoParams {
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
-  int probe;                // timing probes (VMB_LOGMEL_PROBE, wrong results): 1 = half the basis tiles, 2 = none, 4 = no raw tiles
 };
 
 // The band walk of the epilogue with everything about the mel layout resolved at compile time.  kBandOfBin is the
@@ -656,20 +665,14 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint8_t* a_base = smem + stage * eoStageBytes;
             uint8_t* b_base = a_base + eoABytes;
             // samples eoHalf + 32 kb .. + 31 of every frame, and eoHalf - 32 kb - 32 .. eoHalf - 32 kb (+ padding)
-            if (p.probe & 4) {
-              mbar_expect_tx(&raw_full[stage], 0);
-            } else {
-              mbar_expect_tx(&raw_full[stage], kTM * (RawLags<IN>::kRowBytes + RawLags<IN>::kBwdRowBytes));
-              tma_load_3d(a_base, &tmap_x, &raw_full[stage], eoHalf + kb * eoBK, row0, clip);
-              tma_load_3d(a_base + eoRawTile, &tmap_xb, &raw_full[stage], eoHalf - kb * eoBK - eoBK, row0, clip);
-            }
-            const int nb = (p.probe & 2) ? 0 : (p.probe & 1) ? eoPlanes : 2 * eoPlanes;
-            mbar_expect_tx(&full_bar[stage], nb * eoBTile);
+            mbar_expect_tx(&raw_full[stage], kTM * (RawLags<IN>::kRowBytes + RawLags<IN>::kBwdRowBytes));
+            tma_load_3d(a_base, &tmap_x, &raw_full[stage], eoHalf + kb * eoBK, row0, clip);
+            tma_load_3d(a_base + eoRawTile, &tmap_xb, &raw_full[stage], eoHalf - kb * eoBK - eoBK, row0, clip);
+            mbar_expect_tx(&full_bar[stage], eoBBytes);
 #pragma unroll
             for (int t = 0; t < 2 * eoPlanes; ++t)   // tile t = part * 2 + plane; table rows ((plane * 2 + part) * 2 + nt) * 128
-              if (t < nb)
-                tma_load_2d(b_base + t * eoBTile, &tmap_b, &full_bar[stage], kb * eoBK,
-                            (((t % eoPlanes) * 2 + t / eoPlanes) * kNTiles + nt) * eoTN);
+              tma_load_2d(b_base + t * eoBTile, &tmap_b, &full_bar[stage], kb * eoBK,
+                          (((t % eoPlanes) * 2 + t / eoPlanes) * kNTiles + nt) * eoTN);
             if (++stage == eoStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -985,10 +988,6 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
   p.tiles_per_clip = static_cast<int>((frames_out + kTM - 1) / kTM);
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
-  {
-    static const int probe = [] { const char* e = std::getenv("VMB_LOGMEL_PROBE"); return e ? std::atoi(e) : 0; }();
-    p.probe = probe;
-  }
   if (p.total_tiles <= 0) return 0;
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,

@@ -80,6 +80,28 @@ def test_logmel_full_batch_tensor_core_vs_cuda_core():
     assert torch.equal(engine.logmel(waves[200:203]), a[200:203])
 
 
+def test_logmel_unaligned_input_takes_the_plane_kernel():
+    """The centred kernel reads the waveform through TMA (16-byte aligned base / clip stride); anything else is served
+    by the first tensor-core kernel (bf16 planes + straight DFT).  Both stay within the 1e-4 bound, and one launch
+    more shows which path ran."""
+    waves = synth.make_clips(0, 2)
+    w = torch.from_numpy(waves).to(DEV)
+    lib = _lib.lib()
+    for sl, launches in ((slice(0, 32000), 1), (slice(1, 32001), 2), (slice(3, 32003), 2)):
+        x = w[0, sl]
+        before = lib.vmb_launch_count()
+        got = engine.logmel(x)[0].cpu().numpy().astype(np.float64)
+        assert lib.vmb_launch_count() == before + launches
+        ref = frontend_np.log_mel_spectrogram(waves[0, sl].astype(np.float64))
+        assert np.abs(got - ref).max() <= 1e-4
+    # two clips whose stride is not a multiple of four samples
+    odd = torch.zeros(2, 32001, device=DEV)
+    odd[:, :32000] = w[:, :32000]
+    got = engine.logmel(odd[:, :32000]).cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert np.abs(got[i] - frontend_np.log_mel_spectrogram(waves[i, :32000].astype(np.float64))).max() <= 1e-4
+
+
 def test_examples_shape_indexing_and_edges():
     waves = synth.make_clips(0, 2)
     ex = engine.examples_from_wave(torch.from_numpy(waves).to(DEV))
