@@ -60,6 +60,24 @@ STAGES = ("logmel", "conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2"
           "postprocess")
 
 
+
+def _json_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    the communicator is created), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+    original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+_OUT = None
+
+
+def emit(line):
+    (_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_OUT or sys.stdout).flush()
+
 def igemm_traffic():
     """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (None if absent)."""
     try:
@@ -149,7 +167,7 @@ def run_reference(args, rank):
         "e2e": {"value": r["clips_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cpus": os.cpu_count(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -426,12 +444,14 @@ def run_b200(args, rank, local_rank, world):
             "value": r["clips_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
             "sample": f"{r['sample_clips']} of the {args.clips} clips per pass, 3 timed passes after 1 warm-up "
                       f"(numpy float64 front end + torch CPU fp32 VGGish + head); host has {os.cpu_count()} CPUs"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    global _OUT
+    _OUT = _json_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

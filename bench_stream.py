@@ -20,7 +20,27 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 
+
+def _json_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    the communicator is created), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+    original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+_OUT = None
+
+
+def emit(line):
+    (_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_OUT or sys.stdout).flush()
+
 def main():
+    global _OUT
+    _OUT = _json_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=int, default=3600)
     ap.add_argument("--steps", type=int, default=5)
@@ -64,7 +84,7 @@ def main():
         d = np.abs(q[:m].cpu().numpy().astype(np.float32) - refq).astype(np.int64)
         line["uint8_lsb_histogram_vs_oracle"] = np.bincount(d.ravel()).tolist()
         line["embedding_rel_max_err"] = float((emb[:m].cpu() - ref).abs().max() / ref.abs().max())
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -25,7 +25,27 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
+
+def _json_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    the communicator is created), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+    original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+_OUT = None
+
+
+def emit(line):
+    (_OUT or sys.stdout).write(json.dumps(line) + "\n")
+    (_OUT or sys.stdout).flush()
+
 def main():
+    global _OUT
+    _OUT = _json_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -104,7 +124,7 @@ def main():
             dt = (time.perf_counter() - t) / 5
             line["cpu_baseline"] = {"value": 64 / dt, "unit": "samples/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": "forward+backward of 64 rows (no optimiser), 5 passes"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
