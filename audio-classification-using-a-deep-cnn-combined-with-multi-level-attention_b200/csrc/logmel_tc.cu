@@ -959,6 +959,7 @@ bool logmel_eo_accepts(const IN* wave, long long n_clips, long long clip_stride)
 template <class IN>
 int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long clip_stride, long long frames_out,
                       float* logmel, cudaStream_t stream) {
+  if (n_clips <= 0 || frames_out <= 0) return 0;
   CUtensorMap tx, txb, tb;
   {
     // frames as overlapping rows of the waveform: element (sample in frame, frame, clip)

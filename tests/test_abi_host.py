@@ -52,6 +52,33 @@ def test_tables_built_by_the_library_are_bit_exact(golden_front):
     assert np.array_equal(mel, golden_front["mel257x64"])
 
 
+def test_compiled_mel_band_layout_matches_the_reference_matrix(golden_front):
+    """The log-mel kernel's epilogue has the band interval of every evaluated DFT bin compiled in (kBandOfBin in
+    csrc/logmel_tc.cu; the library re-checks it against its own float64 tables on the device box).  Here it is derived
+    again from the reference's own spectrogram_to_mel_matrix output (mel_features.py:114-189, golden vector)."""
+    src = open(os.path.join(ROOT, "audio-classification-using-a-deep-cnn-combined-with-multi-level-attention_b200",
+                            "csrc", "logmel_tc.cu")).read()
+    body = re.search(r"kBandOfBin\[kEvalBins\]\s*=\s*\{([^}]*)\}", src).group(1)
+    compiled = [int(v) for v in body.replace("\n", " ").split(",") if v.strip()]
+    mel = golden_front["mel257x64"]                            # (257, 64)
+    assert mel.shape == (257, 64)
+    lo, n = 4, 240                                             # kBinLo, kEvalBins
+    assert not mel[:lo].any() and not mel[lo + n:].any()       # nothing outside the evaluated bins
+    derived, prev = [], 0
+    for k in range(lo, lo + n):
+        nz = np.nonzero(mel[k])[0]
+        assert len(nz) <= 2 and (len(nz) < 2 or nz[1] == nz[0] + 1)   # every bin feeds at most two adjacent bands
+        e = prev
+        if len(nz) == 2:
+            e = int(nz[1])
+        elif len(nz) == 1:
+            e = int(nz[0]) if nz[0] >= prev else int(nz[0]) + 1
+        assert prev <= e <= prev + 1 and all(m in (e - 1, e) for m in nz)
+        derived.append(e)
+        prev = e
+    assert compiled == derived
+
+
 def test_compute_entry_points_fail_loudly_without_a_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
