@@ -34,12 +34,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // src fp32 [rows][lds] (first `cols` columns meaningful) -> dst bf16 [rows][2 * cpad] = hi | lo, zero padded.
-// One thread converts 4 consecutive columns.
+// One thread converts 4 consecutive columns.  With dst2 != nullptr the un-normalised h = relu(a1 u + b1) goes to dst
+// and a2 h + b2 (the next level's norm0 applied to the same embedding) to dst2: one pass over u for both consumers.
+__device__ __forceinline__ void store_split4(const float (&v)[4], __nv_bfloat16* d, int cpad) {
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __float2bfloat16_rn(v[j]);
+    lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+  }
+  *reinterpret_cast<uint2*>(d) = make_uint2(
+      __bfloat16_as_ushort(hi[0]) | (uint32_t(__bfloat16_as_ushort(hi[1])) << 16),
+      __bfloat16_as_ushort(hi[2]) | (uint32_t(__bfloat16_as_ushort(hi[3])) << 16));
+  *reinterpret_cast<uint2*>(d + cpad) = make_uint2(
+      __bfloat16_as_ushort(lo[0]) | (uint32_t(__bfloat16_as_ushort(lo[1])) << 16),
+      __bfloat16_as_ushort(lo[2]) | (uint32_t(__bfloat16_as_ushort(lo[3])) << 16));
+}
+
 __global__ void __launch_bounds__(256)
 rows_affine_split_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, int cpad, int T,
                          const float* __restrict__ a1, const float* __restrict__ b1, int relu,
                          const float* __restrict__ a2, const float* __restrict__ b2,
-                         __nv_bfloat16* __restrict__ dst) {
+                         __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2) {
   vmb::pdl_launch_dependents();
   vmb::pdl_wait();
   const int quads = cpad / 4;
@@ -51,30 +67,24 @@ rows_affine_split_kernel(const float* __restrict__ src, long long lds, long long
     const int t = static_cast<int>(r % T);
     const float s1 = a1 ? __ldg(a1 + t) : 1.f, o1 = a1 ? __ldg(b1 + t) : 0.f;
     const float s2 = a2 ? __ldg(a2 + t) : 1.f, o2 = a2 ? __ldg(b2 + t) : 0.f;
-    float v[4];
+    float h[4], v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float x = 0.f;
+      float x = 0.f, y = 0.f;
       if (c0 + j < cols) {
         x = fmaf(s1, __ldg(src + r * lds + c0 + j), o1);
         if (relu) x = fmaxf(x, 0.f);
-        x = fmaf(s2, x, o2);
+        y = fmaf(s2, x, o2);
       }
-      v[j] = x;
+      h[j] = x;
+      v[j] = y;
     }
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hi[j] = __float2bfloat16_rn(v[j]);
-      lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+    if (dst2) {
+      store_split4(h, dst + r * (2LL * cpad) + c0, cpad);
+      store_split4(v, dst2 + r * (2LL * cpad) + c0, cpad);
+    } else {
+      store_split4(v, dst + r * (2LL * cpad) + c0, cpad);
     }
-    __nv_bfloat16* d = dst + r * (2LL * cpad) + c0;
-    *reinterpret_cast<uint2*>(d) = make_uint2(
-        __bfloat16_as_ushort(hi[0]) | (uint32_t(__bfloat16_as_ushort(hi[1])) << 16),
-        __bfloat16_as_ushort(hi[2]) | (uint32_t(__bfloat16_as_ushort(hi[3])) << 16));
-    *reinterpret_cast<uint2*>(d + cpad) = make_uint2(
-        __bfloat16_as_ushort(lo[0]) | (uint32_t(__bfloat16_as_ushort(lo[1])) << 16),
-        __bfloat16_as_ushort(lo[2]) | (uint32_t(__bfloat16_as_ushort(lo[3])) << 16));
   }
 }
 
@@ -113,6 +123,55 @@ attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, 
   }
 }
 
+// The same with the clip's z tile staged in shared memory: one coalesced pass over global memory instead of three
+// dependent ones, and each exponential evaluated once.  Same expressions in the same order as attention_pool_kernel
+// (the att numerators are kept instead of recomputed), so the results are bit-identical to it.
+// Dynamic shared memory: 2 * T * kp floats (z and exp(v - max)), kp = K rounded up to 32.
+__global__ void __launch_bounds__(256)
+attention_pool_smem_kernel(const float* __restrict__ z, long long ldz, int K, int T, const float* __restrict__ av,
+                           const float* __restrict__ bv, const float* __restrict__ af, const float* __restrict__ bf,
+                           float* __restrict__ y, long long ystride, int col0) {
+  extern __shared__ float sm_att[];
+  __shared__ float rsum[16];
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
+  const int kp = (K + 31) & ~31;
+  float* sz = sm_att;              // [T][kp] z
+  float* se = sm_att + T * kp;     // [T][kp] exp(a z + b - max)
+  const long long clip = blockIdx.x;
+  const float* zc = z + clip * T * ldz;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < T; t += 8) {
+    const float a = __ldg(av + t), b = __ldg(bv + t);
+    float m = -INFINITY;
+    for (int c = lane; c < K; c += 32) {
+      const float zz = __ldg(zc + t * ldz + c);
+      sz[t * kp + c] = zz;
+      m = fmaxf(m, fmaf(a, zz, b));
+    }
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < K; c += 32) {
+      const float e = expf(fmaf(a, sz[t * kp + c], b) - m);
+      se[t * kp + c] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    if (lane == 0) rsum[t] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float num = 0.f, den = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float att = se[t * kp + k] / rsum[t];
+      const float cla = 1.f / (1.f + expf(-fmaf(__ldg(af + t), sz[t * kp + k], __ldg(bf + t))));
+      num = fmaf(cla, att, num);
+      den += att;
+    }
+    y[clip * ystride + col0 + k] = num / den;
+  }
+}
+
 // scores[clip][c] = sigmoid(a_c * u[clip][c] + b_c): eval-mode BatchNorm1d(K) + sigmoid on the output Linear (model.py:268)
 __global__ void __launch_bounds__(256)
 sigmoid_affine_kernel(const float* __restrict__ u, long long ldu, long long batch, int K, const float* __restrict__ oa,
@@ -133,9 +192,11 @@ unsigned grid_for(long long items, int per_block) {
 }
 
 int split_rows(const float* src, long long lds, long long rows, int cols, int cpad, int T, const float* a1,
-               const float* b1, int relu, const float* a2, const float* b2, void* dst, cudaStream_t st) {
+               const float* b1, int relu, const float* a2, const float* b2, void* dst, cudaStream_t st,
+               void* dst2 = nullptr) {
   if (vmb::launch_pdl(rows_affine_split_kernel, dim3(grid_for(rows * (cpad / 4), 256)), dim3(256), 0, st, src, lds, rows,
-                      cols, cpad, T, a1, b1, relu, a2, b2, static_cast<__nv_bfloat16*>(dst)) != cudaSuccess) {
+                      cols, cpad, T, a1, b1, relu, a2, b2, static_cast<__nv_bfloat16*>(dst),
+                      static_cast<__nv_bfloat16*>(dst2)) != cudaSuccess) {
     vmb::set_kernel_error("rows_affine_split_kernel: launch failed");
     return 1;
   }
@@ -189,18 +250,27 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
     const LevelDev& L = d.lvl[l];
     for (int j = 0; j < L.n_fc && !rc; ++j) {
       gemm(cur, L.fc[j]);
-      // h = relu(BN(u)) as planes for the next Linear of this level (or for fcv)
-      if (!rc) rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, nullptr, nullptr, P[pp], st);
-      if (!rc && j == L.n_fc - 1 && l + 1 < d.n_levels)   // the same embedding with the next level's norm0 applied
-        rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, d.lvl[l + 1].n0a,
-                        d.lvl[l + 1].n0b, Pn, st);
+      // h = relu(BN(u)) as planes for the next Linear of this level (or for fcv); after the level's last Linear the
+      // same pass also writes the embedding with the next level's norm0 applied
+      if (!rc) {
+        if (j == L.n_fc - 1 && l + 1 < d.n_levels)
+          rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, d.lvl[l + 1].n0a,
+                          d.lvl[l + 1].n0b, P[pp], st, Pn);
+        else
+          rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, nullptr, nullptr, P[pp], st);
+      }
       cur = P[pp];
       pp ^= 1;
     }
     gemm(cur, L.fcv);   // z = fcv(emb_l) -> U
     if (!rc) {
-      vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U, hpad, d.K, d.T, L.av,
-                      L.bv, L.af, L.bf, Y, ystride, l * d.K);
+      const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
+      if (att_smem <= 48 * 1024)     // K = 527, T = 10: 42 KB
+        vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, st, U, hpad,
+                        d.K, d.T, L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
+      else
+        vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U, hpad, d.K, d.T,
+                        L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
       vmb::count_launch();
       rc = vmb::check_launch("attention_pool_kernel");
     }
