@@ -351,11 +351,11 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //     E[m] = x[200 + m] + x[200 - m],   O[m] = x[200 + m] - x[200 - m],   m = 0 .. 199
 //     Re Y_k = sum_m E[m] g[m] cos(2 pi k m / 512) (the m = 0 weight halved),   Im Y_k = -sum_m O[m] g[m] sin(2 pi k m / 512)
 // the DFT is two GEMMs with K = 200 (13 steps of 16) and N = 120 bins each instead of one with K = 400 and N = 240: half
-// the tensor-core work.  The price: E and O are not strided views of the waveform, so the A tiles are built by hand —
-// eight producer warps read the samples straight from global memory (L1 / L2; no separate split pass over HBM), form
-// E and O in fp32, split them and write the planes in the no-swizzle core-matrix layout (8 rows x 16 bytes per core
-// matrix: one 16-byte store per lane, a quarter-warp fills one core matrix).  The basis tiles arrive by TMA (64-byte
-// swizzle).
+// the tensor-core work.  The price: E and O are not strided views of the waveform, so the A tiles are built by hand.
+// The raw samples of a stage arrive by TMA (two boxes of the overlapping-rows view of the caller's waveform, no split
+// pass over HBM) in the region the operand planes will occupy; eight producer warps read them, form E and O in fp32,
+// split them and write the planes in the no-swizzle core-matrix layout (8 rows x 16 bytes per core matrix, K chunks
+// 160 bytes apart).  The basis tiles arrive by TMA as well (64-byte swizzle).
 // Operand precision: both operands are split into TWO fp16 terms (v = hi + lo, 22 mantissa bits; fp16 rather than bf16
 // because 2 x 11 bits need three products where 3 x 8 bits need six) and the three products lo*hi, hi*lo, hi*hi are
 // accumulated in one fp32 TMEM accumulator, smallest first.  ncu on the six-product bf16 version of this kernel showed
@@ -363,7 +363,8 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // memory (8 KB per 64 tensor cycles at N = 128), so the number of MMA instructions, not the flops, is what is paid for.
 // Per frame tile (128 frames) and N-tile (120 bins): TMEM columns [0, 128) = Re, [128, 256) = Im (columns 120..127 of
 // each are zero padding); 7 K-blocks of 32 (the last one issues a single K step), each 2 parts x 3 products.
-// 576 threads: warps 0-7 A producers, warp 8 TMA (basis), warp 9 MMA issuer, warps 10-13 / 14-17 epilogue of N-tile 0 / 1.
+// 576 threads: warps 0-7 A producers, warp 8 TMA (raw sample tiles and basis), warp 9 MMA issuer, warps 10-13 / 14-17
+// epilogue of N-tile 0 / 1.
 constexpr int eoHalf = kWin / 2;                 // 200 centred lags
 constexpr int eoBK = 32;                         // K block (lags per stage)
 constexpr int eoKB = 7;                          // blocks 0..6 cover lags 0..223; block 6 issues one K step (192..207)
