@@ -213,3 +213,21 @@ def test_pack_mla_params_layout(head_sd):
     assert torch.equal(flat[:10], head_sd["embedded_mappings.0.norm0.weight"])
     assert torch.equal(flat[40:40 + 600 * 128], head_sd["embedded_mappings.0.fc.0.weight"].reshape(-1))
     assert torch.equal(flat[-527:], head_sd["norm.running_var"])
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: ONE JSON line on stdout (everything else, including what libraries print to fd 1, goes to
+    stderr).  The reference arm runs on the CPU, so it can be exercised here with a tiny time budget."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, VMB_BENCH_CPU_BUDGET_S="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                        "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
