@@ -94,6 +94,15 @@ def test_logmel_unaligned_input_takes_the_plane_kernel():
         assert lib.vmb_launch_count() == before + launches
         ref = frontend_np.log_mel_spectrogram(waves[0, sl].astype(np.float64))
         assert np.abs(got - ref).max() <= 1e-4
+    # the same for 16-bit PCM: an odd sample offset is served by the plane kernel, and both paths agree with the float
+    # path of the same alignment class bit for bit
+    pcm = torch.from_numpy((waves[0, :32001] * 20000).astype(np.int16)).to(DEV)
+    for sl in (slice(0, 32000), slice(1, 32001)):
+        before = lib.vmb_launch_count()
+        a = engine.logmel_pcm16(pcm[sl])
+        assert lib.vmb_launch_count() == before + (1 if sl.start == 0 else 2)
+        ref = frontend_np.log_mel_spectrogram(pcm[sl].cpu().numpy() / 32768.0)
+        assert np.abs(a[0].cpu().numpy() - ref).max() <= 1e-4
     # two clips whose stride is not a multiple of four samples
     odd = torch.zeros(2, 32001, device=DEV)
     odd[:, :32000] = w[:, :32000]
