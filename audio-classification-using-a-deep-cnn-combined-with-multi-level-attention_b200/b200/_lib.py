@@ -33,8 +33,11 @@ SIGNATURES = {
     "vmb_spec_tiles": (_int, [_c_p, _ll, _int, _int, _int, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
+    "vmb_conv1_relu_pool_ex": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _c_p]),
     "vmb_conv1_relu_pool_cudacore": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_conv3x3_relu": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _int, _int, _int, _int, _c_p]),
+    "vmb_conv3x3_relu_ex": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _int, _int, _int, _int, _int, _int, _c_p]),
+    "vmb_linear_ex": (_int, [_c_p, _c_p, _c_p, _c_p, _int, _int, _ll, _int, _int, _int, _c_p]),
     "vmb_linear": (_int, [_c_p, _c_p, _c_p, _c_p, _int, _int, _ll, _int, _int, _c_p]),
     "vmb_postprocess": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
     "vmb_vggish_create": (_int, [C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p),
@@ -42,6 +45,7 @@ SIGNATURES = {
     "vmb_vggish_create_ex": (_int, [C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p), C.POINTER(_c_p),
                                     C.POINTER(_c_p), _int, _c_p]),
     "vmb_vggish_precision": (_int, [_c_p]),
+    "vmb_vggish_saturation": (_int, [_c_p, _int]),
     "vmb_vggish_handle_workspace_bytes": (_sz, [_c_p, _ll]),
     "vmb_vggish_destroy": (None, [_c_p]),
     "vmb_vggish_workspace_bytes": (_sz, [_ll]),

@@ -140,15 +140,22 @@ def postprocess(emb: torch.Tensor, eigen: torch.Tensor, means: torch.Tensor, wan
     return (out, u8) if want_u8 else out
 
 
-class VggishHandle:
-    """Owns the library-side VGGish weights (bf16, implicit-GEMM layout) built from a reference state_dict."""
+PRECISIONS = {"bf16": 0, "split": 1, "fp16": 2}
+DEFAULT_PRECISION = "fp16"
+SAT_LAYERS = ("conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "fc1", "fc2")
 
-    def __init__(self, state_dict: dict, device: torch.device, precision: str = "bf16"):
-        """precision: "bf16" (throughput mode) or "split" (accuracy mode: hi + lo bf16 activations and weights, 3x the
-        tensor work, embeddings within ~1e-5 of fp32 — for 8-bit quantised long-form extraction)."""
+
+class VggishHandle:
+    """Owns the library-side VGGish weights (16-bit, implicit-GEMM layout) built from a reference state_dict."""
+
+    def __init__(self, state_dict: dict, device: torch.device, precision: str = DEFAULT_PRECISION):
+        """precision: "fp16" (default: fp16 activations and weights, fp32 accumulation — the same tensor rate as bf16
+        with 11 instead of 8 mantissa bits; outputs saturate at 65504 and raise, see check_saturation), "bf16" (the
+        same kernels on bf16), or "split" (accuracy mode: hi + lo bf16 activations and weights, 3x the tensor work,
+        embeddings within ~1e-4 of fp32 — for 8-bit quantised long-form extraction)."""
         require_b200(device)
-        if precision not in ("bf16", "split"):
-            raise ValueError("precision must be 'bf16' or 'split'")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be 'fp16', 'bf16' or 'split'")
         self.device = device
         self.precision = precision
         self._h = C.c_void_p()
@@ -165,7 +172,7 @@ class VggishHandle:
             cb = (C.c_void_p * 6)(*[dev(f"features.{k}.bias") for k in CONV_KEYS])
             fw = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.weight") for k in FC_KEYS])
             fb = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.bias") for k in FC_KEYS])
-            check(_lib.lib().vmb_vggish_create_ex(C.byref(self._h), cw, cb, fw, fb, 1 if precision == "split" else 0,
+            check(_lib.lib().vmb_vggish_create_ex(C.byref(self._h), cw, cb, fw, fb, PRECISIONS[precision],
                                                   stream_ptr()), "vmb_vggish_create_ex")
             del keep
 
@@ -186,8 +193,28 @@ class VggishHandle:
             self._ws = torch.empty(nbytes + 1024, device=self.device, dtype=torch.uint8)
         return self._ws
 
+    @property
+    def act_dtype(self) -> torch.dtype:
+        """Element type of the 16-bit activations (and of the bottleneck features forward() can return)."""
+        return torch.float16 if self.precision == "fp16" else torch.bfloat16
+
+    def check_saturation(self, synchronize: bool = True) -> None:
+        """fp16 mode: raise if any layer's output reached the fp16 maximum since the last check.  The flags are written
+        by the kernels into mapped host memory; with synchronize=False only work that already finished is seen
+        (forward() does that on entry, so a saturated batch is reported by the next call at the latest)."""
+        if self.precision != "fp16":
+            return
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        mask = int(_lib.lib().vmb_vggish_saturation(self._h, 1))
+        if mask:
+            layers = [n for i, n in enumerate(SAT_LAYERS) if mask >> i & 1]
+            raise B200Error(f"fp16 activations saturated (65504) in {layers}: the results are invalid; build the handle "
+                            "with precision='bf16' or 'split'")
+
     def forward(self, examples: torch.Tensor, want_bottleneck: bool = False):
         """examples (n, 96, 64) or (n, 1, 96, 64) fp32 CUDA -> (n, 128) fp32 post-ReLU embeddings."""
+        self.check_saturation(synchronize=False)
         examples = _need_cuda(examples, "examples")
         if examples.dim() == 4 and examples.shape[1] == 1:
             examples = examples[:, 0]
@@ -196,7 +223,7 @@ class VggishHandle:
         examples = examples.contiguous()
         n = examples.shape[0]
         emb = torch.empty((n, 128), device=self.device, dtype=torch.float32)
-        bott = torch.empty((n, 12288), device=self.device, dtype=torch.bfloat16) if want_bottleneck else None
+        bott = torch.empty((n, 12288), device=self.device, dtype=self.act_dtype) if want_bottleneck else None
         if n == 0:
             return (emb, bott) if want_bottleneck else emb
         with torch.cuda.device(self.device):
@@ -293,6 +320,7 @@ class Pipeline:
         self._ws: Optional[torch.Tensor] = None
 
     def forward(self, wave: torch.Tensor, want_embeddings: bool = False):
+        self.vggish.check_saturation(synchronize=False)
         wave = _need_cuda(wave, "wave")
         if wave.dim() != 2:
             raise ValueError("wave must be (n_clips, n_samples)")

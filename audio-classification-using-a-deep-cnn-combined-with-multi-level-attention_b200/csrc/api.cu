@@ -32,7 +32,7 @@ void set_api_error(const char* msg) { snprintf(g_api_err, sizeof g_api_err, "%s"
 extern "C" {
 
 const char* vmb_last_error(void) { return g_api_err; }
-int vmb_abi_version(void) { return 1; }
+int vmb_abi_version(void) { return 2; }
 
 int vmb_device_arch(int device) {
   int major = 0, minor = 0;
@@ -124,11 +124,12 @@ int vmb_front_end_tables(double* hann400, double* mel257x64) {
 }
 
 static int conv1_common(const char* who, bool tensor_core, const float* examples, const float* w, const float* b,
-                        void* out, long long n, void* stream) {
+                        void* out, long long n, void* stream, int dtype = 0) {
   if (n < 0) return fail("%s: negative n", who);
+  if (dtype != 0 && dtype != 1) return fail("%s: dtype must be 0 (bf16) or 1 (fp16)", who);
   if (n == 0) return 0;
   if (!examples || !w || !b || !out) return fail("%s: null pointer", who);
-  const int rc = tensor_core ? vmb::conv1_tc_relu_pool(examples, w, b, out, n, S(stream))
+  const int rc = tensor_core ? vmb::conv1_tc_relu_pool(examples, w, b, out, n, S(stream), false, dtype)
                              : vmb::conv1_relu_pool(examples, w, b, out, n, S(stream));
   if (rc) return fail_from(who, vmb::kernels_last_error());
   return 0;
@@ -138,30 +139,47 @@ int vmb_conv1_relu_pool(const float* examples, const float* w, const float* b, v
   return conv1_common("vmb_conv1_relu_pool", true, examples, w, b, out, n, stream);
 }
 
+int vmb_conv1_relu_pool_ex(const float* examples, const float* w, const float* b, void* out, long long n, int dtype,
+                           void* stream) {
+  return conv1_common("vmb_conv1_relu_pool_ex", true, examples, w, b, out, n, stream, dtype);
+}
+
 int vmb_conv1_relu_pool_cudacore(const float* examples, const float* w, const float* b, void* out, long long n,
                                  void* stream) {
   return conv1_common("vmb_conv1_relu_pool_cudacore", false, examples, w, b, out, n, stream);
 }
 
-int vmb_conv3x3_relu(const void* act, const void* w, const float* bias, void* out, long long n, int H, int W, int C_in,
-                     int C_out, int pool, void* stream) {
+int vmb_conv3x3_relu_ex(const void* act, const void* w, const float* bias, void* out, long long n, int H, int W,
+                        int C_in, int C_out, int pool, int dtype, void* stream) {
   if (n < 0 || n > 0x7fffffffLL / 4096) return fail("vmb_conv3x3_relu: bad n %lld", n);
+  if (dtype != 0 && dtype != 1) return fail("vmb_conv3x3_relu: dtype must be 0 (bf16) or 1 (fp16)");
   if (n == 0) return 0;
   if (!act || !w || !bias || !out) return fail("vmb_conv3x3_relu: null pointer");
   if (pool && ((H | W) & 1)) return fail("vmb_conv3x3_relu: pooling needs even H, W");
-  if (vmb::igemm_conv3x3(act, w, bias, out, int(n), H, W, C_in, C_out, pool, S(stream)))
+  if (vmb::igemm_conv3x3(act, w, bias, out, int(n), H, W, C_in, C_out, pool, S(stream), dtype))
     return fail_from("vmb_conv3x3_relu", vmb::igemm_last_error());
+  return 0;
+}
+
+int vmb_conv3x3_relu(const void* act, const void* w, const float* bias, void* out, long long n, int H, int W, int C_in,
+                     int C_out, int pool, void* stream) {
+  return vmb_conv3x3_relu_ex(act, w, bias, out, n, H, W, C_in, C_out, pool, 0, stream);
+}
+
+int vmb_linear_ex(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, long long M, int N,
+                  int K, int dtype, void* stream) {
+  if (M < 0 || M > 0x7fffffffLL) return fail("vmb_linear: bad M %lld", M);
+  if (dtype != 0 && dtype != 1) return fail("vmb_linear: dtype must be 0 (bf16) or 1 (fp16)");
+  if (M == 0) return 0;
+  if (!a || !w || !bias || !out) return fail("vmb_linear: null pointer");
+  if (vmb::igemm_linear(a, w, bias, out, out_f32, relu, int(M), N, K, S(stream), dtype))
+    return fail_from("vmb_linear", vmb::igemm_last_error());
   return 0;
 }
 
 int vmb_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, long long M, int N,
                int K, void* stream) {
-  if (M < 0 || M > 0x7fffffffLL) return fail("vmb_linear: bad M %lld", M);
-  if (M == 0) return 0;
-  if (!a || !w || !bias || !out) return fail("vmb_linear: null pointer");
-  if (vmb::igemm_linear(a, w, bias, out, out_f32, relu, int(M), N, K, S(stream)))
-    return fail_from("vmb_linear", vmb::igemm_last_error());
-  return 0;
+  return vmb_linear_ex(a, w, bias, out, out_f32, relu, M, N, K, 0, stream);
 }
 
 int vmb_postprocess(const float* emb, const float* eigen, const float* means, float* out_f32, uint8_t* out_u8,

@@ -86,7 +86,7 @@ __device__ __forceinline__ void load_window(const float* __restrict__ x, long lo
 template <bool SPLIT_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                const __grid_constant__ CUtensorMap tmap_out, long long n_tiles) {
+                const __grid_constant__ CUtensorMap tmap_out, long long n_tiles, int f16_out, int* sat_flag) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -218,6 +218,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
     const bool store_thread = (warp == kMmaWarp + 1) && lane == 0;
     constexpr int kBufBytes = (SPLIT_OUT ? 2 : 1) * kOutTile;
     uint32_t it = 0;
+    uint32_t sat_max = 0;   // fp16 output: running maximum of the packed results
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t stage = it & 1, ph = (it >> 1) & 1;
       uint8_t* obuf = o_smem + (it & 1) * kBufBytes;
@@ -242,9 +243,14 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                                       fmaxf(__uint_as_float(v2[2 * j]), __uint_as_float(v3[2 * j]))), 0.f);
           const float c = fmaxf(fmaxf(fmaxf(__uint_as_float(v0[2 * j + 1]), __uint_as_float(v1[2 * j + 1])),
                                       fmaxf(__uint_as_float(v2[2 * j + 1]), __uint_as_float(v3[2 * j + 1]))), 0.f);
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
-          pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
+          if (!SPLIT_OUT && f16_out) {
+            pk[j] = pack_f16x2(a, c);
+            sat_max = max_f16x2(sat_max, pk[j]);
+          } else {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            if (SPLIT_OUT) pl[j] = pack_bf16x2(a - __low2float(h2), c - __high2float(h2));
+          }
         }
         // 16-byte pieces 2*ch and 2*ch+1 of this pixel's 128-byte row, at the swizzled positions TMA expects
         uint8_t* orow = obuf + row * 128;
@@ -276,6 +282,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       }
     }
     if (store_thread) bulk_wait_group<0>();       // shared memory stays valid until the last store has read it
+    if (sat_flag && saturated_f16x2(sat_max)) *reinterpret_cast<volatile int*>(sat_flag) = 1;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -288,7 +295,7 @@ conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 }  // namespace
 
 int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out, long long n,
-                       cudaStream_t stream, bool split_out) {
+                       cudaStream_t stream, bool split_out, int fmt, int* sat_flag) {
   const long long tiles = n * kTilesPerExample;
   if (tiles <= 0) return 0;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
@@ -320,9 +327,9 @@ int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, vo
     }
   }
   const cudaError_t e = split_out ? launch_pdl(conv1_tc_kernel<true>, dim3(grid), dim3(kThreads), conv1_smem_bytes<true>(),
-                                               stream, examples, w, b, to, tiles)
+                                               stream, examples, w, b, to, tiles, 0, static_cast<int*>(nullptr))
                                   : launch_pdl(conv1_tc_kernel<false>, dim3(grid), dim3(kThreads), conv1_smem_bytes<false>(),
-                                               stream, examples, w, b, to, tiles);
+                                               stream, examples, w, b, to, tiles, fmt == kFmtF16 ? 1 : 0, sat_flag);
   count_launch();
   if (e != cudaSuccess) {
     set_kernel_error("conv1_tc_kernel: %s", cudaGetErrorString(e));

@@ -203,7 +203,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16_f32(2 * kBlockM, BLOCK_N) : umma_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -308,6 +308,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
 
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + mt * BLOCK_N;
+      uint32_t sat_max = 0;   // fp16 mode: running maximum of the packed outputs
 #pragma unroll 1
       for (int ch = (MT == 2 ? 0 : half); ch < BLOCK_N / 32; ch += (MT == 2 ? 1 : 2)) {
         uint32_t v[32];
@@ -326,17 +327,13 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
-        if (POOL) {
-          pool2x2_relu_store_bf16(pk, sub, p.Wb, p.relu != 0, valid, outp);
-        } else if (valid) {
-          st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-          st_global_256(outp + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
-        }
+        void* outp = static_cast<uint16_t*>(p.out) + out_off + ch * 32;
+        if (p.f16)
+          sat_max = max_f16x2(sat_max, store_row32_16bit<true, POOL>(f, sub, p.Wb, p.relu != 0, valid, outp));
+        else
+          store_row32_16bit<false, POOL>(f, sub, p.Wb, p.relu != 0, valid, outp);
       }
+      if (p.f16 && p.sat_flag && saturated_f16x2(sat_max)) *reinterpret_cast<volatile int*>(p.sat_flag) = 1;
       }  // mt
       tc_fence_before_sync();
       __syncwarp();
@@ -390,7 +387,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams&
 const char* igemm_pair_last_error() { return g_pair_err; }
 
 int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out, int relu, int M, int N, int K,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int fmt, int* sat_flag) {
   if (M <= 0) return 0;
   if (K % kBlockK != 0 || N % 256 != 0) {
     snprintf(g_pair_err, sizeof g_pair_err, "igemm_pair_linear: need K %% 64 == 0 and N %% 256 == 0");
@@ -419,6 +416,8 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   p.ldo = N;
   p.bias = bias;
   p.out = out;
+  p.f16 = fmt == kFmtF16;
+  p.sat_flag = sat_flag;
   // Wave quantisation: T tiles on P SM pairs run as ceil(T / P) rounds.  When the last round would be less than half
   // full (fc1 / fc2 at 2 560 rows: 160 tiles on 74 pairs = 2 full rounds + 12 tiles), the full rounds go to the pair
   // kernel and the left-over tiles — one or two rectangles of the output — to the single-CTA kernel with 128 x 128
@@ -439,7 +438,7 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   if (c > 0) {   // the rest of the partly covered row of tiles
     const int row0 = r * 256, rows = (M - row0 < 256) ? M - row0 : 256, col0 = c * 256;
     if (igemm_linear_rect(a8 + size_t(row0) * K * 2, w8 + size_t(col0) * K * 2, bias ? bias + col0 : nullptr,
-                             o8 + (size_t(row0) * N + col0) * 2, N, relu, rows, N - col0, K, stream)) {
+                             o8 + (size_t(row0) * N + col0) * 2, N, relu, rows, N - col0, K, stream, fmt, sat_flag)) {
       snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
       return 1;
     }
@@ -447,7 +446,8 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
   }
   if (r * 256 < M) {   // whole rows of tiles below
     const int row0 = r * 256;
-    if (igemm_linear_rect(a8 + size_t(row0) * K * 2, w, bias, o8 + size_t(row0) * N * 2, N, relu, M - row0, N, K, stream)) {
+    if (igemm_linear_rect(a8 + size_t(row0) * K * 2, w, bias, o8 + size_t(row0) * N * 2, N, relu, M - row0, N, K, stream, fmt,
+                          sat_flag)) {
       snprintf(g_pair_err, sizeof g_pair_err, "%s", igemm_last_error());
       return 1;
     }
@@ -456,7 +456,7 @@ int igemm_pair_linear(const void* a, const void* w, const float* bias, void* out
 }
 
 int igemm_pair_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
-                       int C_out, int pool, cudaStream_t stream) {
+                       int C_out, int pool, cudaStream_t stream, int fmt, int* sat_flag) {
   if (n_img <= 0) return 0;
   const int Wb = (W % 16 == 0) ? 16 : 8;
   const int Hb = 32 / Wb;
@@ -499,6 +499,8 @@ int igemm_pair_conv3x3(const void* act, const void* w, const float* bias, void* 
   p.ldo = C_out;
   p.bias = bias;
   p.out = out;
+  p.f16 = fmt == kFmtF16;
+  p.sat_flag = sat_flag;
   p.out_img_stride = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
   if (big && Wb == kHaloWb && 4 * Hb + 2 == kHaloRows && igemm_use_halo()) {
     CUtensorMap th;

@@ -220,7 +220,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BLOCK_N);
+    const uint32_t idesc = p.f16 ? umma_idesc_f16_f32(kBlockM, BLOCK_N) : umma_idesc_bf16_f32(kBlockM, BLOCK_N);
     uint32_t stage = 0, phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -336,6 +336,7 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
 
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BLOCK_N) + mt * BLOCK_N;
+      uint32_t sat_max = 0;   // fp16 mode: running maximum of the packed outputs
 
 #pragma unroll 1
       for (int ch = (MT == 2 ? 0 : half); ch < BLOCK_N / 32; ch += (MT == 2 ? 1 : 2)) {
@@ -407,18 +408,14 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
           }
         } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out) + out_off + ch * 32;
-          if (POOL) {
-            pool2x2_relu_store_bf16(pk, sub, p.Wb, p.relu != 0, valid, outp);
-          } else if (valid) {
-            st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-            st_global_256(outp + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
-          }
+          void* outp = static_cast<uint16_t*>(p.out) + out_off + ch * 32;
+          if (p.f16)
+            sat_max = max_f16x2(sat_max, store_row32_16bit<true, POOL>(f, sub, p.Wb, p.relu != 0, valid, outp));
+          else
+            store_row32_16bit<false, POOL>(f, sub, p.Wb, p.relu != 0, valid, outp);
         }
       }
+      if (OUT == kOutBf16 && p.f16 && p.sat_flag && saturated_f16x2(sat_max)) *reinterpret_cast<volatile int*>(p.sat_flag) = 1;
       }  // mt
       tc_fence_before_sync();
       __syncwarp();
@@ -590,7 +587,7 @@ int pair_result(int rc) {
 }  // namespace
 
 int igemm_linear(const void* a, const void* w, const float* bias, void* out, int out_f32, int relu, int M, int N,
-                 int K, cudaStream_t stream) {
+                 int K, cudaStream_t stream, int fmt, int* sat_flag) {
   if (M <= 0) return 0;
   if (misaligned32(out, "igemm_linear")) return 1;
   if (K % kBlockK != 0 || N % 128 != 0) {
@@ -598,7 +595,7 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
     return 1;
   }
   if (!out_f32 && N % 256 == 0 && M >= 256 && igemm_use_pair())
-    return pair_result(igemm_pair_linear(a, w, bias, out, relu, M, N, K, stream));
+    return pair_result(igemm_pair_linear(a, w, bias, out, relu, M, N, K, stream, fmt, sat_flag));
   const int block_n = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   {
@@ -623,6 +620,8 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
   p.ldo = N;
   p.bias = bias;
   p.out = out;
+  p.f16 = fmt == kFmtF16;
+  p.sat_flag = sat_flag;
   if (block_n == 256)
     return out_f32 ? launch<256, 1, false, false, kOutF32>(ta, tb, p, stream)
                    : launch<256, 1, false, false, kOutBf16>(ta, tb, p, stream);
@@ -631,7 +630,7 @@ int igemm_linear(const void* a, const void* w, const float* bias, void* out, int
 }
 
 int igemm_linear_rect(const void* a, const void* w, const float* bias, void* out, long long ldo, int relu, int M, int N,
-                         int K, cudaStream_t stream) {
+                         int K, cudaStream_t stream, int fmt, int* sat_flag) {
   if (M <= 0 || N <= 0) return 0;
   if (misaligned32(out, "igemm_linear_rect")) return 1;
   if (K % kBlockK != 0 || N % 128 != 0 || ldo % 16 != 0) {
@@ -664,6 +663,8 @@ int igemm_linear_rect(const void* a, const void* w, const float* bias, void* out
   p.ldo = ldo;
   p.bias = bias;
   p.out = out;
+  p.f16 = fmt == kFmtF16;
+  p.sat_flag = sat_flag;
   return block_n == 64 ? launch<64, 1, false, false, kOutBf16>(ta, tb, p, stream)
                        : launch<128, 1, false, false, kOutBf16>(ta, tb, p, stream);
 }
@@ -852,7 +853,7 @@ int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const floa
 }
 
 int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, int n_img, int H, int W, int C_in,
-                  int C_out, int pool, cudaStream_t stream) {
+                  int C_out, int pool, cudaStream_t stream, int fmt, int* sat_flag) {
   if (n_img <= 0) return 0;
   if (misaligned32(out, "igemm_conv3x3")) return 1;
   const int Wb = (W % 16 == 0) ? 16 : 8;
@@ -864,7 +865,7 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   // C_out = 128 (conv2) stays on the single-CTA 256 x 128 tiles: at N = 128 the MMA's operand fetch saturates shared
   // memory either way and the pair kernel measured no faster
   if (igemm_use_pair() && C_out % 256 == 0)
-    return pair_result(igemm_pair_conv3x3(act, w, bias, out, n_img, H, W, C_in, C_out, pool, stream));
+    return pair_result(igemm_pair_conv3x3(act, w, bias, out, n_img, H, W, C_in, C_out, pool, stream, fmt, sat_flag));
   const int block_n = (C_out % 256 == 0) ? 256 : 128;
   const int K = 9 * C_in;
   // when the image height allows it, one TMA box brings a whole 128-pixel sub-tile (Wb x 4*Hb pixels) instead of four
@@ -904,6 +905,8 @@ int igemm_conv3x3(const void* act, const void* w, const float* bias, void* out, 
   p.ldo = C_out;
   p.bias = bias;
   p.out = out;
+  p.f16 = fmt == kFmtF16;
+  p.sat_flag = sat_flag;
   p.out_img_stride = static_cast<long long>(pool ? (H / 2) * (W / 2) : H * W) * C_out;
   if (block_n == 256) {
     if (big)

@@ -46,6 +46,8 @@ struct IgemmParams {
   int ksplit;        // PLAIN + atomic fp32 output: number of K slices (<= 1: none)
   int tile_count;    // pair kernel: process only the first tile_count tiles (0 = all); see igemm_pair_linear
   int conv_split;    // CONV: activations are [n][2][H][W][C] hi | lo planes, weights [C_out][2 * 9 C_in]
+  int f16;           // operands (and 16-bit outputs) are fp16 instead of bf16: the fp16 mode of the VGGish body
+  int* sat_flag;     // fp16 mode: set to 1 when an output saturated the fp16 range (may be null; mapped host memory)
   long long out_img_stride;  // CONV: output elements per image (2 planes when the output is split)
   long long lo_off;          // split output: element offset of the lo plane relative to the hi element
   long long ldo;     // PLAIN: output row stride (elements)
@@ -55,8 +57,9 @@ struct IgemmParams {
 
 // Launchers (defined in igemm_sm100.cu).  All return cudaError_t-compatible ints; 0 = ok.
 // PLAIN: out[M][N] (+ldo) = act(A[M][K] B[N][K]^T + bias).  K % 64 == 0, N % block_n == 0.
+// fmt: kFmtBf16 (0) or kFmtF16 (1) — the element format of a, w and of a 16-bit out; sat_flag: see IgemmParams.
 int igemm_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int out_f32, int relu,
-                 int M, int N, int K, cudaStream_t stream);
+                 int M, int N, int K, cudaStream_t stream, int fmt = 0, int* sat_flag = nullptr);
 // PLAIN, split-bf16.  planes = 2: A = [A_hi | A_lo] as bf16 [M][2K], W likewise [N][2K];
 // out fp32 [M][ldo] = act(A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T + bias): ~16 mantissa bits per operand (the
 // eval-mode attention head, where plain bf16 would move the ranking metric).  planes = 3: [hi | mid | lo] as
@@ -79,19 +82,19 @@ int igemm_conv3x3_split(const void* act_planes, const void* w_planes, const floa
 // CONV 3x3 pad 1 (+bias, ReLU, optional 2x2 maxpool): act NHWC bf16 [n][H][W][C_in], weights [C_out][9*C_in]
 // ((kh,kw,c) order), out NHWC bf16 [n][H or H/2][W or W/2][C_out].  C_in % 64 == 0, C_out % 128 == 0.
 int igemm_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
-                  int W, int C_in, int C_out, int pool, cudaStream_t stream);
+                  int W, int C_in, int C_out, int pool, cudaStream_t stream, int fmt = 0, int* sat_flag = nullptr);
 
 // CTA-pair (cta_group::2) kernels for the bf16 layers with C_out / N a multiple of 256 (igemm_pair_sm100.cu);
 // igemm_conv3x3 / igemm_linear route to them when igemm_use_pair() (env VMB_IGEMM_PAIR=0/1 overrides the default).
 int igemm_pair_linear(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, int relu, int M, int N,
-                      int K, cudaStream_t stream);
+                      int K, cudaStream_t stream, int fmt = 0, int* sat_flag = nullptr);
 int igemm_pair_conv3x3(const void* act_bf16, const void* w_bf16, const float* bias, void* out_bf16, int n_img, int H,
-                       int W, int C_in, int C_out, int pool, cudaStream_t stream);
+                       int W, int C_in, int C_out, int pool, cudaStream_t stream, int fmt = 0, int* sat_flag = nullptr);
 const char* igemm_pair_last_error();
 // A rectangle of a PLAIN bf16 GEMM on the single-CTA kernel with 128- or 64-wide tiles: out[M][N] (row stride ldo) =
 // act(A[M][K] W[N][K]^T + bias); used by igemm_pair_linear for the tiles of an incomplete last round.
 int igemm_linear_rect(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, long long ldo, int relu,
-                         int M, int N, int K, cudaStream_t stream);
+                         int M, int N, int K, cudaStream_t stream, int fmt = 0, int* sat_flag = nullptr);
 bool igemm_use_pair();
 int igemm_set_pair(int on);
 // Haloed activation boxes for the C_out = 128 conv (conv2): same contract as igemm_set_pair.

@@ -65,8 +65,9 @@ int logmel_forward(const float* wave, long long n_clips, long long samples_per_c
 
 // ---- VGGish odd layers (layers.cu)
 // conv1 on the tensor cores (conv1_tc.cu): hand-built im2col tiles, pooling as a max over four TMEM column blocks.
+// fmt 1 (kFmtF16): fp16 output (not with split_out); sat_flag: set to 1 when an output saturates the fp16 range.
 int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, void* out_bf16, long long n,
-                       cudaStream_t stream, bool split_out = false);
+                       cudaStream_t stream, bool split_out = false, int fmt = 0, int* sat_flag = nullptr);
 // conv1 on the CUDA cores in fp32 (layers.cu): the first implementation, kept as the on-device cross-check.
 int conv1_relu_pool(const float* examples, const float* w, const float* b, void* out_bf16, long long n,
                     cudaStream_t stream);
@@ -75,12 +76,12 @@ int postprocess(const float* emb, const float* eigen, const float* means, float*
 // dataset.create_spec + split tiling of <= 4 examples per clip into T windows of (64, 96)
 int spec_tiles(const float* examples, long long n_clips, int n_ex, int T, int step, float* out, cudaStream_t stream);
 // OIHW fp32 [C_out][C_in][3][3] -> bf16 [C_out][(kh*3+kw)*C_in + c]
-int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream);
+int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream, int fmt = 0);
 // OIHW fp32 -> bf16 [C_out][hi(9 C_in) | lo(9 C_in)], (kh, kw, c) order inside each plane
 int relayout_conv_weight_split(const float* w_oihw, void* planes, int C_out, int C_in, cudaStream_t stream);
 // fp32 [rows][cols] -> bf16 [rows][hi(cols) | lo(cols)]
 int split_f32_to_planes(const float* src, void* planes, long long rows, long long cols, cudaStream_t stream);
-// fp32 -> bf16 elementwise
-int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+// fp32 -> bf16 (fmt 0) or fp16 (fmt 1, saturating) elementwise
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream, int fmt = 0);
 
 }  // namespace vmb

@@ -132,14 +132,18 @@ spec_tiles_kernel(const float* __restrict__ ex, long long n_clips, int n_ex, int
 }
 
 // ------------------------------------------------------------------ weight re-layout
-__global__ void relayout_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int C_out, int C_in) {
+__device__ __forceinline__ uint16_t to16(float v, int f16) {
+  return f16 ? static_cast<uint16_t>(pack_f16x2(v, 0.f) & 0xFFFFu) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
+__global__ void relayout_conv_kernel(const float* __restrict__ w, uint16_t* __restrict__ o, int C_out, int C_in, int f16) {
   const long long total = static_cast<long long>(C_out) * 9 * C_in;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = int(i % C_in);
     const int tap = int((i / C_in) % 9);
     const long long oc = i / (9LL * C_in);
-    o[i] = __float2bfloat16_rn(__ldg(w + (oc * C_in + c) * 9 + tap));
+    o[i] = to16(__ldg(w + (oc * C_in + c) * 9 + tap), f16);
   }
 }
 
@@ -169,10 +173,10 @@ __global__ void split_planes_kernel(const float* __restrict__ s, __nv_bfloat16* 
   }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+__global__ void cast_bf16_kernel(const float* __restrict__ s, uint16_t* __restrict__ d, long long n, int f16) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    d[i] = __float2bfloat16_rn(__ldg(s + i));
+    d[i] = to16(__ldg(s + i), f16);
 }
 
 }  // namespace
@@ -207,8 +211,8 @@ int spec_tiles(const float* examples, long long n_clips, int n_ex, int T, int st
   return check_launch("spec_tiles_kernel");
 }
 
-int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream) {
-  relayout_conv_kernel<<<1024, 256, 0, stream>>>(w_oihw, static_cast<__nv_bfloat16*>(w_bf16), C_out, C_in);
+int relayout_conv_weight(const float* w_oihw, void* w_bf16, int C_out, int C_in, cudaStream_t stream, int fmt) {
+  relayout_conv_kernel<<<1024, 256, 0, stream>>>(w_oihw, static_cast<uint16_t*>(w_bf16), C_out, C_in, fmt == kFmtF16);
   count_launch();
   return check_launch("relayout_conv_kernel");
 }
@@ -225,8 +229,8 @@ int split_f32_to_planes(const float* src, void* planes, long long rows, long lon
   return check_launch("split_planes_kernel");
 }
 
-int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
-  cast_bf16_kernel<<<2048, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+int cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream, int fmt) {
+  cast_bf16_kernel<<<2048, 256, 0, stream>>>(src, static_cast<uint16_t*>(dst), n, fmt == kFmtF16);
   count_launch();
   return check_launch("cast_bf16_kernel");
 }

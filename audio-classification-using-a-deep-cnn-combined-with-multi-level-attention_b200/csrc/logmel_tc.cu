@@ -64,11 +64,25 @@ constexpr int kBTile = kTN * kBK * 2;   // 15360
 constexpr int kStageBytes = 3 * (kATile + kBTile);  // 70656
 constexpr int kStages = 3;
 constexpr int kThreads = 320;          // producer, MMA issuer, 2 x 4 epilogue warps
-constexpr int kHandFloats = 6;          // per-row walk state handed from the N-tile-0 epilogue to the N-tile-1 one
+constexpr int kHandFloats = 8;          // per-row walk state handed from the N-tile-0 epilogue to the N-tile-1 one
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 512 + 2 * kTM * kHandFloats * 4;
 constexpr int kTmemCols = 512;          // accumulator t lives at column 256 t
 constexpr double kPi = 3.14159265358979323846;
 constexpr float kLogOffset = 0.01f;
+// Ill-conditioned frames.  log(mel + 0.01) amplifies an absolute error of the band sum by 1 / (mel + 0.01), and what the
+// split-precision tensor-core DFT leaves in an (almost) empty band scales with the frame's total spectral energy:
+// operand planes carry 22-24 bits and the fp32 accumulation inside tcgen05.mma truncates.  With
+//     R = sqrt(sum_k |X_k|^2) / (min_band mel + 0.01)
+// the emulation of the kernels' arithmetic (tools/logmel_precision_emulation.py; 22 signal types) gives
+// |log-mel error| <= 3e-6 + 2.3e-8 R.  Frames with R > kExactRatio (a loud tone or band-limited signal over a digitally
+// silent band: > 70 dB between the spectrum's energy and its quietest mel band) are flagged by the epilogue and redone
+// in float64 by logmel_exact_kernel, so that the 1e-4 bound against the float64 reference holds for every input
+// (<= 8.4e-5 from the tensor-core path, ~1e-7 from the exact one).  ~0.35 % of the frames of the synthetic bench batch
+// (the late part of the chirp family) are flagged; noise-like audio never is.
+constexpr float kExactRatio = 3500.f;
+// The plane kernel (straight K = 400 DFT, six bf16 products: 150 truncating accumulation steps per bin) follows
+// |error| <= 3e-6 + 7.3e-8 R in the same emulation, hence its lower threshold.
+constexpr float kExactRatioPlanes = 1200.f;
 
 // mel walk tables: bin kBinLo + i feeds band e-1 with weight wf and band e with weight wr (e in 0..64)
 __constant__ int c_band[kEvalBins];
@@ -133,6 +147,7 @@ struct LogmelParams {
   int n_clips;
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
+  uint32_t* exact_mask;     // [total_tiles][4]: bit r of word q = frame 32 q + r of the tile must be redone exactly
 };
 
 
@@ -140,12 +155,15 @@ struct BandWalk {
   int e = 0;          // lo accumulates band e-1, hi band e
   float lo = 0.f, hi = 0.f;
   float4 pend;        // four finished bands waiting for one 16-byte store
+  float e2 = 0.f;     // sum of |X_k|^2 over the bins walked so far
+  float mn = 3.0e38f; // smallest finished band sum
 };
 
 __device__ __forceinline__ void emit_band(BandWalk& w, float* __restrict__ row_out, bool valid) {
   const int band = w.e - 1;
   if (band >= 0 && band < kMel) {
     const float v = __logf(w.lo + kLogOffset);
+    w.mn = fminf(w.mn, w.lo);
     const int slot = band & 3;
     if (slot == 0) w.pend.x = v;
     else if (slot == 1) w.pend.y = v;
@@ -167,7 +185,9 @@ __device__ __forceinline__ void walk_bins(BandWalk& w, const uint32_t* v, int bi
   for (int j = 0; j < NB; ++j) {
     const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
     float mag;   // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));
+    const float ss = fmaf(re, re, im * im);
+    w.e2 += ss;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(ss));
     const int e = c_band[bin0 + j];
     while (w.e < e) emit_band(w, row_out, valid);      // warp-uniform: depends on the bin index only
     w.lo = fmaf(c_wfall[bin0 + j], mag, w.lo);
@@ -302,6 +322,7 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         w.e = c_band[kTileBins - 1];            // where the walk over bins 0..119 stops (uniform)
         w.lo = hrow[0]; w.hi = hrow[1];
         w.pend = make_float4(hrow[2], hrow[3], hrow[4], 0.f);
+        w.e2 = hrow[6]; w.mn = hrow[7];
         __syncwarp();
         if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
       }
@@ -329,10 +350,14 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&hand_empty[hb * 4 + q], hphase ^ 1);
         hrow[0] = w.lo; hrow[1] = w.hi;
         hrow[2] = w.pend.x; hrow[3] = w.pend.y; hrow[4] = w.pend.z;
+        hrow[6] = w.e2; hrow[7] = w.mn;
         __syncwarp();
         if (lane == 0) mbar_arrive(&hand_full[hb * 4 + q]);
       } else {
         while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
+        const float lim = kExactRatioPlanes * (w.mn + kLogOffset);
+        const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
+        if (lane == 0) p.exact_mask[tile * 4 + q] = bad;
       }
     }
   }
@@ -478,6 +503,7 @@ struct LogmelEoParams {
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
+  uint32_t* exact_mask;     // [total_tiles][4]: frames to redo in float64 (see kExactRatio)
 };
 
 // The band walk of the epilogue with everything about the mel layout resolved at compile time.  kBandOfBin is the
@@ -501,6 +527,8 @@ constexpr unsigned char kBandOfBin[kEvalBins] = {
 struct WalkState {
   float lo, hi;       // running sums of band e - 1 (complete after its falling side) and band e
   float pend[4];      // finished bands of the current group of four, waiting for one 16-byte store
+  float e2;           // sum of re^2 + im^2 (in the operands' 2^22 scale) over the bins walked so far
+  float mn;           // smallest finished band sum
 };
 
 template <int E>   // close interval E: band E - 1 is complete
@@ -508,6 +536,7 @@ __device__ __forceinline__ void emit_static(WalkState& w, float* __restrict__ ro
   constexpr int band = E - 1;
   if constexpr (band >= 0 && band < kMel) {
     w.pend[band & 3] = __logf(w.lo + kLogOffset);
+    w.mn = fminf(w.mn, w.lo);
     if constexpr ((band & 3) == 3) {
       if (valid) *reinterpret_cast<float4*>(row_out + band - 3) = make_float4(w.pend[0], w.pend[1], w.pend[2], w.pend[3]);
     }
@@ -551,7 +580,9 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_addr, uint32_t (&re)[
   for (int j = 0; j < eoChunkBins; ++j) {
     const float r = __uint_as_float(re[j]), i = __uint_as_float(im[j]);
     float m;     // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(r, r, i * i)));
+    const float ss = fmaf(r, r, i * i);
+    w.e2 += ss;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(ss));
     mag[j] = m * eoUnscale;                              // exact: the operands carried 2^12 and 2^10
   }
   if constexpr (CH + 1 < eoChunks) {
@@ -743,6 +774,8 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (set == 0) {
         w.lo = w.hi = 0.f;
         w.pend[0] = w.pend[1] = w.pend[2] = w.pend[3] = 0.f;
+        w.e2 = 0.f;
+        w.mn = 3.0e38f;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after_sync();
         tmem_ld_32x8(t_addr, re);
@@ -754,6 +787,7 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         mbar_wait(&hand_empty[hb * 4 + q], hphase ^ 1);
         hrow[0] = w.lo; hrow[1] = w.hi;
         hrow[2] = w.pend[0]; hrow[3] = w.pend[1]; hrow[4] = w.pend[2]; hrow[5] = w.pend[3];
+        hrow[6] = w.e2; hrow[7] = w.mn;
         __syncwarp();
         if (lane == 0) mbar_arrive(&hand_full[hb * 4 + q]);
       } else {
@@ -764,6 +798,7 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         mbar_wait(&hand_full[hb * 4 + q], hphase);
         w.lo = hrow[0]; w.hi = hrow[1];
         w.pend[0] = hrow[2]; w.pend[1] = hrow[3]; w.pend[2] = hrow[4]; w.pend[3] = hrow[5];
+        w.e2 = hrow[6]; w.mn = hrow[7];
         __syncwarp();
         if (lane == 0) mbar_arrive(&hand_empty[hb * 4 + q]);
         epilogue_chunks<1, 0>(t_addr, re, im, w, row_out, valid);
@@ -771,6 +806,10 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         flush_static<kBandOfBin[kEvalBins - 1]>(w, row_out, valid);   // the remaining bands (up to band 63)
+        // e2 carries the operands' scale (2^-22 per factor): compare sqrt(e2) * 2^-22 with kExactRatio * (min band + 0.01)
+        const float lim = (kExactRatio / eoUnscale) * (w.mn + kLogOffset);
+        const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
+        if (lane == 0) p.exact_mask[tile * 4 + q] = bad;
       }
     }
   }
@@ -783,10 +822,145 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
+// ================================================================== float64 path for the flagged frames
+// The same centred even / odd DFT in float64 on the CUDA cores, one CTA per 128-frame tile that has flagged frames,
+// 16 flagged frames at a time: E, O in shared memory ([lag][frame], so that the 16 frames of a lag are two 64-byte
+// broadcast reads), thread = DFT bin (240 of 256 threads), basis and mel matrix as float64 tables in global memory
+// (768 KB + 120 KB, L2-resident).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
+// float64 reference rounded once.  ~2.6 us of one SM per frame; tiles without flagged frames cost one 16-byte read.
+constexpr int kExactFrames = 16;
+constexpr int kExactThreads = 256;
+constexpr int kExactSmem = 2 * eoHalf * kExactFrames * 8 + kExactFrames * kEvalBins * 8 + 160 * 4;
+
+struct ExactParams {
+  long long frames_out;
+  int tiles_per_clip;
+  long long total_tiles;
+  long long clip_stride;        // samples
+  const uint32_t* mask;         // [total_tiles][4]
+  const double* basis;          // [2: cos, sin][200 lags][240 bins]
+  const double* mel;            // [240 bins][64 bands]
+  float* out;                   // [n_clips][frames_out][64]
+};
+
+template <class IN>
+__device__ __forceinline__ double load_sample_f64(const IN* p);
+template <>
+__device__ __forceinline__ double load_sample_f64<float>(const float* p) { return static_cast<double>(__ldg(p)); }
+template <>
+__device__ __forceinline__ double load_sample_f64<int16_t>(const int16_t* p) { return static_cast<double>(__ldg(p)) / 32768.0; }
+
+template <class IN>
+__global__ void __launch_bounds__(kExactThreads)
+logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
+  extern __shared__ __align__(16) uint8_t exact_smem[];
+  double* E = reinterpret_cast<double*>(exact_smem);                 // [200][16]
+  double* O = E + eoHalf * kExactFrames;                             // [200][16]
+  double* mag = O + eoHalf * kExactFrames;                           // [16][240]
+  int* rows = reinterpret_cast<int*>(mag + kExactFrames * kEvalBins); // [128] flagged frames of the tile + [1] count
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();   // the masks (and the rows this kernel overwrites) come from the tensor-core kernel before it
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(p.mask) + tile);
+    if ((m4.x | m4.y | m4.z | m4.w) == 0u) continue;                 // block-uniform
+    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+    if (tid < kTM) {
+      const int q = tid >> 5, r = tid & 31;
+      if ((mw[q] >> r) & 1u) {
+        int pos = __popc(mw[q] & ((1u << r) - 1u));
+        for (int i = 0; i < q; ++i) pos += __popc(mw[i]);
+        rows[pos] = tid;
+      }
+    }
+    const int n_rows = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
+    const long long clip = tile / p.tiles_per_clip;
+    const long long frame0 = (tile - clip * p.tiles_per_clip) * kTM;
+    const IN* clip_wave = wave + clip * p.clip_stride;
+    __syncthreads();
+    for (int g0 = 0; g0 < n_rows; g0 += kExactFrames) {
+      const int ng = n_rows - g0 < kExactFrames ? n_rows - g0 : kExactFrames;
+      // E[m][f] = x[200 + m] + x[200 - m], O[m][f] = x[200 + m] - x[200 - m] (lag 0: E = 2 x[200], its weight is halved)
+      for (int i = tid; i < eoHalf * kExactFrames; i += kExactThreads) {
+        const int f = i / eoHalf, m = i - f * eoHalf;
+        double e = 0.0, o = 0.0;
+        if (f < ng) {
+          const IN* x = clip_wave + (frame0 + rows[g0 + f]) * kHop + eoHalf;
+          const double xp = load_sample_f64<IN>(x + m), xm = load_sample_f64<IN>(x - m);
+          e = xp + xm;
+          o = xp - xm;
+        }
+        E[m * kExactFrames + f] = e;
+        O[m * kExactFrames + f] = o;
+      }
+      __syncthreads();
+      if (tid < kEvalBins) {
+        double re[kExactFrames], im[kExactFrames];
+#pragma unroll
+        for (int f = 0; f < kExactFrames; ++f) re[f] = im[f] = 0.0;
+        const double* bc = p.basis + tid;
+        const double* bs = p.basis + eoHalf * kEvalBins + tid;
+#pragma unroll 2
+        for (int m = 0; m < eoHalf; ++m) {
+          const double c = __ldg(bc + m * kEvalBins), sn = __ldg(bs + m * kEvalBins);
+          const double2* e2 = reinterpret_cast<const double2*>(E + m * kExactFrames);
+          const double2* o2 = reinterpret_cast<const double2*>(O + m * kExactFrames);
+#pragma unroll
+          for (int f = 0; f < kExactFrames / 2; ++f) {
+            const double2 ev = e2[f], ov = o2[f];
+            re[2 * f] = fma(ev.x, c, re[2 * f]);
+            re[2 * f + 1] = fma(ev.y, c, re[2 * f + 1]);
+            im[2 * f] = fma(ov.x, sn, im[2 * f]);
+            im[2 * f + 1] = fma(ov.y, sn, im[2 * f + 1]);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < kExactFrames; ++f) mag[f * kEvalBins + tid] = sqrt(re[f] * re[f] + im[f] * im[f]);
+      }
+      __syncthreads();
+      for (int i = tid; i < kExactFrames * kMel; i += kExactThreads) {
+        const int f = i / kMel, band = i - f * kMel;
+        if (f < ng) {
+          double acc = 0.0;
+          const double* mg = mag + f * kEvalBins;
+          for (int b = 0; b < kEvalBins; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
+          p.out[(clip * p.frames_out + frame0 + rows[g0 + f]) * kMel + band] = static_cast<float>(log(acc + 0.01));
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <class IN>
+int launch_exact(const IN* wave, long long clip_stride, long long frames_out, int tiles_per_clip, long long total_tiles,
+                 const uint32_t* mask, const double* basis, const double* mel, float* out, cudaStream_t stream) {
+  ExactParams e{};
+  e.frames_out = frames_out;
+  e.tiles_per_clip = tiles_per_clip;
+  e.total_tiles = total_tiles;
+  e.clip_stride = clip_stride;
+  e.mask = mask;
+  e.basis = basis;
+  e.mel = mel;
+  e.out = out;
+  const long long grid = std::min<long long>(total_tiles, 2LL * num_sms());
+  const cudaError_t le = launch_pdl(logmel_exact_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(kExactThreads),
+                                    kExactSmem, stream, wave, e);
+  count_launch();
+  if (le != cudaSuccess) {
+    set_kernel_error("logmel_exact_kernel: %s", cudaGetErrorString(le));
+    return 1;
+  }
+  return check_launch("logmel_exact_kernel");
+}
+
 // ------------------------------------------------------------------ per-device constant tables
 struct TcTables {
   __nv_bfloat16* basis = nullptr;  // [3][480][416] bf16: row = 2*bin_index + {cos, sin}, col = sample in frame
   __half* basis_eo = nullptr;      // [2 planes: hi, lo][2 parts: cos, sin][2 N-tiles][128 bins (120 used)][224 lags (200 used)]
+  double* basis_f64 = nullptr;     // [2: cos, sin][200 lags][240 bins], centred, Hann folded in (logmel_exact_kernel)
+  double* mel_f64 = nullptr;       // [240 bins][64 bands]
   bool ready = false;
 };
 std::mutex g_mu;
@@ -905,6 +1079,26 @@ int build_tables(TcTables& t) {
     return 1;
   }
   t.basis_eo = static_cast<__half*>(de);
+  // float64 tables of the exact path: the same centred basis unsplit and unscaled, and rows 4..243 of the mel matrix
+  std::vector<double> bd(size_t(2) * eoHalf * kEvalBins), md(size_t(kEvalBins) * kMel);
+  for (int m = 0; m < eoHalf; ++m)
+    for (int i = 0; i < kEvalBins; ++i) {
+      const int km = ((kBinLo + i) * m) % kFft;
+      const double ang = 2 * kPi * km / kFft, g = hann[eoHalf + m] * (m == 0 ? 0.5 : 1.0);
+      bd[size_t(m) * kEvalBins + i] = g * std::cos(ang);
+      bd[size_t(eoHalf + m) * kEvalBins + i] = g * std::sin(ang);
+    }
+  for (int i = 0; i < kEvalBins; ++i)
+    for (int b = 0; b < kMel; ++b) md[size_t(i) * kMel + b] = mel[size_t(kBinLo + i) * kMel + b];
+  void *dbd = nullptr, *dmd = nullptr;
+  if (cudaMalloc(&dbd, bd.size() * 8) != cudaSuccess || cudaMalloc(&dmd, md.size() * 8) != cudaSuccess ||
+      cudaMemcpy(dbd, bd.data(), bd.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dmd, md.data(), md.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_kernel_error("logmel: float64 table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  t.basis_f64 = static_cast<double*>(dbd);
+  t.mel_f64 = static_cast<double*>(dmd);
   t.ready = true;
   return 0;
 }
@@ -921,7 +1115,9 @@ int get_tables(TcTables** out) {
     if (build_tables(t)) return 1;
     if (cudaFuncSetAttribute(logmel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(logmel_eo_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, eoSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(logmel_eo_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, eoSmemBytes) != cudaSuccess) {
+        cudaFuncSetAttribute(logmel_eo_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, eoSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(logmel_exact_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(logmel_exact_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExactSmem) != cudaSuccess) {
       set_kernel_error("logmel: cannot raise dynamic shared memory to %d / %d bytes", kSmemBytes, eoSmemBytes);
       return 1;
     }
@@ -991,6 +1187,12 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
   if (p.total_tiles <= 0) return 0;
+  void* mask = nullptr;   // every tile's epilogue writes its four words: no clearing needed
+  if (cudaMallocAsync(&mask, size_t(p.total_tiles) * 16, stream) != cudaSuccess) {
+    set_kernel_error("logmel: flag buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  p.exact_mask = static_cast<uint32_t*>(mask);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
                                     stream, tx, txb, tb, p);
@@ -999,7 +1201,15 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
     set_kernel_error("logmel_eo_kernel: %s", cudaGetErrorString(le));
     return 1;
   }
-  return check_launch("logmel_eo_kernel");
+  if (check_launch("logmel_eo_kernel")) return 1;
+  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.total_tiles, p.exact_mask,
+                       t->basis_f64, t->mel_f64, logmel, stream))
+    return 1;
+  if (cudaFreeAsync(mask, stream) != cudaSuccess) {
+    set_kernel_error("logmel: cudaFreeAsync failed");
+    return 1;
+  }
+  return 0;
 }
 
 template <class IN>
@@ -1056,6 +1266,12 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
   p.n_clips = static_cast<int>(n_clips);
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
+  void* mask = nullptr;
+  if (cudaMallocAsync(&mask, size_t(p.total_tiles) * 16, stream) != cudaSuccess) {
+    set_kernel_error("logmel: flag buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  p.exact_mask = static_cast<uint32_t*>(mask);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_tc_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads), kSmemBytes,
                                     stream, ta, tb, p);
@@ -1065,7 +1281,10 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
     return 1;
   }
   if (check_launch("logmel_tc_kernel")) return 1;
-  if (cudaFreeAsync(planes, stream) != cudaSuccess) {
+  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.total_tiles, p.exact_mask,
+                       t->basis_f64, t->mel_f64, logmel, stream))
+    return 1;
+  if (cudaFreeAsync(mask, stream) != cudaSuccess || cudaFreeAsync(planes, stream) != cudaSuccess) {
     set_kernel_error("logmel: cudaFreeAsync failed");
     return 1;
   }

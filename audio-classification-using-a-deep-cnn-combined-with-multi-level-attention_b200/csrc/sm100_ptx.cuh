@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace vmb {
 
@@ -328,31 +329,84 @@ __device__ __forceinline__ void st_global_256(void* ptr, uint32_t a0, uint32_t a
                : "memory");
 }
 
-// 2x2 max-pool of 32 channels held as 16 packed bf16 pairs per lane, across the four lanes {l, l^1, l^wb} of a pooling
+// fp16 counterparts (the fp16 mode of the VGGish body).  The conversion saturates to the largest finite half instead
+// of producing inf, so a saturated activation stays finite AND is detectable: saturated_f16x2() on the running maximum
+// of the (non-negative-initialised) packed outputs.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t max_f16x2(uint32_t a, uint32_t b) {
+  __half2 x = *reinterpret_cast<__half2*>(&a);
+  __half2 y = *reinterpret_cast<__half2*>(&b);
+  __half2 r = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// true when either half of m (both >= +0 by construction) is the largest finite half, 65504 = 0x7BFF, or beyond
+__device__ __forceinline__ bool saturated_f16x2(uint32_t m) { return (m & 0xFFFFu) >= 0x7BFFu || (m >> 16) >= 0x7BFFu; }
+
+// Element format of the 16-bit activations / weights of the VGGish body: both run at the same tcgen05 kind::f16 rate.
+constexpr int kFmtBf16 = 0, kFmtF16 = 1;
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) { return F16 ? max_f16x2(a, b) : max_bf16x2(a, b); }
+
+// 2x2 max-pool of 32 channels held as 16 packed 16-bit pairs per lane, across the four lanes {l, l^1, l^wb} of a pooling
 // window, followed by ReLU and ONE full-sector store: a transposing exchange with the horizontal neighbour (each lane
 // sends the half it will not keep: 8 shuffles), then a plain exchange with the vertical neighbour (8 shuffles) — half the
 // shuffles of reducing all 16 registers twice.  Afterwards lanes with sub = 0 / 1 hold channels 0-15 / 16-31 of the
-// pooled pixel and store them; sub = (w & 1) | ((h & 1) << 1).  max commutes with the monotone bf16 rounding and with
-// ReLU, so the result equals pooling the fp32 values.
-__device__ __forceinline__ void pool2x2_relu_store_bf16(const uint32_t (&pk)[16], int sub, int wb, bool relu, bool valid,
-                                                        void* out_pixel_chunk) {
+// pooled pixel and store them; sub = (w & 1) | ((h & 1) << 1).  max commutes with the monotone rounding and with
+// ReLU, so the result equals pooling the fp32 values.  Returns the running maximum of the stored values (fp16 mode: the
+// saturation check).
+template <bool F16>
+__device__ __forceinline__ uint32_t pool2x2_relu_store(const uint32_t (&pk)[16], int sub, int wb, bool relu, bool valid,
+                                                       void* out_pixel_chunk) {
   const bool up = sub & 1;
   uint32_t keep[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t send = up ? pk[j] : pk[8 + j];
     const uint32_t own = up ? pk[8 + j] : pk[j];
-    keep[j] = max_bf16x2(own, __shfl_xor_sync(0xffffffffu, send, 1));
+    keep[j] = max16x2<F16>(own, __shfl_xor_sync(0xffffffffu, send, 1));
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) keep[j] = max_bf16x2(keep[j], __shfl_xor_sync(0xffffffffu, keep[j], wb));
+  for (int j = 0; j < 8; ++j) keep[j] = max16x2<F16>(keep[j], __shfl_xor_sync(0xffffffffu, keep[j], wb));
   if (relu) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) keep[j] = max_bf16x2(keep[j], 0u);
+    for (int j = 0; j < 8; ++j) keep[j] = max16x2<F16>(keep[j], 0u);
   }
   if (valid && !(sub & 2))
     st_global_256(static_cast<uint8_t*>(out_pixel_chunk) + (up ? 32 : 0), keep[0], keep[1], keep[2], keep[3], keep[4],
                   keep[5], keep[6], keep[7]);
+  uint32_t m = 0;
+  if (F16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = max_f16x2(m, keep[j]);
+  }
+  return m;
+}
+
+// Epilogue tail shared by the 16-bit-output implicit-GEMM kernels: 32 fp32 results of one accumulator row -> packed
+// bf16 / fp16 -> (2x2 max-pool + ReLU) -> full-sector stores.  Returns the running maximum for the fp16 saturation check.
+template <bool F16, bool POOL>
+__device__ __forceinline__ uint32_t store_row32_16bit(const float (&f)[32], int sub, int wb, bool relu, bool valid,
+                                                      void* outp) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = pack16x2<F16>(f[2 * j], f[2 * j + 1]);
+  if (POOL) return pool2x2_relu_store<F16>(pk, sub, wb, relu, valid, outp);
+  if (valid) {
+    st_global_256(outp, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+    st_global_256(static_cast<uint8_t*>(outp) + 32, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+  }
+  uint32_t m = 0;
+  if (F16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m = max_f16x2(m, pk[j]);
+  }
+  return m;
 }
 
 }  // namespace vmb

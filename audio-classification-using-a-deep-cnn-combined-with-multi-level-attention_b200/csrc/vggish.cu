@@ -34,7 +34,10 @@ struct HostStage {
 };
 
 struct vmb_vggish {
-  int precision = 0;         // 0: bf16 activations and weights; 1: hi | lo split activations and weights (accuracy mode)
+  int precision = 0;         // 0: bf16 activations and weights; 1: hi | lo split bf16 activations and weights (accuracy
+                             // mode); 2: fp16 activations and weights (same tensor rate as bf16, 11 mantissa bits)
+  int* sat = nullptr;        // precision 2: [8] saturation flags (conv1, conv2..conv4_2, fc1, fc2) in mapped pinned host
+                             // memory — the kernels store 1 when an output reached the fp16 maximum
   float* conv1_w = nullptr;  // fp32 [64][9]
   float* conv_b[6] = {};     // fp32 biases (index 0 = conv1)
   void* conv_w[6] = {};      // bf16 [C_out][9*C_in] (precision 1: [C_out][2*9*C_in] hi | lo), index 1..5
@@ -75,7 +78,7 @@ int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w[6], const
 int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], const float* const conv_b[6],
                          const float* const fc_w[3], const float* const fc_b[3], int precision, void* stream) {
   if (!handle || !conv_w || !conv_b || !fc_w || !fc_b) return fail("vmb_vggish_create: null argument");
-  if (precision != 0 && precision != 1) return fail("vmb_vggish_create: precision must be 0 (bf16) or 1 (split)");
+  if (precision < 0 || precision > 2) return fail("vmb_vggish_create: precision must be 0 (bf16), 1 (split) or 2 (fp16)");
   for (int i = 0; i < 6; ++i)
     if (!conv_w[i] || !conv_b[i]) return fail("vmb_vggish_create: null conv tensor");
   for (int i = 0; i < 3; ++i)
@@ -83,8 +86,13 @@ int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vmb_vggish* h = new vmb_vggish();
   h->precision = precision;
-  const size_t wmul = precision ? 2 : 1;
+  const size_t wmul = precision == 1 ? 2 : 1;
+  const int fmt = precision == 2 ? 1 : 0;
   bool ok = true;
+  if (precision == 2) {
+    ok = cudaHostAlloc(reinterpret_cast<void**>(&h->sat), 8 * sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    if (ok) memset(h->sat, 0, 8 * sizeof(int));
+  }
   auto dmalloc = [&](void** p, size_t bytes) { ok = ok && cudaMalloc(p, bytes) == cudaSuccess; };
   auto dcopy = [&](void* d, const void* s, size_t bytes) {
     ok = ok && cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
@@ -101,16 +109,17 @@ int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], co
     dmalloc(reinterpret_cast<void**>(&h->conv_b[i + 1]), size_t(g.C_out) * 4);
     if (!ok) break;
     dcopy(h->conv_b[i + 1], conv_b[i + 1], size_t(g.C_out) * 4);
-    ok = ok && (precision ? vmb::relayout_conv_weight_split(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)
-                          : vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)) == 0;
+    ok = ok && (precision == 1 ? vmb::relayout_conv_weight_split(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)
+                               : vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st, fmt)) == 0;
   }
   for (int i = 0; i < 3 && ok; ++i) {
     dmalloc(&h->fc_w[i], size_t(kFcOut[i]) * kFcIn[i] * 2 * wmul);
     dmalloc(reinterpret_cast<void**>(&h->fc_b[i]), size_t(kFcOut[i]) * 4);
     if (!ok) break;
     dcopy(h->fc_b[i], fc_b[i], size_t(kFcOut[i]) * 4);
-    ok = ok && (precision ? vmb::split_f32_to_planes(fc_w[i], h->fc_w[i], kFcOut[i], kFcIn[i], st)
-                          : vmb::cast_f32_to_bf16(fc_w[i], h->fc_w[i], static_cast<long long>(kFcOut[i]) * kFcIn[i], st)) == 0;
+    ok = ok && (precision == 1 ? vmb::split_f32_to_planes(fc_w[i], h->fc_w[i], kFcOut[i], kFcIn[i], st)
+                               : vmb::cast_f32_to_bf16(fc_w[i], h->fc_w[i], static_cast<long long>(kFcOut[i]) * kFcIn[i], st,
+                                                       fmt)) == 0;
   }
   ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
   if (!ok) {
@@ -133,6 +142,7 @@ void vmb_vggish_destroy(vmb_vggish_t* h) {
     cudaFree(h->fc_w[i]);
     cudaFree(h->fc_b[i]);
   }
+  if (h->sat) cudaFreeHost(h->sat);
   HostStage& hs = h->stage;
   for (int i = 0; i < 2; ++i) {
     cudaFree(hs.d_wave[i]);
@@ -153,11 +163,21 @@ size_t vmb_vggish_workspace_bytes(long long n) {
 
 size_t vmb_vggish_handle_workspace_bytes(const vmb_vggish_t* h, long long n) {
   if (n <= 0 || !h) return 0;
-  const size_t mul = h->precision ? 2 : 1;   // split mode: every activation is a hi | lo pair
+  const size_t mul = h->precision == 1 ? 2 : 1;   // split mode: every activation is a hi | lo pair
   return align_up(size_t(n) * kBufA * mul, 1024) + align_up(size_t(n) * kBufB * mul, 1024);
 }
 
 int vmb_vggish_precision(const vmb_vggish_t* h) { return h ? h->precision : -1; }
+
+int vmb_vggish_saturation(vmb_vggish_t* h, int clear) {
+  if (!h || !h->sat) return 0;
+  int mask = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (*reinterpret_cast<volatile int*>(h->sat + i)) mask |= 1 << i;
+    if (clear) h->sat[i] = 0;
+  }
+  return mask;
+}
 
 int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, float* emb, void* bottleneck,
                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -169,14 +189,16 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
   if (workspace_bytes < vmb_vggish_handle_workspace_bytes(h, n)) return fail("vmb_vggish_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_vggish_forward: workspace must be 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool split = h->precision != 0;
+  const bool split = h->precision == 1;
+  const int fmt = h->precision == 2 ? 1 : 0;
+  int* sat = h->sat;   // null unless fp16
   const size_t mul = split ? 2 : 1;
   char* A = static_cast<char*>(workspace);
   char* B = A + align_up(size_t(n) * kBufA * mul, 1024);
 
   {
     vmb::StageTimer t(VMB_STAGE_CONV1, st);
-    if (vmb::conv1_tc_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st, split))
+    if (vmb::conv1_tc_relu_pool(examples, h->conv1_w, h->conv_b[0], A, n, st, split, fmt, sat))
       return fail("vmb_vggish_forward: %s", vmb::kernels_last_error());
   }
   char* src = A;
@@ -187,7 +209,7 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
     const int rc = split ? vmb::igemm_conv3x3_split(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in,
                                                     g.C_out, g.pool, st)
                          : vmb::igemm_conv3x3(src, h->conv_w[i + 1], h->conv_b[i + 1], dst, int(n), g.H, g.W, g.C_in,
-                                              g.C_out, g.pool, st);
+                                              g.C_out, g.pool, st, fmt, sat ? sat + 1 + i : nullptr);
     if (rc) return fail("vmb_vggish_forward: %s", vmb::igemm_last_error());
     char* sw = src; src = dst; dst = sw;
   }
@@ -207,7 +229,8 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
     vmb::StageTimer t(VMB_STAGE_FC1 + i, st);
     int rc;
     if (!split)
-      rc = vmb::igemm_linear(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], i == 2, 1, int(n), kFcOut[i], kFcIn[i], st);
+      rc = vmb::igemm_linear(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], i == 2, 1, int(n), kFcOut[i], kFcIn[i], st, fmt,
+                             (sat && i < 2) ? sat + 6 + i : nullptr);
     else if (i < 2)
       rc = vmb::igemm_linear_split_out(fc_in[i], h->fc_w[i], h->fc_b[i], fc_out[i], 1, int(n), kFcOut[i], kFcIn[i], st);
     else
@@ -227,7 +250,7 @@ PipeLayout pipe_layout(long long n_clips, long long samples_per_clip, int precis
   L.examples = 0;
   L.emb = align_up(size_t(L.n_ex) * 96 * 64 * 4, 1024);
   L.vgg = L.emb + align_up(size_t(L.n_ex) * 128 * 4, 1024);
-  L.total = L.vgg + vmb_vggish_workspace_bytes(L.n_ex) * (precision ? 2 : 1);
+  L.total = L.vgg + vmb_vggish_workspace_bytes(L.n_ex) * (precision == 1 ? 2 : 1);
   return L;
 }
 }  // namespace
@@ -387,6 +410,12 @@ int vmb_pipeline_wait_host(vmb_vggish_t* vggish, int ticket) {
   vggish->stage.busy[ticket] = false;
   if (cudaEventSynchronize(vggish->stage.done[ticket]) != cudaSuccess)
     return fail("vmb_pipeline_wait_host: %s", cudaGetErrorString(cudaGetLastError()));
+  if (const int mask = vmb_vggish_saturation(vggish, 1)) {
+    char m[16];
+    snprintf(m, sizeof m, "0x%x", mask);
+    return fail("vmb_pipeline_wait_host: fp16 activations saturated (layer mask %s: bit 0 conv1 .. bit 7 fc2); "
+                "create the handle with precision 0 (bf16) or 1 (split)", m);
+  }
   return 0;
 }
 

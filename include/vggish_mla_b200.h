@@ -105,6 +105,10 @@ int vmb_front_end_tables(double* hann400, double* mel257x64);
  * NHWC bf16 [n][48][32][64].  w_dev fp32 [64][9] (OIHW with I = 1), b_dev fp32 [64].                 */
 int vmb_conv1_relu_pool(const float* examples_dev, const float* w_dev, const float* b_dev, void* out_bf16_dev,
                         long long n, void* stream);
+/* The same with the element type of the output chosen: dtype 0 = bf16, 1 = fp16 (the two 16-bit formats tcgen05
+ * kind::f16 multiplies at the same rate; fp16 carries 11 mantissa bits instead of 8).                       */
+int vmb_conv1_relu_pool_ex(const float* examples_dev, const float* w_dev, const float* b_dev, void* out_16bit_dev,
+                           long long n, int dtype, void* stream);
 /* The same layer on the CUDA cores in plain fp32 (the first implementation).  Diagnostic cross-check only. */
 int vmb_conv1_relu_pool_cudacore(const float* examples_dev, const float* w_dev, const float* b_dev,
                                  void* out_bf16_dev, long long n, void* stream);
@@ -115,10 +119,18 @@ int vmb_conv1_relu_pool_cudacore(const float* examples_dev, const float* w_dev, 
 int vmb_conv3x3_relu(const void* act_bf16_dev, const void* w_bf16_dev, const float* bias_dev, void* out_bf16_dev,
                      long long n, int H, int W, int C_in, int C_out, int pool, void* stream);
 
+/* dtype 0 = bf16, 1 = fp16: element type of act, w and out (fp16 outputs saturate at 65504 instead of overflowing). */
+int vmb_conv3x3_relu_ex(const void* act_dev, const void* w_dev, const float* bias_dev, void* out_dev, long long n, int H,
+                        int W, int C_in, int C_out, int pool, int dtype, void* stream);
+
 /* Linear (+ReLU when relu != 0): out[M][N] = act(A[M][K] W[N][K]^T + b).  A, W bf16; out bf16, or fp32 when
  * out_f32 != 0.  K % 64 == 0, N % 128 == 0 (vggish.py:13-19).                                          */
 int vmb_linear(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, void* out_dev, int out_f32,
                int relu, long long M, int N, int K, void* stream);
+
+/* dtype 0 = bf16, 1 = fp16: element type of a, w and of a 16-bit out. */
+int vmb_linear_ex(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int out_f32, int relu,
+                  long long M, int N, int K, int dtype, void* stream);
 
 /* Postprocessor.postprocess (vggish.py:62-102): out = round((clamp(E (x - mu), -2, 2) + 2) * 63.75), values
  * 0..255 stored as fp32 like the reference (F6) and optionally also as uint8.  emb_dev fp32 [n][128],
@@ -136,17 +148,26 @@ int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w_dev[6], c
  * precision 1 = accuracy mode: every activation and weight is carried as a hi + lo bf16 pair (16 mantissa bits) and
  * every conv / FC runs the three products hi*hi, lo*hi, hi*lo on the same tcgen05 kernels — 3x the tensor work, for
  * the long-form embedding extraction where the 8-bit quantised output must match the fp32 reference. */
+/* precision 2 = fp16 activations and weights, fp32 accumulation: the same kernels and the same tensor rate as
+ * precision 0 with 11 mantissa bits instead of 8 (operand rounding 8x smaller: the ranking metric of the scores agrees
+ * with the fp32 reference to 3 decimals).  fp16 ends at 65504: every 16-bit epilogue converts with
+ * saturation and raises a per-layer flag when an output reached that maximum; vmb_vggish_saturation() reads the flags
+ * and vmb_pipeline_wait_host() fails when one is set (activations of VGGish are O(10), vggish.py:21-31).          */
 int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w_dev[6], const float* const conv_b_dev[6],
                          const float* const fc_w_dev[3], const float* const fc_b_dev[3], int precision, void* stream);
 int vmb_vggish_precision(const vmb_vggish_t* handle);
+/* fp16 mode: bit mask of the layers whose 16-bit output saturated since the flags were last cleared (bit 0 conv1,
+ * bits 1-5 conv2 .. conv4_2, bit 6 fc1, bit 7 fc2); 0 for the other precisions.  The flags live in mapped host memory
+ * and are complete for all work the caller has synchronised with.  clear != 0 resets them.                       */
+int vmb_vggish_saturation(vmb_vggish_t* handle, int clear);
 void vmb_vggish_destroy(vmb_vggish_t* handle);
 /* Scratch bytes vmb_vggish_forward needs for n examples (caller allocates, 1024-byte aligned). */
 size_t vmb_vggish_workspace_bytes(long long n_examples);
 /* Same for a given handle (the accuracy mode needs twice as much). */
 size_t vmb_vggish_handle_workspace_bytes(const vmb_vggish_t* handle, long long n_examples);
 /* examples_dev fp32 [n][96][64] -> emb_dev fp32 [n][128] (post-ReLU embeddings, vggish.py:31).
- * If bottleneck_bf16_dev != NULL the (h,w,c)-flattened conv features [n][12288] bf16 (vggish.py:26-29) are
- * copied there as well (the reference's just_bottlenecks variant, model.py:162-167).                      */
+ * If bottleneck_bf16_dev != NULL the (h,w,c)-flattened conv features [n][12288] (vggish.py:26-29; bf16, or fp16
+ * for a precision-2 handle) are copied there as well (the reference's just_bottlenecks variant, model.py:162-167).                      */
 int vmb_vggish_forward(vmb_vggish_t* handle, const float* examples_dev, long long n, float* emb_dev,
                        void* bottleneck_bf16_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} is declared in include/vggish_mla_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names          # the ctypes table mirrors the header one to one
-    assert _lib.lib().vmb_abi_version() == 1
+    assert _lib.lib().vmb_abi_version() == 2
 
 
 def test_frame_arithmetic_matches_reference(golden_front):
