@@ -30,6 +30,7 @@ SIGNATURES = {
     "vmb_logmel": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_logmel_pcm16": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
     "vmb_logmel_cudacore": (_int, [_c_p, _ll, _ll, _ll, _ll, _c_p, _c_p]),
+    "vmb_stft_magnitude": (_int, [_c_p, _ll, _c_p, _c_p]),
     "vmb_spec_tiles": (_int, [_c_p, _ll, _int, _int, _int, _c_p, _c_p]),
     "vmb_front_end_tables": (_int, [_c_p, _c_p]),
     "vmb_conv1_relu_pool": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, _c_p]),
@@ -55,6 +56,8 @@ SIGNATURES = {
     "vmb_mla_num_classes": (_int, [_c_p]),
     "vmb_mla_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int]),
     "vmb_mla_forward": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
+    "vmb_mla_embedded_mapping": (_int, [_c_p, _int, _c_p, _ll, _c_p, _c_p]),
+    "vmb_mla_attention": (_int, [_c_p, _int, _c_p, _ll, _c_p, _c_p]),
     "vmb_mla_forward_fp32": (_int, [_c_p, _c_p, _ll, _c_p, _c_p]),
     "vmb_mla_train_param_count": (_ll, [_int, C.POINTER(_int), _int, _int, _int, _int, C.POINTER(_ll)]),
     "vmb_mla_trainer_create": (_int, [C.POINTER(_c_p), _int, C.POINTER(_int), _int, _int, _int, _int, _ll, _c_p]),

@@ -107,6 +107,22 @@ def logmel_cudacore(wave: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def stft_magnitude(signal: torch.Tensor) -> torch.Tensor:
+    """signal (n_samples,) float64 CUDA -> (n_frames, 257) float64 |rfft(frame * hann, 512)| (mel_features.py:71-92 with
+    the VGGish framing: window 400, hop 160), computed in float64 on the device."""
+    signal = _need_cuda(signal, "signal", torch.float64)
+    if signal.dim() != 1:
+        raise ValueError("signal must be 1-D")
+    nf = num_frames(signal.shape[0])
+    if nf < 0:
+        raise ValueError("negative dimensions are not allowed")
+    out = torch.empty((nf, 257), device=signal.device, dtype=torch.float64)
+    if nf > 0:
+        with torch.cuda.device(signal.device):
+            check(_lib.lib().vmb_stft_magnitude(ptr(signal), signal.shape[0], ptr(out), stream_ptr()), "vmb_stft_magnitude")
+    return out
+
+
 def examples_from_wave(wave: torch.Tensor) -> torch.Tensor:
     """(n_clips, n_samples) fp32 CUDA -> (n_clips * examples_per_clip, 96, 64) fp32 (vggish_input.py:66-76)."""
     if wave.dim() == 1:
@@ -170,8 +186,11 @@ class VggishHandle:
 
             cw = (C.c_void_p * 6)(*[dev(f"features.{k}.weight") for k in CONV_KEYS])
             cb = (C.c_void_p * 6)(*[dev(f"features.{k}.bias") for k in CONV_KEYS])
-            fw = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.weight") for k in FC_KEYS])
-            fb = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.bias") for k in FC_KEYS])
+            # a state_dict without the FC stack (the reference's just_bottlenecks re-wrap, model.py:161-166) gives a
+            # handle that serves the conv features only
+            self.has_fc = all(f"embeddings.{k}.weight" in state_dict for k in FC_KEYS)
+            fw = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.weight") for k in FC_KEYS]) if self.has_fc else None
+            fb = (C.c_void_p * 3)(*[dev(f"embeddings.{k}.bias") for k in FC_KEYS]) if self.has_fc else None
             check(_lib.lib().vmb_vggish_create_ex(C.byref(self._h), cw, cb, fw, fb, PRECISIONS[precision],
                                                   stream_ptr()), "vmb_vggish_create_ex")
             del keep
@@ -212,9 +231,14 @@ class VggishHandle:
             raise B200Error(f"fp16 activations saturated (65504) in {layers}: the results are invalid; build the handle "
                             "with precision='bf16' or 'split'")
 
-    def forward(self, examples: torch.Tensor, want_bottleneck: bool = False):
-        """examples (n, 96, 64) or (n, 1, 96, 64) fp32 CUDA -> (n, 128) fp32 post-ReLU embeddings."""
+    def forward(self, examples: torch.Tensor, want_bottleneck: bool = False, want_embeddings: bool = True):
+        """examples (n, 96, 64) or (n, 1, 96, 64) fp32 CUDA -> (n, 128) fp32 post-ReLU embeddings
+        [, (n, 12288) 16-bit conv features in (h, w, c) order].  want_embeddings=False skips the FC stack."""
         self.check_saturation(synchronize=False)
+        if want_embeddings and not self.has_fc:
+            raise B200Error("this handle was built without the FC stack: only the bottleneck features are available")
+        if not want_embeddings and not want_bottleneck:
+            raise ValueError("nothing to compute")
         examples = _need_cuda(examples, "examples")
         if examples.dim() == 4 and examples.shape[1] == 1:
             examples = examples[:, 0]
@@ -222,7 +246,7 @@ class VggishHandle:
             raise ValueError(f"examples must be (n, 1, 96, 64) or (n, 96, 64), got {tuple(examples.shape)}")
         examples = examples.contiguous()
         n = examples.shape[0]
-        emb = torch.empty((n, 128), device=self.device, dtype=torch.float32)
+        emb = torch.empty((n, 128), device=self.device, dtype=torch.float32) if want_embeddings else None
         bott = torch.empty((n, 12288), device=self.device, dtype=self.act_dtype) if want_bottleneck else None
         if n == 0:
             return (emb, bott) if want_bottleneck else emb
@@ -275,6 +299,7 @@ class MlaHandle:
         self.n_classes = n_classes
         self.t_steps = t_steps
         self.emb_in = emb_in
+        self.hidden = hidden
         self._h = C.c_void_p()
         conf = (C.c_int * len(model_conf))(*[int(v) for v in model_conf])
         with torch.cuda.device(device):
@@ -295,6 +320,28 @@ class MlaHandle:
             self._h = C.c_void_p()
 
     __del__ = close
+
+    def embedded_mapping(self, level: int, x: torch.Tensor) -> torch.Tensor:
+        """EmbeddedMapping.forward of one level (eval mode, model.py:217-222): (B, T, in) -> (B, T, hidden)."""
+        x = _need_cuda(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.t_steps:
+            raise ValueError(f"expected (B, {self.t_steps}, features), got {tuple(x.shape)}")
+        out = torch.empty((x.shape[0], self.t_steps, self.hidden), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().vmb_mla_embedded_mapping(self._h, int(level), ptr(x), x.shape[0], ptr(out), stream_ptr()),
+                  "vmb_mla_embedded_mapping")
+        return out
+
+    def attention(self, level: int, h: torch.Tensor) -> torch.Tensor:
+        """AttentionModule.forward of one level (eval mode, model.py:235-242): (B, T, hidden) -> (B, K)."""
+        h = _need_cuda(h, "h")
+        if h.dim() != 3 or h.shape[1] != self.t_steps or h.shape[2] != self.hidden:
+            raise ValueError(f"expected (B, {self.t_steps}, {self.hidden}), got {tuple(h.shape)}")
+        out = torch.empty((h.shape[0], self.n_classes), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().vmb_mla_attention(self._h, int(level), ptr(h), h.shape[0], ptr(out), stream_ptr()),
+                  "vmb_mla_attention")
+        return out
 
     def forward(self, emb: torch.Tensor, fp32_crosscheck: bool = False) -> torch.Tensor:
         """(B, T, emb_in) fp32 CUDA -> (B, K) scores.  fp32_crosscheck=True runs the diagnostic fused CUDA-core kernel

@@ -99,6 +99,7 @@ class HeadTrainer:
         self.max_batch = int(max_batch)
         self.step_count = 0
         self.num_batches_tracked = 0
+        self.generation = 0      # bumped by every train-mode forward through the autograd bridge (one step in flight)
         self.fcf: Dict[str, torch.Tensor] = {}      # carried through state_dict round trips untouched
 
     def close(self) -> None:
@@ -192,13 +193,23 @@ class _HeadTrainFn(torch.autograd.Function):
             check(_lib.lib().vmb_mla_train_forward(tr._h, ptr(tr.params), ptr(tr.running), ptr(x), x.shape[0],
                                                    float(tr.dropout_p), seed, ptr(scores), stream_ptr()),
                   "vmb_mla_train_forward")
-        ctx.module, ctx.seed, ctx.x = module, seed, x
+        # the activations, BatchNorm statistics and dropout masks the backward pass needs live in the trainer handle,
+        # which holds ONE step: remember which forward this graph belongs to
+        tr.generation += 1
+        ctx.module, ctx.seed, ctx.x, ctx.generation = module, seed, x, tr.generation
+        ctx.param_key = tuple((p.data_ptr(), p._version) for p in params)
         return scores
 
     @staticmethod
     def backward(ctx, dscores):
         st = ctx.module._b200_train_state()
         tr: HeadTrainer = st["trainer"]
+        if ctx.generation != tr.generation:
+            raise B200Error("backward of a stale head forward: the library trainer keeps the activations of ONE train-mode "
+                            "forward per module, and another train-mode forward ran before this backward (e.g. two "
+                            "micro-batches summed into one loss); call backward() before the next forward")
+        if ctx.param_key != tuple((p.data_ptr(), p._version) for _, p in ctx.module.named_parameters()):
+            raise B200Error("the head's parameters changed between forward and backward")
         d = dscores.to(tr.device, torch.float32).contiguous()
         with torch.cuda.device(tr.device):
             check(_lib.lib().vmb_mla_train_backward(tr._h, ptr(tr.params), ptr(ctx.x), ptr(d), ctx.x.shape[0],
@@ -212,6 +223,10 @@ class _HeadTrainFn(torch.autograd.Function):
 
 def head_train_forward(module, x: torch.Tensor) -> torch.Tensor:
     """Train-mode forward of the reference-named head through the library (autograd-aware)."""
+    if isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("the head's backward pass produces parameter gradients only: the gradient with respect "
+                                  "to the embeddings is outside this path (the reference freezes the CNN, "
+                                  "model.py:159-160); pass x.detach()")
     st = module._b200_train_state()
     st["sync_in"]()
     params = [p for _, p in module.named_parameters()]

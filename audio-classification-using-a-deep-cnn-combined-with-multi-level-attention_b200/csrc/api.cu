@@ -104,6 +104,14 @@ int vmb_logmel_cudacore(const float* wave, long long n_clips, long long samples_
                        stream);
 }
 
+int vmb_stft_magnitude(const double* signal, long long n_samples, double* mag, void* stream) {
+  if (n_samples < 0) return fail("vmb_stft_magnitude: negative size");
+  if (vmb_num_frames(n_samples) < 1) return fail("vmb_stft_magnitude: %lld samples is shorter than one 400-sample window", n_samples);
+  if (!signal || !mag) return fail("vmb_stft_magnitude: null pointer");
+  if (vmb::stft_magnitude_f64(signal, n_samples, mag, S(stream))) return fail_from("vmb_stft_magnitude", vmb::kernels_last_error());
+  return 0;
+}
+
 int vmb_spec_tiles(const float* examples, long long n_clips, int n_examples_per_clip, int n_frames, int overlap,
                    float* out, void* stream) {
   if (n_clips < 0) return fail("vmb_spec_tiles: negative n_clips");

@@ -59,6 +59,8 @@ int logmel_tc_forward(const float* wave, long long n_clips, long long samples_pe
 // Same for 16-bit PCM input scaled by 1/32768 (vggish_input.py:96-98): the same kernel with 16-bit TMA boxes.
 int logmel_tc_forward_pcm16(const int16_t* pcm, long long n_clips, long long samples_per_clip, long long clip_stride,
                             long long frames_out, float* logmel, cudaStream_t stream);
+// stft_magnitude (mel_features.py:71-92) on its own, float64 in and out: mag [n_frames][257]
+int stft_magnitude_f64(const double* signal, long long n_samples, double* mag, cudaStream_t stream);
 // CUDA-core fp32 version of the same computation (frontend.cu); kept as an on-device cross-check, not on the path.
 int logmel_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                    long long frames_out, float* logmel, cudaStream_t stream);

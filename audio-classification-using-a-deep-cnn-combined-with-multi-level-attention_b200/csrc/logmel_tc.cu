@@ -88,6 +88,7 @@ constexpr float kExactRatioPlanes = 1200.f;
 __constant__ int c_band[kEvalBins];
 __constant__ float c_wfall[kEvalBins];
 __constant__ float c_wrise[kEvalBins];
+__constant__ int c_mel_lo[kMel], c_mel_hi[kMel];   // evaluated bins [lo, hi) carrying weight for each band (exact path)
 
 // ------------------------------------------------------------------ waveform -> three bf16 planes
 // planes[p][clip][pitch]; samples >= n_samples are written as zero so that K padding never meets garbage.
@@ -527,7 +528,7 @@ constexpr unsigned char kBandOfBin[kEvalBins] = {
 struct WalkState {
   float lo, hi;       // running sums of band e - 1 (complete after its falling side) and band e
   float pend[4];      // finished bands of the current group of four, waiting for one 16-byte store
-  float e2;           // sum of re^2 + im^2 (in the operands' 2^22 scale) over the bins walked so far
+  float e2;           // sum of |X_k|^2 over the bins walked so far
   float mn;           // smallest finished band sum
 };
 
@@ -554,6 +555,7 @@ __device__ __forceinline__ void walk_static(WalkState& w, const float (&mag)[NB]
     if constexpr (e > E) emit_static<E>(w, row_out, valid);
     w.lo = fmaf(c_wfall[g], mag[J], w.lo);
     w.hi = fmaf(c_wrise[g], mag[J], w.hi);
+    w.e2 = fmaf(mag[J], mag[J], w.e2);
     walk_static<G0, J + 1, NB, e>(w, mag, row_out, valid);
   }
 }
@@ -580,9 +582,7 @@ __device__ __forceinline__ void epilogue_chunks(uint32_t t_addr, uint32_t (&re)[
   for (int j = 0; j < eoChunkBins; ++j) {
     const float r = __uint_as_float(re[j]), i = __uint_as_float(im[j]);
     float m;     // sqrt.approx: 2 ulp, far below what the band sums resolve; exact zero stays zero
-    const float ss = fmaf(r, r, i * i);
-    w.e2 += ss;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(ss));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(r, r, i * i)));
     mag[j] = m * eoUnscale;                              // exact: the operands carried 2^12 and 2^10
   }
   if constexpr (CH + 1 < eoChunks) {
@@ -806,8 +806,7 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         flush_static<kBandOfBin[kEvalBins - 1]>(w, row_out, valid);   // the remaining bands (up to band 63)
-        // e2 carries the operands' scale (2^-22 per factor): compare sqrt(e2) * 2^-22 with kExactRatio * (min band + 0.01)
-        const float lim = (kExactRatio / eoUnscale) * (w.mn + kLogOffset);
+        const float lim = kExactRatio * (w.mn + kLogOffset);
         const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
         if (lane == 0) p.exact_mask[tile * 4 + q] = bad;
       }
@@ -823,12 +822,14 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // ================================================================== float64 path for the flagged frames
-// The same centred even / odd DFT in float64 on the CUDA cores, one CTA per 128-frame tile that has flagged frames,
-// 16 flagged frames at a time: E, O in shared memory ([lag][frame], so that the 16 frames of a lag are two 64-byte
-// broadcast reads), thread = DFT bin (240 of 256 threads), basis and mel matrix as float64 tables in global memory
-// (768 KB + 120 KB, L2-resident).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
-// float64 reference rounded once.  ~2.6 us of one SM per frame; tiles without flagged frames cost one 16-byte read.
-constexpr int kExactFrames = 16;
+// The same centred even / odd DFT in float64 on the CUDA cores.  Work unit = (128-frame tile, half): CTA `half` of a
+// tile takes the tile's flagged frames number 8 half .. 8 half + 7 (then + 16, ...), so the usual case — a handful of
+// flagged frames in a tile — is one pass of one or two small CTAs: E, O in shared memory ([lag][frame]: the 8 frames
+// of a lag are one 64-byte broadcast read), thread = DFT bin (240 of 256 threads), basis and mel matrix as float64
+// tables in global memory (768 KB + 120 KB, L2-resident; the basis values of 8 lags are fetched together because the
+// loop is bound by their latency).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
+// float64 reference rounded once.  Tiles without flagged frames cost one 16-byte read.
+constexpr int kExactFrames = 8;      // frames per pass
 constexpr int kExactThreads = 256;
 constexpr int kExactSmem = 2 * eoHalf * kExactFrames * 8 + kExactFrames * kEvalBins * 8 + 160 * 4;
 
@@ -854,31 +855,36 @@ template <class IN>
 __global__ void __launch_bounds__(kExactThreads)
 logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
   extern __shared__ __align__(16) uint8_t exact_smem[];
-  double* E = reinterpret_cast<double*>(exact_smem);                 // [200][16]
-  double* O = E + eoHalf * kExactFrames;                             // [200][16]
-  double* mag = O + eoHalf * kExactFrames;                           // [16][240]
-  int* rows = reinterpret_cast<int*>(mag + kExactFrames * kEvalBins); // [128] flagged frames of the tile + [1] count
+  double* E = reinterpret_cast<double*>(exact_smem);                 // [200][8]
+  double* O = E + eoHalf * kExactFrames;                             // [200][8]
+  double* mag = O + eoHalf * kExactFrames;                           // [8][240]
+  int* rows = reinterpret_cast<int*>(mag + kExactFrames * kEvalBins); // [128] flagged frames of the tile
   const int tid = threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();   // the masks (and the rows this kernel overwrites) come from the tensor-core kernel before it
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  for (long long unit = blockIdx.x; unit < 2 * p.total_tiles; unit += gridDim.x) {
+    const long long tile = unit >> 1;
+    const int half = static_cast<int>(unit & 1);
     const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(p.mask) + tile);
-    if ((m4.x | m4.y | m4.z | m4.w) == 0u) continue;                 // block-uniform
-    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+    const int n_rows = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
+    if (n_rows <= half * kExactFrames) continue;                     // block-uniform
     if (tid < kTM) {
       const int q = tid >> 5, r = tid & 31;
-      if ((mw[q] >> r) & 1u) {
-        int pos = __popc(mw[q] & ((1u << r) - 1u));
-        for (int i = 0; i < q; ++i) pos += __popc(mw[i]);
+      const uint32_t w0 = m4.x, w1 = m4.y, w2 = m4.z, w3 = m4.w;
+      const uint32_t mine = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
+      if ((mine >> r) & 1u) {
+        int pos = __popc(mine & ((1u << r) - 1u));
+        if (q > 0) pos += __popc(w0);
+        if (q > 1) pos += __popc(w1);
+        if (q > 2) pos += __popc(w2);
         rows[pos] = tid;
       }
     }
-    const int n_rows = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
     const long long clip = tile / p.tiles_per_clip;
     const long long frame0 = (tile - clip * p.tiles_per_clip) * kTM;
     const IN* clip_wave = wave + clip * p.clip_stride;
     __syncthreads();
-    for (int g0 = 0; g0 < n_rows; g0 += kExactFrames) {
+    for (int g0 = half * kExactFrames; g0 < n_rows; g0 += 2 * kExactFrames) {
       const int ng = n_rows - g0 < kExactFrames ? n_rows - g0 : kExactFrames;
       // E[m][f] = x[200 + m] + x[200 - m], O[m][f] = x[200 + m] - x[200 - m] (lag 0: E = 2 x[200], its weight is halved)
       for (int i = tid; i < eoHalf * kExactFrames; i += kExactThreads) {
@@ -900,18 +906,26 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
         for (int f = 0; f < kExactFrames; ++f) re[f] = im[f] = 0.0;
         const double* bc = p.basis + tid;
         const double* bs = p.basis + eoHalf * kEvalBins + tid;
-#pragma unroll 2
-        for (int m = 0; m < eoHalf; ++m) {
-          const double c = __ldg(bc + m * kEvalBins), sn = __ldg(bs + m * kEvalBins);
-          const double2* e2 = reinterpret_cast<const double2*>(E + m * kExactFrames);
-          const double2* o2 = reinterpret_cast<const double2*>(O + m * kExactFrames);
+#pragma unroll 1
+        for (int m0 = 0; m0 < eoHalf; m0 += 8) {
+          double c[8], sn[8];
 #pragma unroll
-          for (int f = 0; f < kExactFrames / 2; ++f) {
-            const double2 ev = e2[f], ov = o2[f];
-            re[2 * f] = fma(ev.x, c, re[2 * f]);
-            re[2 * f + 1] = fma(ev.y, c, re[2 * f + 1]);
-            im[2 * f] = fma(ov.x, sn, im[2 * f]);
-            im[2 * f + 1] = fma(ov.y, sn, im[2 * f + 1]);
+          for (int u = 0; u < 8; ++u) {
+            c[u] = __ldg(bc + (m0 + u) * kEvalBins);
+            sn[u] = __ldg(bs + (m0 + u) * kEvalBins);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double2* e2 = reinterpret_cast<const double2*>(E + (m0 + u) * kExactFrames);
+            const double2* o2 = reinterpret_cast<const double2*>(O + (m0 + u) * kExactFrames);
+#pragma unroll
+            for (int f = 0; f < kExactFrames / 2; ++f) {
+              const double2 ev = e2[f], ov = o2[f];
+              re[2 * f] = fma(ev.x, c[u], re[2 * f]);
+              re[2 * f + 1] = fma(ev.y, c[u], re[2 * f + 1]);
+              im[2 * f] = fma(ov.x, sn[u], im[2 * f]);
+              im[2 * f + 1] = fma(ov.y, sn[u], im[2 * f + 1]);
+            }
           }
         }
 #pragma unroll
@@ -921,9 +935,12 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
       for (int i = tid; i < kExactFrames * kMel; i += kExactThreads) {
         const int f = i / kMel, band = i - f * kMel;
         if (f < ng) {
+          // band `band` has weight on a short run of bins only (HTK triangles): [c_mel_lo, c_mel_hi)
           double acc = 0.0;
           const double* mg = mag + f * kEvalBins;
-          for (int b = 0; b < kEvalBins; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
+          const int b_lo = c_mel_lo[band], b_hi = c_mel_hi[band];
+#pragma unroll 4
+          for (int b = b_lo; b < b_hi; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
           p.out[(clip * p.frames_out + frame0 + rows[g0 + f]) * kMel + band] = static_cast<float>(log(acc + 0.01));
         }
       }
@@ -944,7 +961,8 @@ int launch_exact(const IN* wave, long long clip_stride, long long frames_out, in
   e.basis = basis;
   e.mel = mel;
   e.out = out;
-  const long long grid = std::min<long long>(total_tiles, 2LL * num_sms());
+  // one CTA per (tile, half) up to 32 CTAs per SM's worth; idle units exit after one 16-byte read
+  const long long grid = std::min<long long>(2 * total_tiles, 32LL * num_sms());
   const cudaError_t le = launch_pdl(logmel_exact_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(kExactThreads),
                                     kExactSmem, stream, wave, e);
   count_launch();
@@ -955,12 +973,66 @@ int launch_exact(const IN* wave, long long clip_stride, long long frames_out, in
   return check_launch("logmel_exact_kernel");
 }
 
+// ================================================================== stft_magnitude (mel_features.py:71-92) on its own
+// |rfft(frame * hann, 512)| for all 257 bins in float64: the reference's standalone function returns float64, and the
+// fused log-mel kernel never materialises the magnitudes (it evaluates bins 4..243 only), so the drop-in gets the same
+// centred even / odd DFT as logmel_exact_kernel over the whole bin range.  16 frames per CTA, thread = bin.
+constexpr int kStftThreads = 288;   // 9 warps: bins 0..256
+constexpr int kStftFrames = 8;      // frames per CTA (E, O in static shared memory: 25.6 KB)
+
+__global__ void __launch_bounds__(kStftThreads)
+stft_magnitude_kernel(const double* __restrict__ signal, long long n_frames, const double* __restrict__ basis,
+                      double* __restrict__ out) {
+  __shared__ __align__(16) double E[eoHalf * kStftFrames];
+  __shared__ __align__(16) double O[eoHalf * kStftFrames];
+  const int tid = threadIdx.x;
+  const long long f0 = static_cast<long long>(blockIdx.x) * kStftFrames;
+  const int ng = n_frames - f0 < kStftFrames ? static_cast<int>(n_frames - f0) : kStftFrames;
+  for (int i = tid; i < eoHalf * kStftFrames; i += kStftThreads) {
+    const int f = i / eoHalf, m = i - f * eoHalf;
+    double e = 0.0, o = 0.0;
+    if (f < ng) {
+      const double* x = signal + (f0 + f) * kHop + eoHalf;
+      const double xp = __ldg(x + m), xm = __ldg(x - m);
+      e = xp + xm;
+      o = xp - xm;
+    }
+    E[m * kStftFrames + f] = e;
+    O[m * kStftFrames + f] = o;
+  }
+  __syncthreads();
+  if (tid >= kBins) return;
+  double re[kStftFrames], im[kStftFrames];
+#pragma unroll
+  for (int f = 0; f < kStftFrames; ++f) re[f] = im[f] = 0.0;
+  const double* bc = basis + tid;
+  const double* bs = basis + eoHalf * kBins + tid;
+#pragma unroll 2
+  for (int m = 0; m < eoHalf; ++m) {
+    const double c = __ldg(bc + m * kBins), sn = __ldg(bs + m * kBins);
+    const double2* e2 = reinterpret_cast<const double2*>(E + m * kStftFrames);
+    const double2* o2 = reinterpret_cast<const double2*>(O + m * kStftFrames);
+#pragma unroll
+    for (int f = 0; f < kStftFrames / 2; ++f) {
+      const double2 ev = e2[f], ov = o2[f];
+      re[2 * f] = fma(ev.x, c, re[2 * f]);
+      re[2 * f + 1] = fma(ev.y, c, re[2 * f + 1]);
+      im[2 * f] = fma(ov.x, sn, im[2 * f]);
+      im[2 * f + 1] = fma(ov.y, sn, im[2 * f + 1]);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < kStftFrames; ++f)
+    if (f < ng) out[(f0 + f) * kBins + tid] = sqrt(re[f] * re[f] + im[f] * im[f]);
+}
+
 // ------------------------------------------------------------------ per-device constant tables
 struct TcTables {
   __nv_bfloat16* basis = nullptr;  // [3][480][416] bf16: row = 2*bin_index + {cos, sin}, col = sample in frame
   __half* basis_eo = nullptr;      // [2 planes: hi, lo][2 parts: cos, sin][2 N-tiles][128 bins (120 used)][224 lags (200 used)]
   double* basis_f64 = nullptr;     // [2: cos, sin][200 lags][240 bins], centred, Hann folded in (logmel_exact_kernel)
   double* mel_f64 = nullptr;       // [240 bins][64 bands]
+  double* basis257 = nullptr;      // [2: cos, sin][200 lags][257 bins] (stft_magnitude_kernel; built on first use)
   bool ready = false;
 };
 std::mutex g_mu;
@@ -1090,6 +1162,18 @@ int build_tables(TcTables& t) {
     }
   for (int i = 0; i < kEvalBins; ++i)
     for (int b = 0; b < kMel; ++b) md[size_t(i) * kMel + b] = mel[size_t(kBinLo + i) * kMel + b];
+  std::vector<int> mlo(kMel, kEvalBins), mhi(kMel, 0);
+  for (int i = 0; i < kEvalBins; ++i)
+    for (int b = 0; b < kMel; ++b)
+      if (md[size_t(i) * kMel + b] != 0.0) {
+        mlo[b] = std::min(mlo[b], i);
+        mhi[b] = std::max(mhi[b], i + 1);
+      }
+  if (cudaMemcpyToSymbol(c_mel_lo, mlo.data(), sizeof(int) * kMel) != cudaSuccess ||
+      cudaMemcpyToSymbol(c_mel_hi, mhi.data(), sizeof(int) * kMel) != cudaSuccess) {
+    set_kernel_error("logmel: band range upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
   void *dbd = nullptr, *dmd = nullptr;
   if (cudaMalloc(&dbd, bd.size() * 8) != cudaSuccess || cudaMalloc(&dmd, md.size() * 8) != cudaSuccess ||
       cudaMemcpy(dbd, bd.data(), bd.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -1292,6 +1376,41 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
 }
 
 }  // namespace
+
+int stft_magnitude_f64(const double* signal, long long n_samples, double* mag, cudaStream_t stream) {
+  const long long n_frames = n_samples < kWin ? 0 : 1 + (n_samples - kWin) / kHop;
+  if (n_frames <= 0) return 0;
+  TcTables* t = nullptr;
+  if (get_tables(&t)) return 1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!t->basis257) {
+      std::vector<double> hann(kWin), mel(size_t(kBins) * kMel), b(size_t(2) * eoHalf * kBins);
+      front_end_tables_host(hann.data(), mel.data());
+      for (int m = 0; m < eoHalf; ++m)
+        for (int k = 0; k < kBins; ++k) {
+          const double ang = 2 * kPi * ((k * m) % kFft) / kFft, g = hann[eoHalf + m] * (m == 0 ? 0.5 : 1.0);
+          b[size_t(m) * kBins + k] = g * std::cos(ang);
+          b[size_t(eoHalf + m) * kBins + k] = g * std::sin(ang);
+        }
+      void* d = nullptr;
+      if (cudaMalloc(&d, b.size() * 8) != cudaSuccess ||
+          cudaMemcpy(d, b.data(), b.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_kernel_error("stft_magnitude: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+      }
+      t->basis257 = static_cast<double*>(d);
+    }
+  }
+  const long long blocks = (n_frames + kStftFrames - 1) / kStftFrames;
+  if (blocks > 0x7fffffffLL) {
+    set_kernel_error("stft_magnitude: signal too long for one call");
+    return 1;
+  }
+  stft_magnitude_kernel<<<static_cast<unsigned>(blocks), kStftThreads, 0, stream>>>(signal, n_frames, t->basis257, mag);
+  count_launch();
+  return check_launch("stft_magnitude_kernel");
+}
 
 int logmel_tc_forward(const float* wave, long long n_clips, long long samples_per_clip, long long clip_stride,
                       long long frames_out, float* logmel, cudaStream_t stream) {

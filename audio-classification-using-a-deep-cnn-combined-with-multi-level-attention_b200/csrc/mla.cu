@@ -387,6 +387,28 @@ int vmb_mla_forward(vmb_mla_t* h, const float* emb, long long batch, float* scor
   return 0;
 }
 
+int vmb_mla_embedded_mapping(vmb_mla_t* h, int level, const float* x, long long batch, float* out, void* stream) {
+  if (!h) return fail("vmb_mla_embedded_mapping: null handle");
+  if (level < 0 || level >= h->dev.n_levels) return fail("vmb_mla_embedded_mapping: no such level");
+  if (batch < 0) return fail("vmb_mla_embedded_mapping: negative batch");
+  if (batch == 0) return 0;
+  if (!x || !out) return fail("vmb_mla_embedded_mapping: null pointer");
+  if (vmb_head::tc_embedded_mapping(*h, level, x, batch, out, static_cast<cudaStream_t>(stream)))
+    return fail(vmb::kernels_last_error());
+  return 0;
+}
+
+int vmb_mla_attention(vmb_mla_t* h, int level, const float* hemb, long long batch, float* y, void* stream) {
+  if (!h) return fail("vmb_mla_attention: null handle");
+  if (level < 0 || level >= h->dev.n_levels) return fail("vmb_mla_attention: no such level");
+  if (batch < 0) return fail("vmb_mla_attention: negative batch");
+  if (batch == 0) return 0;
+  if (!hemb || !y) return fail("vmb_mla_attention: null pointer");
+  if (vmb_head::tc_attention(*h, level, hemb, batch, y, static_cast<cudaStream_t>(stream)))
+    return fail(vmb::kernels_last_error());
+  return 0;
+}
+
 int vmb_mla_forward_fp32(vmb_mla_t* h, const float* emb, long long batch, float* scores, void* stream) {
   if (!h) return fail("vmb_mla_forward_fp32: null handle");
   if (batch < 0) return fail("vmb_mla_forward_fp32: negative batch");

@@ -187,6 +187,25 @@ sigmoid_affine_kernel(const float* __restrict__ u, long long ldu, long long batc
   }
 }
 
+// out[r][c] = relu?(a_t * u[r][c] + b_t), t = r % T: the fp32 result of an EmbeddedMapping (model.py:217-222) when it is
+// asked for on its own rather than consumed by the next GEMM as planes
+__global__ void __launch_bounds__(256)
+rows_affine_f32_kernel(const float* __restrict__ src, long long lds, long long rows, int cols, int T,
+                       const float* __restrict__ a1, const float* __restrict__ b1, int relu, float* __restrict__ dst) {
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const int t = static_cast<int>(r % T);
+    float x = fmaf(__ldg(a1 + t), __ldg(src + r * lds + c), __ldg(b1 + t));
+    if (relu) x = fmaxf(x, 0.f);
+    dst[i] = x;
+  }
+}
+
 unsigned grid_for(long long items, int per_block) {
   return static_cast<unsigned>(std::min<long long>((items + per_block - 1) / per_block, 148LL * 8));
 }
@@ -287,6 +306,90 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
                     d.out_b, scores);
     vmb::count_launch();
     rc = vmb::check_launch("sigmoid_affine_kernel");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+// EmbeddedMapping.forward of level `level` on its own (eval mode, model.py:217-222): x fp32 [batch * T][in] ->
+// out fp32 [batch * T][hidden] = the level's chain norm0 -> (Linear -> BN_T -> ReLU) x n_fc.  Same kernels and the same
+// arithmetic as inside tc_forward.
+int tc_embedded_mapping(const Handle& h, int level, const float* x, long long batch, float* out, cudaStream_t st) {
+  const HeadDev& d = h.dev;
+  const LevelDev& L = d.lvl[level];
+  const long long rows = batch * d.T;
+  if (rows > 0x7fffffffLL) {
+    vmb::set_kernel_error("mla: too many rows for one call");
+    return 1;
+  }
+  const int in_dim = level == 0 ? d.emb_in : d.hidden;
+  const int in_pad = L.fc[0].kpad, hpad = kPad;
+  const size_t sz_x = up(size_t(rows) * 2 * in_pad * 2), sz_p = up(size_t(rows) * 2 * hpad * 2);
+  const size_t sz_u = up(size_t(rows) * hpad * 4);
+  char* ws = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), sz_x + sz_p + sz_u, st) != cudaSuccess) {
+    vmb::set_kernel_error("mla: workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  void* X = ws;
+  void* P = ws + sz_x;
+  float* U = reinterpret_cast<float*>(ws + sz_x + sz_p);
+  int rc = split_rows(x, in_dim, rows, in_dim, in_pad, d.T, L.n0a, L.n0b, 0, nullptr, nullptr, X, st);
+  const void* cur = X;
+  for (int j = 0; j < L.n_fc && !rc; ++j) {
+    if (vmb::igemm_linear_split(cur, L.fc[j].wp, L.fc[j].bias, U, hpad, 0, int(rows), hpad, L.fc[j].kpad, st)) {
+      vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+      rc = 1;
+      break;
+    }
+    if (j + 1 < L.n_fc) {
+      // the planes buffer is free again: the GEMM that read it (as `cur`) precedes this kernel in the stream
+      rc = split_rows(U, hpad, rows, d.hidden, hpad, d.T, L.fc[j].a, L.fc[j].b, 1, nullptr, nullptr, P, st);
+      cur = P;
+    } else {
+      vmb::launch_pdl(rows_affine_f32_kernel, dim3(grid_for(rows * d.hidden, 256)), dim3(256), 0, st, U,
+                      static_cast<long long>(hpad), rows, d.hidden, d.T, L.fc[j].a, L.fc[j].b, 1, out);
+      vmb::count_launch();
+      rc = vmb::check_launch("rows_affine_f32_kernel");
+    }
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+// AttentionModule.forward of level `level` on its own (eval mode, model.py:235-242): hemb fp32 [batch * T][hidden] ->
+// y fp32 [batch][K].
+int tc_attention(const Handle& h, int level, const float* hemb, long long batch, float* y, cudaStream_t st) {
+  const HeadDev& d = h.dev;
+  const LevelDev& L = d.lvl[level];
+  const long long rows = batch * d.T;
+  if (rows > 0x7fffffffLL) {
+    vmb::set_kernel_error("mla: too many rows for one call");
+    return 1;
+  }
+  const int hpad = kPad;
+  const size_t sz_p = up(size_t(rows) * 2 * hpad * 2), sz_u = up(size_t(rows) * hpad * 4);
+  char* ws = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), sz_p + sz_u, st) != cudaSuccess) {
+    vmb::set_kernel_error("mla: workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  float* U = reinterpret_cast<float*>(ws + sz_p);
+  int rc = split_rows(hemb, d.hidden, rows, d.hidden, hpad, d.T, nullptr, nullptr, 0, nullptr, nullptr, ws, st);
+  if (!rc && vmb::igemm_linear_split(ws, L.fcv.wp, L.fcv.bias, U, hpad, 0, int(rows), hpad, L.fcv.kpad, st)) {
+    vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+    rc = 1;
+  }
+  if (!rc) {
+    const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
+    if (att_smem <= 48 * 1024)
+      vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, st, U,
+                      static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, y, static_cast<long long>(d.K), 0);
+    else
+      vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U,
+                      static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, y, static_cast<long long>(d.K), 0);
+    vmb::count_launch();
+    rc = vmb::check_launch("attention_pool_kernel");
   }
   cudaFreeAsync(ws, st);
   return rc;

@@ -36,6 +36,7 @@ struct HostStage {
 struct vmb_vggish {
   int precision = 0;         // 0: bf16 activations and weights; 1: hi | lo split bf16 activations and weights (accuracy
                              // mode); 2: fp16 activations and weights (same tensor rate as bf16, 11 mantissa bits)
+  bool has_fc = true;        // false: built without the FC stack (conv features only, model.py:161-166)
   int* sat = nullptr;        // precision 2: [8] saturation flags (conv1, conv2..conv4_2, fc1, fc2) in mapped pinned host
                              // memory — the kernels store 1 when an output reached the fp16 maximum
   float* conv1_w = nullptr;  // fp32 [64][9]
@@ -77,15 +78,18 @@ int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w[6], const
 
 int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], const float* const conv_b[6],
                          const float* const fc_w[3], const float* const fc_b[3], int precision, void* stream) {
-  if (!handle || !conv_w || !conv_b || !fc_w || !fc_b) return fail("vmb_vggish_create: null argument");
+  if (!handle || !conv_w || !conv_b) return fail("vmb_vggish_create: null argument");
+  if ((fc_w == nullptr) != (fc_b == nullptr)) return fail("vmb_vggish_create: fc weights and biases go together");
+  const bool has_fc = fc_w != nullptr;   // without them the handle serves the conv features only (just_bottlenecks)
   if (precision < 0 || precision > 2) return fail("vmb_vggish_create: precision must be 0 (bf16), 1 (split) or 2 (fp16)");
   for (int i = 0; i < 6; ++i)
     if (!conv_w[i] || !conv_b[i]) return fail("vmb_vggish_create: null conv tensor");
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3 && has_fc; ++i)
     if (!fc_w[i] || !fc_b[i]) return fail("vmb_vggish_create: null fc tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vmb_vggish* h = new vmb_vggish();
   h->precision = precision;
+  h->has_fc = has_fc;
   const size_t wmul = precision == 1 ? 2 : 1;
   const int fmt = precision == 2 ? 1 : 0;
   bool ok = true;
@@ -112,7 +116,7 @@ int vmb_vggish_create_ex(vmb_vggish_t** handle, const float* const conv_w[6], co
     ok = ok && (precision == 1 ? vmb::relayout_conv_weight_split(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st)
                                : vmb::relayout_conv_weight(conv_w[i + 1], h->conv_w[i + 1], g.C_out, g.C_in, st, fmt)) == 0;
   }
-  for (int i = 0; i < 3 && ok; ++i) {
+  for (int i = 0; i < 3 && ok && has_fc; ++i) {
     dmalloc(&h->fc_w[i], size_t(kFcOut[i]) * kFcIn[i] * 2 * wmul);
     dmalloc(reinterpret_cast<void**>(&h->fc_b[i]), size_t(kFcOut[i]) * 4);
     if (!ok) break;
@@ -185,7 +189,8 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
   if (n < 0) return fail("vmb_vggish_forward: negative n");
   if (n == 0) return 0;
   if (n > 1000000) return fail("vmb_vggish_forward: at most 1 000 000 examples per call (chunk on the host)");
-  if (!examples || !emb || !workspace) return fail("vmb_vggish_forward: null pointer");
+  if (!examples || !workspace || (!emb && !bottleneck)) return fail("vmb_vggish_forward: null pointer");
+  if (emb && !h->has_fc) return fail("vmb_vggish_forward: this handle was built without the FC stack (bottleneck features only)");
   if (workspace_bytes < vmb_vggish_handle_workspace_bytes(h, n)) return fail("vmb_vggish_forward: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail("vmb_vggish_forward: workspace must be 1024-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -222,6 +227,7 @@ int vmb_vggish_forward(vmb_vggish_t* h, const float* examples, long long n, floa
         : cudaMemcpyAsync(bottleneck, src, size_t(n) * 12288 * 2, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail("vmb_vggish_forward: bottleneck copy failed");
   }
+  if (!emb) return 0;   // conv features only
   // fc1: B -> A, fc2: A -> B, fc3: B -> emb (fp32)
   const void* fc_in[3] = {src, dst, src};
   void* fc_out[3] = {dst, src, emb};

@@ -6,7 +6,7 @@ As in the reference, `T`, `H`, `DR`, `K` are module globals star-imported from p
 is CONSTRUCTED: set `model.K = 527` before building the head for AudioSet.
 
 The nn.Linear / nn.BatchNorm1d children own the parameters (and running statistics) under the reference's key
-names; their forward methods are never used.  Eval mode runs the fused head kernel (csrc/mla.cu); training mode
+names; their forward methods are never used.  Eval mode runs the tensor-core head (csrc/mla_tc.cu); training mode
 runs the library's forward/backward kernels through a torch.autograd.Function (csrc/mla_train.cu) so that
 `loss.backward()` and `torch.optim.Adam` from the reference's train loop keep working.  The ResNet50 branch is
 third-party torchvision code outside this path: asking for it raises.
@@ -19,7 +19,7 @@ from torch import nn
 from b200 import engine as _engine
 from b200._lib import B200Error
 from params import *  # noqa: F401,F403  (T, H, DR, K, M_VGGISH, ... bound here like in the reference)
-from torchvggish.vggish import VGGish
+from torchvggish.vggish import B200HandleMixin, VGGish, VGGishFeatures
 
 _RESNET_MSG = ("the ResNet50 branch is third-party torchvision code outside the B200 waveform->VGGish->MLA path "
                "(SURVEY.md §2)")
@@ -92,11 +92,12 @@ class CNN(nn.Module):
         self.just_bottlenecks = just_bottlenecks
         if not cnn_trainable:
             set_requires_grad(self.cnn_model, False)
+        if just_bottlenecks:
+            # the reference keeps only the first child (the conv stack) and re-wraps it with CnnFlatten in an
+            # nn.Sequential (model.py:161-166): state_dict keys become cnn_model.0.N.*, the FC stack is gone
+            self.cnn_model = VGGishFeatures(list(self.cnn_model.children())[0], CnnFlatten(cnn_type))
 
     def forward(self, x):
-        if self.just_bottlenecks:
-            # the reference drops the FC layers and flattens the conv features in (h, w, c) order (model.py:162-167)
-            return self.cnn_model.bottlenecks(x).float()
         return self.cnn_model(x)
 
 
@@ -115,8 +116,32 @@ class CnnFlatten(nn.Module):
         raise Exception("Invalid CNN model name specified.")
 
 
-class EmbeddedMapping(nn.Module):
-    """Parameter holder for one embedding level: norm0, fc[j], norms[j], dropouts[j] (model.py:200-222)."""
+def _bn_identity(sd, prefix, n, dev):
+    sd[prefix + ".weight"] = torch.ones(n, device=dev)
+    sd[prefix + ".bias"] = torch.zeros(n, device=dev)
+    sd[prefix + ".running_mean"] = torch.zeros(n, device=dev)
+    sd[prefix + ".running_var"] = torch.ones(n, device=dev)
+
+
+def _sub_module_handle(mod, build):
+    """Library handle of a sub-module used on its own: a one-level head built around the module's parameters."""
+    tensors = list(mod.parameters()) + list(mod.buffers())
+    dev = tensors[0].device
+    if dev.type != "cuda":
+        raise B200Error("parameters are on %s: move the module to a CUDA device; this build has no CPU path" % dev)
+    key = mod._tensor_key(tensors, dev)
+    if mod._sub_handle is None or key != mod._sub_handle_key:
+        if mod._sub_handle is not None:
+            mod._sub_handle.close()
+        mod._sub_handle = build(dev)
+        mod._sub_handle_key = key
+    return mod._sub_handle
+
+
+class EmbeddedMapping(B200HandleMixin, nn.Module):
+    """One embedding level: norm0, fc[j], norms[j], dropouts[j] (model.py:200-222).  Inside MultiLevelAttention the
+    level is part of the head's kernel sequence; called on its own (eval mode) it runs the same kernels through
+    vmb_mla_embedded_mapping."""
 
     def __init__(self, n_fc, is_first, emb_input_size):
         super().__init__()
@@ -126,14 +151,35 @@ class EmbeddedMapping(nn.Module):
         self.fc = nn.ModuleList(nn.Linear(w, H) for w in widths)
         self.dropouts = nn.ModuleList(nn.Dropout(p=DR) for _ in range(n_fc))
         self.norms = nn.ModuleList(nn.BatchNorm1d(T) for _ in range(n_fc))
+        self._t, self._h = T, H
+        self._sub_handle = None
+        self._sub_handle_key = None
+
+    def _build(self, dev):
+        # a one-level head around this level's parameters; the attention / output parameters are placeholders that
+        # vmb_mla_embedded_mapping never touches
+        sd = {"embedded_mappings.0." + k: v for k, v in self.state_dict().items()}
+        sd["attention_modules.0.fcv.weight"] = torch.zeros(1, self._h, device=dev)
+        sd["attention_modules.0.fcv.bias"] = torch.zeros(1, device=dev)
+        _bn_identity(sd, "attention_modules.0.normv", self._t, dev)
+        _bn_identity(sd, "attention_modules.0.normf", self._t, dev)
+        sd["fc.weight"] = torch.zeros(1, 1, device=dev)
+        sd["fc.bias"] = torch.zeros(1, device=dev)
+        _bn_identity(sd, "norm", 1, dev)
+        return _engine.MlaHandle(sd, [self.n_fc], self.fc[0].in_features, self._h, 1, self._t, dev)
 
     def forward(self, x):
-        raise B200Error("EmbeddedMapping is fused into MultiLevelAttention.forward on the B200 path; call the head")
+        """(B, T, in) -> (B, T, H): norm0, then Dropout(ReLU(BN_T(Linear))) per fc (model.py:217-222), eval mode."""
+        if self.training:
+            raise NotImplementedError("train-mode EmbeddedMapping runs inside MultiLevelAttention.forward on this path "
+                                      "(csrc/mla_train.cu); call the head, or .eval() to use the level on its own")
+        h = _sub_module_handle(self, self._build)
+        return h.embedded_mapping(0, x.detach().to(device=h.device, dtype=torch.float32))
 
 
-class AttentionModule(nn.Module):
-    """Parameter holder for one attention level: fcv, fcf (constructed but unused, F3), normv, normf
-    (model.py:226-242)."""
+class AttentionModule(B200HandleMixin, nn.Module):
+    """One attention level: fcv, fcf (constructed but unused, F3), normv, normf (model.py:226-242); on its own (eval
+    mode) it runs through vmb_mla_attention."""
 
     def __init__(self):
         super().__init__()
@@ -141,12 +187,32 @@ class AttentionModule(nn.Module):
         self.fcf = nn.Linear(H, K)
         self.normv = nn.BatchNorm1d(T)
         self.normf = nn.BatchNorm1d(T)
+        self._t, self._h, self._k = T, H, K
+        self._sub_handle = None
+        self._sub_handle_key = None
+
+    def _build(self, dev):
+        sd = {"attention_modules.0." + k: v for k, v in self.state_dict().items()}
+        _bn_identity(sd, "embedded_mappings.0.norm0", self._t, dev)          # placeholders: never evaluated
+        sd["embedded_mappings.0.fc.0.weight"] = torch.zeros(self._h, self._h, device=dev)
+        sd["embedded_mappings.0.fc.0.bias"] = torch.zeros(self._h, device=dev)
+        _bn_identity(sd, "embedded_mappings.0.norms.0", self._t, dev)
+        sd["fc.weight"] = torch.zeros(self._k, self._k, device=dev)
+        sd["fc.bias"] = torch.zeros(self._k, device=dev)
+        _bn_identity(sd, "norm", self._k, dev)
+        return _engine.MlaHandle(sd, [1], self._h, self._h, self._k, self._t, dev)
 
     def forward(self, h):
-        raise B200Error("AttentionModule is fused into MultiLevelAttention.forward on the B200 path; call the head")
+        """(B, T, H) -> (B, K): att = softmax_K(normv(fcv h)), cla = sigmoid(normf(fcv h)), sum_t cla att / sum_t att
+        (model.py:235-242, with its fcv-twice and softmax-over-classes quirks), eval mode."""
+        if self.training:
+            raise NotImplementedError("train-mode AttentionModule runs inside MultiLevelAttention.forward on this path "
+                                      "(csrc/mla_train.cu); call the head, or .eval() to use the level on its own")
+        hd = _sub_module_handle(self, self._build)
+        return hd.attention(0, h.detach().to(device=hd.device, dtype=torch.float32))
 
 
-class MultiLevelAttention(nn.Module):
+class MultiLevelAttention(B200HandleMixin, nn.Module):
     """Multi-level attention head (model.py:246-269): (B, T, M) embeddings -> (B, K) sigmoid scores."""
 
     def __init__(self, model_conf, emb_input_size):
@@ -162,18 +228,19 @@ class MultiLevelAttention(nn.Module):
         self._t, self._h, self._k, self._dr = T, H, K, DR
         self._handle = None
         self._handle_key = None
+        self._train_state = None
 
     def _b200_handle(self):
         dev = self.fc.weight.device
         if dev.type != "cuda":
             raise B200Error("head parameters are on %s: move the module to a CUDA device; this build has no CPU "
                             "path" % dev)
-        sd = self.state_dict()
-        key = tuple((v.data_ptr(), v._version) for v in sd.values()) + (str(dev),)
+        key = self._tensor_key(list(self.parameters()) + list(self.buffers()), dev)
         if self._handle is None or key != self._handle_key:
             if self._handle is not None:
                 self._handle.close()
-            self._handle = _engine.MlaHandle(sd, list(self.model), self.emb_input_size, self._h, self._k, self._t, dev)
+            self._handle = _engine.MlaHandle(self.state_dict(), list(self.model), self.emb_input_size, self._h, self._k,
+                                             self._t, dev)
             self._handle_key = key
         return self._handle
 
@@ -207,6 +274,12 @@ class MultiLevelAttention(nn.Module):
 
         self._train_state = dict(trainer=tr, param_names=names, sync_in=sync_in, sync_out=sync_out)
         return self._train_state
+
+    def invalidate(self):
+        st = self.__dict__.get("_train_state")
+        if st is not None:
+            st["trainer"].close()
+        super().invalidate()
 
     def forward(self, x):
         if self.training:

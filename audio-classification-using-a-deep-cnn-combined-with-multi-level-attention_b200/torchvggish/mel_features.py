@@ -90,8 +90,21 @@ def _check_vggish_params(audio_sample_rate, log_offset, window_length_secs, hop_
 
 
 def stft_magnitude(signal, fft_length, hop_length=None, window_length=None):
-    """Not exposed separately by the fused kernel (the magnitudes never leave shared memory)."""
-    raise NotImplementedError("stft_magnitude is fused into log_mel_spectrogram on the GPU; call that instead")
+    """(num_frames, fft_length / 2 + 1) magnitudes of the Hann-windowed frames (reference mel_features.py:71-92),
+    computed in float64 on the GPU (vmb_stft_magnitude: the fused log-mel kernel never materialises the magnitudes, so
+    the standalone function has its own kernel over all 257 bins).  numpy in -> float64 numpy out like the reference;
+    CUDA tensor in -> float64 CUDA tensor.  Specialised for the VGGish framing (fft 512, hop 160, window 400)."""
+    if (int(fft_length), hop_length, window_length) != (512, 160, 400):
+        raise NotImplementedError("the CUDA front end is specialised for the VGGish framing (fft_length 512, "
+                                  "hop_length 160, window_length 400); got %r" % ((fft_length, hop_length, window_length),))
+    if isinstance(signal, torch.Tensor):
+        if signal.dim() != 1:
+            raise ValueError("expected a 1-D waveform")
+        return _engine.stft_magnitude(signal.to(device="cuda", dtype=torch.float64))
+    sig = np.ascontiguousarray(signal, dtype=np.float64)
+    if sig.ndim != 1:
+        raise ValueError("expected a 1-D waveform")
+    return _engine.stft_magnitude(torch.from_numpy(sig).to("cuda")).cpu().numpy()
 
 
 def log_mel_spectrogram(data, audio_sample_rate=8000, log_offset=0.0, window_length_secs=0.025,

@@ -31,12 +31,52 @@ def make_layers():
     return nn.Sequential(*mods)
 
 
-def _param_fingerprint(module):
-    return tuple((p.data_ptr(), p._version, str(p.device)) for p in module.parameters())
+class B200HandleMixin:
+    """Caches the library-side copy of a module's weights (a ctypes handle) next to the nn.Module that owns them.
+
+    The copy is rebuilt when a parameter or buffer was replaced, moved, or modified in place through torch (tensor
+    version counters); edits that bypass the counters (`p.data.copy_()`, `p.data.mul_()`, EMA / clipping code) need an
+    explicit `invalidate()`.  The handle never travels with the module: pickling, `torch.save(model)` and
+    `copy.deepcopy` (the reference checkpoints whole objects, train.py:259-268) drop it and the copy rebuilds it on its
+    first forward."""
+    _B200_TRANSIENT = ("_handle", "_handle_key", "_train_state", "_sub_handle", "_sub_handle_key")
+
+    def invalidate(self):
+        """Forget the cached library copy of the weights (call after editing parameters through `.data`)."""
+        for name in self._B200_TRANSIENT:
+            h = self.__dict__.get(name)
+            if hasattr(h, "close"):
+                h.close()
+            if name in self.__dict__:
+                self.__dict__[name] = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for name in self._B200_TRANSIENT:
+            if name in state:
+                state[name] = None
+        return state
+
+    @staticmethod
+    def _tensor_key(tensors, dev):
+        return tuple((t.data_ptr(), t._version) for t in tensors) + (str(dev),)
 
 
-class VGG(nn.Module):
-    """VGGish body: (N, 1, 96, 64) log-mel examples -> (N, 128) post-ReLU embeddings (vggish.py:9-31)."""
+def _body_tensors(features, embeddings):
+    named = [(f"features.{k}", v) for k, v in features.named_parameters()]
+    if embeddings is not None:
+        named += [(f"embeddings.{k}", v) for k, v in embeddings.named_parameters()]
+    return named
+
+
+class VGG(B200HandleMixin, nn.Module):
+    """VGGish body: (N, 1, 96, 64) log-mel examples -> (N, 128) post-ReLU embeddings (vggish.py:9-31).
+
+    `b200_precision` selects the arithmetic of the library copy: "fp16" (default; fp16 operands, fp32 accumulation),
+    "bf16" (same kernels and speed, 8 mantissa bits) or "split" (hi + lo bf16 pairs, 3x the tensor work — the mode in
+    which `postprocess=True` reproduces the reference's 8-bit output up to +-1 LSB at quantisation boundaries).  The
+    reference's constructor has no such argument; set the attribute (or pass it to `set_precision`) before forward."""
+    b200_precision = _engine.DEFAULT_PRECISION
 
     def __init__(self, features):
         super().__init__()
@@ -49,18 +89,24 @@ class VGG(nn.Module):
         self._handle = None
         self._handle_key = None
 
+    def set_precision(self, precision):
+        if precision not in _engine.PRECISIONS:
+            raise ValueError("precision must be 'fp16', 'bf16' or 'split'")
+        self.b200_precision = precision
+        return self
+
     # -- library handle, rebuilt when a parameter was modified in place, replaced or moved
     def _b200_handle(self):
-        dev = next(self.features.parameters()).device
+        named = _body_tensors(self.features, self.embeddings)
+        dev = named[0][1].device
         if dev.type != "cuda":
             raise B200Error("VGGish parameters are on %s: move the module to a CUDA device (.to('cuda')); this build "
                             "has no CPU path" % dev)
-        body = {k: v for k, v in self.state_dict().items() if k.startswith(("features.", "embeddings."))}
-        key = tuple((v.data_ptr(), v._version) for v in body.values()) + (str(dev),)
+        key = self._tensor_key((v for _, v in named), dev) + (self.b200_precision,)
         if self._handle is None or key != self._handle_key:
             if self._handle is not None:
                 self._handle.close()
-            self._handle = _engine.VggishHandle(body, dev)
+            self._handle = _engine.VggishHandle(dict(named), dev, precision=self.b200_precision)
             self._handle_key = key
         return self._handle
 
@@ -75,9 +121,41 @@ class VGG(nn.Module):
         return h.forward(x)
 
     def bottlenecks(self, x):
-        """(N, 12288) bf16 conv features in (h, w, c) order (the flatten of vggish.py:26-29)."""
+        """(N, 12288) 16-bit conv features in (h, w, c) order (the flatten of vggish.py:26-29)."""
         h = self._b200_handle()
-        return h.forward(x.detach().to(device=h.device, dtype=torch.float32), want_bottleneck=True)[1]
+        return h.forward(x.detach().to(device=h.device, dtype=torch.float32), want_bottleneck=True,
+                         want_embeddings=False)[1]
+
+
+class VGGishFeatures(B200HandleMixin, nn.Sequential):
+    """The reference's just_bottlenecks re-wrap of VGGish: nn.Sequential(features, CnnFlatten) (model.py:161-166), so
+    that its state_dict keys are `0.{0,3,6,8,11,13}.{weight,bias}` and the FC stack is gone.  forward runs the library's
+    conv stack and returns the (N, 12288) features in (h, w, c) order as float32."""
+    b200_precision = _engine.DEFAULT_PRECISION
+
+    def __init__(self, features, flatten):
+        super().__init__(features, flatten)
+        self._handle = None
+        self._handle_key = None
+
+    def _b200_handle(self):
+        named = _body_tensors(self[0], None)
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise B200Error("VGGish parameters are on %s: move the module to a CUDA device; this build has no CPU "
+                            "path" % dev)
+        key = self._tensor_key((v for _, v in named), dev) + (self.b200_precision,)
+        if self._handle is None or key != self._handle_key:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = _engine.VggishHandle(dict(named), dev, precision=self.b200_precision)
+            self._handle_key = key
+        return self._handle
+
+    def forward(self, x):
+        h = self._b200_handle()
+        x = x.detach().to(device=h.device, dtype=torch.float32)
+        return h.forward(x, want_bottleneck=True, want_embeddings=False)[1].float()
 
 
 class Postprocessor(nn.Module):

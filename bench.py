@@ -12,9 +12,15 @@ One JSON line is printed by rank 0:
   value      clips/s over all GPUs, inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e        the same metric through the host-buffer C-ABI call (vmb_pipeline_forward_host): pinned host input,
              H2D copy, compute, D2H copy of the scores inside the timed region
-  roofline   the dominant kernel (tcgen05 implicit GEMM: 5 convs + 3 FCs per step) against the measured bf16 peak
+  roofline   the dominant kernel (tcgen05 implicit GEMM: 5 convs + 3 FCs per step) against the measured 16-bit
+             tensor peak: the short timed region against the BURST peak, the >= 3 s back-to-back leg (`sustained`)
+             against the SUSTAINED peak
   cpu_baseline  the oracle (numpy front end + torch-CPU VGGish + head = the reference's algorithm) on the host cores
---impl reference times that CPU path alone (rank 0 only) on a bounded sample of the same workload.
+  configs    compact legs for BASELINE.json configs[2..4]: batch8192 (8192 / N clips per rank through the host-buffer
+             entry point, micro-batched), stream_1h (1-hour stream, accuracy mode, PCA / uint8), train (head training
+             with the NCCL all-reduce of the gradient bucket at N > 1)
+  e2e_dropin the reference-named API: per-clip waveform_to_examples + Ensemble.forward, and Ensemble.forward_waveform
+--impl reference times the CPU path alone (rank 0 only) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -79,12 +85,14 @@ def emit(line):
     (_OUT or sys.stdout).flush()
 
 def igemm_traffic():
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (None if absent)."""
+    """(DRAM bytes per launch of the dominant kernel, where the figure comes from): read from the committed ncu
+    capture — a profiler figure, not a measurement of this run."""
     try:
         with open(os.path.join(ROOT, "profiles", "igemm_traffic.json")) as fh:
-            return float(json.load(fh)["dram_bytes_per_launch"])
+            d = json.load(fh)
+        return float(d["dram_bytes_per_launch"]), "ncu --set full, " + str(d.get("source", "profiles/igemm_traffic.json"))
     except Exception:
-        return None
+        return None, None
 
 
 def tensor_pipe_util():
@@ -163,6 +171,10 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
+        "reference_sample_clips_per_step": r["sample_clips"],
+        "note": f"this arm times {r['sample_clips']} of the step's {args.clips} clips per pass (ms_per_step is per "
+                "sample, value is clips/s); the reference is pure Python and cannot travel to the GPU box, so this is the "
+                "oracle port of its algorithm (kind: port)",
         "cpu_baseline": {"value": r["clips_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                          "sample": sample},
         "e2e": {"value": r["clips_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,8 +190,9 @@ class ClockSampler(threading.Thread):
                0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
                0x100: "display_clock_setting"}
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, period_s=0.01):
         super().__init__(daemon=True)
+        self.period_s = period_s
         self.stop_flag = threading.Event()
         self.mhz, self.mask, self.max_mhz, self.power, self.ok = [], 0, None, [], False
         try:
@@ -211,7 +224,7 @@ class ClockSampler(threading.Thread):
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period_s)
 
     def summary(self):
         if not self.ok or not self.mhz:
@@ -245,7 +258,9 @@ def bind_to_gpu_numa_node(device_index):
 
 def workload_config(args, world):
     return {"workload": f"batch {args.clips} synthetic 10 s 16 kHz clips per GPU, waveform -> log-mel -> VGGish -> "
-                        f"multi-level attention scores ({N_CLASSES} classes, model_conf [2,1])",
+                        f"multi-level attention scores ({N_CLASSES} classes, model_conf [2,1]) = BASELINE.json configs[1]",
+            "reference_arm": "the CPU reference arm (--impl reference) times a bounded sample of this step — at most 16 "
+                             "of its clips per pass, the exact count is in its cpu_baseline.sample — and reports clips/s",
             "clips_per_gpu_per_step": args.clips, "global_clips_per_step": args.clips * world,
             "samples_per_clip": CLIP_SAMPLES, "examples_per_clip": 10, "n_classes": N_CLASSES,
             "parallelism": f"batch-sharded x{world}, no collective on the data path",
@@ -255,6 +270,241 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def _timed(fn, steps, barrier, max_over_ranks):
+    """Device time of `steps` calls of fn (CUDA events on the current stream), barriers on both sides, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1))
+
+
+def leg_h2d_probe(wave_host, dev, barrier, max_over_ranks, world):
+    """Copy-only probe: what the box gives this rank for pinned host -> device copies of one step's input while every
+    other rank does the same (one cudaMemcpyAsync per copy on one stream, like csrc/vggish.cu submit_host_any; and the
+    same bytes as two halves on two streams)."""
+    dst = torch.empty_like(wave_host, device=dev)
+    nbytes = wave_host.numel() * 4
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    half = wave_host.shape[0] // 2
+    out = {}
+
+    def one():
+        dst.copy_(wave_host, non_blocking=True)
+
+    def two():
+        cur = torch.cuda.current_stream(dev)
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            dst[:half].copy_(wave_host[:half], non_blocking=True)
+        with torch.cuda.stream(s2):
+            dst[half:].copy_(wave_host[half:], non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+
+    for name, fn in (("one_stream", one), ("two_streams", two)):
+        for _ in range(2):
+            fn()
+        ms = _timed(fn, 10, barrier, max_over_ranks)          # max over ranks = the slowest rank's rate
+        out[name + "_gbs_per_gpu"] = nbytes * 10 / (ms * 1e-3) / 1e9
+    out["bytes_per_copy"] = nbytes
+    out["aggregate_gbs"] = max(out["one_stream_gbs_per_gpu"], out["two_streams_gbs_per_gpu"]) * world
+    return out
+
+
+def leg_sustained(pipe, wave_dev, clips, world, local_rank, barrier, max_over_ranks, seconds, peaks):
+    """The device-resident step back to back for >= `seconds` (independent of --steps): the regime in which the board's
+    power limit, not the burst clock, sets the tensor rate.  NVML sampled every ~2 ms."""
+    from b200 import _lib
+    L = _lib.lib()
+    sampler = ClockSampler(local_rank, period_s=0.002)
+    L.vmb_profile_collect(None, None, 1)
+    for _ in range(3):
+        pipe.forward(wave_dev)
+    barrier()
+    sampler.start()
+    chunk = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n = 0
+    # stage timers only on the last chunk: their event pairs would otherwise pile up for thousands of steps
+    while True:
+        for _ in range(chunk):
+            pipe.forward(wave_dev)
+        n += chunk
+        torch.cuda.current_stream().synchronize() if n % (4 * chunk) == 0 else None
+        if time.perf_counter() - t0 >= seconds:
+            break
+    L.vmb_profile_enable(1)
+    for _ in range(chunk):
+        pipe.forward(wave_dev)
+    n += chunk
+    e1.record()
+    barrier()
+    L.vmb_profile_enable(0)
+    sampler.stop_flag.set()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    stage_ms = np.zeros(len(STAGES), dtype=np.float64)
+    stage_calls = np.zeros(len(STAGES), dtype=np.int64)
+    L.vmb_profile_collect(stage_ms.ctypes.data, stage_calls.ctypes.data, 1)
+    sampler.join(timeout=1.0)
+    n_ex = clips * 10
+    per_stage = {STAGES[i]: float(stage_ms[i]) / chunk for i in range(len(STAGES)) if stage_calls[i]}
+    stage_flop = dict(zip(STAGES[1:10], [f * n_ex for f in FLOP_CONV + FLOP_FC]))
+    ig_ms = sum(per_stage.get(k, 0.0) for k in STAGES[2:10])
+    ig_tflops = FLOP_IGEMM_PER_EXAMPLE * n_ex / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else None
+    clk = sampler.summary()
+    ms_step = ms / n
+    return {"seconds": ms * 1e-3, "steps": n, "value": clips * world / (ms_step * 1e-3), "unit": UNIT,
+            "ms_per_step": ms_step, "sm_mhz_median": clk.get("sm_mhz"), "power_w_max": clk.get("power_w_max"),
+            "clock_reasons": clk.get("reasons"), "nvml_samples": clk.get("samples"),
+            "stage_ms_per_step": {k: round(v, 4) for k, v in per_stage.items()},
+            "stage_tflops": {k: round(stage_flop[k] / (per_stage[k] * 1e-3) / 1e12, 1) for k in stage_flop
+                             if per_stage.get(k)},
+            "igemm_tflops": ig_tflops, "igemm_frac_of_sustained_peak": ig_tflops / peaks["tflops"] if ig_tflops else None,
+            "whole_step_tflops": FLOP_PER_CLIP * clips / (ms_step * 1e-3) / 1e12,
+            "whole_step_frac_of_sustained_peak": FLOP_PER_CLIP * clips / (ms_step * 1e-3) / 1e12 / peaks["tflops"]}
+
+
+def leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks):
+    """BASELINE.json configs[2]: 8192 clips sharded by batch, 8192 / N per rank, through the host-buffer entry point in
+    micro-batches of 256 (H2D of micro-batch i+1 overlaps the compute of micro-batch i); scores land in host memory."""
+    per_rank = 8192 // world
+    reps = (per_rank + wave_host.shape[0] - 1) // wave_host.shape[0]
+    big = wave_host.repeat(reps, 1)[:per_rank].contiguous().pin_memory()     # this rank's shard (the step batch, tiled)
+    out = torch.empty(per_rank, N_CLASSES).pin_memory()
+    pipe.forward_host(big[:512], out[:512], clips_per_batch=256)
+    barrier()
+    t0 = time.perf_counter()
+    pipe.forward_host(big, out, clips_per_batch=256)
+    barrier()
+    ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    nb = wave_host.shape[0]
+    ok = bool(torch.isfinite(out).all().item())
+    if per_rank >= 2 * nb:                       # the shard is the step batch tiled: its blocks must come out identical
+        ok = ok and bool(torch.equal(out[:nb], out[nb:2 * nb]))
+    return {"value": 8192 / (ms * 1e-3), "unit": UNIT, "ms": ms, "clips_per_rank": per_rank, "microbatch_clips": 256,
+            "h2d_bytes_per_rank": per_rank * CLIP_SAMPLES * 4, "scores_ok": ok,
+            "api": "vmb_pipeline_forward_host (one blocking call per rank; pinned host in, pinned host out)"}
+
+
+def leg_stream_1h(dev, rank, world, barrier, max_over_ranks, vsd):
+    """BASELINE.json configs[3]: one 1-hour 16 kHz stream (230 MB fp32, pinned host) -> 3 749 examples -> VGGish in the
+    accuracy mode -> PCA / 8-bit; at N > 1 the stream is sharded by example (sharding.stream_chunks), no collective."""
+    import torch.distributed as dist
+    from b200 import engine, sharding, stream, synth
+    n = 3600 * 16000
+    g = torch.Generator().manual_seed(7)
+    t = torch.arange(n, dtype=torch.float32) / 16000.0
+    wave = (0.3 * torch.sin(2 * np.pi * (110.0 + 40.0 * torch.sin(2 * np.pi * 0.05 * t)) * t)
+            + 0.05 * torch.randn(n, generator=g)).pin_memory()
+    del t
+    vgg = engine.VggishHandle(vsd, dev, precision="split")
+    eig, means = synth.pca_params(1)
+    for _ in range(2):
+        emb, q = stream.embed_stream(vgg, wave, eig, means, 2048, rank, world)
+    barrier()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        emb, q = stream.embed_stream(vgg, wave, eig, means, 2048, rank, world)
+        checksum = torch.tensor([int(q.sum().item())], device=dev, dtype=torch.int64)   # forces completion, 8 B D2H
+    barrier()
+    ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / steps
+    if world > 1:
+        dist.all_reduce(checksum)
+    vgg.close()
+    n_ex = sharding.num_examples(n)
+    return {"value": n_ex / (ms * 1e-3), "unit": "examples/s", "ms_per_stream": ms, "n_examples": n_ex,
+            "realtime_factor": 3600.0 / (ms * 1e-3), "h2d_bytes": n * 4, "uint8_checksum": int(checksum.item()),
+            "dtype": "split bf16 (hi + lo planes; uint8 output within +-1 LSB of the fp32 reference)",
+            "api": "b200.stream.embed_stream (chunks of 2048 examples, H2D overlapped with compute)"}
+
+
+def leg_train(dev, rank, world, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: head training on synthetic 10 x 128 embeddings, 4096 / 8 = 512 rows per GPU, one NCCL
+    all-reduce of the flat gradient bucket per step at N > 1 (train.py:119-142, :369-372 semantics)."""
+    from b200 import _lib, synth, training
+    per_gpu, conf = 512, MODEL_CONF
+    tr = training.HeadTrainer(conf, 128, 600, N_CLASSES, 10, per_gpu, dev, lr=1e-3, dropout_p=0.4, seed=1234)
+    tr.load_state_dict(synth.mla_state_dict(conf, 128, 600, N_CLASSES, 10, seed=2))
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(per_gpu, 10, 128, generator=g).to(dev)
+    labels = torch.randint(0, N_CLASSES, (per_gpu,), generator=g).to(dev)
+    for _ in range(5):
+        tr.step(x, labels)
+    steps = 20
+    l0 = _lib.lib().vmb_launch_count()
+    ms = _timed(lambda: tr.step(x, labels), steps, barrier, max_over_ranks) / steps
+    launches = _lib.lib().vmb_launch_count() - l0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    phases = [0.0, 0.0, 0.0]
+    for _ in range(10):
+        ev[0].record()
+        tr.forward_backward(x, labels)
+        ev[1].record()
+        w = tr.all_reduce_grads()
+        ev[2].record()
+        tr.adam(w)
+        ev[3].record()
+        torch.cuda.synchronize()
+        for i in range(3):
+            phases[i] += ev[i].elapsed_time(ev[i + 1]) / 10
+    loss = float(tr.loss.item())
+    tr.close()
+    return {"value": per_gpu * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "rows_per_gpu": per_gpu,
+            "global_batch": per_gpu * world, "allreduce_bytes": tr.n_params * 4 if world > 1 else 0,
+            "phase_ms": {"forward_backward": phases[0], "allreduce": phases[1], "adam": phases[2]},
+            "gpu_launches_per_step": launches / steps, "final_loss": loss,
+            "dtype": "fp32-equivalent (3-plane split bf16 on tcgen05)"}
+
+
+def leg_dropin(dev, vsd, msd, wave_host, barrier, max_over_ranks, world):
+    """What a user of the reference calls: vggish_input.waveform_to_examples(w, 16000) per clip
+    (vggish_input.py:30) then Ensemble.forward (model.py:58-62), with host numpy waveforms in and scores read back; and
+    the one-call fast path Ensemble.forward_waveform."""
+    import model
+    from torchvggish.vggish_input import waveform_to_examples
+    old = model.K
+    try:
+        model.K = N_CLASSES
+        conf = dict(cnn_type="vggish", num_classes=N_CLASSES, use_pretrained=False, just_bottlenecks=False,
+                    cnn_trainable=False, first_cnn_layer_trainable=False, in_channels=1)
+        ens = model.Ensemble("repeat", conf, list(MODEL_CONF), dev)
+    finally:
+        model.K = old
+    ens.cnn.cnn_model.load_state_dict(vsd)
+    ens.mla.load_state_dict(msd)
+    ens = ens.to(dev).eval()
+    n = 64
+    waves_np = [wave_host[i].numpy().astype(np.float64) for i in range(n)]
+
+    def per_clip():
+        ex = torch.stack([waveform_to_examples(w, 16000) for w in waves_np])     # (n, 10, 1, 96, 64) on the device
+        return ens(ex).cpu()
+
+    def one_call():
+        return ens.forward_waveform(wave_host[:n].to(dev, non_blocking=True)).cpu()
+
+    out = {}
+    for name, fn in (("per_clip_waveform_to_examples_then_forward", per_clip), ("forward_waveform", one_call)):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            y = fn()
+        barrier()
+        ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / 3
+        out[name] = {"value": n * world / (ms * 1e-3), "unit": UNIT, "ms_per_call": ms, "clips_per_call": n}
+    out["scores_agree"] = bool((per_clip() - one_call()).abs().max().item() <= 1e-4)
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
     from b200 import _lib, engine, synth
@@ -269,7 +519,7 @@ def run_b200(args, rank, local_rank, world):
 
     vsd = synth.vggish_state_dict(0)
     msd = synth.mla_state_dict(MODEL_CONF, 128, 600, N_CLASSES, 10, seed=2)
-    vgg = engine.VggishHandle(vsd, dev)
+    vgg = engine.VggishHandle(vsd, dev, precision=args.precision)
     head = engine.MlaHandle(msd, MODEL_CONF, 128, 600, N_CLASSES, 10, dev)
     pipe = engine.Pipeline(vgg, head)
 
@@ -295,7 +545,7 @@ def run_b200(args, rank, local_rank, world):
     for _ in range(max(3, args.warmup)):
         scores = pipe.forward(wave_dev)
     L.vmb_profile_collect(None, None, 1)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period_s=0.002)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
@@ -315,7 +565,13 @@ def run_b200(args, rank, local_rank, world):
     stage_calls = np.zeros(len(STAGES), dtype=np.int64)
     L.vmb_profile_collect(stage_ms.ctypes.data, stage_calls.ctypes.data, 1)
     sampler.join(timeout=1.0)
+    vgg.check_saturation()
     finite = bool(torch.isfinite(scores).all().item())
+    peaks = measured_peaks()
+
+    # ---- the same step back to back for >= 3 s: the sustained regime
+    sustained = leg_sustained(pipe, wave_dev, args.clips, world, local_rank, barrier, max_over_ranks,
+                              args.sustained_seconds, peaks) if args.sustained_seconds > 0 else None
 
     # ---- end to end through the host-buffer C-ABI entry points (pinned host in, pinned host out).  Every step's
     # H2D copy of its inputs, its compute and its D2H copy of the scores happen inside the timed region; two steps
@@ -362,6 +618,7 @@ def run_b200(args, rank, local_rank, world):
         pipe.forward_host(wave_host, scores_host, clips_per_batch=args.serial_microbatch)
     barrier()
     serial_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    h2d = leg_h2d_probe(wave_host, dev, barrier, max_over_ranks, world)
 
     # ---- latency of BASELINE.json configs[0]: ONE 10 s clip, host buffer in -> scores on the host (blocking call)
     one_host = wave_host[:1].clone().pin_memory()
@@ -373,22 +630,28 @@ def run_b200(args, rank, local_rank, world):
         pipe.forward_host(one_host, one_out, clips_per_batch=1)
     b1_ms = 1e3 * (time.perf_counter() - t0) / 50
 
-    # ---- the same device-resident step with the accuracy mode of the VGGish body (hi + lo bf16 planes, 3x the tensor
-    # work): the mode whose ranking metric / uint8 output agree with the fp32 reference; reported, not the metric
-    acc_steps = max(3, min(10, args.steps))
-    vgg_split = engine.VggishHandle(vsd, dev, precision="split")
-    pipe_split = engine.Pipeline(vgg_split, head)
-    for _ in range(2):
-        pipe_split.forward(wave_dev)
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    for _ in range(acc_steps):
-        pipe_split.forward(wave_dev)
-    a1.record()
-    barrier()
-    acc_ms = max_over_ranks(a0.elapsed_time(a1)) / acc_steps
-    vgg_split.close()
+    # ---- the same device-resident step in the other two modes of the VGGish body: bf16 (the same kernels on 8 mantissa
+    # bits) and split (hi + lo bf16 planes, 3x the tensor work: the mode whose uint8 output matches the fp32 reference)
+    other = {}
+    for mode in ("bf16", "fp16", "split"):
+        if mode == args.precision:
+            continue
+        h2 = engine.VggishHandle(vsd, dev, precision=mode)
+        p2 = engine.Pipeline(h2, head)
+        for _ in range(3):
+            p2.forward(wave_dev)
+        k = max(3, min(10, args.steps))
+        other[mode] = _timed(lambda: p2.forward(wave_dev), k, barrier, max_over_ranks) / k
+        h2.close()
+    acc_ms = other["split"]
+
+    # ---- compact legs for BASELINE.json configs[2..4] and the reference-named API
+    legs = {}
+    if not args.no_config_legs:
+        legs["batch8192"] = leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks)
+        legs["stream_1h"] = leg_stream_1h(dev, rank, world, barrier, max_over_ranks, vsd)
+        legs["train"] = leg_train(dev, rank, world, barrier, max_over_ranks)
+        legs["e2e_dropin"] = leg_dropin(dev, vsd, msd, wave_host, barrier, max_over_ranks, world)
 
     if rank != 0:
         if world > 1:
@@ -400,43 +663,61 @@ def run_b200(args, rank, local_rank, world):
     ig_ms_per_step = float(stage_ms[ig].sum()) / args.steps
     ig_launches_per_step = int(stage_calls[ig].sum()) // args.steps
     ig_flop_per_step = FLOP_IGEMM_PER_EXAMPLE * n_ex
-    peaks = measured_peaks()
     achieved = ig_flop_per_step / (ig_ms_per_step * 1e-3) / 1e12 if ig_ms_per_step > 0 else None
     per_stage = {STAGES[i]: round(float(stage_ms[i]) / args.steps, 4) for i in range(len(STAGES)) if stage_calls[i]}
     stage_flop = dict(zip(STAGES[1:10], [f * n_ex for f in FLOP_CONV + FLOP_FC]))
     stage_tflops = {k: round(stage_flop[k] / (per_stage[k] * 1e-3) / 1e12, 1) for k in stage_flop if per_stage.get(k)}
     clips_per_s = args.clips * world / (ms_step * 1e-3)
+    whole_tflops = FLOP_PER_CLIP * args.clips / (ms_step * 1e-3) / 1e12
+    e2e_step_ms = e2e_ms / args.steps
+    traffic, traffic_src = igemm_traffic()
     line = {
         "metric": METRIC, "value": clips_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": args.clips * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
+        "e2e": {"value": args.clips * world / (e2e_step_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": args.clips * CLIP_SAMPLES * 4, "d2h_bytes_per_step": args.clips * N_CLASSES * 4,
-                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+                "ms_per_step": e2e_step_ms, "wall_ms_per_step": wall_ms / args.steps,
                 "microbatch_clips": args.e2e_microbatch, "matches_device_path": e2e_equal, "steps_in_flight": 2,
                 "serial_value": args.clips * world / (serial_ms / args.steps * 1e-3),
                 "serial_ms_per_step": serial_ms / args.steps, "serial_microbatch_clips": args.serial_microbatch,
                 "pcm16_value": args.clips * world / (pcm_ms / args.steps * 1e-3),
                 "pcm16_h2d_bytes_per_step": args.clips * CLIP_SAMPLES * 2,
+                # achieved H2D rate of this leg per GPU, beside what a copy-only loop of the same shape gets on this
+                # box with all ranks copying at once: when the two agree the leg is bound by the host -> device link
+                "h2d_gbs_per_gpu": args.clips * CLIP_SAMPLES * 4 / (e2e_step_ms * 1e-3) / 1e9,
+                "h2d_ceiling_gbs": max(h2d["one_stream_gbs_per_gpu"], h2d["two_streams_gbs_per_gpu"]),
+                "h2d_probe": h2d,
+                "compute_bound_value": clips_per_s,
                 "api": "vmb_pipeline_submit_host / vmb_pipeline_wait_host via b200.engine.Pipeline (serial_*: one "
                        "blocking vmb_pipeline_forward_host call per step)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": igemm_traffic(),
-                     "frac_of_burst_peak": (achieved / peaks["tflops_burst"]) if achieved else None,
+        # the timed region is short (steps x ~3.5 ms): the GPU runs at its burst clock, so the matching peak is the
+        # measured BURST 16-bit tensor rate; the >= 3 s leg below is compared with the SUSTAINED one
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                     "frac": (achieved / peaks["tflops_burst"]) if achieved else None,
+                     "regime": f"burst ({ms_total * 1e-3:.3f} s timed region)", "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "tensor_pipe_active_pct_ncu": tensor_pipe_util(),
                      "kernel": "igemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM: conv3_1..conv4_2, fc1, fc2) + "
                                "igemm_bf16_kernel (cta_group::1: conv2, fc3)",
                      "launches_per_step": ig_launches_per_step, "algorithmic_flop_per_launch":
                          ig_flop_per_step / max(1, ig_launches_per_step),
                      "avg_launch_ms": ig_ms_per_step / max(1, ig_launches_per_step), "peak_source": peaks["source"],
-                     "whole_step_tflops": FLOP_PER_CLIP * args.clips / (ms_step * 1e-3) / 1e12,
-                     "whole_step_frac": FLOP_PER_CLIP * args.clips / (ms_step * 1e-3) / 1e12 / peaks["tflops"]},
+                     "whole_step_tflops": whole_tflops, "whole_step_frac": whole_tflops / peaks["tflops_burst"],
+                     "sustained": None if sustained is None else {
+                         "achieved": sustained["igemm_tflops"], "peak": peaks["tflops"],
+                         "frac": sustained["igemm_frac_of_sustained_peak"],
+                         "whole_step_frac": sustained["whole_step_frac_of_sustained_peak"],
+                         "regime": f"sustained ({sustained['seconds']:.1f} s back to back)"}},
+        "sustained": sustained,
         "stage_ms_per_step": per_stage, "stage_tflops": stage_tflops,
         "single_clip_latency_ms": b1_ms, "host_affinity": numa,
+        "modes": {m: {"value": args.clips * world / (v * 1e-3), "unit": UNIT, "ms_per_step": v} for m, v in other.items()},
         "accuracy_mode": {"value": args.clips * world / (acc_ms * 1e-3), "unit": UNIT, "ms_per_step": acc_ms,
                           "dtype": "split bf16 (hi + lo planes, fp32-class body)"},
+        "configs": legs,
         "scores_finite": finite,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -464,6 +745,12 @@ def main():
                     help="clips per micro-batch in the serial (one blocking call per step) e2e variant")
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", choices=("fp16", "bf16", "split"), default="fp16",
+                    help="arithmetic of the VGGish body for the headline legs (fp16 and bf16 run at the same tensor rate)")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0,
+                    help="length of the back-to-back leg that measures the sustained regime (0 = skip)")
+    ap.add_argument("--no-config-legs", action="store_true",
+                    help="skip the batch8192 / stream_1h / train / e2e_dropin legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

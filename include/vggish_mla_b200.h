@@ -82,6 +82,11 @@ int vmb_logmel(const float* wave_dev, long long n_clips, long long samples_per_c
 int vmb_logmel_pcm16(const int16_t* pcm_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
                      long long frames_out, float* logmel_dev, void* stream);
 
+/* stft_magnitude() on its own (mel_features.py:71-92 with fft_length 512, hop 160, window 400): float64 samples in,
+ * float64 magnitudes out like the reference, mag_dev [vmb_num_frames(n_samples)][257].  The fused log-mel kernel never
+ * materialises the magnitudes; this is the same centred even / odd DFT in float64 on the CUDA cores, all 257 bins. */
+int vmb_stft_magnitude(const double* signal_dev, long long n_samples, double* mag_dev, void* stream);
+
 /* The same computation on the CUDA cores in plain fp32 (the first implementation).  Diagnostic only: an on-device
  * cross-check for the tensor-core kernel at sizes the CPU oracle cannot reach; vmb_pipeline_forward never uses it. */
 int vmb_logmel_cudacore(const float* wave_dev, long long n_clips, long long samples_per_clip, long long clip_stride,
@@ -148,7 +153,9 @@ int vmb_vggish_create(vmb_vggish_t** handle, const float* const conv_w_dev[6], c
  * precision 1 = accuracy mode: every activation and weight is carried as a hi + lo bf16 pair (16 mantissa bits) and
  * every conv / FC runs the three products hi*hi, lo*hi, hi*lo on the same tcgen05 kernels — 3x the tensor work, for
  * the long-form embedding extraction where the 8-bit quantised output must match the fp32 reference. */
-/* precision 2 = fp16 activations and weights, fp32 accumulation: the same kernels and the same tensor rate as
+/* fc_w_dev and fc_b_dev may both be NULL: the handle then holds the conv stack only and vmb_vggish_forward serves the
+ * bottleneck features (emb_dev = NULL) — the reference's just_bottlenecks re-wrap drops the FC layers (model.py:161-166).
+ * precision 2 = fp16 activations and weights, fp32 accumulation: the same kernels and the same tensor rate as
  * precision 0 with 11 mantissa bits instead of 8 (operand rounding 8x smaller: the ranking metric of the scores agrees
  * with the fp32 reference to 3 decimals).  fp16 ends at 65504: every 16-bit epilogue converts with
  * saturation and raises a per-layer flag when an output reached that maximum; vmb_vggish_saturation() reads the flags
@@ -168,6 +175,7 @@ size_t vmb_vggish_handle_workspace_bytes(const vmb_vggish_t* handle, long long n
 /* examples_dev fp32 [n][96][64] -> emb_dev fp32 [n][128] (post-ReLU embeddings, vggish.py:31).
  * If bottleneck_bf16_dev != NULL the (h,w,c)-flattened conv features [n][12288] (vggish.py:26-29; bf16, or fp16
  * for a precision-2 handle) are copied there as well (the reference's just_bottlenecks variant, model.py:162-167).                      */
+/* emb_dev may be NULL when only the bottleneck features are wanted (the FC stack is then skipped).            */
 int vmb_vggish_forward(vmb_vggish_t* handle, const float* examples_dev, long long n, float* emb_dev,
                        void* bottleneck_bf16_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
@@ -187,6 +195,15 @@ long long vmb_mla_param_count(int n_levels, const int* n_fc, int emb_in, int hid
 /* emb_dev fp32 [B][T][emb_in] -> scores_dev fp32 [B][K] (sigmoid outputs, model.py:268).  Every Linear runs as a
  * split-bf16 tcgen05 GEMM (hi + lo operand planes, fp32 accumulation).                                   */
 int vmb_mla_forward(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);
+/* One level on its own, for callers that use the reference's sub-modules directly (eval mode):
+ *   EmbeddedMapping.forward (model.py:217-222): x_dev fp32 [B][T][in] (in = emb_in for level 0, hidden otherwise) ->
+ *     out_dev fp32 [B][T][hidden] = norm0 -> (Linear -> BatchNorm1d(T) -> ReLU) x n_fc (dropout is the identity in eval);
+ *   AttentionModule.forward (model.py:235-242): h_dev fp32 [B][T][hidden] -> y_dev fp32 [B][K]
+ *     (softmax over the class axis, fcv feeding both branches: SURVEY F3, F4).
+ * Same kernels and arithmetic as inside vmb_mla_forward.                                                       */
+int vmb_mla_embedded_mapping(vmb_mla_t* handle, int level, const float* x_dev, long long batch, float* out_dev,
+                             void* stream);
+int vmb_mla_attention(vmb_mla_t* handle, int level, const float* h_dev, long long batch, float* y_dev, void* stream);
 /* The same head as ONE fused CUDA-core fp32 kernel (the first implementation; emb_in <= 608).  Diagnostic: the
  * on-device cross-check for vmb_mla_forward; vmb_pipeline_forward never uses it.                         */
 int vmb_mla_forward_fp32(vmb_mla_t* handle, const float* emb_dev, long long batch, float* scores_dev, void* stream);

@@ -184,6 +184,29 @@ def head():
     np.savez_compressed(os.path.join(HERE, "head.npz"), **out)
 
 
+def levels():
+    """Standalone EmbeddedMapping.forward / AttentionModule.forward (model.py:217-222, :235-242) of the K = 527 head, and the
+    state_dict key set of Ensemble(just_bottlenecks=True), whose CNN is re-wrapped as nn.Sequential (model.py:161-166)."""
+    ref_model.K = 527
+    m = ref_model.MultiLevelAttention([2, 1], 128)
+    m.load_state_dict(synth.mla_state_dict([2, 1], 128, 600, 527, 10, seed=2))
+    m.eval()
+    x = torch.randn(6, 10, 128, generator=torch.Generator().manual_seed(11)).abs() * 2.0      # == head.npz x_k527
+    with torch.no_grad():
+        e0 = m.embedded_mappings[0](x)
+        e1 = m.embedded_mappings[1](e0)
+        y0 = m.attention_modules[0](e0)
+        y1 = m.attention_modules[1](e1)
+    ref_model.K = 10
+    conf = dict(cnn_type="vggish", num_classes=10, use_pretrained=False, just_bottlenecks=True, cnn_trainable=False,
+                first_cnn_layer_trainable=False, in_channels=1)
+    ens = ref_model.Ensemble("repeat", conf, [1], torch.device("cpu"))
+    sd = ens.state_dict()
+    np.savez_compressed(os.path.join(HERE, "levels.npz"), x=x.numpy(), emb0=e0.numpy(), emb1=e1.numpy(), y0=y0.numpy(),
+                        y1=y1.numpy(), jb_keys=np.array(sorted(sd.keys())),
+                        jb_shapes=np.array([",".join(map(str, sd[k].shape)) for k in sorted(sd.keys())]))
+
+
 def ensemble(front):
     """Ensemble.forward for the vggish branch (model.py:58-62): 2 clips x T = 10 examples, K = 527."""
     ref_model.K = 527
@@ -224,6 +247,7 @@ if __name__ == "__main__":
     f = front_end()
     vggish(f)
     head()
+    levels()
     ensemble(f)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):

@@ -147,6 +147,47 @@ def test_shim_state_dict_keys_match_reference(golden_vggish, golden_head, golden
     assert model.MultiLevelAttention([2], 128).fc.out_features == old         # K is bound at construction (F1)
 
 
+def test_just_bottlenecks_keys_pickling_and_host_side_guards():
+    """CPU-side halves of the boundary checks: the just_bottlenecks Ensemble has the reference's re-wrapped key layout
+    (model.py:161-166, tests/golden/levels.npz), modules pickle / deep-copy (the reference checkpoints whole objects,
+    train.py:259-268), sub-modules raise instead of falling back without a GPU."""
+    import copy
+    import io
+    import model
+    from conftest import load_golden
+    lv = load_golden("levels.npz")
+    old = model.K
+    try:
+        model.K = 10
+        conf = dict(cnn_type="vggish", num_classes=10, use_pretrained=False, just_bottlenecks=True, cnn_trainable=False,
+                    first_cnn_layer_trainable=False, in_channels=1)
+        ens = model.Ensemble("repeat", conf, [1], torch.device("cpu"))
+    finally:
+        model.K = old
+    sd = ens.state_dict()
+    assert sorted(sd.keys()) == list(lv["jb_keys"])
+    assert [",".join(map(str, sd[k].shape)) for k in lv["jb_keys"]] == list(lv["jb_shapes"])
+    assert not any(k.startswith("cnn.cnn_model.embeddings") for k in sd)
+    clone = copy.deepcopy(ens)
+    assert sorted(clone.state_dict().keys()) == sorted(sd.keys())
+    buf = io.BytesIO()
+    torch.save({"model": ens}, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)["model"]
+    assert all(torch.equal(a, b) for a, b in zip(back.state_dict().values(), sd.values()))
+    state = ens.mla.__getstate__()
+    assert state["_handle"] is None and state["_train_state"] is None
+    with pytest.raises(B200Error):
+        ens.mla.embedded_mappings[0].eval()(torch.zeros(1, 10, 12288))         # CPU module: no fallback
+    with pytest.raises(B200Error):
+        ens.mla.attention_modules[0].eval()(torch.zeros(1, 10, 600))
+    with pytest.raises(NotImplementedError):
+        ens.mla.attention_modules[0].train()(torch.zeros(1, 10, 600))
+    from torchvggish import mel_features as mf
+    with pytest.raises(NotImplementedError):
+        mf.stft_magnitude(np.zeros(1000), 1024, 160, 400)
+
+
 def test_shim_error_behaviour():
     from torchvggish import mel_features as mf
     from torchvggish.vggish import Postprocessor, VGGish

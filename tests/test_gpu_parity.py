@@ -448,6 +448,134 @@ def test_reference_named_head_module(golden_head):
     assert np.abs(y.cpu().numpy() - golden_head["y_k527"]).max() <= 2e-5
 
 
+def test_standalone_embedded_mapping_and_attention_module():
+    """EmbeddedMapping.forward / AttentionModule.forward on their own (model.py:217-222, :235-242) against the outputs
+    of the reference's own sub-modules (tests/golden/levels.npz), and consistency with the whole head."""
+    import model
+    from conftest import load_golden
+    lv = load_golden("levels.npz")
+    old = model.K
+    try:
+        model.K = 527
+        m = model.MultiLevelAttention([2, 1], 128)
+    finally:
+        model.K = old
+    m.load_state_dict(synth.mla_state_dict((2, 1), 128, 600, 527, 10, seed=2))
+    m = m.to(DEV).eval()
+    x = torch.from_numpy(lv["x"]).to(DEV)
+    e0 = m.embedded_mappings[0](x)
+    e1 = m.embedded_mappings[1](e0)
+    y0 = m.attention_modules[0](e0)
+    y1 = m.attention_modules[1](e1)
+    for name, got, ref, tol in (("emb0", e0, lv["emb0"], 5e-5), ("emb1", e1, lv["emb1"], 5e-5), ("y0", y0, lv["y0"], 2e-5),
+                                ("y1", y1, lv["y1"], 2e-5)):
+        err = np.abs(got.cpu().numpy() - ref).max()
+        print(f"standalone {name}: max-abs-err {err:.2e} (max |ref| {np.abs(ref).max():.2f})")
+        assert got.shape == ref.shape and err <= tol * max(1.0, np.abs(ref).max()), name
+    # the same sub-modules composed by hand like MultiLevelAttention.forward does (model.py:258-269)
+    out = torch.sigmoid(torch.nn.functional.batch_norm(
+        torch.nn.functional.linear(torch.cat([y0, y1], dim=1), m.fc.weight, m.fc.bias), m.norm.running_mean,
+        m.norm.running_var, m.norm.weight, m.norm.bias, False, 0.0, 1e-5))
+    assert (out - m(x)).abs().max().item() <= 2e-5
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.embedded_mappings[0](x)
+
+
+def test_stft_magnitude_vs_reference_golden(golden_front):
+    """mel_features.stft_magnitude (mel_features.py:71-92) on its own: float64 on the device, all 257 bins."""
+    from torchvggish import mel_features
+    w = golden_front["waves_f32"][1].astype(np.float64)
+    got = mel_features.stft_magnitude(w, 512, 160, 400)
+    ref = golden_front["stft_mag_clip1"]
+    assert got.dtype == np.float64 and got.shape == (118, 257)
+    err = np.abs(got[:8] - ref).max() / np.abs(ref).max()
+    full = np.abs(np.fft.rfft(mel_features.frame(w, 400, 160) * mel_features.periodic_hann(400), 512))
+    err_full = np.abs(got - full).max() / np.abs(full).max()
+    print(f"stft_magnitude vs reference golden: rel-max-err {err:.2e}; vs numpy on all frames {err_full:.2e}")
+    assert err <= 1e-12 and err_full <= 1e-12
+    t = mel_features.stft_magnitude(torch.from_numpy(w).to(DEV), 512, 160, 400)
+    assert t.is_cuda and t.dtype == torch.float64 and np.array_equal(t.cpu().numpy(), got)
+    with pytest.raises(NotImplementedError):
+        mel_features.stft_magnitude(w, 1024, 160, 400)
+    with pytest.raises(ValueError):
+        mel_features.stft_magnitude(np.zeros(100), 512, 160, 400)
+
+
+def test_modules_pickle_and_deepcopy_after_forward(tmp_path, vgg_sd, head_sd):
+    """The reference checkpoints WHOLE objects (torch.save({'model': model, ...}), train.py:259-268) and deep-copies
+    state (train.py:150-158): the cached library handles must not travel with the module."""
+    import copy
+    import model
+    old = model.K
+    try:
+        model.K = 527
+        conf = dict(cnn_type="vggish", num_classes=527, use_pretrained=False, just_bottlenecks=False,
+                    cnn_trainable=False, first_cnn_layer_trainable=False, in_channels=1)
+        ens = model.Ensemble("repeat", conf, [2, 1], DEV)
+    finally:
+        model.K = old
+    ens.cnn.cnn_model.load_state_dict(vgg_sd)
+    ens.mla.load_state_dict(head_sd)
+    ens = ens.to(DEV).eval()
+    x = engine.examples_from_wave(torch.from_numpy(synth.make_clips(4, 2)).to(DEV)).reshape(2, 10, 1, 96, 64)
+    y = ens(x)
+    clone = copy.deepcopy(ens)                               # after an eval forward
+    assert torch.equal(clone(x), y)
+    path = str(tmp_path / "ckpt.pt")
+    ens.train()
+    ens.cnn.eval()
+    loss = torch.nn.CrossEntropyLoss()(ens(x), torch.tensor([3, 5], device=DEV))
+    loss.backward()                                          # after a train forward + backward
+    torch.save({"model": ens, "epoch": 1}, path)             # _save_checkpoint, train.py:259-268
+    back = torch.load(path, map_location=DEV, weights_only=False)["model"]      # _resume_from_checkpoint
+    back.eval()
+    ens.eval()
+    assert torch.equal(back(x), ens(x))
+    # edits through .data bypass the version counters: invalidate() is the documented way to refresh the library copy
+    before = ens(x).clone()
+    ens.mla.fc.bias.data.add_(3.0)
+    ens.mla.invalidate()
+    assert not torch.equal(ens(x), before)
+
+
+def test_vggish_module_precision_knob(golden_front, golden_vggish, vgg_sd):
+    """VGGish(postprocess=True) in the accuracy mode meets the +-1 LSB bar of north_star; the default (fp16) mode is
+    reported next to it."""
+    from torchvggish.vggish import VGGish
+    eig, means = synth.pca_params(1)
+    ref = golden_vggish["preprocess_postprocess"]
+    hist = {}
+    for prec in ("fp16", "bf16", "split"):
+        net = VGGish(urls={}, pretrained=False, preprocess=True, postprocess=True)
+        net.load_state_dict({**vgg_sd, "pproc.pca_eigen_vectors": eig, "pproc.pca_means": means})
+        net = net.to(DEV).eval().set_precision(prec)
+        d = np.abs(net(golden_front["waves_f32"][2].astype(np.float64), 16000).cpu().numpy() - ref).astype(np.int64)
+        hist[prec] = np.bincount(d).tolist()
+    print("VGGish(preprocess, postprocess) uint8 LSB histograms vs reference:", hist)
+    assert len(hist["split"]) <= 2 and len(hist["fp16"]) <= 2                   # nothing further than 1 LSB
+    assert hist["split"][0] >= 126 and hist["fp16"][0] >= 120
+
+
+def test_fp16_saturation_is_reported(vgg_sd):
+    """fp16 ends at 65504: the epilogues convert with saturation and raise a flag that the host API turns into an error
+    (weights scaled so that conv2's outputs overflow)."""
+    sd = {k: v.clone() for k, v in vgg_sd.items()}
+    sd["features.3.weight"] *= 3.0e4
+    h = engine.VggishHandle(sd, DEV, precision="fp16")
+    x = engine.examples_from_wave(torch.from_numpy(synth.make_clips(0, 1)).to(DEV))
+    emb = h.forward(x)
+    assert torch.isfinite(emb).all()                          # saturated, not inf / nan
+    with pytest.raises(engine.B200Error, match="saturated"):
+        h.check_saturation()
+    h.check_saturation()                                      # the flags were cleared by the failed check
+    h.close()
+    ok = engine.VggishHandle(vgg_sd, DEV, precision="fp16")
+    ok.forward(x)
+    ok.check_saturation()
+    ok.close()
+
+
 # ------------------------------------------------------------------------------------------------ whole path
 def test_pipeline_vs_reference_golden(golden_ensemble, vgg_handle, head_handle):
     pipe = engine.Pipeline(vgg_handle, head_handle)
@@ -629,7 +757,13 @@ def test_just_bottlenecks_variant(vgg_sd):
         model.K = old
     assert ens.emb_input_size == 12288
     head_sd = synth.mla_state_dict((1,), 12288, 600, 10, 10, seed=4)
-    ens.cnn.cnn_model.load_state_dict(vgg_sd)
+    # the reference re-wraps the conv stack as nn.Sequential(features, CnnFlatten) (model.py:161-166): keys 0.N.*, no FCs
+    from conftest import load_golden
+    lv = load_golden("levels.npz")
+    assert sorted(ens.state_dict().keys()) == list(lv["jb_keys"])
+    assert [",".join(map(str, ens.state_dict()[k].shape)) for k in lv["jb_keys"]] == list(lv["jb_shapes"])
+    ens.cnn.cnn_model.load_state_dict({k.replace("features.", "0."): v for k, v in vgg_sd.items()
+                                       if k.startswith("features.")})
     ens.mla.load_state_dict(head_sd)
     ens = ens.to(DEV).eval()
     waves = synth.make_clips(8, 2)

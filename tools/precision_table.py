@@ -74,7 +74,7 @@ def layer_chain(sd, x, dtype):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--clips", type=int, default=128)
+    ap.add_argument("--clips", type=int, default=256)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "precision_table.json"))
     args = ap.parse_args()
     n = args.clips
@@ -89,10 +89,20 @@ def main():
         model_torch.vgg_forward(vsd, torch.from_numpy(ex[:20])[:, None], per_layer_ref)
     eig, means = synth.pca_params(1)
     q_ref = model_torch.postprocess(eig, means, emb_ref).numpy()
-    labels = synth.multihot_labels(n, 527, p=0.2, seed=3)
-    ranked = (want >= np.quantile(want, 0.8, axis=0, keepdims=True)).astype(labels.dtype)
-    out = {"clips": n, "oracle": {"mAP_random_labels": synth.mean_average_precision(labels, want),
-                                  "mAP_oracle_ranked_labels": synth.mean_average_precision(ranked, want)}}
+    # label sets: SURVEY 8d's (Bernoulli(0.05) multi-hot over the whole batch, every class >= 1 positive, seed 3 = the
+    # defaults of synth.multihot_labels), round 1's (first 128 clips, p = 0.2, seed 3), labels that follow the oracle's
+    # own ranking (top 20 % per class), and 20 more seeds of the SURVEY recipe for the spread
+    sets = {"survey_8d": (slice(0, n), synth.multihot_labels(n, 527)),
+            "round1_p02_128": (slice(0, 128), synth.multihot_labels(128, 527, p=0.2, seed=3)),
+            "oracle_ranked": (slice(0, n), (want >= np.quantile(want, 0.8, axis=0, keepdims=True)).astype(np.int64))}
+    for sd_ in range(20):
+        sets[f"seed{100 + sd_}"] = (slice(0, n), synth.multihot_labels(n, 527, seed=100 + sd_))
+
+    def maps(scores):
+        return {k: synth.mean_average_precision(lab, scores[sl]) for k, (sl, lab) in sets.items()}
+
+    ref_maps = maps(want)
+    out = {"clips": n, "oracle": {"mAP": ref_maps}}
     head = engine.MlaHandle(hsd, (2, 1), 128, 600, 527, 10, DEV)
     wave_dev = torch.from_numpy(waves).to(DEV)
     x20 = torch.from_numpy(ex[:20]).to(DEV)
@@ -106,8 +116,12 @@ def main():
         r = {"embeddings": err(emb, emb_ref), "scores_max_abs": float(np.abs(got - want).max()),
              "uint8_lsb_histogram": np.bincount(d.ravel()).tolist(),
              "uint8_exact_frac": float((d == 0).mean()), "uint8_within_1_frac": float((d <= 1).mean()),
-             "mAP_random_labels": synth.mean_average_precision(labels, got),
-             "mAP_oracle_ranked_labels": synth.mean_average_precision(ranked, got)}
+             "mAP": maps(got)}
+        r["mAP_three_decimals_equal"] = {k: f"{v:.3f}" == f"{ref_maps[k]:.3f}" for k, v in r["mAP"].items()}
+        d = np.array([r["mAP"][k] - ref_maps[k] for k in ref_maps if k.startswith("seed")])
+        r["mAP_abs_delta_over_20_seeds"] = {"mean": float(np.abs(d).mean()), "max": float(np.abs(d).max()),
+                                            "three_decimals_equal": int(sum(r["mAP_three_decimals_equal"][k]
+                                                                            for k in ref_maps if k.startswith("seed")))}
         if mode != "split":
             acts = layer_chain(vsd, x20, 1 if mode == "fp16" else 0)
             r["layers"] = {nm: err(a, ref) for nm, a, ref in zip(NAMES, acts, per_layer_ref)}
@@ -117,13 +131,16 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(out, fh, indent=1)
-    o = out["oracle"]
-    print(f"oracle: mAP random {o['mAP_random_labels']:.5f}  ranked {o['mAP_oracle_ranked_labels']:.5f}")
+    o = out["oracle"]["mAP"]
+    main3 = ("survey_8d", "round1_p02_128", "oracle_ranked")
+    print("oracle: mAP " + "  ".join(f"{k} {o[k]:.5f}" for k in main3))
     for mode in ("bf16", "fp16", "split"):
         r = out[mode]
         print(f"{mode:5s}: emb rel-max {r['embeddings']['rel_max']:.2e} cos {r['embeddings']['cos']:.7f}  scores "
-              f"{r['scores_max_abs']:.2e}  mAP random {r['mAP_random_labels']:.5f} ranked "
-              f"{r['mAP_oracle_ranked_labels']:.5f}  uint8 exact {r['uint8_exact_frac']:.4f} <=1 "
+              f"{r['scores_max_abs']:.2e}  mAP " + "  ".join(f"{k} {r['mAP'][k]:.5f}" for k in main3) +
+              f"  |dmAP| over 20 seeds mean {r['mAP_abs_delta_over_20_seeds']['mean']:.2e} max "
+              f"{r['mAP_abs_delta_over_20_seeds']['max']:.2e} 3-dec equal "
+              f"{r['mAP_abs_delta_over_20_seeds']['three_decimals_equal']}/20  uint8 exact {r['uint8_exact_frac']:.4f} <=1 "
               f"{r['uint8_within_1_frac']:.4f} hist {r['uint8_lsb_histogram'][:8]}")
         for nm, e in r.get("layers", {}).items():
             print(f"        {nm:8s} rel-max {e['rel_max']:.2e} cos {e['cos']:.7f}")
