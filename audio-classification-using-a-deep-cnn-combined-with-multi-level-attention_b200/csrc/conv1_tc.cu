@@ -299,16 +299,16 @@ int conv1_tc_relu_pool(const float* examples, const float* w, const float* b, vo
   const long long tiles = n * kTilesPerExample;
   if (tiles <= 0) return 0;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
+  if (device_needs_setup(attr_set)) {
     if (cudaFuncSetAttribute(conv1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              conv1_smem_bytes<false>()) != cudaSuccess ||
         cudaFuncSetAttribute(conv1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              conv1_smem_bytes<true>()) != cudaSuccess) {
+      device_setup_failed(attr_set);
       set_kernel_error("conv1: cannot set the dynamic shared memory size");
       return 1;
     }
-    attr_set = true;
   }
   // the output as [rows = n * (1 or 2 planes) * 48 * 32][64 channels]; one box = one tile = 128 rows
   CUtensorMap to;

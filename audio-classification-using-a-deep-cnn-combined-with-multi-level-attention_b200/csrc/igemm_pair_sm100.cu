@@ -357,15 +357,15 @@ thread_local char g_pair_err[512] = "";
 template <int BLOCK_N, int MT, bool CONV, bool POOL, bool BIG, bool HALO = false>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
   auto kern = igemm_pair_kernel<BLOCK_N, MT, CONV, POOL, BIG, HALO>;
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
   constexpr int smem = PairCfg<BLOCK_N, MT, HALO>::kSmemBytes;
-  if (!attr_set) {
+  if (device_needs_setup(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
+      device_setup_failed(attr_set);
       snprintf(g_pair_err, sizeof g_pair_err, "cudaFuncSetAttribute(pair, smem=%d): %s", smem, cudaGetErrorString(e));
       return 1;
     }
-    attr_set = true;
   }
   const int all_pair_tiles = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * p.num_n_tiles;
   const int pair_tiles = (p.tile_count > 0 && p.tile_count < all_pair_tiles) ? p.tile_count : all_pair_tiles;

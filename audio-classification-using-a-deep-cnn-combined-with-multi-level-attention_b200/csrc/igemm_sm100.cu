@@ -500,12 +500,15 @@ int make_tmap_plain(CUtensorMap* m, const void* base, int elem_bytes, int rank, 
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];   // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -515,15 +518,15 @@ namespace {
 template <int BLOCK_N, int MT, bool CONV, bool POOL, int OUT, bool BIG = false, bool HALO = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
   auto kern = igemm_bf16_kernel<BLOCK_N, MT, CONV, POOL, OUT, BIG, HALO>;
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
   constexpr int smem = Cfg<BLOCK_N, MT, HALO>::kSmemBytes;
-  if (!attr_set) {
+  if (device_needs_setup(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
+      device_setup_failed(attr_set);
       snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
       return 1;
     }
-    attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();

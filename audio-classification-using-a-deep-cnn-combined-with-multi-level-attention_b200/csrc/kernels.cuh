@@ -2,6 +2,7 @@
 // kernels_last_error() holds the reason.  Device pointers throughout.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <utility>
 
@@ -28,6 +29,22 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// One-time, PER DEVICE set-up of a kernel (cudaFuncSetAttribute is a per-device property: a process that runs on
+// cuda:0 and then on cuda:1 must opt in on both).  `mask` is the call site's static flag word, one bit per device id.
+// Returns true when the current device has not been set up through this flag yet; call device_setup_failed() when the
+// set-up then fails so that the next call retries.
+inline bool device_needs_setup(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit, std::memory_order_acq_rel) & bit);
+}
+inline void device_setup_failed(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  mask.fetch_and(~(1ull << (dev & 63)), std::memory_order_acq_rel);
 }
 
 // ---- accounting (profile.cu)

@@ -148,7 +148,8 @@ struct LogmelParams {
   int n_clips;
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
-  uint32_t* exact_mask;     // [total_tiles][4]: bit r of word q = frame 32 q + r of the tile must be redone exactly
+  uint2* exact_list;        // flagged 32-frame groups: (tile * 4 + quarter, bit r = frame 32 quarter + r must be redone)
+  unsigned* exact_count;    // entries in exact_list (zeroed by the host before the launch)
 };
 
 
@@ -358,7 +359,7 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
         const float lim = kExactRatioPlanes * (w.mn + kLogOffset);
         const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
-        if (lane == 0) p.exact_mask[tile * 4 + q] = bad;
+        if (lane == 0 && bad) p.exact_list[atomicAdd(p.exact_count, 1u)] = make_uint2(static_cast<uint32_t>(tile * 4 + q), bad);
       }
     }
   }
@@ -504,7 +505,8 @@ struct LogmelEoParams {
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
-  uint32_t* exact_mask;     // [total_tiles][4]: frames to redo in float64 (see kExactRatio)
+  uint2* exact_list;        // flagged 32-frame groups for logmel_exact_kernel (see kExactRatio): (tile * 4 + quarter,
+  unsigned* exact_count;    // bit r = frame 32 quarter + r of the tile); entry count, zeroed by the host before the launch
 };
 
 // The band walk of the epilogue with everything about the mel layout resolved at compile time.  kBandOfBin is the
@@ -808,7 +810,7 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         flush_static<kBandOfBin[kEvalBins - 1]>(w, row_out, valid);   // the remaining bands (up to band 63)
         const float lim = kExactRatio * (w.mn + kLogOffset);
         const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
-        if (lane == 0) p.exact_mask[tile * 4 + q] = bad;
+        if (lane == 0 && bad) p.exact_list[atomicAdd(p.exact_count, 1u)] = make_uint2(static_cast<uint32_t>(tile * 4 + q), bad);
       }
     }
   }
@@ -822,23 +824,24 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 }
 
 // ================================================================== float64 path for the flagged frames
-// The same centred even / odd DFT in float64 on the CUDA cores.  Work unit = (128-frame tile, half): CTA `half` of a
-// tile takes the tile's flagged frames number 8 half .. 8 half + 7 (then + 16, ...), so the usual case — a handful of
-// flagged frames in a tile — is one pass of one or two small CTAs: E, O in shared memory ([lag][frame]: the 8 frames
-// of a lag are one 64-byte broadcast read), thread = DFT bin (240 of 256 threads), basis and mel matrix as float64
-// tables in global memory (768 KB + 120 KB, L2-resident; the basis values of 8 lags are fetched together because the
-// loop is bound by their latency).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
-// float64 reference rounded once.  Tiles without flagged frames cost one 16-byte read.
+// The same centred even / odd DFT in float64 on the CUDA cores.  The epilogues of the tensor-core kernels append every
+// 32-frame group that holds flagged frames to a list (one atomicAdd per group; the order of the list varies from run to
+// run, the results do not: every frame is computed on its own).  One CTA per SM walks the list round-robin, 8 flagged
+// frames per pass: E, O in shared memory ([lag][frame]: the frames of a lag are 64-byte broadcast reads), thread =
+// (DFT bin, 4 of the 8 frames, half of the lags), basis and mel matrix as float64 tables in global memory (768 KB +
+// 120 KB, L2-resident).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the float64 reference
+// rounded once.  An empty list costs one 4-byte read per CTA.
 constexpr int kExactFrames = 8;      // frames per pass
-constexpr int kExactThreads = 256;
-constexpr int kExactSmem = 2 * eoHalf * kExactFrames * 8 + kExactFrames * kEvalBins * 8 + 160 * 4;
+constexpr int kExactThreads = 1024;  // thread = (bin, 4 of the 8 frames, half of the 200 lags): the pass is bound by the
+                                     // latency of its basis loads, so the lag loop is split and deeply prefetched
+constexpr int kExactSmem = 2 * eoHalf * kExactFrames * 8 + 3 * kExactFrames * kEvalBins * 8 + 160 * 4;   // E, O | mag | partial (re, im) | rows
 
 struct ExactParams {
   long long frames_out;
   int tiles_per_clip;
-  long long total_tiles;
   long long clip_stride;        // samples
-  const uint32_t* mask;         // [total_tiles][4]
+  const uint2* list;            // (tile * 4 + quarter, frame mask) entries
+  const unsigned* count;
   const double* basis;          // [2: cos, sin][200 lags][240 bins]
   const double* mel;            // [240 bins][64 bands]
   float* out;                   // [n_clips][frames_out][64]
@@ -858,33 +861,22 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
   double* E = reinterpret_cast<double*>(exact_smem);                 // [200][8]
   double* O = E + eoHalf * kExactFrames;                             // [200][8]
   double* mag = O + eoHalf * kExactFrames;                           // [8][240]
-  int* rows = reinterpret_cast<int*>(mag + kExactFrames * kEvalBins); // [128] flagged frames of the tile
+  int* rows = reinterpret_cast<int*>(mag + 3 * kExactFrames * kEvalBins); // [128] flagged frames of the tile
   const int tid = threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();   // the masks (and the rows this kernel overwrites) come from the tensor-core kernel before it
-  for (long long unit = blockIdx.x; unit < 2 * p.total_tiles; unit += gridDim.x) {
-    const long long tile = unit >> 1;
-    const int half = static_cast<int>(unit & 1);
-    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(p.mask) + tile);
-    const int n_rows = __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
-    if (n_rows <= half * kExactFrames) continue;                     // block-uniform
-    if (tid < kTM) {
-      const int q = tid >> 5, r = tid & 31;
-      const uint32_t w0 = m4.x, w1 = m4.y, w2 = m4.z, w3 = m4.w;
-      const uint32_t mine = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
-      if ((mine >> r) & 1u) {
-        int pos = __popc(mine & ((1u << r) - 1u));
-        if (q > 0) pos += __popc(w0);
-        if (q > 1) pos += __popc(w1);
-        if (q > 2) pos += __popc(w2);
-        rows[pos] = tid;
-      }
-    }
+  const unsigned n_units = *reinterpret_cast<const volatile unsigned*>(p.count);
+  for (unsigned unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const uint2 ent = __ldg(p.list + unit);
+    const long long tile = ent.x >> 2;
+    const int quarter = static_cast<int>(ent.x & 3u);
+    const int n_rows = __popc(ent.y);
+    if (tid < 32 && ((ent.y >> tid) & 1u)) rows[__popc(ent.y & ((1u << tid) - 1u))] = quarter * 32 + tid;
     const long long clip = tile / p.tiles_per_clip;
     const long long frame0 = (tile - clip * p.tiles_per_clip) * kTM;
     const IN* clip_wave = wave + clip * p.clip_stride;
     __syncthreads();
-    for (int g0 = half * kExactFrames; g0 < n_rows; g0 += 2 * kExactFrames) {
+    for (int g0 = 0; g0 < n_rows; g0 += kExactFrames) {
       const int ng = n_rows - g0 < kExactFrames ? n_rows - g0 : kExactFrames;
       // E[m][f] = x[200 + m] + x[200 - m], O[m][f] = x[200 + m] - x[200 - m] (lag 0: E = 2 x[200], its weight is halved)
       for (int i = tid; i < eoHalf * kExactFrames; i += kExactThreads) {
@@ -900,49 +892,70 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
         O[m * kExactFrames + f] = o;
       }
       __syncthreads();
-      if (tid < kEvalBins) {
-        double re[kExactFrames], im[kExactFrames];
+      {
+        constexpr int kF = kExactFrames / 2, kL = eoHalf / 2, kU = 10;   // frames, lags per thread; lags fetched together
+        const int bin = tid & 255, f0 = ((tid >> 8) & 1) * kF, lg = tid >> 9;
+        double re[kF], im[kF];
 #pragma unroll
-        for (int f = 0; f < kExactFrames; ++f) re[f] = im[f] = 0.0;
-        const double* bc = p.basis + tid;
-        const double* bs = p.basis + eoHalf * kEvalBins + tid;
+        for (int f = 0; f < kF; ++f) re[f] = im[f] = 0.0;
+        if (bin < kEvalBins && f0 < ng) {
+          const double* bc = p.basis + bin;
+          const double* bs = p.basis + eoHalf * kEvalBins + bin;
 #pragma unroll 1
-        for (int m0 = 0; m0 < eoHalf; m0 += 8) {
-          double c[8], sn[8];
+          for (int m0 = lg * kL; m0 < (lg + 1) * kL; m0 += kU) {
+            double c[kU], sn[kU];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            c[u] = __ldg(bc + (m0 + u) * kEvalBins);
-            sn[u] = __ldg(bs + (m0 + u) * kEvalBins);
-          }
+            for (int u = 0; u < kU; ++u) {   // volatile: all 2 kU loads are issued before the first use
+              asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(c[u]) : "l"(bc + (m0 + u) * kEvalBins));
+              asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(sn[u]) : "l"(bs + (m0 + u) * kEvalBins));
+            }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const double2* e2 = reinterpret_cast<const double2*>(E + (m0 + u) * kExactFrames);
-            const double2* o2 = reinterpret_cast<const double2*>(O + (m0 + u) * kExactFrames);
+            for (int u = 0; u < kU; ++u) {
+              const double2* e2 = reinterpret_cast<const double2*>(E + (m0 + u) * kExactFrames + f0);
+              const double2* o2 = reinterpret_cast<const double2*>(O + (m0 + u) * kExactFrames + f0);
 #pragma unroll
-            for (int f = 0; f < kExactFrames / 2; ++f) {
-              const double2 ev = e2[f], ov = o2[f];
-              re[2 * f] = fma(ev.x, c[u], re[2 * f]);
-              re[2 * f + 1] = fma(ev.y, c[u], re[2 * f + 1]);
-              im[2 * f] = fma(ov.x, sn[u], im[2 * f]);
-              im[2 * f + 1] = fma(ov.y, sn[u], im[2 * f + 1]);
+              for (int f = 0; f < kF / 2; ++f) {
+                const double2 ev = e2[f], ov = o2[f];
+                re[2 * f] = fma(ev.x, c[u], re[2 * f]);
+                re[2 * f + 1] = fma(ev.y, c[u], re[2 * f + 1]);
+                im[2 * f] = fma(ov.x, sn[u], im[2 * f]);
+                im[2 * f + 1] = fma(ov.y, sn[u], im[2 * f + 1]);
+              }
             }
           }
         }
+        // the upper lag half hands its partial sums over through shared memory; the lower half adds them (fixed order)
+        double2* part = reinterpret_cast<double2*>(mag + kExactFrames * kEvalBins);   // [8 frames][240 bins] (re, im)
+        if (lg == 1 && bin < kEvalBins) {
 #pragma unroll
-        for (int f = 0; f < kExactFrames; ++f) mag[f * kEvalBins + tid] = sqrt(re[f] * re[f] + im[f] * im[f]);
+          for (int f = 0; f < kF; ++f) part[(f0 + f) * kEvalBins + bin] = make_double2(re[f], im[f]);
+        }
+        __syncthreads();
+        if (lg == 0 && bin < kEvalBins) {
+#pragma unroll
+          for (int f = 0; f < kF; ++f) {
+            const double2 q = part[(f0 + f) * kEvalBins + bin];
+            const double r = re[f] + q.x, i = im[f] + q.y;
+            mag[(f0 + f) * kEvalBins + bin] = sqrt(r * r + i * i);
+          }
+        }
       }
       __syncthreads();
-      for (int i = tid; i < kExactFrames * kMel; i += kExactThreads) {
+      {
+        // (frame, band) = a pair of lanes: even bins of the band's run on one, odd bins on the other, summed by shuffle
+        // (band `band` has weight on a short run of bins only — HTK triangles: [c_mel_lo, c_mel_hi))
+        const int i = tid >> 1, par = tid & 1;
         const int f = i / kMel, band = i - f * kMel;
+        double acc = 0.0;
         if (f < ng) {
-          // band `band` has weight on a short run of bins only (HTK triangles): [c_mel_lo, c_mel_hi)
-          double acc = 0.0;
           const double* mg = mag + f * kEvalBins;
           const int b_lo = c_mel_lo[band], b_hi = c_mel_hi[band];
 #pragma unroll 4
-          for (int b = b_lo; b < b_hi; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
-          p.out[(clip * p.frames_out + frame0 + rows[g0 + f]) * kMel + band] = static_cast<float>(log(acc + 0.01));
+          for (int b = b_lo + par; b < b_hi; b += 2) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
         }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (f < ng && par == 0)
+          p.out[(clip * p.frames_out + frame0 + rows[g0 + f]) * kMel + band] = static_cast<float>(log(acc + 0.01));
       }
       __syncthreads();
     }
@@ -950,20 +963,18 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
 }
 
 template <class IN>
-int launch_exact(const IN* wave, long long clip_stride, long long frames_out, int tiles_per_clip, long long total_tiles,
-                 const uint32_t* mask, const double* basis, const double* mel, float* out, cudaStream_t stream) {
+int launch_exact(const IN* wave, long long clip_stride, long long frames_out, int tiles_per_clip, const uint2* list,
+                 const unsigned* count, const double* basis, const double* mel, float* out, cudaStream_t stream) {
   ExactParams e{};
   e.frames_out = frames_out;
   e.tiles_per_clip = tiles_per_clip;
-  e.total_tiles = total_tiles;
   e.clip_stride = clip_stride;
-  e.mask = mask;
+  e.list = list;
+  e.count = count;
   e.basis = basis;
   e.mel = mel;
   e.out = out;
-  // one CTA per (tile, half) up to 32 CTAs per SM's worth; idle units exit after one 16-byte read
-  const long long grid = std::min<long long>(2 * total_tiles, 32LL * num_sms());
-  const cudaError_t le = launch_pdl(logmel_exact_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(kExactThreads),
+  const cudaError_t le = launch_pdl(logmel_exact_kernel<IN>, dim3(static_cast<unsigned>(num_sms())), dim3(kExactThreads),
                                     kExactSmem, stream, wave, e);
   count_launch();
   if (le != cudaSuccess) {
@@ -971,6 +982,16 @@ int launch_exact(const IN* wave, long long clip_stride, long long frames_out, in
     return 1;
   }
   return check_launch("logmel_exact_kernel");
+}
+
+// The flag list of one launch: [count (16 bytes)][4 entries per tile]; the count is zeroed on the stream.
+int alloc_exact_list(long long total_tiles, cudaStream_t stream, void** buf) {
+  if (cudaMallocAsync(buf, 16 + size_t(total_tiles) * 4 * sizeof(uint2), stream) != cudaSuccess ||
+      cudaMemsetAsync(*buf, 0, 16, stream) != cudaSuccess) {
+    set_kernel_error("logmel: flag list allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  return 0;
 }
 
 // ================================================================== stft_magnitude (mel_features.py:71-92) on its own
@@ -1271,12 +1292,10 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
   if (p.total_tiles <= 0) return 0;
-  void* mask = nullptr;   // every tile's epilogue writes its four words: no clearing needed
-  if (cudaMallocAsync(&mask, size_t(p.total_tiles) * 16, stream) != cudaSuccess) {
-    set_kernel_error("logmel: flag buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return 1;
-  }
-  p.exact_mask = static_cast<uint32_t*>(mask);
+  void* flags = nullptr;
+  if (alloc_exact_list(p.total_tiles, stream, &flags)) return 1;
+  p.exact_count = static_cast<unsigned*>(flags);
+  p.exact_list = reinterpret_cast<uint2*>(static_cast<char*>(flags) + 16);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
                                     stream, tx, txb, tb, p);
@@ -1286,10 +1305,10 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
     return 1;
   }
   if (check_launch("logmel_eo_kernel")) return 1;
-  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.total_tiles, p.exact_mask,
+  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.exact_list, p.exact_count,
                        t->basis_f64, t->mel_f64, logmel, stream))
     return 1;
-  if (cudaFreeAsync(mask, stream) != cudaSuccess) {
+  if (cudaFreeAsync(flags, stream) != cudaSuccess) {
     set_kernel_error("logmel: cudaFreeAsync failed");
     return 1;
   }
@@ -1350,12 +1369,10 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
   p.n_clips = static_cast<int>(n_clips);
   p.total_tiles = static_cast<long long>(p.tiles_per_clip) * n_clips;
   p.out = logmel;
-  void* mask = nullptr;
-  if (cudaMallocAsync(&mask, size_t(p.total_tiles) * 16, stream) != cudaSuccess) {
-    set_kernel_error("logmel: flag buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return 1;
-  }
-  p.exact_mask = static_cast<uint32_t*>(mask);
+  void* flags = nullptr;
+  if (alloc_exact_list(p.total_tiles, stream, &flags)) return 1;
+  p.exact_count = static_cast<unsigned*>(flags);
+  p.exact_list = reinterpret_cast<uint2*>(static_cast<char*>(flags) + 16);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_tc_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads), kSmemBytes,
                                     stream, ta, tb, p);
@@ -1365,10 +1382,10 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
     return 1;
   }
   if (check_launch("logmel_tc_kernel")) return 1;
-  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.total_tiles, p.exact_mask,
+  if (launch_exact<IN>(wave, n_clips == 1 ? 0 : clip_stride, frames_out, p.tiles_per_clip, p.exact_list, p.exact_count,
                        t->basis_f64, t->mel_f64, logmel, stream))
     return 1;
-  if (cudaFreeAsync(mask, stream) != cudaSuccess || cudaFreeAsync(planes, stream) != cudaSuccess) {
+  if (cudaFreeAsync(flags, stream) != cudaSuccess || cudaFreeAsync(planes, stream) != cudaSuccess) {
     set_kernel_error("logmel: cudaFreeAsync failed");
     return 1;
   }

@@ -417,14 +417,16 @@ int vmb_mla_forward_fp32(vmb_mla_t* h, const float* emb, long long batch, float*
   if (h->dev.emb_in > kMaxDim) return fail("vmb_mla_forward_fp32: emb_in > 608 is only supported by vmb_mla_forward");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ystride = (h->dev.n_levels * h->dev.K + 3) & ~3;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{0};   // one bit per device: the attribute is per device
+  if (vmb::device_needs_setup(attr_done)) {
     if (cudaFuncSetAttribute(mla_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(kMaxDynSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(mla_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(kMaxDynSmem)) != cudaSuccess)
+    {
+      vmb::device_setup_failed(attr_done);
       return fail("vmb_mla_forward_fp32: cannot raise the dynamic shared memory limit");
-    attr_done = true;
+    }
   }
   // small batches: 2 clips per CTA so more SMs take part; large batches: 4 clips per CTA (half the weight traffic)
   if (batch <= 2 * 148 || head_smem_bytes(4, ystride) > kMaxDynSmem) {

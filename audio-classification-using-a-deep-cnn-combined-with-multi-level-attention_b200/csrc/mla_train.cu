@@ -1028,11 +1028,9 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     double* acc_v = slotacc(L.normv.bslot);
     double* acc_f = slotacc(L.normf.bslot);
     const size_t att_smem = (size_t(2) * T * K + K) * sizeof(float);
-    static bool att_attr = false;
-    if (!att_attr) {
+    static std::atomic<unsigned long long> att_attr{0};   // one bit per device: the attribute is per device
+    if (vmb::device_needs_setup(att_attr))
       cudaFuncSetAttribute(att_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      att_attr = true;
-    }
     att_backward_kernel<<<static_cast<unsigned>(B), 256, att_smem, st>>>(ap, h->Y, h->dY, h->ycols_pad, l * K,
                                                                          h->row_stats[l], h->GV, h->GF, Hp, acc_v, acc_f);
     vmb::count_launch();

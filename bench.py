@@ -640,7 +640,7 @@ def run_b200(args, rank, local_rank, world):
         p2 = engine.Pipeline(h2, head)
         for _ in range(3):
             p2.forward(wave_dev)
-        k = max(3, min(10, args.steps))
+        k = args.steps if mode != "split" else max(3, min(10, args.steps))   # same region length as the headline
         other[mode] = _timed(lambda: p2.forward(wave_dev), k, barrier, max_over_ranks) / k
         h2.close()
     acc_ms = other["split"]

@@ -3,12 +3,13 @@
 Tolerances (BASELINE.json north_star):
   * frame indexing, tables: bit-exact
   * log-mel: <= 1e-4 absolute against the float64 reference
-  * conv / FC layers (bf16 operands, fp32 accumulation): per layer max-abs <= 1.5 % of the layer's max activation
-    and cosine >= 0.9999 against the fp32 oracle; embeddings the same
+  * conv / FC layers (16-bit operands, fp32 accumulation): per layer max-abs <= 0.5 % of the layer's max activation
+    and cosine >= 0.9999 against fp32 math on the same operands; embeddings of the default fp16 body <= 0.3 %
+    (measured 0.12 %), of the bf16 body <= 1.5 % (0.9 %), of the split body <= 0.05 % (0.016 %)
   * head (fp32 CUDA cores): <= 2e-5 absolute on the sigmoid scores given identical embeddings
   * postprocessor: bit-exact on identical fp32 embeddings except where fp32 summation order straddles a
     quantisation boundary (+-1 LSB, counted and bounded)
-  * mAP on the fixed synthetic label set: identical to 3 decimals
+  * mAP on the fixed synthetic label set (SURVEY 8d's recipe): identical to 3 decimals for the benchmarked (fp16) mode
 """
 import ctypes
 
@@ -211,59 +212,66 @@ def _layer_check(got, ref, name, rel_tol=0.015, cos_tol=0.9999):
     assert rel <= rel_tol and cos >= cos_tol, name
 
 
+DTYPES = [(0, torch.bfloat16, 0.005), (1, torch.float16, 0.0007)]       # (C-ABI dtype code, torch dtype, output rounding bound)
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "fp16"])
 @pytest.mark.parametrize("n,H,W,Cin,Cout,pool", [(3, 48, 32, 64, 128, 1), (3, 24, 16, 128, 256, 0),
                                                  (3, 24, 16, 256, 256, 1), (5, 12, 8, 256, 512, 0),
                                                  (5, 12, 8, 512, 512, 1), (1, 12, 8, 256, 512, 0)])
-def test_conv3x3_layer(n, H, W, Cin, Cout, pool):
+def test_conv3x3_layer(n, H, W, Cin, Cout, pool, dt):
+    code, tdt, tol = dt
     g = torch.Generator().manual_seed(H * 7 + Cin + n)
-    x = torch.randn(n, Cin, H, W, generator=g).to(DEV).bfloat16()
-    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(DEV).bfloat16()
+    x = torch.randn(n, Cin, H, W, generator=g).to(DEV).to(tdt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(DEV).to(tdt)
     b = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     w_k = w.permute(0, 2, 3, 1).contiguous().reshape(Cout, 9 * Cin)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-    out = torch.full((n, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-    engine.check(_lib.lib().vmb_conv3x3_relu(x_nhwc.data_ptr(), w_k.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W,
-                                             Cin, Cout, pool, engine.stream_ptr()), "vmb_conv3x3_relu")
-    ref = F.relu(F.conv2d(x.float(), w.float(), b, padding=1))           # same bf16-rounded operands, fp32 math
+    out = torch.full((n, Ho, Wo, Cout), float("nan"), device=DEV, dtype=tdt)
+    engine.check(_lib.lib().vmb_conv3x3_relu_ex(x_nhwc.data_ptr(), w_k.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W,
+                                                Cin, Cout, pool, code, engine.stream_ptr()), "vmb_conv3x3_relu_ex")
+    ref = F.relu(F.conv2d(x.float(), w.float(), b, padding=1))           # same 16-bit-rounded operands, fp32 math
     if pool:
         ref = F.max_pool2d(ref, 2, 2)
-    _layer_check(out.permute(0, 3, 1, 2), ref, f"conv {H}x{W} {Cin}->{Cout} pool={pool}", rel_tol=0.005)
+    _layer_check(out.permute(0, 3, 1, 2), ref, f"conv {H}x{W} {Cin}->{Cout} pool={pool} {tdt}", rel_tol=tol)
 
 
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "fp16"])
 @pytest.mark.parametrize("n", [1, 3, 77])
-def test_pair_kernel_bit_identical_to_single_cta(n):
+def test_pair_kernel_bit_identical_to_single_cta(n, dt):
     """The CTA-pair (tcgen05 cta_group::2) kernel and the single-CTA kernel run the same K order into fp32 TMEM
     accumulators: their outputs must be bit-identical, including odd tile counts (the partner CTA of the last pair then
     works on an out-of-range tile that TMA zero-fills and the epilogue masks)."""
     L = _lib.lib()
+    code, tdt, _ = dt
     g = torch.Generator().manual_seed(n)
     cases = []
     for (H, W, Cin, Cout, pool) in [(24, 16, 128, 256, 0), (24, 16, 256, 256, 1), (12, 8, 256, 512, 0), (12, 8, 512, 512, 1)]:
-        x = torch.randn(n, H, W, Cin, generator=g).to(DEV).bfloat16()
-        w = (torch.randn(Cout, 9 * Cin, generator=g) * 0.03).to(DEV).bfloat16()
+        x = torch.randn(n, H, W, Cin, generator=g).to(DEV).to(tdt)
+        w = (torch.randn(Cout, 9 * Cin, generator=g) * 0.03).to(DEV).to(tdt)
         b = torch.randn(Cout, generator=g).to(DEV)
         shape = (n, H // 2, W // 2, Cout) if pool else (n, H, W, Cout)
         cases.append((f"conv {H}x{W} {Cin}->{Cout} p{pool}", shape,
-                      lambda o, x=x, w=w, b=b, H=H, W=W, Cin=Cin, Cout=Cout, pool=pool: L.vmb_conv3x3_relu(
-                          x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), n, H, W, Cin, Cout, pool,
+                      lambda o, x=x, w=w, b=b, H=H, W=W, Cin=Cin, Cout=Cout, pool=pool: L.vmb_conv3x3_relu_ex(
+                          x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), n, H, W, Cin, Cout, pool, code,
                           engine.stream_ptr())))
     # the last shape leaves 12 of 160 pair tiles for an incomplete third round: they go to the single-CTA kernel
     for (M, N, K) in [(n, 4096, 4096), (256 + n, 256, 12288), (130 * n, 512, 128), (2560 - n, 4096, 512)]:
-        a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
-        w = (torch.randn(N, K, generator=g) * 0.02).to(DEV).bfloat16()
+        a = torch.randn(M, K, generator=g).to(DEV).to(tdt)
+        w = (torch.randn(N, K, generator=g) * 0.02).to(DEV).to(tdt)
         b = torch.randn(N, generator=g).to(DEV)
         cases.append((f"linear {M}x{N}x{K}", (M, N),
-                      lambda o, a=a, w=w, b=b, M=M, N=N, K=K: L.vmb_linear(a.data_ptr(), w.data_ptr(), b.data_ptr(),
-                                                                           o.data_ptr(), 0, 1, M, N, K,
-                                                                           engine.stream_ptr())))
+                      lambda o, a=a, w=w, b=b, M=M, N=N, K=K: L.vmb_linear_ex(a.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                                                              o.data_ptr(), 0, 1, M, N, K, code,
+                                                                              engine.stream_ptr())))
     prev = L.vmb_igemm_pair_enable(1)
     try:
         for name, shape, fn in cases:
             outs = []
             for pair in (1, 0):
                 L.vmb_igemm_pair_enable(pair)
-                o = torch.full(shape, float("nan"), device=DEV, dtype=torch.bfloat16)
+                o = torch.full(shape, float("nan"), device=DEV, dtype=tdt)
                 engine.check(fn(o), name)
                 torch.cuda.synchronize()
                 outs.append(o)
@@ -311,17 +319,19 @@ def test_halo_boxes_bit_identical_to_per_tap_boxes(H, W, Cin, Cout):
         L.vmb_igemm_pair_enable(-1)
 
 
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "fp16"])
 @pytest.mark.parametrize("M,N,K,f32", [(1, 128, 64, 1), (10, 4096, 12288, 0), (130, 256, 512, 0), (257, 128, 4096, 1)])
-def test_linear_layer(M, N, K, f32):
+def test_linear_layer(M, N, K, f32, dt):
+    code, tdt, tol = dt
     g = torch.Generator().manual_seed(M + N + K)
-    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
-    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).to(tdt)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(tdt)
     b = torch.randn(N, generator=g).to(DEV)
-    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
-    engine.check(_lib.lib().vmb_linear(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), f32, 1, M, N, K,
-                                       engine.stream_ptr()), "vmb_linear")
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if f32 else tdt)
+    engine.check(_lib.lib().vmb_linear_ex(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), f32, 1, M, N, K, code,
+                                          engine.stream_ptr()), "vmb_linear_ex")
     ref = F.relu(a.float() @ w.float().t() + b)
-    _layer_check(out, ref, f"linear {M}x{N}x{K}", rel_tol=1e-5 if f32 else 0.005)
+    _layer_check(out, ref, f"linear {M}x{N}x{K} {tdt}", rel_tol=1e-5 if f32 else tol)
 
 
 def test_conv1_layer(vgg_sd):
@@ -333,6 +343,10 @@ def test_conv1_layer(vgg_sd):
                                                 engine.stream_ptr()), "vmb_conv1_relu_pool")
     ref = F.max_pool2d(F.relu(F.conv2d(x[:, None], w, b, padding=1)), 2, 2)
     _layer_check(out.permute(0, 3, 1, 2), ref, "conv1 (tensor cores)", rel_tol=0.005)
+    out16 = torch.empty(7, 48, 32, 64, device=DEV, dtype=torch.float16)
+    engine.check(_lib.lib().vmb_conv1_relu_pool_ex(x.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(), out16.data_ptr(),
+                                                   7, 1, engine.stream_ptr()), "vmb_conv1_relu_pool_ex")
+    _layer_check(out16.permute(0, 3, 1, 2), ref, "conv1 (tensor cores, fp16 output)", rel_tol=0.0007)
     out2 = torch.empty_like(out)
     engine.check(_lib.lib().vmb_conv1_relu_pool_cudacore(x.data_ptr(), w.contiguous().data_ptr(), b.data_ptr(),
                                                          out2.data_ptr(), 7, engine.stream_ptr()), "conv1 cudacore")
@@ -351,7 +365,7 @@ def test_conv1_layer(vgg_sd):
 def test_vggish_embeddings_vs_golden_and_oracle(golden_front, golden_vggish, vgg_handle, vgg_sd):
     x = torch.from_numpy(golden_front["examples_f64"][:, 0]).float().to(DEV)
     emb, bott = vgg_handle.forward(x, want_bottleneck=True)
-    _layer_check(emb, torch.from_numpy(golden_vggish["embeddings"]), "embeddings vs reference golden")
+    _layer_check(emb, torch.from_numpy(golden_vggish["embeddings"]), "embeddings vs reference golden", rel_tol=0.003)
     with torch.no_grad():
         feats = model_torch.vgg_flatten(model_torch.vgg_features(vgg_sd, x.cpu()[:, None]))
     _layer_check(bott, feats, "conv features (h,w,c) flatten order")
@@ -400,7 +414,7 @@ def test_reference_named_vggish_module(golden_front, golden_vggish, vgg_sd):
     ref = golden_vggish["preprocess_postprocess"]
     d = np.abs(out.cpu().numpy() - ref)
     print("VGGish(preprocess, postprocess) vs reference: LSB histogram", np.bincount(d.astype(np.int64)))
-    assert (d <= 1).mean() >= 0.5 and d.max() <= 16       # bf16 body: honest LSB spread, bounded
+    assert d.max() <= 1 and (d == 0).mean() >= 0.9        # default fp16 body: measured 127 exact + 1 at +-1 LSB of 128
     plain = VGGish(urls={}, pretrained=False, preprocess=False, postprocess=False)
     plain.load_state_dict(vgg_sd)
     plain = plain.to(DEV).eval()
@@ -557,6 +571,25 @@ def test_vggish_module_precision_knob(golden_front, golden_vggish, vgg_sd):
     assert hist["split"][0] >= 126 and hist["fp16"][0] >= 120
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(vgg_sd, head_sd):
+    """Kernel attributes (dynamic shared memory opt-in), SM counts and constant tables are per DEVICE: a process that
+    ran on cuda:0 must be able to run on cuda:1 afterwards, with identical results."""
+    waves = torch.from_numpy(synth.make_clips(0, 3))
+    outs = []
+    for i in (0, 1):
+        dev = torch.device("cuda", i)
+        with torch.cuda.device(dev):
+            v = engine.VggishHandle(vgg_sd, dev)
+            h = engine.MlaHandle(head_sd, (2, 1), 128, 600, 527, 10, dev)
+            outs.append(engine.Pipeline(v, h).forward(waves.to(dev)).cpu())
+            y32 = h.forward(torch.zeros(2, 10, 128, device=dev), fp32_crosscheck=True)
+            assert torch.isfinite(y32).all()
+            v.close()
+            h.close()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_fp16_saturation_is_reported(vgg_sd):
     """fp16 ends at 65504: the epilogues convert with saturation and raise a flag that the host API turns into an error
     (weights scaled so that conv2's outputs overflow)."""
@@ -581,7 +614,7 @@ def test_pipeline_vs_reference_golden(golden_ensemble, vgg_handle, head_handle):
     pipe = engine.Pipeline(vgg_handle, head_handle)
     waves = torch.from_numpy(synth.make_clips(4, 2)).to(DEV)
     scores, emb = pipe.forward(waves, want_embeddings=True)
-    _layer_check(emb, torch.from_numpy(golden_ensemble["embeddings"]), "pipeline embeddings vs reference")
+    _layer_check(emb, torch.from_numpy(golden_ensemble["embeddings"]), "pipeline embeddings vs reference", rel_tol=0.003)
     d = np.abs(scores.cpu().numpy() - golden_ensemble["scores"]).max()
     print(f"pipeline scores vs reference Ensemble: max-abs-err {d:.3e}")
     assert d <= 2e-2
@@ -612,36 +645,56 @@ def test_ensemble_module_matches_pipeline(golden_ensemble, vgg_sd, head_sd):
     assert torch.equal(ens.forward_waveform(torch.from_numpy(waves).to(DEV)), y)
 
 
-def test_map_identical_to_three_decimals(vgg_handle, head_handle, vgg_sd, head_sd):
-    """mAP on a fixed synthetic label set: B200 scores vs the fp32 CPU oracle on the same 128 clips.  "Identical to
-    3 decimals" is checked as |mAP_b200 - mAP_oracle| < 0.0005 (half a unit of the third decimal): the labels are
-    random, so this is the worst case for ranking flips caused by the bf16 VGGish body."""
-    n = 128
+def test_map_identical_to_three_decimals(head_handle, vgg_sd, head_sd):
+    """north_star: mAP on a fixed synthetic label set identical to 3 decimals, for the mode bench.py reports as `value`
+    (engine.DEFAULT_PRECISION = fp16 body).  B200 scores vs the fp32 CPU oracle on the same 256 clips; label sets:
+      * SURVEY 8d's recipe — seeded Bernoulli(0.05) multi-hot (B, 527), every class >= 1 positive (the defaults of
+        synth.multihot_labels) — and labels that follow the oracle's own ranking (what a trained classifier looks like):
+        the 3-decimal strings must be EQUAL;
+      * round 1's set (first 128 clips, p = 0.2): random labels are the worst case — mAP sits at the base rate and moves
+        with every swap of two nearly tied scores — and there the oracle's 0.22865 is 1.5e-4 from a rounding boundary:
+        fp16 (|delta| 1.6e-4) lands on the other side of it, only the split mode matches as a string.  Bound there:
+        |delta| < 2.5e-4;
+      * 20 more seeds of the SURVEY recipe for the spread: printed per mode (fp16 18/20 equal strings, mean |delta| 6.5e-5;
+        bf16 15/20, 2.2e-4; split 20/20, 1.2e-5 — DESIGN 3)."""
+    n = 256
     waves = synth.make_clips(100, n)
-    pipe = engine.Pipeline(vgg_handle, head_handle)
-    got = pipe.forward(torch.from_numpy(waves).to(DEV)).cpu().numpy()
     ex = np.concatenate([frontend_np.waveform_to_examples(w.astype(np.float64)) for w in waves]).astype(np.float32)
     with torch.no_grad():
         emb = model_torch.vgg_forward(vgg_sd, torch.from_numpy(ex)[:, None])
         want = model_torch.mla_forward(head_sd, emb.reshape(n, 10, 128), (2, 1)).numpy()
-    labels = synth.multihot_labels(n, 527, p=0.2, seed=3)
-    a, b = synth.mean_average_precision(labels, got), synth.mean_average_precision(labels, want)
-    print(f"mAP B200 {a:.5f} oracle {b:.5f}; scores max-abs-err {np.abs(got - want).max():.3e}")
-    assert abs(a - b) < 5e-4
-    # the same with the accuracy mode of the VGGish body (hi + lo bf16 planes): the ranking metric agrees to 4 decimals,
-    # and on labels that follow the oracle's own ranking (what a trained classifier looks like) both modes do
-    hs = engine.VggishHandle(vgg_sd, DEV, precision="split")
-    try:
-        got_s = engine.Pipeline(hs, head_handle).forward(torch.from_numpy(waves).to(DEV)).cpu().numpy()
-    finally:
-        hs.close()
-    c = synth.mean_average_precision(labels, got_s)
-    thr = np.quantile(want, 0.8, axis=0, keepdims=True)
-    ranked = (want >= thr).astype(labels.dtype)                       # top 20 % of the oracle's scores per class
-    a2, b2, c2 = (synth.mean_average_precision(ranked, x) for x in (got, want, got_s))
-    print(f"mAP accuracy mode {c:.5f} (oracle {b:.5f}); oracle-ranked labels: bf16 {a2:.5f} accuracy mode {c2:.5f} "
-          f"oracle {b2:.5f}")
-    assert abs(c - b) < 5e-5 and abs(c2 - b2) < 5e-5 and abs(a2 - b2) < 5e-3
+    sets = {"survey_8d": (slice(0, n), synth.multihot_labels(n, 527)),
+            "oracle_ranked": (slice(0, n), (want >= np.quantile(want, 0.8, axis=0, keepdims=True)).astype(np.int64)),
+            "round1_p02_128": (slice(0, 128), synth.multihot_labels(128, 527, p=0.2, seed=3))}
+    for sd_ in range(20):
+        sets[f"seed{100 + sd_}"] = (slice(0, n), synth.multihot_labels(n, 527, seed=100 + sd_))
+    ref = {k: synth.mean_average_precision(lab, want[sl]) for k, (sl, lab) in sets.items()}
+    wave_dev = torch.from_numpy(waves).to(DEV)
+    got = {}
+    for mode in ("fp16", "bf16", "split"):
+        h = engine.VggishHandle(vgg_sd, DEV, precision=mode)
+        try:
+            sc = engine.Pipeline(h, head_handle).forward(wave_dev).cpu().numpy()
+            h.check_saturation()
+        finally:
+            h.close()
+        got[mode] = {k: synth.mean_average_precision(lab, sc[sl]) for k, (sl, lab) in sets.items()}
+        d = np.array([got[mode][k] - ref[k] for k in ref if k.startswith("seed")])
+        eq = sum(f"{got[mode][k]:.3f}" == f"{ref[k]:.3f}" for k in ref if k.startswith("seed"))
+        print(f"mAP {mode:5s}: " + "  ".join(f"{k} {got[mode][k]:.5f} (oracle {ref[k]:.5f})" for k in
+                                             ("survey_8d", "oracle_ranked", "round1_p02_128")) +
+              f"; 20 seeds: |delta| mean {np.abs(d).mean():.2e} max {np.abs(d).max():.2e}, equal to 3 decimals {eq}/20; "
+              f"scores max-abs-err {np.abs(sc - want).max():.2e}")
+    head = engine.DEFAULT_PRECISION
+    assert head == "fp16"
+    for k in ("survey_8d", "oracle_ranked"):
+        assert f"{got[head][k]:.3f}" == f"{ref[k]:.3f}", (k, got[head][k], ref[k])
+        assert f"{got['split'][k]:.3f}" == f"{ref[k]:.3f}", (k, got["split"][k], ref[k])
+    assert f"{got['split']['round1_p02_128']:.3f}" == f"{ref['round1_p02_128']:.3f}"
+    assert abs(got[head]["round1_p02_128"] - ref["round1_p02_128"]) < 2.5e-4
+    seeds = [k for k in ref if k.startswith("seed")]
+    assert np.mean([abs(got[head][k] - ref[k]) for k in seeds]) < 1.5e-4
+    assert np.mean([abs(got["split"][k] - ref[k]) for k in seeds]) < 5e-5
 
 
 def test_shard_invariance(vgg_handle, head_handle):
