@@ -148,7 +148,7 @@ struct LogmelParams {
   int n_clips;
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
-  uint2* exact_list;        // flagged 32-frame groups: (tile * 4 + quarter, bit r = frame 32 quarter + r must be redone)
+  uint32_t* exact_list;     // flagged frames (tile * 128 + row in the tile) to be redone in float64, see kExactRatio
   unsigned* exact_count;    // entries in exact_list (zeroed by the host before the launch)
 };
 
@@ -358,8 +358,14 @@ logmel_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else {
         while (w.e <= kMel) emit_band(w, row_out, valid);   // flush the remaining bands (up to band 63)
         const float lim = kExactRatioPlanes * (w.mn + kLogOffset);
-        const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
-        if (lane == 0 && bad) p.exact_list[atomicAdd(p.exact_count, 1u)] = make_uint2(static_cast<uint32_t>(tile * 4 + q), bad);
+        const bool mine = valid && w.e2 > lim * lim;
+        const uint32_t bad = __ballot_sync(0xffffffffu, mine);
+        if (bad) {   // one atomic per warp reserves the slots, every flagged frame writes its own entry
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(p.exact_count, static_cast<unsigned>(__popc(bad)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (mine) p.exact_list[base + __popc(bad & ((1u << lane) - 1u))] = static_cast<uint32_t>(tile * kTM + row);
+        }
       }
     }
   }
@@ -505,8 +511,8 @@ struct LogmelEoParams {
   int tiles_per_clip;       // ceil(frames_out / 128)
   long long total_tiles;    // n_clips * tiles_per_clip
   float* out;               // [n_clips][frames_out][64]
-  uint2* exact_list;        // flagged 32-frame groups for logmel_exact_kernel (see kExactRatio): (tile * 4 + quarter,
-  unsigned* exact_count;    // bit r = frame 32 quarter + r of the tile); entry count, zeroed by the host before the launch
+  uint32_t* exact_list;     // flagged frames (tile * 128 + row in the tile) for logmel_exact_kernel, see kExactRatio
+  unsigned* exact_count;    // entry count, zeroed by the host before the launch
 };
 
 // The band walk of the epilogue with everything about the mel layout resolved at compile time.  kBandOfBin is the
@@ -809,8 +815,14 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         flush_static<kBandOfBin[kEvalBins - 1]>(w, row_out, valid);   // the remaining bands (up to band 63)
         const float lim = kExactRatio * (w.mn + kLogOffset);
-        const uint32_t bad = __ballot_sync(0xffffffffu, valid && w.e2 > lim * lim);
-        if (lane == 0 && bad) p.exact_list[atomicAdd(p.exact_count, 1u)] = make_uint2(static_cast<uint32_t>(tile * 4 + q), bad);
+        const bool mine = valid && w.e2 > lim * lim;
+        const uint32_t bad = __ballot_sync(0xffffffffu, mine);
+        if (bad) {   // one atomic per warp reserves the slots, every flagged frame writes its own entry
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(p.exact_count, static_cast<unsigned>(__popc(bad)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (mine) p.exact_list[base + __popc(bad & ((1u << lane) - 1u))] = static_cast<uint32_t>(tile * kTM + row);
+        }
       }
     }
   }
@@ -825,22 +837,26 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 // ================================================================== float64 path for the flagged frames
 // The same centred even / odd DFT in float64 on the CUDA cores.  The epilogues of the tensor-core kernels append every
-// 32-frame group that holds flagged frames to a list (one atomicAdd per group; the order of the list varies from run to
-// run, the results do not: every frame is computed on its own).  One CTA per SM walks the list round-robin, 8 flagged
-// frames per pass: E, O in shared memory ([lag][frame]: the frames of a lag are 64-byte broadcast reads), thread =
-// (DFT bin, 4 of the 8 frames, half of the lags), basis and mel matrix as float64 tables in global memory (768 KB +
-// 120 KB, L2-resident).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the float64 reference
-// rounded once.  An empty list costs one 4-byte read per CTA.
-constexpr int kExactFrames = 8;      // frames per pass
-constexpr int kExactThreads = 1024;  // thread = (bin, 4 of the 8 frames, half of the 200 lags): the pass is bound by the
-                                     // latency of its basis loads, so the lag loop is split and deeply prefetched
-constexpr int kExactSmem = 2 * eoHalf * kExactFrames * 8 + 3 * kExactFrames * kEvalBins * 8 + 160 * 4;   // E, O | mag | partial (re, im) | rows
+// flagged frame to a list (one atomicAdd per warp; the order of the list varies from run to run, the results do not:
+// every frame is computed on its own).  One CTA per SM takes the list 16 frames at a time: E, O of the 16 frames in shared
+// memory ([lag][frame]: the frames of a lag are broadcast reads), thread = (DFT bin, 4 of the 16 frames).  The float64
+// basis (768 KB, L2-resident) is streamed through a three-stage shared-memory ring by 1-D bulk copies, 10 lags per
+// stage — register-staged loads left the loop bound by one L2 round trip per pair of lags (33 us per pass; the copies
+// take it to the L2 -> SM bandwidth).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
+// float64 reference rounded once.  An empty list costs one 4-byte read per CTA.
+constexpr int kExactFrames = 16;     // frames per pass: every pass streams the whole basis, so with all SMs busy the
+                                     // aggregate L2 traffic (passes x 768 KB), not the arithmetic, sets the time
+constexpr int kExactThreads = 1024;  // thread = (bin [256, 240 used], four of the 16 frames)
+constexpr int kExactLags = 10;       // lags per basis stage
+constexpr int kExactStages = 3;      // two chunks in flight while one is being consumed
+constexpr int kExactStageBytes = 2 * kExactLags * kEvalBins * 8;   // cos rows | sin rows: 38 400 B
+constexpr int kExactSmem = kExactStages * kExactStageBytes + 2 * eoHalf * kExactFrames * 8 + kExactFrames * kEvalBins * 8 + kExactFrames * 8;
 
 struct ExactParams {
   long long frames_out;
   int tiles_per_clip;
   long long clip_stride;        // samples
-  const uint2* list;            // (tile * 4 + quarter, frame mask) entries
+  const uint32_t* list;         // flagged frames: tile * 128 + row
   const unsigned* count;
   const double* basis;          // [2: cos, sin][200 lags][240 bins]
   const double* mel;            // [240 bins][64 bands]
@@ -857,113 +873,120 @@ __device__ __forceinline__ double load_sample_f64<int16_t>(const int16_t* p) { r
 template <class IN>
 __global__ void __launch_bounds__(kExactThreads)
 logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
-  extern __shared__ __align__(16) uint8_t exact_smem[];
-  double* E = reinterpret_cast<double*>(exact_smem);                 // [200][8]
-  double* O = E + eoHalf * kExactFrames;                             // [200][8]
-  double* mag = O + eoHalf * kExactFrames;                           // [8][240]
-  int* rows = reinterpret_cast<int*>(mag + 3 * kExactFrames * kEvalBins); // [128] flagged frames of the tile
+  extern __shared__ __align__(128) uint8_t exact_smem[];
+  double* ring = reinterpret_cast<double*>(exact_smem);                               // [3][cos 10 x 240 | sin 10 x 240]
+  double* E = reinterpret_cast<double*>(exact_smem + kExactStages * kExactStageBytes);  // [200][16]
+  double* O = E + eoHalf * kExactFrames;                                                // [200][16]
+  double* mag = O + eoHalf * kExactFrames;                                              // [16][240]
+  long long* frame_of = reinterpret_cast<long long*>(mag + kExactFrames * kEvalBins);   // [16] clip * frames_out + frame
+  __shared__ uint64_t full_bar[kExactStages];
   const int tid = threadIdx.x;
   pdl_launch_dependents();
-  pdl_wait();   // the masks (and the rows this kernel overwrites) come from the tensor-core kernel before it
-  const unsigned n_units = *reinterpret_cast<const volatile unsigned*>(p.count);
-  for (unsigned unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const uint2 ent = __ldg(p.list + unit);
-    const long long tile = ent.x >> 2;
-    const int quarter = static_cast<int>(ent.x & 3u);
-    const int n_rows = __popc(ent.y);
-    if (tid < 32 && ((ent.y >> tid) & 1u)) rows[__popc(ent.y & ((1u << tid) - 1u))] = quarter * 32 + tid;
-    const long long clip = tile / p.tiles_per_clip;
-    const long long frame0 = (tile - clip * p.tiles_per_clip) * kTM;
-    const IN* clip_wave = wave + clip * p.clip_stride;
-    __syncthreads();
-    for (int g0 = 0; g0 < n_rows; g0 += kExactFrames) {
-      const int ng = n_rows - g0 < kExactFrames ? n_rows - g0 : kExactFrames;
-      // E[m][f] = x[200 + m] + x[200 - m], O[m][f] = x[200 + m] - x[200 - m] (lag 0: E = 2 x[200], its weight is halved)
-      for (int i = tid; i < eoHalf * kExactFrames; i += kExactThreads) {
-        const int f = i / eoHalf, m = i - f * eoHalf;
-        double e = 0.0, o = 0.0;
-        if (f < ng) {
-          const IN* x = clip_wave + (frame0 + rows[g0 + f]) * kHop + eoHalf;
-          const double xp = load_sample_f64<IN>(x + m), xm = load_sample_f64<IN>(x - m);
-          e = xp + xm;
-          o = xp - xm;
-        }
-        E[m * kExactFrames + f] = e;
-        O[m * kExactFrames + f] = o;
-      }
-      __syncthreads();
-      {
-        constexpr int kF = kExactFrames / 2, kL = eoHalf / 2, kU = 10;   // frames, lags per thread; lags fetched together
-        const int bin = tid & 255, f0 = ((tid >> 8) & 1) * kF, lg = tid >> 9;
-        double re[kF], im[kF];
-#pragma unroll
-        for (int f = 0; f < kF; ++f) re[f] = im[f] = 0.0;
-        if (bin < kEvalBins && f0 < ng) {
-          const double* bc = p.basis + bin;
-          const double* bs = p.basis + eoHalf * kEvalBins + bin;
-#pragma unroll 1
-          for (int m0 = lg * kL; m0 < (lg + 1) * kL; m0 += kU) {
-            double c[kU], sn[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {   // volatile: all 2 kU loads are issued before the first use
-              asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(c[u]) : "l"(bc + (m0 + u) * kEvalBins));
-              asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(sn[u]) : "l"(bs + (m0 + u) * kEvalBins));
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const double2* e2 = reinterpret_cast<const double2*>(E + (m0 + u) * kExactFrames + f0);
-              const double2* o2 = reinterpret_cast<const double2*>(O + (m0 + u) * kExactFrames + f0);
-#pragma unroll
-              for (int f = 0; f < kF / 2; ++f) {
-                const double2 ev = e2[f], ov = o2[f];
-                re[2 * f] = fma(ev.x, c[u], re[2 * f]);
-                re[2 * f + 1] = fma(ev.y, c[u], re[2 * f + 1]);
-                im[2 * f] = fma(ov.x, sn[u], im[2 * f]);
-                im[2 * f + 1] = fma(ov.y, sn[u], im[2 * f + 1]);
-              }
-            }
-          }
-        }
-        // the upper lag half hands its partial sums over through shared memory; the lower half adds them (fixed order)
-        double2* part = reinterpret_cast<double2*>(mag + kExactFrames * kEvalBins);   // [8 frames][240 bins] (re, im)
-        if (lg == 1 && bin < kEvalBins) {
-#pragma unroll
-          for (int f = 0; f < kF; ++f) part[(f0 + f) * kEvalBins + bin] = make_double2(re[f], im[f]);
-        }
-        __syncthreads();
-        if (lg == 0 && bin < kEvalBins) {
-#pragma unroll
-          for (int f = 0; f < kF; ++f) {
-            const double2 q = part[(f0 + f) * kEvalBins + bin];
-            const double r = re[f] + q.x, i = im[f] + q.y;
-            mag[(f0 + f) * kEvalBins + bin] = sqrt(r * r + i * i);
-          }
-        }
-      }
-      __syncthreads();
-      {
-        // (frame, band) = a pair of lanes: even bins of the band's run on one, odd bins on the other, summed by shuffle
-        // (band `band` has weight on a short run of bins only — HTK triangles: [c_mel_lo, c_mel_hi))
-        const int i = tid >> 1, par = tid & 1;
-        const int f = i / kMel, band = i - f * kMel;
-        double acc = 0.0;
-        if (f < ng) {
-          const double* mg = mag + f * kEvalBins;
-          const int b_lo = c_mel_lo[band], b_hi = c_mel_hi[band];
-#pragma unroll 4
-          for (int b = b_lo + par; b < b_hi; b += 2) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (f < ng && par == 0)
-          p.out[(clip * p.frames_out + frame0 + rows[g0 + f]) * kMel + band] = static_cast<float>(log(acc + 0.01));
-      }
-      __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kExactStages; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_wait();   // the list (and the rows this kernel overwrites) come from the tensor-core kernel before it
+  const unsigned n_frames = *reinterpret_cast<const volatile unsigned*>(p.count);
+  constexpr int kChunks = eoHalf / kExactLags;   // 20
+  uint32_t fills = 0;                            // bulk copies issued so far (thread 0), chunks consumed so far (all)
+  uint32_t used = 0;
+  auto issue = [&](int chunk) {                  // thread 0 only
+    const uint32_t s = fills % kExactStages;
+    double* dst = ring + s * (kExactStageBytes / 8);
+    mbar_expect_tx(&full_bar[s], kExactStageBytes);
+    bulk_load_1d(dst, p.basis + chunk * kExactLags * kEvalBins, kExactStageBytes / 2, &full_bar[s]);
+    bulk_load_1d(dst + kExactLags * kEvalBins, p.basis + (eoHalf + chunk * kExactLags) * kEvalBins, kExactStageBytes / 2,
+                 &full_bar[s]);
+    ++fills;
+  };
+  for (unsigned g0 = blockIdx.x * kExactFrames; g0 < n_frames; g0 += gridDim.x * kExactFrames) {
+    const int ng = n_frames - g0 < kExactFrames ? static_cast<int>(n_frames - g0) : kExactFrames;
+    if (tid == 0) {
+      for (int c = 0; c < kExactStages - 1; ++c) issue(c);
     }
+    if (tid < kExactFrames) {
+      long long fo = -1;
+      if (tid < ng) {
+        const uint32_t id = __ldg(p.list + g0 + tid);
+        const long long tile = id / kTM;
+        const long long clip = tile / p.tiles_per_clip;
+        fo = clip * p.frames_out + (tile - clip * p.tiles_per_clip) * kTM + (id % kTM);
+      }
+      frame_of[tid] = fo;
+    }
+    __syncthreads();
+    // E[m][f] = x[200 + m] + x[200 - m], O[m][f] = x[200 + m] - x[200 - m] (lag 0: E = 2 x[200], its weight is halved)
+    for (int i = tid; i < eoHalf * kExactFrames; i += kExactThreads) {
+      const int f = i / eoHalf, m = i - f * eoHalf;
+      double e = 0.0, o = 0.0;
+      const long long fo = frame_of[f];
+      if (fo >= 0) {
+        const long long clip = fo / p.frames_out;
+        const IN* x = wave + clip * p.clip_stride + (fo - clip * p.frames_out) * kHop + eoHalf;
+        const double xp = load_sample_f64<IN>(x + m), xm = load_sample_f64<IN>(x - m);
+        e = xp + xm;
+        o = xp - xm;
+      }
+      E[m * kExactFrames + f] = e;
+      O[m * kExactFrames + f] = o;
+    }
+    __syncthreads();
+    const int bin = tid & 255, f0 = (tid >> 8) * 4;
+    const int bsafe = bin < kEvalBins ? bin : 0;
+    double re[4] = {0.0, 0.0, 0.0, 0.0}, im[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int ch = 0; ch < kChunks; ++ch, ++used) {
+      // the stage of chunk ch - 1 was released by the barrier at the end of the previous iteration: refill it
+      if (tid == 0 && ch + kExactStages - 1 < kChunks) issue(ch + kExactStages - 1);
+      const uint32_t s = used % kExactStages;
+      mbar_wait(&full_bar[s], (used / kExactStages) & 1);
+      const double* cs = ring + s * (kExactStageBytes / 8) + bsafe;
+      const double* sn = cs + kExactLags * kEvalBins;
+      const double* e = E + ch * kExactLags * kExactFrames + f0;
+      const double* o = O + ch * kExactLags * kExactFrames + f0;
+#pragma unroll
+      for (int u = 0; u < kExactLags; ++u) {
+        const double c = cs[u * kEvalBins], sv = sn[u * kEvalBins];
+        const double2 e0 = *reinterpret_cast<const double2*>(e + u * kExactFrames);
+        const double2 e1 = *reinterpret_cast<const double2*>(e + u * kExactFrames + 2);
+        const double2 o0 = *reinterpret_cast<const double2*>(o + u * kExactFrames);
+        const double2 o1 = *reinterpret_cast<const double2*>(o + u * kExactFrames + 2);
+        re[0] = fma(e0.x, c, re[0]);
+        re[1] = fma(e0.y, c, re[1]);
+        re[2] = fma(e1.x, c, re[2]);
+        re[3] = fma(e1.y, c, re[3]);
+        im[0] = fma(o0.x, sv, im[0]);
+        im[1] = fma(o0.y, sv, im[1]);
+        im[2] = fma(o1.x, sv, im[2]);
+        im[3] = fma(o1.y, sv, im[3]);
+      }
+      __syncthreads();                                   // every thread is done with stage s
+    }
+    if (bin < kEvalBins) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mag[(f0 + j) * kEvalBins + bin] = sqrt(re[j] * re[j] + im[j] * im[j]);
+    }
+    __syncthreads();
+    {
+      // thread = (frame, band); band `band` has weight on a short run of bins only (HTK triangles): [c_mel_lo, c_mel_hi)
+      const int f = tid / kMel, band = tid - f * kMel;
+      const long long fo = frame_of[f];
+      if (fo >= 0) {
+        double acc = 0.0;
+        const double* mg = mag + f * kEvalBins;
+        const int b_lo = c_mel_lo[band], b_hi = c_mel_hi[band];
+#pragma unroll 4
+        for (int b = b_lo; b < b_hi; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
+        p.out[fo * kMel + band] = static_cast<float>(log(acc + 0.01));
+      }
+    }
+    __syncthreads();
   }
 }
 
 template <class IN>
-int launch_exact(const IN* wave, long long clip_stride, long long frames_out, int tiles_per_clip, const uint2* list,
+int launch_exact(const IN* wave, long long clip_stride, long long frames_out, int tiles_per_clip, const uint32_t* list,
                  const unsigned* count, const double* basis, const double* mel, float* out, cudaStream_t stream) {
   ExactParams e{};
   e.frames_out = frames_out;
@@ -984,9 +1007,9 @@ int launch_exact(const IN* wave, long long clip_stride, long long frames_out, in
   return check_launch("logmel_exact_kernel");
 }
 
-// The flag list of one launch: [count (16 bytes)][4 entries per tile]; the count is zeroed on the stream.
+// The flag list of one launch: [count (16 bytes)][one entry per frame]; the count is zeroed on the stream.
 int alloc_exact_list(long long total_tiles, cudaStream_t stream, void** buf) {
-  if (cudaMallocAsync(buf, 16 + size_t(total_tiles) * 4 * sizeof(uint2), stream) != cudaSuccess ||
+  if (cudaMallocAsync(buf, 16 + size_t(total_tiles) * kTM * sizeof(uint32_t), stream) != cudaSuccess ||
       cudaMemsetAsync(*buf, 0, 16, stream) != cudaSuccess) {
     set_kernel_error("logmel: flag list allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 1;
@@ -1295,7 +1318,7 @@ int logmel_eo_forward(TcTables* t, const IN* wave, long long n_clips, long long 
   void* flags = nullptr;
   if (alloc_exact_list(p.total_tiles, stream, &flags)) return 1;
   p.exact_count = static_cast<unsigned*>(flags);
-  p.exact_list = reinterpret_cast<uint2*>(static_cast<char*>(flags) + 16);
+  p.exact_list = reinterpret_cast<uint32_t*>(static_cast<char*>(flags) + 16);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_eo_kernel<IN>, dim3(static_cast<unsigned>(grid)), dim3(eoThreads), eoSmemBytes,
                                     stream, tx, txb, tb, p);
@@ -1372,7 +1395,7 @@ int logmel_tc_forward_impl(const IN* wave, long long n_clips, long long samples_
   void* flags = nullptr;
   if (alloc_exact_list(p.total_tiles, stream, &flags)) return 1;
   p.exact_count = static_cast<unsigned*>(flags);
-  p.exact_list = reinterpret_cast<uint2*>(static_cast<char*>(flags) + 16);
+  p.exact_list = reinterpret_cast<uint32_t*>(static_cast<char*>(flags) + 16);
   const long long grid = std::min<long long>(p.total_tiles, num_sms());
   const cudaError_t le = launch_pdl(logmel_tc_kernel, dim3(static_cast<unsigned>(grid)), dim3(kThreads), kSmemBytes,
                                     stream, ta, tb, p);

@@ -117,6 +117,15 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` (a multiple of 16, both addresses 16-byte aligned) land in
+// shared memory asynchronously and are credited to the mbarrier like a tensor load.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // TMA store of a shared-memory box (bulk async-group completion): whole 128-byte lines reach L2 without going through
 // the LSU.  The issuing thread commits a group and later waits for the group's reads of shared memory (wait_read<N>:
 // at most N groups still reading) before the staging buffer is rewritten.

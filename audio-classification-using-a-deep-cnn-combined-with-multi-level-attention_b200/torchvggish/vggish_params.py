@@ -1,7 +1,8 @@
 """Drop-in for torchvggish/vggish_params.py: the VGGish constants, same names and values
 (reference vggish_params.py:22-53).  The CUDA front end hard-codes the derived numbers (400-sample window,
 160-sample hop, 512-point DFT, 64 mel bands 125-7500 Hz, log offset 0.01, 96-frame examples) and
-tests/test_constants.py checks that they agree with this file.
+tests/test_abi_host.py::test_constants_match_reference_values checks this file against the reference's values and
+tests/test_abi_host.py::test_frame_arithmetic_matches_reference the derived frame counts.
 """
 
 # architecture

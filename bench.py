@@ -632,7 +632,7 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- the same device-resident step in the other two modes of the VGGish body: bf16 (the same kernels on 8 mantissa
     # bits) and split (hi + lo bf16 planes, 3x the tensor work: the mode whose uint8 output matches the fp32 reference)
-    other = {}
+    other, other_stages = {}, {}
     for mode in ("bf16", "fp16", "split"):
         if mode == args.precision:
             continue
@@ -641,7 +641,13 @@ def run_b200(args, rank, local_rank, world):
         for _ in range(3):
             p2.forward(wave_dev)
         k = args.steps if mode != "split" else max(3, min(10, args.steps))   # same region length as the headline
+        L.vmb_profile_collect(None, None, 1)
+        L.vmb_profile_enable(1)
         other[mode] = _timed(lambda: p2.forward(wave_dev), k, barrier, max_over_ranks) / k
+        L.vmb_profile_enable(0)
+        sm, sc = np.zeros(len(STAGES), dtype=np.float64), np.zeros(len(STAGES), dtype=np.int64)
+        L.vmb_profile_collect(sm.ctypes.data, sc.ctypes.data, 1)
+        other_stages[mode] = {STAGES[i]: round(float(sm[i]) / k, 4) for i in range(len(STAGES)) if sc[i]}
         h2.close()
     acc_ms = other["split"]
 
@@ -714,7 +720,8 @@ def run_b200(args, rank, local_rank, world):
         "sustained": sustained,
         "stage_ms_per_step": per_stage, "stage_tflops": stage_tflops,
         "single_clip_latency_ms": b1_ms, "host_affinity": numa,
-        "modes": {m: {"value": args.clips * world / (v * 1e-3), "unit": UNIT, "ms_per_step": v} for m, v in other.items()},
+        "modes": {m: {"value": args.clips * world / (v * 1e-3), "unit": UNIT, "ms_per_step": v,
+                      "stage_ms_per_step": other_stages.get(m)} for m, v in other.items()},
         "accuracy_mode": {"value": args.clips * world / (acc_ms * 1e-3), "unit": UNIT, "ms_per_step": acc_ms,
                           "dtype": "split bf16 (hi + lo planes, fp32-class body)"},
         "configs": legs,

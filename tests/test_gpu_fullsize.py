@@ -100,3 +100,23 @@ def test_one_hour_stream(vgg_sd):
     print("1-hour stream, accuracy mode, last 64 examples: uint8 LSB histogram", np.bincount(d.numpy().astype(np.int64).ravel()).tolist())
     assert d.max() <= 1 and (d > 0).float().mean() <= 0.02
     vgg.close()
+
+
+def test_sanitize_case_runs_clean():
+    """tools/sanitize_case.py touches every kernel family on tiny inputs; it is what would run under
+    `compute-sanitizer --tool memcheck` (the tool is refused on the pool's boxes).  Here it must at least exit 0 in a
+    fresh process, and under the sanitizer when the box allows it."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "sanitize_case.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sanitize case ok" in r.stdout
+    cs = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if os.path.exists(cs) and os.environ.get("VMB_RUN_SANITIZER") == "1":
+        r = subprocess.run([cs, "--tool", "memcheck", "--error-exitcode", "3", sys.executable, script],
+                           capture_output=True, text=True, timeout=3000)
+        assert r.returncode == 0, r.stdout[-3000:]
