@@ -32,11 +32,22 @@ def embed_stream(vgg: "engine.VggishHandle", wave: torch.Tensor, pca_eigen: Opti
     if pca_eigen is not None:
         pca_eigen = pca_eigen.to(dev, torch.float32).contiguous()
         pca_means = pca_means.to(dev, torch.float32).reshape(-1).contiguous()
-    copy_stream = torch.cuda.Stream(device=dev) if not wave.is_cuda else None
     main = torch.cuda.current_stream(dev)
-    staged = [None, None]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    # The copy stream, its events and the two staging buffers live with the handle and are reused by every call: a fresh
+    # stream per call would strand the caching allocator's blocks in that stream's pool (they cannot serve another
+    # stream), so each call would cudaMalloc its staging buffers again and, once memory ran short, stall on cudaFree.
+    st = getattr(vgg, "_stream_state", None)
+    if st is None:
+        st = vgg._stream_state = dict(copy=torch.cuda.Stream(device=dev), staged=[None, None],
+                                      ready=[torch.cuda.Event(), torch.cuda.Event()],
+                                      freed=[torch.cuda.Event(), torch.cuda.Event()])
+    copy_stream, staged, ready, freed = st["copy"], st["staged"], st["ready"], st["freed"]
+    max_samples = max((s1 - s0 for _, _, s0, s1 in chunks), default=0)
+    if not wave.is_cuda:
+        copy_stream.wait_stream(main)            # whatever used the buffers in an earlier call has been enqueued on main
+        for b in range(2):
+            if staged[b] is None or staged[b].numel() < max_samples:
+                staged[b] = torch.empty(max_samples, device=dev, dtype=torch.float32)
 
     def stage(i):
         e0, e1, s0, s1 = chunks[i]
@@ -46,9 +57,9 @@ def embed_stream(vgg: "engine.VggishHandle", wave: torch.Tensor, pca_eigen: Opti
         with torch.cuda.stream(copy_stream):
             if i >= 2:
                 copy_stream.wait_event(freed[b])
-            staged[b] = wave[s0:s1].to(dev, non_blocking=True)
+            staged[b][:s1 - s0].copy_(wave[s0:s1], non_blocking=True)
             ready[b].record(copy_stream)
-        return staged[b]
+        return staged[b][:s1 - s0]
 
     pos = 0
     nxt = stage(0) if chunks else None

@@ -838,17 +838,18 @@ logmel_eo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // ================================================================== float64 path for the flagged frames
 // The same centred even / odd DFT in float64 on the CUDA cores.  The epilogues of the tensor-core kernels append every
 // flagged frame to a list (one atomicAdd per warp; the order of the list varies from run to run, the results do not:
-// every frame is computed on its own).  One CTA per SM takes the list 16 frames at a time: E, O of the 16 frames in shared
-// memory ([lag][frame]: the frames of a lag are broadcast reads), thread = (DFT bin, 4 of the 16 frames).  The float64
-// basis (768 KB, L2-resident) is streamed through a three-stage shared-memory ring by 1-D bulk copies, 10 lags per
+// every frame is computed on its own).  One CTA per SM takes the list 8 frames at a time: E, O of the 8 frames in shared
+// memory ([lag][frame]: the frames of a lag are broadcast reads), thread = (DFT bin, 2 of the 8 frames).  The float64
+// basis (768 KB, L2-resident) is streamed through a four-stage shared-memory ring by 1-D bulk copies, 10 lags per
 // stage — register-staged loads left the loop bound by one L2 round trip per pair of lags (33 us per pass; the copies
 // take it to the L2 -> SM bandwidth).  Follows mel_features.py:86-92, :215-223 to ~1e-13, so the fp32 output is the
 // float64 reference rounded once.  An empty list costs one 4-byte read per CTA.
-constexpr int kExactFrames = 16;     // frames per pass: every pass streams the whole basis, so with all SMs busy the
-                                     // aggregate L2 traffic (passes x 768 KB), not the arithmetic, sets the time
-constexpr int kExactThreads = 1024;  // thread = (bin [256, 240 used], four of the 16 frames)
+constexpr int kExactFrames = 8;      // frames per pass.  Measured: a pass costs ~26 us + 2 us per frame (float64 FMAs), so
+                                     // with ~800 flagged frames in a batch small passes on all SMs beat big ones (8 per
+                                     // pass: 42 us, 16 per pass: 58 us for the bench batch)
+constexpr int kExactThreads = 1024;  // thread = (bin [256, 240 used], two of the 8 frames)
 constexpr int kExactLags = 10;       // lags per basis stage
-constexpr int kExactStages = 3;      // two chunks in flight while one is being consumed
+constexpr int kExactStages = 4;      // three chunks in flight while one is being consumed
 constexpr int kExactStageBytes = 2 * kExactLags * kEvalBins * 8;   // cos rows | sin rows: 38 400 B
 constexpr int kExactSmem = kExactStages * kExactStageBytes + 2 * eoHalf * kExactFrames * 8 + kExactFrames * kEvalBins * 8 + kExactFrames * 8;
 
@@ -874,11 +875,11 @@ template <class IN>
 __global__ void __launch_bounds__(kExactThreads)
 logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
   extern __shared__ __align__(128) uint8_t exact_smem[];
-  double* ring = reinterpret_cast<double*>(exact_smem);                               // [3][cos 10 x 240 | sin 10 x 240]
-  double* E = reinterpret_cast<double*>(exact_smem + kExactStages * kExactStageBytes);  // [200][16]
-  double* O = E + eoHalf * kExactFrames;                                                // [200][16]
-  double* mag = O + eoHalf * kExactFrames;                                              // [16][240]
-  long long* frame_of = reinterpret_cast<long long*>(mag + kExactFrames * kEvalBins);   // [16] clip * frames_out + frame
+  double* ring = reinterpret_cast<double*>(exact_smem);                               // [4][cos 10 x 240 | sin 10 x 240]
+  double* E = reinterpret_cast<double*>(exact_smem + kExactStages * kExactStageBytes);  // [200][8]
+  double* O = E + eoHalf * kExactFrames;                                                // [200][8]
+  double* mag = O + eoHalf * kExactFrames;                                              // [8][240]
+  long long* frame_of = reinterpret_cast<long long*>(mag + kExactFrames * kEvalBins);   // [8] clip * frames_out + frame
   __shared__ uint64_t full_bar[kExactStages];
   const int tid = threadIdx.x;
   pdl_launch_dependents();
@@ -933,9 +934,9 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
       O[m * kExactFrames + f] = o;
     }
     __syncthreads();
-    const int bin = tid & 255, f0 = (tid >> 8) * 4;
+    const int bin = tid & 255, f0 = (tid >> 8) * 2;
     const int bsafe = bin < kEvalBins ? bin : 0;
-    double re[4] = {0.0, 0.0, 0.0, 0.0}, im[4] = {0.0, 0.0, 0.0, 0.0};
+    double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
     for (int ch = 0; ch < kChunks; ++ch, ++used) {
       // the stage of chunk ch - 1 was released by the barrier at the end of the previous iteration: refill it
       if (tid == 0 && ch + kExactStages - 1 < kChunks) issue(ch + kExactStages - 1);
@@ -948,38 +949,35 @@ logmel_exact_kernel(const IN* __restrict__ wave, const ExactParams p) {
 #pragma unroll
       for (int u = 0; u < kExactLags; ++u) {
         const double c = cs[u * kEvalBins], sv = sn[u * kEvalBins];
-        const double2 e0 = *reinterpret_cast<const double2*>(e + u * kExactFrames);
-        const double2 e1 = *reinterpret_cast<const double2*>(e + u * kExactFrames + 2);
-        const double2 o0 = *reinterpret_cast<const double2*>(o + u * kExactFrames);
-        const double2 o1 = *reinterpret_cast<const double2*>(o + u * kExactFrames + 2);
-        re[0] = fma(e0.x, c, re[0]);
-        re[1] = fma(e0.y, c, re[1]);
-        re[2] = fma(e1.x, c, re[2]);
-        re[3] = fma(e1.y, c, re[3]);
-        im[0] = fma(o0.x, sv, im[0]);
-        im[1] = fma(o0.y, sv, im[1]);
-        im[2] = fma(o1.x, sv, im[2]);
-        im[3] = fma(o1.y, sv, im[3]);
+        const double2 ev = *reinterpret_cast<const double2*>(e + u * kExactFrames);
+        const double2 ov = *reinterpret_cast<const double2*>(o + u * kExactFrames);
+        re0 = fma(ev.x, c, re0);
+        re1 = fma(ev.y, c, re1);
+        im0 = fma(ov.x, sv, im0);
+        im1 = fma(ov.y, sv, im1);
       }
       __syncthreads();                                   // every thread is done with stage s
     }
     if (bin < kEvalBins) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mag[(f0 + j) * kEvalBins + bin] = sqrt(re[j] * re[j] + im[j] * im[j]);
+      mag[f0 * kEvalBins + bin] = sqrt(re0 * re0 + im0 * im0);
+      mag[(f0 + 1) * kEvalBins + bin] = sqrt(re1 * re1 + im1 * im1);
     }
     __syncthreads();
     {
-      // thread = (frame, band); band `band` has weight on a short run of bins only (HTK triangles): [c_mel_lo, c_mel_hi)
-      const int f = tid / kMel, band = tid - f * kMel;
+      // (frame, band) = a pair of lanes: even bins of the band's run on one, odd bins on the other, summed by shuffle
+      // (band `band` has weight on a short run of bins only — HTK triangles: [c_mel_lo, c_mel_hi))
+      const int i = tid >> 1, par = tid & 1;
+      const int f = i / kMel, band = i - f * kMel;
       const long long fo = frame_of[f];
+      double acc = 0.0;
       if (fo >= 0) {
-        double acc = 0.0;
         const double* mg = mag + f * kEvalBins;
         const int b_lo = c_mel_lo[band], b_hi = c_mel_hi[band];
 #pragma unroll 4
-        for (int b = b_lo; b < b_hi; ++b) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
-        p.out[fo * kMel + band] = static_cast<float>(log(acc + 0.01));
+        for (int b = b_lo + par; b < b_hi; b += 2) acc = fma(mg[b], __ldg(p.mel + b * kMel + band), acc);
       }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (fo >= 0 && par == 0) p.out[fo * kMel + band] = static_cast<float>(log(acc + 0.01));
     }
     __syncthreads();
   }
