@@ -393,10 +393,13 @@ igemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             st_global_256(outp + p.lo_off + 16, lo[8], lo[9], lo[10], lo[11], lo[12], lo[13], lo[14], lo[15]);
           }
         } else if (OUT == kOutF32Atomic) {
-          if (valid) {
+          if (valid) {   // split-K partial sums: 16-byte vector reductions (one L2 request per four columns)
             float* dst = static_cast<float*>(p.out) + out_off + ch * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, f[j]);
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(f[j]), "f"(f[j + 1]),
+                           "f"(f[j + 2]), "f"(f[j + 3])
+                           : "memory");
           }
         } else if (OUT == kOutF32) {
           if (valid) {
@@ -722,6 +725,10 @@ int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float*
                               int K, cudaStream_t stream, int planes) {
   if (M <= 0) return 0;
   if (misaligned32(out_zeroed, "igemm_linear_split_ksplit")) return 1;
+  if (ldo % 4 != 0) {
+    snprintf(g_err, sizeof g_err, "igemm_linear_split_ksplit: ldo must be a multiple of 4 floats (16-byte vector reductions)");
+    return 1;
+  }
   if (K % kBlockK != 0 || N % 128 != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split_ksplit: need K %% 64 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d)", K, N);
     return 1;
@@ -747,9 +754,10 @@ int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float*
   p.num_kb = (planes == 3 ? 6 : 3) * p.split_nkb;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
   p.num_n_tiles = N / 128;
-  // enough K slices to give every SM a tile, each slice at least 8 K-blocks long
+  // as many K slices as fit in ONE wave of tiles (rounding up would leave a second wave of a few tiles that doubles the
+  // kernel's time: 25 output tiles x 6 slices = 150 tiles on 148 SMs), each slice at least 8 K-blocks long
   const int mn = p.num_m_tiles * p.num_n_tiles;
-  int ks = (num_sms() + mn - 1) / mn;
+  int ks = num_sms() / mn;
   if (ks > p.num_kb / 8) ks = p.num_kb / 8;
   p.ksplit = ks < 1 ? 1 : ks;
   p.relu = 0;

@@ -26,7 +26,9 @@ def waveform_to_examples(data, sample_rate, return_tensor=True):
         data = np.asarray(data)
         if len(data.shape) > 1:
             data = np.mean(data, axis=1)
-        wave = torch.from_numpy(np.ascontiguousarray(data)).to(device="cuda")
+        # the kernel reads fp32 samples: round on the host (the same round-to-nearest the device cast would do) so that
+        # only half of a float64 waveform's bytes cross the host -> device link
+        wave = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(device="cuda")
     if sample_rate != vggish_params.SAMPLE_RATE:
         raise NotImplementedError("resampling to 16 kHz (resampy in the reference) is outside the B200 path")
     examples = _engine.examples_from_wave(wave.to(torch.float32))
