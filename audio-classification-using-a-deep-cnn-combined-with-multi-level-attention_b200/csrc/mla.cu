@@ -371,6 +371,15 @@ int vmb_mla_num_classes(const vmb_mla_t* h) { return h ? h->dev.K : -1; }
 
 void vmb_mla_destroy(vmb_mla_t* h) {
   if (!h) return;
+  if (h->side) {
+    cudaStreamSynchronize(h->side);
+    cudaStreamDestroy(h->side);
+  }
+  for (int i = 0; i < kMaxLevels; ++i) {
+    if (h->fork_ev[i]) cudaEventDestroy(h->fork_ev[i]);
+    if (h->gemm_ev[i]) cudaEventDestroy(h->gemm_ev[i]);
+    if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
+  }
   if (h->blob) cudaFree(h->blob);
   if (h->planes) cudaFree(h->planes);
   delete h;

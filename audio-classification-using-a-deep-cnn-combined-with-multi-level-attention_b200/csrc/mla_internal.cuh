@@ -49,10 +49,14 @@ struct Handle {
   float* blob = nullptr;      // every folded fp32 table
   void* planes = nullptr;     // every bf16 weight plane
   int device = 0;
+  // tc_forward runs each level's attention branch (fcv GEMM + pooling) on a side stream while the next level's embedding
+  // chain continues on the caller's stream: created on first use, owned by the handle
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork_ev[kMaxLevels] = {}, gemm_ev[kMaxLevels] = {}, join_ev[kMaxLevels] = {};
 };
 
 // Tensor-core forward (mla_tc.cu).  Returns 0 / 1 (message via vmb::kernels_last_error()).
-int tc_forward(const Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st);
+int tc_forward(Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st);
 // One level's EmbeddedMapping / AttentionModule on its own (model.py:217-222, :235-242), from the same kernels.
 int tc_embedded_mapping(const Handle& h, int level, const float* x, long long batch, float* out, cudaStream_t st);
 int tc_attention(const Handle& h, int level, const float* hemb, long long batch, float* y, cudaStream_t st);

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "igemm_sm100.cuh"
 #include "kernels.cuh"
@@ -227,7 +228,16 @@ size_t up(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 }  // namespace
 
-int tc_forward(const Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st) {
+// VMB_MLA_FORK=0 keeps every kernel of the head on the caller's stream (A/B timing; results are identical either way)
+static bool mla_fork_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VMB_MLA_FORK");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+int tc_forward(Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st) {
   const HeadDev& d = h.dev;
   const long long rows = batch * d.T;
   if (rows > 0x7fffffffLL) {
@@ -241,7 +251,23 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
   const size_t sz_x = up(size_t(rows) * 2 * in_pad * 2), sz_p = up(size_t(rows) * 2 * hpad * 2);
   const size_t sz_u = up(size_t(rows) * hpad * 4), sz_y = up(size_t(batch) * ystride * 4);
   const size_t sz_yp = up(size_t(batch) * 2 * d.fc_kpad * 2);
-  const size_t total = sz_x + 3 * sz_p + sz_u + sz_y + sz_yp;
+  // The attention branch of a level (z = fcv(emb_l), pooling) does not feed the next level: with more than one level it
+  // runs on the handle's side stream, concurrently with the next level's Linear chain (these kernels are 4-22 us each
+  // on a fraction of the SMs, so two of them share the GPU).  Needs its own fp32 GEMM output per forked level.
+  bool fork = d.n_levels > 1 && mla_fork_enabled();
+  if (fork && !h.side) {
+    bool ok = cudaStreamCreateWithFlags(&h.side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < kMaxLevels && ok; ++i)
+      ok = cudaEventCreateWithFlags(&h.fork_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.gemm_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      vmb::set_kernel_error("mla: cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+  }
+  const int n_fork = fork ? d.n_levels - 1 : 0;
+  const size_t total = sz_x + 3 * sz_p + (1 + n_fork) * sz_u + sz_y + sz_yp;
   char* ws = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&ws), total, st) != cudaSuccess) {
     vmb::set_kernel_error("mla: workspace allocation of %zu bytes failed: %s", total,
@@ -252,23 +278,30 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
   void* P[2] = {ws + sz_x, ws + sz_x + sz_p};
   void* Pn = ws + sz_x + 2 * sz_p;
   float* U = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p);
-  float* Y = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p + sz_u);
-  void* Yp = ws + sz_x + 3 * sz_p + sz_u + sz_y;
+  float* Y = reinterpret_cast<float*>(ws + sz_x + 3 * sz_p + (1 + n_fork) * sz_u);
+  void* Yp = ws + sz_x + 3 * sz_p + (1 + n_fork) * sz_u + sz_y;
   int rc = 0;
-  auto gemm = [&](const void* a, const FcDev& fc) {
-    if (!rc && vmb::igemm_linear_split(a, fc.wp, fc.bias, U, hpad, 0, int(rows), hpad, fc.kpad, st)) {
+  auto gemm_to = [&](const void* a, const FcDev& fc, float* out, cudaStream_t s) {
+    if (!rc && vmb::igemm_linear_split(a, fc.wp, fc.bias, out, hpad, 0, int(rows), hpad, fc.kpad, s)) {
       vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
       rc = 1;
     }
   };
+  auto gemm = [&](const void* a, const FcDev& fc) { gemm_to(a, fc, U, st); };
   // level 0 input: norm0 applied to the embeddings
   rc = split_rows(emb, d.emb_in, rows, d.emb_in, in_pad, d.T, d.lvl[0].n0a, d.lvl[0].n0b, 0, nullptr, nullptr, X, st);
   const void* cur = X;
   int pp = 0;
+  const void* side_buf[kMaxLevels] = {};   // planes buffer the forked fcv GEMM of level l may still be reading
   for (int l = 0; l < d.n_levels && !rc; ++l) {
     const LevelDev& L = d.lvl[l];
     for (int j = 0; j < L.n_fc && !rc; ++j) {
       gemm(cur, L.fc[j]);
+      for (int s = 0; s < l; ++s)
+        if (side_buf[s] == P[pp]) {   // the ping-pong comes back to a buffer a forked fcv GEMM reads: wait for that GEMM
+          cudaStreamWaitEvent(st, h.gemm_ev[s], 0);
+          side_buf[s] = nullptr;
+        }
       // h = relu(BN(u)) as planes for the next Linear of this level (or for fcv); after the level's last Linear the
       // same pass also writes the embedding with the next level's norm0 applied
       if (!rc) {
@@ -281,20 +314,36 @@ int tc_forward(const Handle& h, const float* emb, long long batch, float* scores
       cur = P[pp];
       pp ^= 1;
     }
-    gemm(cur, L.fcv);   // z = fcv(emb_l) -> U
+    // attention branch of this level: on the side stream unless it is the last level (nothing left to overlap with)
+    const bool side = fork && l + 1 < d.n_levels;
+    cudaStream_t as = side ? h.side : st;
+    float* Uz = side ? U + (1 + l) * (sz_u / sizeof(float)) : U;
+    if (side && !rc) {
+      cudaEventRecord(h.fork_ev[l], st);            // emb_l planes (cur) are complete here
+      cudaStreamWaitEvent(h.side, h.fork_ev[l], 0);
+    }
+    gemm_to(cur, L.fcv, Uz, as);   // z = fcv(emb_l)
+    if (side) {
+      cudaEventRecord(h.gemm_ev[l], h.side);
+      side_buf[l] = cur;
+    }
     if (!rc) {
       const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
       if (att_smem <= 48 * 1024)     // K = 527, T = 10: 42 KB
-        vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, st, U, hpad,
+        vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, as, Uz, hpad,
                         d.K, d.T, L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
       else
-        vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U, hpad, d.K, d.T,
+        vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, as, Uz, hpad, d.K, d.T,
                         L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
       vmb::count_launch();
       rc = vmb::check_launch("attention_pool_kernel");
     }
+    if (side) cudaEventRecord(h.join_ev[l], h.side);
     cur = Pn;
   }
+  // the concatenated y needs every level's pooling: join the side branches (also on the error path, so that the
+  // workspace is not freed under them)
+  for (int l = 0; l + 1 < d.n_levels && fork; ++l) cudaStreamWaitEvent(st, h.join_ev[l], 0);
   // out = sigmoid(BN_K(fc(concat y))): y -> planes, one more split GEMM into U ([batch][640]), then the sigmoid
   if (!rc) rc = split_rows(Y, ystride, batch, d.n_levels * d.K, d.fc_kpad, 1, nullptr, nullptr, 0, nullptr, nullptr, Yp, st);
   if (!rc && vmb::igemm_linear_split(Yp, d.fc_wp, d.fc_bias, U, hpad, 0, int(batch), hpad, d.fc_kpad, st)) {

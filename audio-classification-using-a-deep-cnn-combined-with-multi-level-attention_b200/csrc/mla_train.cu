@@ -644,6 +644,9 @@ struct vmb_mla_trainer {
   int n_slots = 0;          // statistic slots; slot s: acc at s*kSlot doubles, stat at s*kSlot floats
   char* ws = nullptr;       // single workspace allocation
   size_t ws_bytes = 0;
+  // the weight-gradient GEMMs (dW = dU^T A) feed nothing but `grads`: they run on a side stream, next to the dX chain
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr;
   // carved pointers
   double* acc = nullptr; size_t acc_bytes = 0;      // zeroed every step (together with the counters)
   unsigned* counters = nullptr;
@@ -866,6 +869,12 @@ int vmb_mla_trainer_create(vmb_mla_trainer_t** handle, int n_levels, const int* 
 }
 
 void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
+  if (h && h->side) {
+    cudaStreamSynchronize(h->side);
+    cudaStreamDestroy(h->side);
+  }
+  if (h && h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h && h->ev_dw) cudaEventDestroy(h->ev_dw);
   if (!h) return;
   cudaFree(h->ws);
   delete h;
@@ -999,6 +1008,47 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   }  // do_fwd
   if (do_bwd) {
   // =============================================================================== backward
+  // Weight-gradient GEMMs on the side stream: each reads the transposed gradient planes G_pt the tile kernel just wrote
+  // and an activation's transposed planes, and writes only its slice of `grads` — nothing on the dX chain waits for it.
+  // The chain only has to wait (ev_dw) before the NEXT tile kernel overwrites G_pt, one dX GEMM and one reduction later.
+  static const bool fork_env = [] {
+    const char* e = getenv("VMB_TRAIN_FORK");
+    return !(e && e[0] == '0');
+  }();
+  if (fork_env && !h->side) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_dw, cudaEventDisableTiming) != cudaSuccess)
+      return fail("vmb_mla_train: cannot create the side stream");
+  }
+  const bool forked = fork_env;
+  bool dw_pending = false;
+  // dW (M x N, contraction over the rows) -> dst [rows_out][cols_out] of `grads`
+  auto dw_job = [&](const void* at, const void* bt, long long ldo, int M, int N, long long Kc, float* dst,
+                    size_t dst_pitch, size_t width, size_t height) {
+    cudaStream_t s = forked ? h->side : st;
+    if (forked) {
+      cudaEventRecord(h->ev_fork, st);
+      cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    }
+    int r = gemm_dw(at, bt, h->dWtmp, ldo, M, N, Kc, s);
+    if (!r && cudaMemcpy2DAsync(dst, dst_pitch, h->dWtmp, size_t(ldo) * 4, width, height, cudaMemcpyDeviceToDevice, s) !=
+                  cudaSuccess) {
+      vmb::set_kernel_error("dW copy failed");
+      r = 1;
+    }
+    if (forked) {
+      cudaEventRecord(h->ev_dw, h->side);
+      dw_pending = true;
+    }
+    return r;
+  };
+  auto before_g_overwrite = [&]() {   // G_p / G_pt (and dWtmp's reader) are about to be rewritten by the chain
+    if (dw_pending) {
+      cudaStreamWaitEvent(st, h->ev_dw, 0);
+      dw_pending = false;
+    }
+  };
   if (!rc) {
     const float* stat = slotstat(h->norm_out.slot);
     out_bn_backward_kernel<<<(K + 31) / 32, 256, 0, st>>>(h->O, Hp, K, stat, params + h->norm_out.g, params + h->norm_out.b,
@@ -1012,10 +1062,8 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + h->fc_out.b, B, Bp, K, Hp};
     TRY(run_tile(FIdentity{h->dO, Hp}, o, st, "dO split"));
     // dW_fc [K][L*K] = dO^T [K x B] * Y^T [L*K x B]^T
-    TRY(gemm_dw(h->G_pt, h->Y_pt, h->dWtmp, h->ycols_pad, Hp, h->ycols_pad, Bp, st));
-    if (!rc && cudaMemcpy2DAsync(grads + h->fc_out.w, size_t(h->ycols) * 4, h->dWtmp, size_t(h->ycols_pad) * 4,
-                                 size_t(h->ycols) * 4, K, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-      rc = 1;
+    TRY(dw_job(h->G_pt, h->Y_pt, h->ycols_pad, Hp, h->ycols_pad, Bp, grads + h->fc_out.w, size_t(h->ycols) * 4,
+               size_t(h->ycols) * 4, K));
     // dY [B][L*K] = dO [B x K] * W_fc [K x L*K]
     TRY(gemm(h->G_p, h->fc_out.wtp, nullptr, h->dY, h->ycols_pad, B, h->ycols_pad, Hp, st));
   }
@@ -1039,13 +1087,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       FAttCombine f{ap, h->GV, h->GF, Hp, acc_v, acc_f, double(B) * K, grads + L.normv.g, grads + L.normv.b,
                     grads + L.normf.g, grads + L.normf.b};
       TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
+      before_g_overwrite();
       TRY(run_tile(f, o, st, "attention BN backward"));
     }
     // dWv [K][H] = dZ^T * E^T ; dE_att [R][H] = dZ * Wv
-    TRY(gemm_dw(h->G_pt, e_pt, h->dWtmp, Hp, Hp, Hp, Rp, st));
-    if (!rc && cudaMemcpy2DAsync(grads + L.fcv.w, size_t(H) * 4, h->dWtmp, size_t(Hp) * 4, size_t(H) * 4, K,
-                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-      rc = 1;
+    TRY(dw_job(h->G_pt, e_pt, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
     TRY(gemm(h->G_p, L.fcv.wtp, nullptr, h->dA, Hp, R, Hp, Hp, st));
     // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
     const float* da1 = h->dA;
@@ -1061,13 +1107,12 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
       FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
       TileOut o{h->G_p, h->G_pt, nullptr, Hp, grads + fc.b, R, Rp, H, Hp};
+      before_g_overwrite();
       TRY(run_tile(f, o, st, "fc BN backward"));
       // dW [H][n_in] = dU^T * A_prev^T ; dA_prev [R][n_in] = dU * W
       const __nv_bfloat16* prev_pt = j > 0 ? h->A_pt[l][j - 1] : (l == 0 ? h->xin_pt : h->N_pt[l]);
-      TRY(gemm_dw(h->G_pt, prev_pt, h->dWtmp, fc.n_in_pad, Hp, fc.n_in_pad, Rp, st));
-      if (!rc && cudaMemcpy2DAsync(grads + fc.w, size_t(fc.n_in) * 4, h->dWtmp, size_t(fc.n_in_pad) * 4,
-                                   size_t(fc.n_in) * 4, H, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        rc = 1;
+      TRY(dw_job(h->G_pt, prev_pt, fc.n_in_pad, Hp, fc.n_in_pad, Rp, grads + fc.w, size_t(fc.n_in) * 4,
+                 size_t(fc.n_in) * 4, H));
       float* dprev = (da1 == h->dA) ? h->dB : h->dA;
       TRY(gemm(h->G_p, fc.wtp, nullptr, dprev, Hp, R, fc.n_in_pad, Hp, st));
       da1 = dprev;
@@ -1093,6 +1138,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(run_tile(f, o, st, "norm0 backward"));
     }
   }
+  before_g_overwrite();   // join: every weight gradient is in `grads` before anything the caller enqueues next
   }  // do_bwd
 #undef TRY
   if (rc) return fail("vmb_mla_train: %s", vmb::kernels_last_error());

@@ -100,6 +100,18 @@ def test_one_hour_stream(vgg_sd):
     print("1-hour stream, accuracy mode, last 64 examples: uint8 LSB histogram", np.bincount(d.numpy().astype(np.int64).ravel()).tolist())
     assert d.max() <= 1 and (d > 0).float().mean() <= 0.02
     vgg.close()
+    # the default (fp16) body on the same stream: every value within +-1 LSB of the reference too (north_star's bar),
+    # with more values sitting on the other side of a quantisation boundary than in the split mode
+    v16 = engine.VggishHandle(vgg_sd, DEV, precision="fp16")
+    emb16, q16 = stream.embed_stream(v16, wave, eig, means, examples_per_chunk=2048)
+    v16.check_saturation()
+    d16 = (q16[-m:].cpu().float() - ref).abs()
+    dq = (q16.int() - q.int()).abs()
+    print("1-hour stream, fp16 mode, last 64 examples: uint8 LSB histogram vs the oracle",
+          np.bincount(d16.numpy().astype(np.int64).ravel()).tolist(), "; all 3 749 examples vs the split mode",
+          torch.bincount(dq.flatten()).tolist())
+    assert d16.max() <= 1 and (d16 > 0).float().mean() <= 0.08 and dq.max() <= 1
+    v16.close()
 
 
 def test_sanitize_case_runs_clean():
