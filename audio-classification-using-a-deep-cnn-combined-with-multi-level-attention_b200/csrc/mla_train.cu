@@ -646,7 +646,7 @@ struct vmb_mla_trainer {
   size_t ws_bytes = 0;
   // the weight-gradient GEMMs (dW = dU^T A) feed nothing but `grads`: they run on a side stream, next to the dX chain
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_att = nullptr;
   // carved pointers
   double* acc = nullptr; size_t acc_bytes = 0;      // zeroed every step (together with the counters)
   unsigned* counters = nullptr;
@@ -875,6 +875,7 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
   }
   if (h && h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h && h->ev_dw) cudaEventDestroy(h->ev_dw);
+  if (h && h->ev_att) cudaEventDestroy(h->ev_att);
   if (!h) return;
   cudaFree(h->ws);
   delete h;
@@ -921,11 +922,26 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     return StatJob{slotacc(bn.slot), slotstat(bn.slot), h->counters + bn.slot, running + bn.rm, running + bn.rm + bn.n,
                    count, bn.n};
   };
-  auto time_stats = [&](const float* src, long long ld, int F, const BnRef& bn, bool update_running) {
+  // Side stream (created on first use): work that feeds nothing on the critical chain runs there — in the forward pass
+  // the attention branch of every level but the last (fcv GEMM, statistics, pooling: only the concatenation at the end
+  // needs it), in the backward pass the weight-gradient GEMMs.  VMB_TRAIN_FORK=0 keeps everything on the caller's stream.
+  static const bool fork_env = [] {
+    const char* e = getenv("VMB_TRAIN_FORK");
+    return !(e && e[0] == '0');
+  }();
+  if (fork_env && !h->side) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_dw, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess)
+      return fail("vmb_mla_train: cannot create the side stream");
+  }
+  const bool forked = fork_env;
+  auto time_stats = [&](const float* src, long long ld, int F, const BnRef& bn, bool update_running, cudaStream_t ss) {
     StatJob j = statjob(bn, double(B) * F);
     if (!update_running) j.run_mean = j.run_var = nullptr;
     const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F + 256 * 8 - 1) / (256 * 8), 64));
-    vmb::launch_pdl(bn_time_stats_kernel, dim3(chunks, T), dim3(256), 0, st, src, ld, B, F, T, j);
+    vmb::launch_pdl(bn_time_stats_kernel, dim3(chunks, T), dim3(256), 0, ss, src, ld, B, F, T, j);
     vmb::count_launch();
     return vmb::check_launch("bn_time_stats_kernel");
   };
@@ -943,6 +959,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   TRY(weights(h->fc_out));
 
   // =============================================================================== forward
+  bool att_pending = false;
   for (int l = 0; l < h->n_levels && !rc; ++l) {
     const LevelRef& L = h->lvl[l];
     const float* in = l == 0 ? x : h->E[l - 1];
@@ -951,7 +968,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     const int in_pad = l == 0 ? inpad : Hp;
     __nv_bfloat16* np = l == 0 ? h->xin_p : h->N_p[l];
     __nv_bfloat16* npt = l == 0 ? h->xin_pt : h->N_pt[l];
-    TRY(time_stats(in, ld_in, F_in, L.norm0, true));
+    TRY(time_stats(in, ld_in, F_in, L.norm0, true, st));
     {
       FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, seed, 0};
       TileOut o{np, npt, nullptr, 0, nullptr, R, Rp, F_in, in_pad};
@@ -961,7 +978,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     for (int j = 0; j < L.n_fc && !rc; ++j) {
       const FcRef& fc = L.fc[j];
       TRY(gemm(a, fc.wp, fc.bias_pad, h->U[l][j], Hp, R, Hp, fc.n_in_pad, st));
-      TRY(time_stats(h->U[l][j], Hp, H, L.norms[j], true));
+      TRY(time_stats(h->U[l][j], Hp, H, L.norms[j], true, st));
       const bool last = j == L.n_fc - 1;
       FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
                dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
@@ -969,25 +986,37 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(run_tile(f, o, st, "fc forward activation"));
       a = h->A_p[l][j];
     }
-    // attention branch of this level
-    TRY(gemm(a, L.fcv.wp, L.fcv.bias_pad, h->Z[l], Hp, R, Hp, Hp, st));
-    TRY(time_stats(h->Z[l], Hp, K, L.normv, true));
+    // attention branch of this level: every buffer it writes is per level (Z[l], its statistic slots, columns l*K.. of Y),
+    // so with another level still to come it runs on the side stream next to that level's chain
+    const bool side = forked && l + 1 < h->n_levels;
+    cudaStream_t as = side ? h->side : st;
+    if (side && !rc) {
+      cudaEventRecord(h->ev_fork, st);               // the level's last activation planes (a) are complete
+      cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    }
+    TRY(gemm(a, L.fcv.wp, L.fcv.bias_pad, h->Z[l], Hp, R, Hp, Hp, as));
+    TRY(time_stats(h->Z[l], Hp, K, L.normv, true, as));
     if (!rc) {
       // normf shares the batch statistics but keeps its own running buffers
       StatJob j = statjob(L.normf, double(B) * K);
       j.acc = slotacc(L.normv.slot);
       j.stat = slotstat(L.normf.slot);
-      bn_running_only_kernel<<<1, 32, 0, st>>>(j);
+      bn_running_only_kernel<<<1, 32, 0, as>>>(j);
       vmb::count_launch();
       TRY(vmb::check_launch("bn_running_only_kernel"));
       AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
                    params + L.normf.g, params + L.normf.b};
-      vmb::launch_pdl(att_forward_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0, st, ap, h->Y, h->ycols_pad, l * K,
+      vmb::launch_pdl(att_forward_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0, as, ap, h->Y, h->ycols_pad, l * K,
                       h->row_stats[l]);
       vmb::count_launch();
       TRY(vmb::check_launch("att_forward_kernel"));
     }
+    if (side) {
+      cudaEventRecord(h->ev_att, h->side);
+      att_pending = true;
+    }
   }
+  if (att_pending) cudaStreamWaitEvent(st, h->ev_att, 0);   // join: the concatenation below reads every level's pooling
   // output layer
   {
     TileOut o{h->Y_p, h->Y_pt, nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
@@ -1011,17 +1040,6 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   // Weight-gradient GEMMs on the side stream: each reads the transposed gradient planes G_pt the tile kernel just wrote
   // and an activation's transposed planes, and writes only its slice of `grads` — nothing on the dX chain waits for it.
   // The chain only has to wait (ev_dw) before the NEXT tile kernel overwrites G_pt, one dX GEMM and one reduction later.
-  static const bool fork_env = [] {
-    const char* e = getenv("VMB_TRAIN_FORK");
-    return !(e && e[0] == '0');
-  }();
-  if (fork_env && !h->side) {
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_dw, cudaEventDisableTiming) != cudaSuccess)
-      return fail("vmb_mla_train: cannot create the side stream");
-  }
-  const bool forked = fork_env;
   bool dw_pending = false;
   // dW (M x N, contraction over the rows) -> dst [rows_out][cols_out] of `grads`
   auto dw_job = [&](const void* at, const void* bt, long long ldo, int M, int N, long long Kc, float* dst,
