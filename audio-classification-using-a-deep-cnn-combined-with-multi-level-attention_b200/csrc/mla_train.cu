@@ -647,6 +647,13 @@ struct vmb_mla_trainer {
   // the weight-gradient GEMMs (dW = dU^T A) feed nothing but `grads`: they run on a side stream, next to the dX chain
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_att = nullptr;
+  // backward: the attention branches of every level but the last need only dY and forward state, so they run on a second
+  // side stream (with their own scratch: G_p2 .. dWtmp2, one dAtt per level) while the last level's chain runs
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev_attb[kMaxLevels] = {};
+  __nv_bfloat16 *G_p2 = nullptr, *G_pt2 = nullptr;
+  float *GV2 = nullptr, *GF2 = nullptr, *dWtmp2 = nullptr;
+  float* dAtt[kMaxLevels] = {};
   // carved pointers
   double* acc = nullptr; size_t acc_bytes = 0;      // zeroed every step (together with the counters)
   unsigned* counters = nullptr;
@@ -723,6 +730,14 @@ void carve(vmb_mla_trainer* h, char* base) {
   h->dEnext = c.take<float>(size_t(R) * Hp);
   const int widest = std::max(h->ycols_pad, std::max(Hp, inpad));
   h->dWtmp = c.take<float>(size_t(Hp) * widest);
+  if (h->n_levels > 1) {
+    h->G_p2 = c.take<__nv_bfloat16>(size_t(Rp) * kPl * Hp);
+    h->G_pt2 = c.take<__nv_bfloat16>(size_t(Hp) * kPl * Rp);
+    h->GV2 = c.take<float>(size_t(R) * Hp);
+    h->GF2 = c.take<float>(size_t(R) * Hp);
+    h->dWtmp2 = c.take<float>(size_t(Hp) * Hp);
+    for (int l = 0; l + 1 < h->n_levels; ++l) h->dAtt[l] = c.take<float>(size_t(R) * Hp);
+  }
   auto planes_for = [&](FcRef& f) {
     f.bias_pad = c.take<float>(size_t(f.n_out_pad));
     f.wp = c.take<__nv_bfloat16>(size_t(f.n_out_pad) * kPl * f.n_in_pad);
@@ -876,6 +891,12 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
   if (h && h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h && h->ev_dw) cudaEventDestroy(h->ev_dw);
   if (h && h->ev_att) cudaEventDestroy(h->ev_att);
+  if (h && h->side2) {
+    cudaStreamSynchronize(h->side2);
+    cudaStreamDestroy(h->side2);
+  }
+  for (int i = 0; h && i < kMaxLevels; ++i)
+    if (h->ev_attb[i]) cudaEventDestroy(h->ev_attb[i]);
   if (!h) return;
   cudaFree(h->ws);
   delete h;
@@ -933,8 +954,12 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_dw, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking) != cudaSuccess)
       return fail("vmb_mla_train: cannot create the side stream");
+    for (int i = 0; i < kMaxLevels; ++i)
+      if (cudaEventCreateWithFlags(&h->ev_attb[i], cudaEventDisableTiming) != cudaSuccess)
+        return fail("vmb_mla_train: cannot create the side stream");
   }
   const bool forked = fork_env;
   auto time_stats = [&](const float* src, long long ld, int F, const BnRef& bn, bool update_running, cudaStream_t ss) {
@@ -1085,34 +1110,68 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     // dY [B][L*K] = dO [B x K] * W_fc [K x L*K]
     TRY(gemm(h->G_p, h->fc_out.wtp, nullptr, h->dY, h->ycols_pad, B, h->ycols_pad, Hp, st));
   }
-  // levels in reverse
-  for (int l = h->n_levels - 1; l >= 0 && !rc; --l) {
+  // attention branch of level l: d(loss)/dZ_l from dY, its BatchNorm / fcv parameter gradients, dWv, and the gradient it
+  // sends into the level's embedding (dE_att -> out_dA).  With own_side == false it runs on the caller's stream with the
+  // chain's scratch (and its dW GEMM goes through dw_job); with own_side == true everything runs on `s` with the second
+  // set of scratch buffers.
+  static std::atomic<unsigned long long> att_attr{0};   // one bit per device: the attribute is per device
+  if (vmb::device_needs_setup(att_attr))
+    cudaFuncSetAttribute(att_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  auto att_branch = [&](int l, cudaStream_t s, bool own_side, float* out_dA) {
     const LevelRef& L = h->lvl[l];
     const __nv_bfloat16* e_pt = h->A_pt[l][L.n_fc - 1];
+    __nv_bfloat16* gp = own_side ? h->G_p2 : h->G_p;
+    __nv_bfloat16* gpt = own_side ? h->G_pt2 : h->G_pt;
+    float* gv = own_side ? h->GV2 : h->GV;
+    float* gf = own_side ? h->GF2 : h->GF;
     AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
                  params + L.normf.g, params + L.normf.b};
     double* acc_v = slotacc(L.normv.bslot);
     double* acc_f = slotacc(L.normf.bslot);
     const size_t att_smem = (size_t(2) * T * K + K) * sizeof(float);
-    static std::atomic<unsigned long long> att_attr{0};   // one bit per device: the attribute is per device
-    if (vmb::device_needs_setup(att_attr))
-      cudaFuncSetAttribute(att_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    att_backward_kernel<<<static_cast<unsigned>(B), 256, att_smem, st>>>(ap, h->Y, h->dY, h->ycols_pad, l * K,
-                                                                         h->row_stats[l], h->GV, h->GF, Hp, acc_v, acc_f);
+    att_backward_kernel<<<static_cast<unsigned>(B), 256, att_smem, s>>>(ap, h->Y, h->dY, h->ycols_pad, l * K,
+                                                                        h->row_stats[l], gv, gf, Hp, acc_v, acc_f);
     vmb::count_launch();
     TRY(vmb::check_launch("att_backward_kernel"));
     {
-      FAttCombine f{ap, h->GV, h->GF, Hp, acc_v, acc_f, double(B) * K, grads + L.normv.g, grads + L.normv.b,
+      FAttCombine f{ap, gv, gf, Hp, acc_v, acc_f, double(B) * K, grads + L.normv.g, grads + L.normv.b,
                     grads + L.normf.g, grads + L.normf.b};
-      TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
-      before_g_overwrite();
-      TRY(run_tile(f, o, st, "attention BN backward"));
+      TileOut o{gp, gpt, nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
+      if (!own_side) before_g_overwrite();
+      TRY(run_tile(f, o, s, "attention BN backward"));
     }
     // dWv [K][H] = dZ^T * E^T ; dE_att [R][H] = dZ * Wv
-    TRY(dw_job(h->G_pt, e_pt, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
-    TRY(gemm(h->G_p, L.fcv.wtp, nullptr, h->dA, Hp, R, Hp, Hp, st));
-    // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
+    if (own_side) {
+      TRY(gemm_dw(gpt, e_pt, h->dWtmp2, Hp, Hp, Hp, Rp, s));
+      if (!rc && cudaMemcpy2DAsync(grads + L.fcv.w, size_t(H) * 4, h->dWtmp2, size_t(Hp) * 4, size_t(H) * 4, K,
+                                   cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        rc = 1;
+    } else {
+      TRY(dw_job(gpt, e_pt, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
+    }
+    TRY(gemm(gp, L.fcv.wtp, nullptr, out_dA, Hp, R, Hp, Hp, s));
+  };
+  // fork: every level below the last starts its attention branch now (dY is complete), on the second side stream
+  const bool att_fork = forked && h->n_levels > 1;
+  if (att_fork && !rc) {
+    cudaEventRecord(h->ev_fork, st);
+    cudaStreamWaitEvent(h->side2, h->ev_fork, 0);
+    for (int l = h->n_levels - 2; l >= 0; --l) {
+      att_branch(l, h->side2, true, h->dAtt[l]);
+      cudaEventRecord(h->ev_attb[l], h->side2);
+    }
+  }
+  // levels in reverse
+  for (int l = h->n_levels - 1; l >= 0 && !rc; --l) {
+    const LevelRef& L = h->lvl[l];
     const float* da1 = h->dA;
+    if (att_fork && l + 1 < h->n_levels) {
+      cudaStreamWaitEvent(st, h->ev_attb[l], 0);    // this level's attention gradient comes from the side branch
+      da1 = h->dAtt[l];
+    } else {
+      att_branch(l, st, false, h->dA);
+    }
+    // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
     const float* da2 = (l + 1 < h->n_levels) ? h->dEnext : nullptr;
     for (int j = L.n_fc - 1; j >= 0 && !rc; --j) {
       const FcRef& fc = L.fc[j];
