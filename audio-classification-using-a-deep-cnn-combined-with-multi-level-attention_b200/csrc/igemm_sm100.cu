@@ -691,6 +691,14 @@ int igemm_linear_split(const void* a_planes, const void* w_planes, const float* 
     snprintf(g_err, sizeof g_err, "igemm_linear_split: need K %% 64 == 0 and N %% 128 == 0 (got K=%d N=%d)", K, N);
     return 1;
   }
+  if (planes_gemm_enabled()) {
+    // every plane of a K-block loaded once per tile (planes_gemm_sm100.cu); the kernel below is kept for A/B timing
+    if (planes_gemm(a_planes, w_planes, bias, out, ldo, relu, M, N, K, planes, 0, stream)) {
+      snprintf(g_err, sizeof g_err, "%s", planes_gemm_last_error());
+      return 1;
+    }
+    return 0;
+  }
   const int block_n = (N % 256 == 0) ? 256 : 128;
   CUtensorMap ta, tb;
   {
@@ -732,6 +740,18 @@ int igemm_linear_split_ksplit(const void* a_planes, const void* w_planes, float*
   if (K % kBlockK != 0 || N % 128 != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_err, sizeof g_err, "igemm_linear_split_ksplit: need K %% 64 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d)", K, N);
     return 1;
+  }
+  if (planes_gemm_enabled()) {
+    // one wave of (K slice, tile) work items, each slice at least four 32-column K-blocks long
+    const int mn = ((M + kBlockM - 1) / kBlockM) * (N / 128);
+    int ks = num_sms() / mn;
+    if (ks > K / 32 / 4) ks = K / 32 / 4;
+    if (ks < 1) ks = 1;
+    if (planes_gemm(a_planes, w_planes, nullptr, out_zeroed, ldo, 0, M, N, K, planes, ks > 1 ? ks : -1, stream)) {
+      snprintf(g_err, sizeof g_err, "%s", planes_gemm_last_error());
+      return 1;
+    }
+    return 0;
   }
   CUtensorMap ta, tb;
   {

@@ -103,6 +103,17 @@ int igemm_set_halo(int on);   // 1 / 0 force the choice, -1 returns to the defau
 
 const char* igemm_last_error();
 
+// planes_gemm_sm100.cu: the split GEMMs with every operand plane of a K-block loaded once per tile and the hi * hi
+// product in its own TMEM accumulator.  igemm_linear_split / igemm_linear_split_ksplit route to it when
+// planes_gemm_enabled() (default; env VMB_PLANES_GEMM=0 or planes_gemm_set(0) selects the long-K-loop kernel above).
+// ksplit > 1: that many K slices, vector reductions into a zeroed out; ksplit == -1: one slice but still adding into
+// out; ksplit == 0: plain stores (+ bias, optional ReLU).
+int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
+                int N, int K, int planes, int ksplit, cudaStream_t stream);
+bool planes_gemm_enabled();
+int planes_gemm_set(int on);   // 1 / 0 force the choice, -1 returns to the default; returns the previous setting
+const char* planes_gemm_last_error();
+
 // Shared host helpers (igemm_sm100.cu): bf16 tensor map with 128- or 64-byte swizzle (error text goes to
 // igemm_last_error()), and the SM count of the current device.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -1,0 +1,342 @@
+// fp32-equivalent GEMM from bf16 operand planes on tcgen05 (the Linear layers of the attention head and of its
+// training step: reference model.py:217-222, :235-242, :258-269 and their autograd transposes, train.py:130-138).
+//
+//   out[M][N] (+)= sum over plane pairs (pa, pb), pa + pb <= PLANES - 1, of  A_pa[M][K] * B_pb[N][K]^T   (+ bias)
+//
+// A is stored as bf16 [M][PLANES * K] (the planes hi | (mid |) lo of every row side by side), B likewise [N][PLANES * K].
+// igemm_bf16_kernel runs the same contraction as ONE long K loop over the plane pairs, which loads every plane K-block
+// once per product it takes part in: 6 x 32 KB per 64 columns of K for PLANES = 3, twice the 96 KB that are distinct,
+// and the kernel is bound by exactly that L2 -> shared memory traffic (ncu: 41 us for a 5120 x 640 x 640 GEMM whose
+// MMAs take 8 us per tile).  Here a pipeline stage holds ALL planes of one 32-column K-block of A and of B (SWIZZLE_64B
+// rows of 64 bytes: 48 KB per stage for three planes, four stages; 32 KB and six stages for two) and the MMA warp issues
+// every plane product from it, so each operand byte crosses L2 -> shared memory once per tile.
+//
+// Two TMEM accumulators per tile: the hi * hi product goes to one, the small cross products to the other, and the
+// epilogue adds them in fp32.  tcgen05.mma truncates when it aligns an addend to the accumulator, so small products
+// added into a large running sum would lose their low bits on every K step; kept apart they are accumulated among
+// themselves (the order the long-K-loop kernel had: small products first) whatever the K-block interleaving.
+//
+// Warp roles as in igemm_bf16_kernel: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue (two
+// per TMEM lane quarter, alternating 32-column chunks).  Persistent over tiles; both accumulators double-buffered
+// (2 x 2 x 128 = 512 TMEM columns).  Split-K (the weight-gradient GEMMs: a few output tiles, K = batch * T rows): tile
+// index = (K slice, m tile, n tile), partial sums added with 16-byte vector reductions into a zeroed output.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+
+#include "igemm_sm100.cuh"
+#include "kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vmb {
+
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;
+constexpr int kPlaneBytes = 128 * kBK * 2;   // one plane of one K-block of one operand: 128 rows x 64 bytes = 8 KB
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+
+template <int PLANES>
+struct PCfg {
+  static constexpr int kStageBytes = 2 * PLANES * kPlaneBytes;          // A planes, then B planes
+  static constexpr int kStages = 192 * 1024 / kStageBytes;               // 4 (three planes) or 6 (two)
+  static constexpr int kBiasBytes = 2 * kBN * 4;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes;
+  static constexpr int kTmemCols = 512;                                  // 2 buffers x (hi*hi | cross products) x 128
+};
+
+struct PlanesParams {
+  int M, N;
+  int num_kb;        // K / 32 (of one plane)
+  int num_m_tiles, num_n_tiles;
+  int ksplit;        // <= 1: none
+  int relu;
+  long long ldo;
+  const float* bias;
+  float* out;
+};
+
+template <int PLANES, bool ATOMIC>
+__global__ void __launch_bounds__(kThreads, 1)
+planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const PlanesParams p) {
+  using C = PCfg<PLANES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* bias_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kBiasBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_tiles = mn_tiles * ksplit;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const int plane_cols = p.num_kb * kBK;   // K of one plane
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile / mn_tiles;
+        const int mn = tile - ks * mn_tiles;
+        const int kb0 = p.num_kb * ks / ksplit, kb1 = p.num_kb * (ks + 1) / ksplit;
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * C::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_2d(dst + pl * kPlaneBytes, &tmap_a, &full_bar[stage], pl * plane_cols + kb * kBK, m_tile * kBM);
+#pragma unroll
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_2d(dst + (PLANES + pl) * kPlaneBytes, &tmap_b, &full_bar[stage], pl * plane_cols + kb * kBK,
+                        n_tile * kBN);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    // cross products (a plane, b plane), smallest magnitude first; hi * hi has its own accumulator
+    constexpr int kCross = PLANES == 3 ? 5 : 2;
+    constexpr int cross_a3[5] = {2, 1, 0, 1, 0}, cross_b3[5] = {0, 1, 2, 0, 1};
+    constexpr int cross_a2[2] = {1, 0}, cross_b2[2] = {0, 1};
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int ks = tile / mn_tiles;
+      const int kb0 = p.num_kb * ks / ksplit, kb1 = p.num_kb * (ks + 1) / ksplit;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_big = tmem_base + acc * (2 * kBN);
+      const uint32_t d_small = d_big + kBN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t b0 = a0 + PLANES * kPlaneBytes;
+          const uint32_t first = static_cast<uint32_t>(kb - kb0);
+#pragma unroll
+          for (int q = 0; q < kCross; ++q) {
+            const int pa = PLANES == 3 ? cross_a3[q] : cross_a2[q];
+            const int pb = PLANES == 3 ? cross_b3[q] : cross_b2[q];
+            const uint64_t a_desc = umma_desc_kmajor_sw64(a0 + pa * kPlaneBytes);
+            const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + pb * kPlaneBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (>>4 = 2) per 16-element K step
+              umma_bf16_ss(d_small, a_desc + 2 * k, b_desc + 2 * k, idesc, (first | q | k) != 0);
+          }
+          {
+            const uint64_t a_desc = umma_desc_kmajor_sw64(a0);
+            const uint64_t b_desc = umma_desc_kmajor_sw64(b0);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss(d_big, a_desc + 2 * k, b_desc + 2 * k, idesc, (first | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;    // the two warps of a quarter alternate over the 32-column chunks
+    const int ep_tid = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int ks = tile / mn_tiles;
+      const int mn = tile - ks * mn_tiles;
+      const int m_tile = mn / p.num_n_tiles;
+      const int n_tile = mn - m_tile * p.num_n_tiles;
+      const int n0 = n_tile * kBN;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      float* bias_t = bias_s + acc * kBN;
+      for (int i = ep_tid; i < kBN; i += kEpiThreads) bias_t[i] = (p.bias && ks == 0) ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = m_tile * kBM + q * 32 + lane;
+      const bool valid = row < p.M;
+      float* out_row = p.out + static_cast<size_t>(row) * p.ldo + n0;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * kBN);
+#pragma unroll 1
+      for (int ch = half; ch < kBN / 32; ch += 2) {
+        uint32_t big[32], small[32];
+        tmem_ld_32x32(t_addr + ch * 32, big);
+        tmem_ld_32x32(t_addr + kBN + ch * 32, small);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_t + ch * 32 + j);
+          f[j + 0] = (__uint_as_float(big[j + 0]) + __uint_as_float(small[j + 0])) + b4.x;
+          f[j + 1] = (__uint_as_float(big[j + 1]) + __uint_as_float(small[j + 1])) + b4.y;
+          f[j + 2] = (__uint_as_float(big[j + 2]) + __uint_as_float(small[j + 2])) + b4.z;
+          f[j + 3] = (__uint_as_float(big[j + 3]) + __uint_as_float(small[j + 3])) + b4.w;
+        }
+        if (!ATOMIC && p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          float* dst = out_row + ch * 32;
+          if (ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(f[j]), "f"(f[j + 1]),
+                           "f"(f[j + 2]), "f"(f[j + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              st_global_256(dst + j, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]),
+                            __float_as_uint(f[j + 3]), __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]),
+                            __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7]));
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+thread_local char g_perr[384] = "";
+
+template <int PLANES, bool ATOMIC>
+int launch_planes(const CUtensorMap& ta, const CUtensorMap& tb, const PlanesParams& p, cudaStream_t stream) {
+  auto kern = planes_gemm_kernel<PLANES, ATOMIC>;
+  static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
+  constexpr int smem = PCfg<PLANES>::kSmemBytes;
+  if (device_needs_setup(attr_set)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      device_setup_failed(attr_set);
+      snprintf(g_perr, sizeof g_perr, "planes_gemm: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, ta, tb, p);
+  count_launch();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_perr, sizeof g_perr, "planes_gemm launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+std::atomic<int> g_planes_override{-1};
+
+}  // namespace
+
+const char* planes_gemm_last_error() { return g_perr; }
+
+bool planes_gemm_enabled() {
+  const int o = g_planes_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o != 0;
+  static const bool on = [] {
+    const char* e = getenv("VMB_PLANES_GEMM");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+int planes_gemm_set(int on) {
+  const int prev = g_planes_override.exchange(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
+  return prev;
+}
+
+// out fp32 [M][ldo] = act(sum of plane products + bias), or with ksplit > 1 / == -1: out += the K slices' partial sums.
+// K % 32 == 0, N % 128 == 0, planes 2 or 3; the operands' rows are planes * K bf16 long.
+int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
+                int N, int K, int planes, int ksplit, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBK != 0 || N % kBN != 0 || (planes != 2 && planes != 3)) {
+    snprintf(g_perr, sizeof g_perr, "planes_gemm: need K %% 32 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d planes=%d)", K, N,
+             planes);
+    return 1;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(M)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
+    uint32_t box[2] = {kBK, kBM};
+    if (make_tmap_bf16(&ta, a_planes, 2, dims, str, box, 64)) {
+      snprintf(g_perr, sizeof g_perr, "planes_gemm: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  {
+    uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(N)};
+    uint64_t str[1] = {uint64_t(planes) * K * 2};
+    uint32_t box[2] = {kBK, kBN};
+    if (make_tmap_bf16(&tb, b_planes, 2, dims, str, box, 64)) {
+      snprintf(g_perr, sizeof g_perr, "planes_gemm: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  PlanesParams p{};
+  p.M = M;
+  p.N = N;
+  p.num_kb = K / kBK;
+  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_n_tiles = N / kBN;
+  p.ksplit = ksplit;
+  p.relu = relu;
+  p.ldo = ldo;
+  p.bias = bias;
+  p.out = out;
+  if (ksplit > 1 || ksplit == -1)
+    return planes == 3 ? launch_planes<3, true>(ta, tb, p, stream) : launch_planes<2, true>(ta, tb, p, stream);
+  return planes == 3 ? launch_planes<3, false>(ta, tb, p, stream) : launch_planes<2, false>(ta, tb, p, stream);
+}
+
+}  // namespace vmb
