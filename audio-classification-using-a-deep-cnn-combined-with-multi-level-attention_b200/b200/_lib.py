@@ -23,6 +23,7 @@ SIGNATURES = {
     "vmb_launch_count": (_ll, []),
     "vmb_igemm_pair_enable": (_int, [_int]),
     "vmb_igemm_halo_enable": (_int, [_int]),
+    "vmb_mla_fuse_enable": (_int, [_int]),
     "vmb_profile_enable": (_int, [_int]),
     "vmb_profile_collect": (_int, [_c_p, _c_p, _int]),
     "vmb_num_frames": (_ll, [_ll]),

@@ -110,6 +110,34 @@ const char* igemm_last_error();
 // out; ksplit == 0: plain stores (+ bias, optional ReLU).
 int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
                 int N, int K, int planes, int ksplit, cudaStream_t stream);
+// Fused epilogue of the eval-mode head (two planes, no K split): the accumulator row u of (clip, time step
+// t = row % T) becomes h = relu?(a1_t u + b1_t) [columns >= cols: 0], written as bf16 hi | lo planes dst[M][2 * cpad]
+// (and, with dst2, a2_t h + b2_t likewise) — BatchNorm1d(T) in eval mode + ReLU + the operand split of the next Linear
+// (model.py:219-221).  Same expressions, same order as rows_affine_split_kernel (mla_tc.cu).
+struct PlanesEpi {
+  int mode;                        // 1
+  int T, relu, cols, cpad;
+  const float *a1, *b1, *a2, *b2;  // [T]; a1 may be null (identity), a2 / b2 only with dst2
+  void *dst, *dst2;                // bf16 planes, 32-byte aligned
+};
+int planes_gemm_fused(const void* a_planes, const void* b_planes, const float* bias, const PlanesEpi& epi, int M, int N,
+                      int K, cudaStream_t stream);
+// Statistics epilogue (head training): besides storing out fp32 [M][ldo] = products + bias, the kernel accumulates
+// {sum, sum of squares} of the first `cols` columns per channel = row % channels (BatchNorm1d(T) over a (clip, time step)
+// row index, model.py:221 in train mode) into acc (double [channels][2], zeroed by the caller), and the CTA that finishes
+// last writes stat[channels][2] = {mean, 1 / sqrt(var + eps)} and, when run_mean != null, updates the running statistics
+// with torch's momentum rule (unbiased variance).  counter must be zero on entry.  channels <= 16.
+struct PlanesStats {
+  double* acc;
+  float* stat;
+  unsigned* counter;
+  float *run_mean, *run_var;
+  double count;       // elements per channel
+  int channels, cols;
+  float eps, momentum;
+};
+int planes_gemm_stats(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int M,
+                      int N, int K, int planes, const PlanesStats& stats, cudaStream_t stream);
 bool planes_gemm_enabled();
 int planes_gemm_set(int on);   // 1 / 0 force the choice, -1 returns to the default; returns the previous setting
 const char* planes_gemm_last_error();

@@ -396,6 +396,8 @@ int vmb_mla_forward(vmb_mla_t* h, const float* emb, long long batch, float* scor
   return 0;
 }
 
+int vmb_mla_fuse_enable(int on) { return vmb_head::mla_fuse_set(on); }
+
 int vmb_mla_embedded_mapping(vmb_mla_t* h, int level, const float* x, long long batch, float* out, void* stream) {
   if (!h) return fail("vmb_mla_embedded_mapping: null handle");
   if (level < 0 || level >= h->dev.n_levels) return fail("vmb_mla_embedded_mapping: no such level");

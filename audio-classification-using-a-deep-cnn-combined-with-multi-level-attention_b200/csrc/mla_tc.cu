@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "igemm_sm100.cuh"
@@ -131,7 +132,8 @@ attention_pool_kernel(const float* __restrict__ z, long long ldz, int K, int T, 
 __global__ void __launch_bounds__(256)
 attention_pool_smem_kernel(const float* __restrict__ z, long long ldz, int K, int T, const float* __restrict__ av,
                            const float* __restrict__ bv, const float* __restrict__ af, const float* __restrict__ bf,
-                           float* __restrict__ y, long long ystride, int col0) {
+                           float* __restrict__ y, long long ystride, int col0, __nv_bfloat16* __restrict__ yp, int yp_kpad,
+                           int yp_zero_to) {
   extern __shared__ float sm_att[];
   __shared__ float rsum[16];
   vmb::pdl_launch_dependents();
@@ -169,8 +171,20 @@ attention_pool_smem_kernel(const float* __restrict__ z, long long ldz, int K, in
       num = fmaf(cla, att, num);
       den += att;
     }
-    y[clip * ystride + col0 + k] = num / den;
+    const float r = num / den;
+    if (y) y[clip * ystride + col0 + k] = r;
+    if (yp) {   // the operand planes of the output Linear, written here instead of by a split pass over y
+      const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+      yp[clip * (2LL * yp_kpad) + col0 + k] = hi;
+      yp[clip * (2LL * yp_kpad) + yp_kpad + col0 + k] = __float2bfloat16_rn(r - __bfloat162float(hi));
+    }
   }
+  // the last level also clears the K padding of the planes (columns col0 + K .. yp_zero_to - 1)
+  if (yp)
+    for (int k = col0 + K + threadIdx.x; k < yp_zero_to; k += blockDim.x) {
+      yp[clip * (2LL * yp_kpad) + k] = __float2bfloat16_rn(0.f);
+      yp[clip * (2LL * yp_kpad) + yp_kpad + k] = __float2bfloat16_rn(0.f);
+    }
 }
 
 // scores[clip][c] = sigmoid(a_c * u[clip][c] + b_c): eval-mode BatchNorm1d(K) + sigmoid on the output Linear (model.py:268)
@@ -237,8 +251,27 @@ static bool mla_fork_enabled() {
   return on;
 }
 
+// Fused GEMM epilogues (planes_gemm_fused): default on whenever the planes GEMM kernel is; VMB_MLA_FUSE=0 or
+// mla_fuse_set(0) keep the stand-alone affine / split / sigmoid passes (A/B timing and the bit-identity test).
+static std::atomic<int> g_fuse_override{-1};
+int mla_fuse_set(int on) { return g_fuse_override.exchange(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed); }
+static bool mla_fuse_enabled() {
+  if (!vmb::planes_gemm_enabled()) return false;
+  const int o = g_fuse_override.load(std::memory_order_relaxed);
+  if (o >= 0) return o != 0;
+  static const bool on = [] {
+    const char* e = getenv("VMB_MLA_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+static int tc_forward_fused(Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st);
+
 int tc_forward(Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st) {
   const HeadDev& d = h.dev;
+  const size_t pool_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
+  if (mla_fuse_enabled() && pool_smem <= 48 * 1024) return tc_forward_fused(h, emb, batch, scores, st);
   const long long rows = batch * d.T;
   if (rows > 0x7fffffffLL) {
     vmb::set_kernel_error("mla: too many rows for one call");
@@ -331,7 +364,7 @@ int tc_forward(Handle& h, const float* emb, long long batch, float* scores, cuda
       const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
       if (att_smem <= 48 * 1024)     // K = 527, T = 10: 42 KB
         vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, as, Uz, hpad,
-                        d.K, d.T, L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
+                        d.K, d.T, L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K, static_cast<__nv_bfloat16*>(nullptr), 0, 0);
       else
         vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, as, Uz, hpad, d.K, d.T,
                         L.av, L.bv, L.af, L.bf, Y, ystride, l * d.K);
@@ -355,6 +388,131 @@ int tc_forward(Handle& h, const float* emb, long long batch, float* scores, cuda
                     d.out_b, scores);
     vmb::count_launch();
     rc = vmb::check_launch("sigmoid_affine_kernel");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+// The same forward with the glue folded into the GEMMs: every Linear of an embedding chain writes the next Linear's
+// operand planes from its epilogue (BatchNorm1d(T) affine + ReLU + split, and the next level's norm0 for the level's
+// last Linear), the pooling kernel writes the output Linear's operand planes; the output Linear's
+// BatchNorm1d(K) + sigmoid stays a pass of its own.  10 launches for model_conf [2, 1] instead of 14, no fp32 round trip
+// of the hidden activations; each value is computed by the same expressions as in tc_forward above, so the scores are
+// bit-identical to it (tested).
+static int tc_forward_fused(Handle& h, const float* emb, long long batch, float* scores, cudaStream_t st) {
+  const HeadDev& d = h.dev;
+  const long long rows = batch * d.T;
+  if (rows > 0x7fffffffLL) {
+    vmb::set_kernel_error("mla: too many rows for one call");
+    return 1;
+  }
+  const int in_pad = d.lvl[0].fc[0].kpad, hpad = kPad;
+  const size_t sz_x = up(size_t(rows) * 2 * in_pad * 2), sz_p = up(size_t(rows) * 2 * hpad * 2);
+  const size_t sz_u = up(size_t(rows) * hpad * 4), sz_yp = up(size_t(batch) * 2 * d.fc_kpad * 2);
+  bool fork = d.n_levels > 1 && mla_fork_enabled();
+  if (fork && !h.side) {
+    bool ok = cudaStreamCreateWithFlags(&h.side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < kMaxLevels && ok; ++i)
+      ok = cudaEventCreateWithFlags(&h.fork_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.gemm_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      vmb::set_kernel_error("mla: cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+  }
+  // workspace: x planes | three rotating activation plane buffers | normed-input planes | one fp32 z buffer per level |
+  // y planes.  Three buffers, not two: a forked fcv GEMM still reads the level's embedding planes while the next level's
+  // chain runs, and with two buffers the second GEMM of that chain would have to wait for it before it may start.
+  const size_t total = sz_x + 4 * sz_p + d.n_levels * sz_u + sz_yp;
+  char* ws = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&ws), total, st) != cudaSuccess) {
+    vmb::set_kernel_error("mla: workspace allocation of %zu bytes failed: %s", total,
+                          cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  void* X = ws;
+  void* P[3] = {ws + sz_x, ws + sz_x + sz_p, ws + sz_x + 2 * sz_p};
+  void* Pn = ws + sz_x + 3 * sz_p;
+  float* U = reinterpret_cast<float*>(ws + sz_x + 4 * sz_p);
+  void* Yp = ws + sz_x + 4 * sz_p + d.n_levels * sz_u;
+  int rc = split_rows(emb, d.emb_in, rows, d.emb_in, in_pad, d.T, d.lvl[0].n0a, d.lvl[0].n0b, 0, nullptr, nullptr, X, st);
+  const void* cur = X;
+  int pp = 0;
+  const void* side_buf[kMaxLevels] = {};   // planes buffer the forked fcv GEMM of level l may still be reading
+  for (int l = 0; l < d.n_levels && !rc; ++l) {
+    const LevelDev& L = d.lvl[l];
+    for (int j = 0; j < L.n_fc && !rc; ++j) {
+      for (int s = 0; s < l; ++s)
+        if (side_buf[s] == P[pp]) {   // this GEMM overwrites a buffer a forked fcv GEMM reads: wait for that GEMM
+          cudaStreamWaitEvent(st, h.gemm_ev[s], 0);
+          side_buf[s] = nullptr;
+        }
+      vmb::PlanesEpi e{};
+      e.mode = 1;
+      e.T = d.T;
+      e.relu = 1;
+      e.cols = d.hidden;
+      e.cpad = hpad;
+      e.a1 = L.fc[j].a;
+      e.b1 = L.fc[j].b;
+      e.dst = P[pp];
+      if (j == L.n_fc - 1 && l + 1 < d.n_levels) {   // the embedding with the next level's norm0 applied, same pass
+        e.a2 = d.lvl[l + 1].n0a;
+        e.b2 = d.lvl[l + 1].n0b;
+        e.dst2 = Pn;
+      }
+      if (vmb::planes_gemm_fused(cur, L.fc[j].wp, L.fc[j].bias, e, int(rows), hpad, L.fc[j].kpad, st)) {
+        vmb::set_kernel_error("mla: %s", vmb::planes_gemm_last_error());
+        rc = 1;
+      }
+      cur = P[pp];
+      pp = (pp + 1) % 3;
+    }
+    if (rc) break;
+    const bool side = fork && l + 1 < d.n_levels;
+    cudaStream_t as = side ? h.side : st;
+    float* Uz = U + l * (sz_u / sizeof(float));
+    if (side) {
+      cudaEventRecord(h.fork_ev[l], st);            // emb_l planes (cur) are complete here
+      cudaStreamWaitEvent(h.side, h.fork_ev[l], 0);
+    }
+    if (vmb::igemm_linear_split(cur, L.fcv.wp, L.fcv.bias, Uz, hpad, 0, int(rows), hpad, L.fcv.kpad, as)) {   // z = fcv(emb_l)
+      vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+      rc = 1;
+    }
+    if (side) {
+      cudaEventRecord(h.gemm_ev[l], h.side);
+      side_buf[l] = cur;
+    }
+    if (!rc) {
+      const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
+      const bool last = l + 1 == d.n_levels;
+      vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, as, Uz,
+                      static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, static_cast<float*>(nullptr), 0LL,
+                      l * d.K, static_cast<__nv_bfloat16*>(Yp), d.fc_kpad, last ? d.fc_kpad : 0);
+      vmb::count_launch();
+      rc = vmb::check_launch("attention_pool_smem_kernel");
+    }
+    if (side) cudaEventRecord(h.join_ev[l], h.side);
+    cur = Pn;
+  }
+  // join the side branches (also on the error path, so that the workspace is not freed under them)
+  for (int l = 0; l + 1 < d.n_levels && fork; ++l) cudaStreamWaitEvent(st, h.join_ev[l], 0);
+  // The output Linear keeps its separate sigmoid pass: a fused epilogue (planes_gemm mode 2) was measured at 30 us against
+  // 12.5 + 3.8 us — ten CTAs each writing 527-float rows with scalar stores lose more than the launch saves.
+  if (!rc) {
+    float* Uo = U;   // level 0's z buffer is free again: its pooling has been joined
+    if (vmb::igemm_linear_split(Yp, d.fc_wp, d.fc_bias, Uo, hpad, 0, int(batch), hpad, d.fc_kpad, st)) {
+      vmb::set_kernel_error("mla: %s", vmb::igemm_last_error());
+      rc = 1;
+    }
+    if (!rc) {
+      vmb::launch_pdl(sigmoid_affine_kernel, dim3(grid_for(batch * d.K, 256)), dim3(256), 0, st, Uo,
+                      static_cast<long long>(hpad), batch, d.K, d.out_a, d.out_b, scores);
+      vmb::count_launch();
+      rc = vmb::check_launch("sigmoid_affine_kernel");
+    }
   }
   cudaFreeAsync(ws, st);
   return rc;
@@ -433,7 +591,8 @@ int tc_attention(const Handle& h, int level, const float* hemb, long long batch,
     const size_t att_smem = size_t(2) * d.T * ((d.K + 31) & ~31) * sizeof(float);
     if (att_smem <= 48 * 1024)
       vmb::launch_pdl(attention_pool_smem_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), att_smem, st, U,
-                      static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, y, static_cast<long long>(d.K), 0);
+                      static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, y, static_cast<long long>(d.K), 0,
+                      static_cast<__nv_bfloat16*>(nullptr), 0, 0);
     else
       vmb::launch_pdl(attention_pool_kernel, dim3(static_cast<unsigned>(batch)), dim3(256), 0, st, U,
                       static_cast<long long>(hpad), d.K, d.T, L.av, L.bv, L.af, L.bf, y, static_cast<long long>(d.K), 0);

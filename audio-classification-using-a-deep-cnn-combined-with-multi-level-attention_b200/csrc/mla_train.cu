@@ -646,7 +646,7 @@ struct vmb_mla_trainer {
   size_t ws_bytes = 0;
   // the weight-gradient GEMMs (dW = dU^T A) feed nothing but `grads`: they run on a side stream, next to the dX chain
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_att = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_att = nullptr, ev_w = nullptr;
   // backward: the attention branches of every level but the last need only dY and forward state, so they run on a second
   // side stream (with their own scratch: G_p2 .. dWtmp2, one dAtt per level) while the last level's chain runs
   cudaStream_t side2 = nullptr;
@@ -828,6 +828,26 @@ int gemm(const void* a_planes, const void* w_planes, const float* bias, float* o
   return 0;
 }
 
+// Linear + the BatchNorm statistics of its output in one kernel (planes_gemm_stats): replaces gemm() followed by
+// bn_time_stats_kernel.  Falls back to the two-kernel form when the planes GEMM is switched off or T > 16.
+bool stats_in_gemm(int T) {
+  static const bool env_on = [] {
+    const char* e = getenv("VMB_TRAIN_STATS_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return env_on && vmb::planes_gemm_enabled() && T <= 16;
+}
+
+int gemm_stats(const void* a_planes, const void* w_planes, const float* bias, float* out, long long ldo, long long M, int N,
+               int K, const StatJob& j, int cols, cudaStream_t st) {
+  vmb::PlanesStats ps{j.acc, j.stat, j.counter, j.run_mean, j.run_var, j.count, j.channels, cols, kBnEps, kBnMomentum};
+  if (vmb::planes_gemm_stats(a_planes, w_planes, bias, out, ldo, int(M), N, K, kPl, ps, st)) {
+    vmb::set_kernel_error("%s", vmb::planes_gemm_last_error());
+    return 1;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -891,6 +911,7 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
   if (h && h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h && h->ev_dw) cudaEventDestroy(h->ev_dw);
   if (h && h->ev_att) cudaEventDestroy(h->ev_att);
+  if (h && h->ev_w) cudaEventDestroy(h->ev_w);
   if (h && h->side2) {
     cudaStreamSynchronize(h->side2);
     cudaStreamDestroy(h->side2);
@@ -955,6 +976,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_dw, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_att, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_w, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking) != cudaSuccess)
       return fail("vmb_mla_train: cannot create the side stream");
     for (int i = 0; i < kMaxLevels; ++i)
@@ -970,18 +992,34 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     vmb::count_launch();
     return vmb::check_launch("bn_time_stats_kernel");
   };
+  // weights -> operand planes run on the side stream: the first Linear needs them only after the level-0 norm0
+  // statistics and its activation pass, which do not depend on the weights
+  cudaStream_t ws_stream = forked ? h->side : st;
   auto weights = [&](const FcRef& f) {
     TileOut o{f.wp, f.wtp, nullptr, 0, nullptr, f.n_out, f.n_out_pad, f.n_in, f.n_in_pad};
-    return run_tile(FIdentity{params + f.w, f.n_in, params + f.b, f.bias_pad, f.n_out}, o, st, "weight split");
+    return run_tile(FIdentity{params + f.w, f.n_in, params + f.b, f.bias_pad, f.n_out}, o, ws_stream, "weight split");
+  };
+  const bool fuse_stats = stats_in_gemm(T);
+  // Linear (+ bias) into `out` and the BatchNorm statistics of its first `cols` columns
+  auto gemm_bn = [&](const void* a, const FcRef& fc, float* out, int k_pad, int cols, const BnRef& bn, cudaStream_t ss) {
+    if (fuse_stats) return gemm_stats(a, fc.wp, fc.bias_pad, out, Hp, R, Hp, k_pad, statjob(bn, double(B) * cols), cols, ss);
+    int r = gemm(a, fc.wp, fc.bias_pad, out, Hp, R, Hp, k_pad, ss);
+    return r ? r : time_stats(out, Hp, cols, bn, true, ss);
   };
 
   if (do_fwd) {
   // ---- weights -> hi|lo planes, row-major and transposed (they changed in the last optimiser step)
+  if (forked) {
+    cudaEventRecord(h->ev_fork, st);                 // after the optimiser step (and everything else) on the caller's stream
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+  }
   for (int l = 0; l < h->n_levels; ++l) {
     for (int j = 0; j < h->lvl[l].n_fc; ++j) TRY(weights(h->lvl[l].fc[j]));
     TRY(weights(h->lvl[l].fcv));
   }
   TRY(weights(h->fc_out));
+  if (forked) cudaEventRecord(h->ev_w, h->side);
+  bool weights_pending = forked;
 
   // =============================================================================== forward
   bool att_pending = false;
@@ -1000,10 +1038,13 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(run_tile(f, o, st, "norm0 forward"));
     }
     const __nv_bfloat16* a = np;
+    if (weights_pending) {
+      cudaStreamWaitEvent(st, h->ev_w, 0);           // join: every weight plane is written
+      weights_pending = false;
+    }
     for (int j = 0; j < L.n_fc && !rc; ++j) {
       const FcRef& fc = L.fc[j];
-      TRY(gemm(a, fc.wp, fc.bias_pad, h->U[l][j], Hp, R, Hp, fc.n_in_pad, st));
-      TRY(time_stats(h->U[l][j], Hp, H, L.norms[j], true, st));
+      TRY(gemm_bn(a, fc, h->U[l][j], fc.n_in_pad, H, L.norms[j], st));
       const bool last = j == L.n_fc - 1;
       FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
                dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
@@ -1019,8 +1060,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       cudaEventRecord(h->ev_fork, st);               // the level's last activation planes (a) are complete
       cudaStreamWaitEvent(h->side, h->ev_fork, 0);
     }
-    TRY(gemm(a, L.fcv.wp, L.fcv.bias_pad, h->Z[l], Hp, R, Hp, Hp, as));
-    TRY(time_stats(h->Z[l], Hp, K, L.normv, true, as));
+    TRY(gemm_bn(a, L.fcv, h->Z[l], Hp, K, L.normv, as));
     if (!rc) {
       // normf shares the batch statistics but keeps its own running buffers
       StatJob j = statjob(L.normf, double(B) * K);

@@ -20,6 +20,13 @@
 // per TMEM lane quarter, alternating 32-column chunks).  Persistent over tiles; both accumulators double-buffered
 // (2 x 2 x 128 = 512 TMEM columns).  Split-K (the weight-gradient GEMMs: a few output tiles, K = batch * T rows): tile
 // index = (K slice, m tile, n tile), partial sums added with 16-byte vector reductions into a zeroed output.
+//
+// Fused epilogue of the eval-mode head (PlanesEpi, EPI = 1): what used to be a separate pass over the fp32 GEMM output
+// — BatchNorm1d(T) as a per-time-step affine + ReLU + the hi | lo split that feeds the next Linear (model.py:219-221) —
+// is applied to the accumulator row each epilogue thread already holds, with the same expressions in the same order as
+// rows_affine_split_kernel (mla_tc.cu), so the results are bit-identical to the unfused chain.  (A second mode that
+// applied BatchNorm1d(K) + sigmoid in the output Linear's epilogue was measured slower than the separate 4 us pass —
+// ten CTAs writing unaligned 527-float rows with scalar stores — and removed.)
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +44,7 @@ constexpr int kPlaneBytes = 128 * kBK * 2;   // one plane of one K-block of one 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kMaxStatChannels = 16;         // BatchNorm1d(T) channels the statistics epilogue can carry (T = 10)
 
 template <int PLANES>
 struct PCfg {
@@ -44,7 +52,8 @@ struct PCfg {
   static constexpr int kStages = 192 * 1024 / kStageBytes;               // 4 (three planes) or 6 (two)
   static constexpr int kBiasBytes = 2 * kBN * 4;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes;
+  static constexpr int kStatBytes = kMaxStatChannels * 2 * 8 + 16;      // {sum, sum of squares} per channel + a flag
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes + kStatBytes;
   static constexpr int kTmemCols = 512;                                  // 2 buffers x (hi*hi | cross products) x 128
 };
 
@@ -57,9 +66,28 @@ struct PlanesParams {
   long long ldo;
   const float* bias;
   float* out;
+  PlanesEpi epi;     // EPI == 1 only
+  PlanesStats stats; // EPI == 3 only
 };
 
-template <int PLANES, bool ATOMIC>
+// hi | lo bf16 split of 32 consecutive values of one row -> two 64-byte runs (full 32-byte sectors)
+__device__ __forceinline__ void store_split32(const float (&v)[32], __nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j]), h1 = __float2bfloat16_rn(v[j + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[j] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 1] - __bfloat162float(h1));
+    h[j / 2] = __bfloat16_as_ushort(h0) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+    l[j / 2] = __bfloat16_as_ushort(l0) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+  }
+  st_global_256(hi_dst, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+  st_global_256(hi_dst + 16, h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+  st_global_256(lo_dst, l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]);
+  st_global_256(lo_dst + 16, l[8], l[9], l[10], l[11], l[12], l[13], l[14], l[15]);
+}
+
+template <int PLANES, bool ATOMIC, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const PlanesParams p) {
@@ -72,6 +100,8 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  double* stat_s = reinterpret_cast<double*>(smem + C::kStages * C::kStageBytes + C::kBiasBytes + C::kBarBytes);
+  int* last_flag = reinterpret_cast<int*>(stat_s + 2 * kMaxStatChannels);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +123,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     mbar_fence_init();
   }
+  if (EPI == 3 && threadIdx.x < 2 * kMaxStatChannels) stat_s[threadIdx.x] = 0.0;
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
@@ -195,7 +226,14 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int row = m_tile * kBM + q * 32 + lane;
       const bool valid = row < p.M;
       float* out_row = p.out + static_cast<size_t>(row) * p.ldo + n0;
+      float s1 = 1.f, o1 = 0.f, s2 = 1.f, o2 = 0.f;
+      if (EPI == 1 && valid) {
+        const int t = row % p.epi.T;
+        if (p.epi.a1) { s1 = __ldg(p.epi.a1 + t); o1 = __ldg(p.epi.b1 + t); }
+        if (p.epi.a2) { s2 = __ldg(p.epi.a2 + t); o2 = __ldg(p.epi.b2 + t); }
+      }
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * kBN);
+      double st1 = 0.0, st2 = 0.0;   // EPI == 3: this row's sum / sum of squares over the tile's valid columns
 #pragma unroll 1
       for (int ch = half; ch < kBN / 32; ch += 2) {
         uint32_t big[32], small[32];
@@ -215,7 +253,41 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (valid) {
+        if (EPI == 3 && valid) {
+          const int c0 = n0 + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.stats.cols) {
+              st1 += f[j];
+              st2 += double(f[j]) * f[j];
+            }
+        }
+        if (EPI == 1) {
+          // h = relu?(a1_t u + b1_t) as hi | lo planes; with dst2 also a2_t h + b2_t (the next level's norm0).  Columns
+          // past `cols` are the zero padding of the next GEMM's K.
+          if (valid) {
+            const int c0 = n0 + ch * 32;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = fmaf(s1, f[j], o1);
+              if (p.epi.relu) t = fmaxf(t, 0.f);
+              x[j] = c0 + j < p.epi.cols ? t : 0.f;
+            }
+            __nv_bfloat16* d = static_cast<__nv_bfloat16*>(p.epi.dst) + static_cast<size_t>(row) * (2 * p.epi.cpad) + c0;
+            if (p.epi.dst2) {
+              float y[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] = c0 + j < p.epi.cols ? fmaf(s2, x[j], o2) : 0.f;
+              __nv_bfloat16* d2 =
+                  static_cast<__nv_bfloat16*>(p.epi.dst2) + static_cast<size_t>(row) * (2 * p.epi.cpad) + c0;
+              store_split32(x, d, d + p.epi.cpad);
+              store_split32(y, d2, d2 + p.epi.cpad);
+            } else {
+              store_split32(x, d, d + p.epi.cpad);
+            }
+          }
+        } else if (valid) {
           float* dst = out_row + ch * 32;
           if (ATOMIC) {
 #pragma unroll
@@ -235,6 +307,38 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (EPI == 3 && valid) {   // channel = time step of the row
+        const int t = row % p.stats.channels;
+        atomicAdd(stat_s + 2 * t, st1);
+        atomicAdd(stat_s + 2 * t + 1, st2);
+      }
+    }
+    if (EPI == 3) {
+      // BatchNorm statistics of the output (model.py:221 in train mode): this CTA's partial sums go to the global
+      // accumulators; the CTA that arrives last turns them into {mean, rstd} and updates the running statistics, exactly
+      // as bn_time_stats_kernel does after its own pass over the matrix
+      const PlanesStats& j = p.stats;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (ep_tid < 2 * j.channels) atomicAdd(j.acc + ep_tid, stat_s[ep_tid]);
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (ep_tid == 0) *last_flag = atomicAdd(j.counter, 1u) == gridDim.x - 1;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      if (*last_flag) {
+        __threadfence();
+        for (int c = ep_tid; c < j.channels; c += kEpiThreads) {
+          const double mean = __ldcg(j.acc + 2 * c) / j.count;
+          double var = __ldcg(j.acc + 2 * c + 1) / j.count - mean * mean;
+          if (var < 0) var = 0;
+          j.stat[2 * c] = static_cast<float>(mean);
+          j.stat[2 * c + 1] = static_cast<float>(1.0 / sqrt(var + double(j.eps)));
+          if (j.run_mean) {
+            const double unbiased = j.count > 1 ? var * j.count / (j.count - 1) : var;
+            j.run_mean[c] = (1.f - j.momentum) * j.run_mean[c] + j.momentum * static_cast<float>(mean);
+            j.run_var[c] = (1.f - j.momentum) * j.run_var[c] + j.momentum * static_cast<float>(unbiased);
+          }
+        }
+      }
     }
   }
 
@@ -248,9 +352,9 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 thread_local char g_perr[384] = "";
 
-template <int PLANES, bool ATOMIC>
+template <int PLANES, bool ATOMIC, int EPI = 0>
 int launch_planes(const CUtensorMap& ta, const CUtensorMap& tb, const PlanesParams& p, cudaStream_t stream) {
-  auto kern = planes_gemm_kernel<PLANES, ATOMIC>;
+  auto kern = planes_gemm_kernel<PLANES, ATOMIC, EPI>;
   static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
   constexpr int smem = PCfg<PLANES>::kSmemBytes;
   if (device_needs_setup(attr_set)) {
@@ -295,14 +399,24 @@ int planes_gemm_set(int on) {
 }
 
 // out fp32 [M][ldo] = act(sum of plane products + bias), or with ksplit > 1 / == -1: out += the K slices' partial sums.
-// K % 32 == 0, N % 128 == 0, planes 2 or 3; the operands' rows are planes * K bf16 long.
-int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
-                int N, int K, int planes, int ksplit, cudaStream_t stream) {
+// K % 32 == 0, N % 128 == 0, planes 2 or 3; the operands' rows are planes * K bf16 long.  With epi != nullptr (planes
+// == 2, no K split) the epilogue of PlanesEpi::mode replaces the fp32 store.
+static int planes_gemm_any(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo,
+                           int relu, int M, int N, int K, int planes, int ksplit, const PlanesEpi* epi,
+                           cudaStream_t stream, const PlanesStats* stats = nullptr) {
   if (M <= 0) return 0;
   if (K % kBK != 0 || N % kBN != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_perr, sizeof g_perr, "planes_gemm: need K %% 32 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d planes=%d)", K, N,
              planes);
     return 1;
+  }
+  if (epi) {
+    if (planes != 2 || ksplit != 0 || epi->mode != 1 || epi->cols <= 0 || epi->cols > N || !epi->dst || epi->T <= 0 ||
+        epi->cpad < N || epi->cpad % 16 != 0 || (epi->a1 && !epi->b1) || (epi->dst2 && (!epi->a2 || !epi->b2)) ||
+        (reinterpret_cast<uintptr_t>(epi->dst) & 31) || (reinterpret_cast<uintptr_t>(epi->dst2) & 31)) {
+      snprintf(g_perr, sizeof g_perr, "planes_gemm: bad fused-epilogue arguments (mode %d)", epi->mode);
+      return 1;
+    }
   }
   CUtensorMap ta, tb;
   {
@@ -334,9 +448,37 @@ int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, f
   p.ldo = ldo;
   p.bias = bias;
   p.out = out;
+  if (epi) {
+    p.epi = *epi;
+    return launch_planes<2, false, 1>(ta, tb, p, stream);
+  }
+  if (stats) {
+    if (ksplit != 0 || stats->channels <= 0 || stats->channels > kMaxStatChannels || stats->cols <= 0 || stats->cols > N ||
+        !stats->acc || !stats->stat || !stats->counter || (stats->run_mean && !stats->run_var)) {
+      snprintf(g_perr, sizeof g_perr, "planes_gemm: bad statistics arguments");
+      return 1;
+    }
+    p.stats = *stats;
+    return planes == 3 ? launch_planes<3, false, 3>(ta, tb, p, stream) : launch_planes<2, false, 3>(ta, tb, p, stream);
+  }
   if (ksplit > 1 || ksplit == -1)
     return planes == 3 ? launch_planes<3, true>(ta, tb, p, stream) : launch_planes<2, true>(ta, tb, p, stream);
   return planes == 3 ? launch_planes<3, false>(ta, tb, p, stream) : launch_planes<2, false>(ta, tb, p, stream);
+}
+
+int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
+                int N, int K, int planes, int ksplit, cudaStream_t stream) {
+  return planes_gemm_any(a_planes, b_planes, bias, out, ldo, relu, M, N, K, planes, ksplit, nullptr, stream);
+}
+
+int planes_gemm_stats(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int M,
+                      int N, int K, int planes, const PlanesStats& stats, cudaStream_t stream) {
+  return planes_gemm_any(a_planes, b_planes, bias, out, ldo, 0, M, N, K, planes, 0, nullptr, stream, &stats);
+}
+
+int planes_gemm_fused(const void* a_planes, const void* b_planes, const float* bias, const PlanesEpi& epi, int M, int N,
+                      int K, cudaStream_t stream) {
+  return planes_gemm_any(a_planes, b_planes, bias, nullptr, 0, 0, M, N, K, 2, 0, &epi, stream);
 }
 
 }  // namespace vmb

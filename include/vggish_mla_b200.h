@@ -43,6 +43,11 @@ int vmb_igemm_pair_enable(int on);
  * 1 (default) / 0 / -1 as above; every bf16 conv kernel adds its partial products in the same order, so the results are
  * bit-identical either way. */
 int vmb_igemm_halo_enable(int on);
+/* Eval-mode head (model.py:258-269): 1 (default) = the glue between the Linear layers of an embedding chain —
+ * BatchNorm1d(T) affine + ReLU + operand split (model.py:219-221) — runs in the GEMM epilogues; 0 = as separate
+ * kernels (the A/B baseline: every value is computed by the same expressions, so the scores are bit-identical);
+ * -1 = back to the default (environment VMB_MLA_FUSE, else 1).  Returns the previous override (-1 / 0 / 1). */
+int vmb_mla_fuse_enable(int on);
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each stage of
  * vmb_vggish_forward / vmb_pipeline_forward.  Stage ids: */
 enum {

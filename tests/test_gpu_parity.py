@@ -448,6 +448,36 @@ def test_head_vs_golden(golden_head, tag, K, conf, seed):
     h.close()
 
 
+@pytest.mark.parametrize("K,conf,emb_in,seed", [(527, (2, 1), 128, 2), (10, (1, 2, 1), 128, 5), (527, (1,), 128, 6),
+                                                (33, (3,), 12288, 4)])
+def test_head_fused_epilogues_are_bit_identical(K, conf, emb_in, seed):
+    """The glue of the eval-mode head (model.py:219-221 BatchNorm1d(T) + ReLU, :268 BatchNorm1d(K) + sigmoid) runs in
+    the GEMM epilogues by default; with vmb_mla_fuse_enable(0) it runs as separate kernels.  Both evaluate the same
+    expressions in the same order: the scores must be equal bit for bit, at full and ragged tile sizes."""
+    L = _lib.lib()
+    sd = synth.mla_state_dict(conf, emb_in, 600, K, 10, seed=seed)
+    h = engine.MlaHandle(sd, conf, emb_in, 600, K, 10, DEV)
+    g = torch.Generator().manual_seed(seed)
+    try:
+        for batch in (1, 13, 256, 300):
+            x = (torch.randn(batch, 10, emb_in, generator=g) * 1.5).to(DEV)
+            L.vmb_mla_fuse_enable(1)
+            n0 = L.vmb_launch_count()
+            fused = h.forward(x)
+            n_fused = L.vmb_launch_count() - n0
+            L.vmb_mla_fuse_enable(0)
+            n0 = L.vmb_launch_count()
+            plain = h.forward(x)
+            n_plain = L.vmb_launch_count() - n0
+            torch.cuda.synchronize()
+            assert torch.equal(fused, plain), f"K={K} conf={conf} batch={batch}"
+            assert n_fused < n_plain
+        print(f"head {conf} K={K}: {n_fused} launches fused, {n_plain} as separate kernels")
+    finally:
+        L.vmb_mla_fuse_enable(-1)
+        h.close()
+
+
 def test_reference_named_head_module(golden_head):
     import model
     old = model.K
