@@ -64,10 +64,21 @@ SIGNATURES = {
     "vmb_mla_trainer_create": (_int, [C.POINTER(_c_p), _int, C.POINTER(_int), _int, _int, _int, _int, _ll, _c_p]),
     "vmb_mla_trainer_destroy": (None, [_c_p]),
     "vmb_mla_train_step": (_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p, _c_p, _c_p]),
+    "vmb_mla_train_tail_offset": (_ll, [_c_p]),
+    "vmb_mla_train_wait_tail": (_int, [_c_p, _c_p]),
     "vmb_mla_train_forward": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p]),
     "vmb_mla_train_backward": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_ulonglong, _c_p, _c_p]),
     "vmb_adam_step": (_int, [_c_p, _c_p, _c_p, _c_p, _ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _ll,
                              C.c_float, _c_p]),
+    "vmb_dp_slice": (None, [_ll, _int, _int, C.POINTER(_ll), C.POINTER(_ll)]),
+    "vmb_dp_create": (_int, [C.POINTER(_c_p), _ll, _int, _int, _c_p]),
+    "vmb_dp_connect": (_int, [_c_p, _c_p]),
+    "vmb_dp_params": (_c_p, [_c_p]),
+    "vmb_dp_grads": (_c_p, [_c_p, _int]),
+    "vmb_dp_adam_step": (_int, [_c_p, _int, _c_p, _c_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _ll, _c_p]),
+    "vmb_dp_status": (_int, [_c_p]),
+    "vmb_dp_disconnect": (None, [_c_p]),
+    "vmb_dp_destroy": (None, [_c_p]),
     "vmb_pipeline_workspace_bytes": (_sz, [_ll, _ll]),
     "vmb_pipeline_forward": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _c_p, _c_p, _sz, _c_p]),
     "vmb_pipeline_forward_host": (_int, [_c_p, _c_p, _c_p, _ll, _ll, _c_p, _ll, _c_p]),

@@ -65,6 +65,14 @@ def train_layout(model_conf: Sequence[int], emb_in: int, hidden: int, n_classes:
     return params, running, po, ro
 
 
+class _DeviceArray:
+    """A float32 device array the library owns, presented to torch through __cuda_array_interface__."""
+
+    def __init__(self, address: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(address), False),
+                                         "version": 2}
+
+
 class HeadTrainer:
     """Owns the library trainer handle and the flat buffers of one data-parallel rank."""
 
@@ -97,17 +105,83 @@ class HeadTrainer:
                                                     n_classes, t_steps, int(max_batch), stream_ptr()),
                   "vmb_mla_trainer_create")
         self.max_batch = int(max_batch)
+        self._dp = None              # vmb_dp handle once enable_peer_step() has run
+        self._parity = 0
+        self._comm_stream = None     # created by the first overlapped all-reduce
+        self._tail = 0
         self.step_count = 0
         self.num_batches_tracked = 0
         self.generation = 0      # bumped by every train-mode forward through the autograd bridge (one step in flight)
         self.fcf: Dict[str, torch.Tensor] = {}      # carried through state_dict round trips untouched
 
-    def close(self) -> None:
-        if getattr(self, "_h", None) and self._h.value and _lib is not None:     # _lib is None at interpreter exit
+    def close(self, _collective: bool = True) -> None:
+        if _lib is None:                                                         # interpreter exit
+            return
+        if getattr(self, "_dp", None):
+            # the arena is mapped by the other ranks: everybody unmaps, then everybody frees
+            import torch.distributed as dist
+            dp, self._dp = self._dp, None
+            self.params = self.params.clone()
+            self.grads = self.grads.clone()
+            self._grads2 = None
+            _lib.lib().vmb_dp_disconnect(dp)
+            if _collective and dist.is_available() and dist.is_initialized():
+                try:
+                    dist.barrier(group=self.group)
+                except Exception:                                                # a peer is already gone
+                    pass
+            _lib.lib().vmb_dp_destroy(dp)
+        if getattr(self, "_h", None) and self._h.value:
             _lib.lib().vmb_mla_trainer_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    # -- data parallel over the GPUs of one box without NCCL on the step
+    def enable_peer_step(self) -> bool:
+        """Move params / grads into a library-owned arena that every rank of the process group maps through CUDA IPC,
+        so that step() can use vmb_dp_adam_step: ONE kernel per rank that reduce-scatters the gradients over NVLink peer
+        loads, applies Adam to the rank's slice and all-gathers the new parameters with peer stores (csrc/dp_adam.cu),
+        instead of an NCCL all-reduce followed by the Adam kernel on every rank.  The Adam moments become sharded: each
+        rank keeps its slice.  Collective over the group; returns False (and changes nothing) for a single rank."""
+        import torch.distributed as dist
+        if self._dp is not None:
+            return True
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return False
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        L = _lib.lib()
+        handle = (C.c_char * 64)()
+        dp = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(L.vmb_dp_create(C.byref(dp), self.n_params, rank, world, C.cast(handle, C.c_void_p)), "vmb_dp_create")
+            every = [None] * world
+            dist.all_gather_object(every, bytes(handle.raw), group=self.group)
+            blob = b"".join(every)
+            check(L.vmb_dp_connect(dp, C.cast(C.c_char_p(blob), C.c_void_p)), "vmb_dp_connect")
+            npad = (self.n_params + 3) // 4 * 4
+            params = torch.as_tensor(_DeviceArray(L.vmb_dp_params(dp), self.n_params), device=self.device)
+            params.copy_(self.params)
+            self._grads2 = [torch.as_tensor(_DeviceArray(L.vmb_dp_grads(dp, i), self.n_params), device=self.device)
+                            for i in (0, 1)]
+            for name in ("exp_avg", "exp_avg_sq"):
+                full = torch.zeros(npad, device=self.device)
+                full[:self.n_params].copy_(getattr(self, name))
+                setattr(self, name, full)
+            self.params, self.grads, self._parity, self._dp = params, self._grads2[0], 0, dp
+            b, e = C.c_longlong(0), C.c_longlong(0)
+            L.vmb_dp_slice(self.n_params, world, rank, C.byref(b), C.byref(e))
+            self.slice = (b.value, e.value)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        return True
+
+    def peer_step_status(self) -> None:
+        """Raises if a cross-GPU barrier of vmb_dp_adam_step gave up waiting for a rank (synchronises the device)."""
+        if self._dp is not None:
+            with torch.cuda.device(self.device):
+                check(_lib.lib().vmb_dp_status(self._dp), "vmb_dp_status")
+
+    def __del__(self):
+        self.close(_collective=False)      # no collective from the garbage collector
 
     # -- reference-format state_dict in / out
     def load_state_dict(self, sd: dict) -> None:
@@ -172,9 +246,49 @@ class HeadTrainer:
                                            float(self.eps), 0.0, self.step_count, 1.0 / world, stream_ptr()),
                   "vmb_adam_step")
 
-    def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def all_reduce_grads_overlapped(self) -> int:
+        """The same SUM all-reduce in two pieces, the first one overlapped with the rest of the backward pass: the
+        library computes level 0's embedding chain last, and its parameters come first in the flat order, so
+        grads[tail:] are final while that chain still runs (vmb_mla_train_wait_tail).  The tail (78 % of the bucket for
+        model_conf [2, 1]) is reduced from a communication stream that waits for that point only; the head follows
+        when the step is complete.  Call right after forward_backward(); returns the world size."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return 1
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+            self._tail = int(_lib.lib().vmb_mla_train_tail_offset(self._h))
+        main = torch.cuda.current_stream(self.device)
+        check(_lib.lib().vmb_mla_train_wait_tail(self._h, C.c_void_p(self._comm_stream.cuda_stream)),
+              "vmb_mla_train_wait_tail")
+        with torch.cuda.stream(self._comm_stream):
+            work = dist.all_reduce(self.grads[self._tail:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        dist.all_reduce(self.grads[:self._tail], op=dist.ReduceOp.SUM, group=self.group)
+        work.wait()                                   # the current stream waits for the tail's reduction
+        main.wait_stream(self._comm_stream)
+        return world
+
+    def step(self, x: torch.Tensor, labels: torch.Tensor, overlap: bool = True) -> torch.Tensor:
+        """forward + backward, gradient averaging over the ranks, Adam.  After enable_peer_step(): the fused
+        reduce-scatter + Adam + all-gather kernel over NVLink peer memory.  Otherwise an NCCL all-reduce (overlapped
+        with the end of the backward pass unless overlap=False — the same sums either way) and the Adam kernel."""
+        if self._dp is not None:
+            # gradients alternate between the arena's two buffers (a slower rank may still be reading the previous one)
+            self.grads = self._grads2[self._parity]
+            loss, _ = self.forward_backward(x, labels)
+            self.step_count += 1
+            with torch.cuda.device(self.device):
+                check(_lib.lib().vmb_dp_adam_step(self._dp, self._parity, ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                  float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                                                  float(self.eps), 0.0, self.step_count, stream_ptr()),
+                      "vmb_dp_adam_step")
+            self._parity ^= 1
+            return loss
         loss, _ = self.forward_backward(x, labels)
-        self.adam(self.all_reduce_grads())
+        self.adam(self.all_reduce_grads_overlapped() if overlap else self.all_reduce_grads())
         return loss
 
 

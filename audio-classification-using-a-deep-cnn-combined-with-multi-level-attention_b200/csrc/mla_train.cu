@@ -127,26 +127,29 @@ bn_time_stats_kernel(const float* __restrict__ x, long long ld, long long batch,
 // normf normalises the same tensor as normv: re-derive the statistics and update ITS running buffers
 __global__ void bn_running_only_kernel(StatJob job) { finalize_stats(job); }
 
-// BatchNorm1d(K) on [batch][K]: channel = column.  grid = ceil(K / 32); block (32, 8).
+// BatchNorm1d(K) on [batch][K]: channel = column.  grid = ceil(K / 8); block = 8 columns x 32 row groups (a warp reads
+// four rows of 32 bytes: whole sectors), so that K = 527 spreads over 66 CTAs rather than 17.
+constexpr int kColsPerCta = 8, kRowGroups = 32;
 __global__ void __launch_bounds__(256)
 bn_col_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int K, StatJob job) {
   vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
   vmb::pdl_wait();
-  const int c = blockIdx.x * 32 + threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int tx = threadIdx.x % kColsPerCta, ty = threadIdx.x / kColsPerCta;
+  const int c = blockIdx.x * kColsPerCta + tx;
   double s1 = 0, s2 = 0;
   if (c < K)
-    for (long long b = ty; b < batch; b += 8) {
+    for (long long b = ty; b < batch; b += kRowGroups) {
       const float v = __ldg(x + b * ld + c);
       s1 += v;
       s2 += double(v) * v;
     }
-  __shared__ double r1[8][32], r2[8][32];
-  r1[ty][threadIdx.x % 32] = s1;
-  r2[ty][threadIdx.x % 32] = s2;
+  __shared__ double r1[kRowGroups][kColsPerCta], r2[kRowGroups][kColsPerCta];
+  r1[ty][tx] = s1;
+  r2[ty][tx] = s2;
   __syncthreads();
   if (ty == 0 && c < K) {
     double a = 0, b = 0;
-    for (int w = 0; w < 8; ++w) { a += r1[w][threadIdx.x]; b += r2[w][threadIdx.x]; }
+    for (int w = 0; w < kRowGroups; ++w) { a += r1[w][tx]; b += r2[w][tx]; }
     job.acc[2 * c] = a;
     job.acc[2 * c + 1] = b;
   }
@@ -554,7 +557,8 @@ out_loss_rows_kernel(const float* __restrict__ o, long long ldo, int K, const fl
 
 // dp[b][k] = dout * out (1 - out) with dout = (exp(out - lse_b) - [k == label_b]) / B (cross-entropy on the sigmoid
 // outputs) or an externally supplied d(loss)/d(scores); BN_K backward over the batch per class:
-// do = gamma rstd (dp - mean_b dp - xhat mean_b(dp xhat)).  grid = ceil(K/32), block (32, 8); writes do fp32 [B][ld].
+// do = gamma rstd (dp - mean_b dp - xhat mean_b(dp xhat)).  grid = ceil(K/8), block = 8 columns x 32 row groups (see
+// bn_col_stats_kernel); a thread keeps dp and xhat of its first kKeep rows in registers between the two passes.
 __global__ void __launch_bounds__(256)
 out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const float* __restrict__ stat,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -562,10 +566,11 @@ out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const 
                        const float* __restrict__ dscores, long long batch, float* __restrict__ d_o, long long ldd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
   vmb::pdl_wait();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + tx;
-  __shared__ double r1[8][32], r2[8][32];
-  __shared__ float m1[32], m2[32];
+  constexpr int kKeep = 16;       // batch <= 512 rows: everything stays in registers
+  const int tx = threadIdx.x % kColsPerCta, ty = threadIdx.x / kColsPerCta;
+  const int k = blockIdx.x * kColsPerCta + tx;
+  __shared__ double r1[kRowGroups][kColsPerCta], r2[kRowGroups][kColsPerCta];
+  __shared__ float m1[kColsPerCta], m2[kColsPerCta];
   const bool ok = k < K;
   const float mu = ok ? stat[2 * k] : 0.f, rstd = ok ? stat[2 * k + 1] : 0.f, g = ok ? gamma[k] : 0.f,
               be = ok ? beta[k] : 0.f;
@@ -576,31 +581,50 @@ out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const 
                                : (expf(s - lse[b]) - (labels[b] == k ? 1.f : 0.f)) / static_cast<float>(batch);
     return dout * s * (1.f - s);
   };
+  float keep_dp[kKeep], keep_xh[kKeep];
   double s1 = 0, s2 = 0;
-  if (ok)
-    for (long long b = ty; b < batch; b += 8) {
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+      const long long b = ty + static_cast<long long>(i) * kRowGroups;
+      keep_dp[i] = 0.f;
+      keep_xh[i] = 0.f;
+      if (b < batch) {
+        keep_dp[i] = dp_of(b, keep_xh[i]);
+        s1 += keep_dp[i];
+        s2 += double(keep_dp[i]) * keep_xh[i];
+      }
+    }
+    for (long long b = ty + static_cast<long long>(kKeep) * kRowGroups; b < batch; b += kRowGroups) {
       float xh;
       const float dp = dp_of(b, xh);
       s1 += dp;
       s2 += double(dp) * xh;
     }
+  }
   r1[ty][tx] = s1;
   r2[ty][tx] = s2;
   __syncthreads();
   if (ty == 0) {
     double a = 0, b = 0;
-    for (int w = 0; w < 8; ++w) { a += r1[w][tx]; b += r2[w][tx]; }
+    for (int w = 0; w < kRowGroups; ++w) { a += r1[w][tx]; b += r2[w][tx]; }
     m1[tx] = static_cast<float>(a / double(batch));
     m2[tx] = static_cast<float>(b / double(batch));
     if (ok) { dbeta[k] = static_cast<float>(a); dgamma[k] = static_cast<float>(b); }
   }
   __syncthreads();
-  if (ok)
-    for (long long b = ty; b < batch; b += 8) {
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+      const long long b = ty + static_cast<long long>(i) * kRowGroups;
+      if (b < batch) d_o[b * ldd + k] = g * rstd * (keep_dp[i] - m1[tx] - keep_xh[i] * m2[tx]);
+    }
+    for (long long b = ty + static_cast<long long>(kKeep) * kRowGroups; b < batch; b += kRowGroups) {
       float xh;
       const float dp = dp_of(b, xh);
       d_o[b * ldd + k] = g * rstd * (dp - m1[tx] - xh * m2[tx]);
     }
+  }
 }
 
 // ------------------------------------------------------------------ Adam (torch.optim.Adam, amsgrad = False)
@@ -647,6 +671,10 @@ struct vmb_mla_trainer {
   // the weight-gradient GEMMs (dW = dU^T A) feed nothing but `grads`: they run on a side stream, next to the dX chain
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_att = nullptr, ev_w = nullptr;
+  // recorded in the backward pass where every gradient from `tail_offset` on is final (all but level 0's embedding chain):
+  // a data-parallel caller starts the all-reduce of that part of the bucket while the rest of the backward pass runs
+  cudaEvent_t ev_tail = nullptr;
+  long long tail_offset = 0;
   // backward: the attention branches of every level but the last need only dY and forward state, so they run on a second
   // side stream (with their own scratch: G_p2 .. dWtmp2, one dAtt per level) while the last level's chain runs
   cudaStream_t side2 = nullptr;
@@ -792,6 +820,8 @@ void build_layout(vmb_mla_trainer* h, const int* n_fc) {
   h->n_params = p;
   h->n_running = r;
   h->n_slots = slot;
+  // level 0's embedding chain is the last thing the backward pass computes; everything after it in the flat order is final earlier
+  h->tail_offset = h->n_levels > 1 ? h->lvl[1].norm0.g : h->lvl[0].fcv.w;
 }
 
 dim3 tile_grid(long long rows_pad, int cols_pad) {
@@ -912,6 +942,7 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
   if (h && h->ev_dw) cudaEventDestroy(h->ev_dw);
   if (h && h->ev_att) cudaEventDestroy(h->ev_att);
   if (h && h->ev_w) cudaEventDestroy(h->ev_w);
+  if (h && h->ev_tail) cudaEventDestroy(h->ev_tail);
   if (h && h->side2) {
     cudaStreamSynchronize(h->side2);
     cudaStreamDestroy(h->side2);
@@ -1090,7 +1121,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   TRY(gemm(h->Y_p, h->fc_out.wp, h->fc_out.bias_pad, h->O, Hp, B, Hp, h->ycols_pad, st));
   if (!rc) {
     StatJob j = statjob(h->norm_out, double(B));
-    vmb::launch_pdl(bn_col_stats_kernel, dim3((K + 31) / 32), dim3(256), 0, st, h->O, Hp, B, K, j);
+    vmb::launch_pdl(bn_col_stats_kernel, dim3((K + kColsPerCta - 1) / kColsPerCta), dim3(256), 0, st, h->O, Hp, B, K, j);
     vmb::count_launch();
     TRY(vmb::check_launch("bn_col_stats_kernel"));
     const float* stat = slotstat(h->norm_out.slot);
@@ -1134,7 +1165,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   };
   if (!rc) {
     const float* stat = slotstat(h->norm_out.slot);
-    out_bn_backward_kernel<<<(K + 31) / 32, 256, 0, st>>>(h->O, Hp, K, stat, params + h->norm_out.g, params + h->norm_out.b,
+    out_bn_backward_kernel<<<(K + kColsPerCta - 1) / kColsPerCta, 256, 0, st>>>(h->O, Hp, K, stat, params + h->norm_out.g, params + h->norm_out.b,
                                                           labels, h->lse, dscores, B, h->dO, Hp, grads + h->norm_out.g,
                                                           grads + h->norm_out.b);
     vmb::count_launch();
@@ -1211,6 +1242,16 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     } else {
       att_branch(l, st, false, h->dA);
     }
+    if (l == 0) {
+      // everything but level 0's embedding chain has its gradient: the weight-gradient GEMMs still on the side stream
+      // are joined, then the tail event marks grads[tail_offset ..] final (vmb_mla_train_wait_tail)
+      before_g_overwrite();
+      if (!h->ev_tail && cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
+        vmb::set_kernel_error("cannot create the tail event");
+        rc = 1;
+      }
+      if (h->ev_tail) cudaEventRecord(h->ev_tail, st);
+    }
     // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
     const float* da2 = (l + 1 < h->n_levels) ? h->dEnext : nullptr;
     for (int j = L.n_fc - 1; j >= 0 && !rc; --j) {
@@ -1271,6 +1312,19 @@ int vmb_mla_train_step(vmb_mla_trainer_t* h, const float* params, float* running
   if (!labels) return fail("vmb_mla_train_step: labels are required");
   return train_phases(kPhaseForward | kPhaseBackward, h, params, running, x, labels, nullptr, batch, dropout_p, seed,
                       grads, loss, scores, stream);
+}
+
+long long vmb_mla_train_tail_offset(const vmb_mla_trainer_t* h) {
+  if (!h) return -1;
+  return h->tail_offset;
+}
+
+int vmb_mla_train_wait_tail(vmb_mla_trainer_t* h, void* stream) {
+  if (!h) return fail("vmb_mla_train_wait_tail: null handle");
+  if (!h->ev_tail) return fail("vmb_mla_train_wait_tail: no backward pass has been enqueued on this trainer");
+  if (cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_tail, 0) != cudaSuccess)
+    return fail("vmb_mla_train_wait_tail: cudaStreamWaitEvent failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
 }
 
 int vmb_mla_train_forward(vmb_mla_trainer_t* h, const float* params, float* running, const float* x, long long batch,

@@ -448,12 +448,29 @@ def leg_train(dev, rank, world, barrier, max_over_ranks):
     for _ in range(5):
         tr.step(x, labels)
     steps = 20
+    # the two NCCL forms first (A/B in the same run): the whole bucket reduced after the backward pass, and its tail
+    # reduced while the backward pass finishes
+    ms_serial = ms_overlap = None
+    if world > 1:
+        ms_serial = _timed(lambda: tr.step(x, labels, overlap=False), steps, barrier, max_over_ranks) / steps
+        ms_overlap = _timed(lambda: tr.step(x, labels, overlap=True), steps, barrier, max_over_ranks) / steps
+        # the product path: reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory (csrc/dp_adam.cu)
+        tr.enable_peer_step()
+        for _ in range(5):
+            tr.step(x, labels)
     l0 = _lib.lib().vmb_launch_count()
     ms = _timed(lambda: tr.step(x, labels), steps, barrier, max_over_ranks) / steps
     launches = _lib.lib().vmb_launch_count() - l0
+    tr.peer_step_status()
+    peer = tr._dp is not None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     phases = [0.0, 0.0, 0.0]
-    for _ in range(10):
+    loss = float(tr.loss.item())
+    tr.close()
+    # phase split with the NCCL form (events between the phases): a second trainer, the arena is gone
+    tr = training.HeadTrainer(conf, 128, 600, N_CLASSES, 10, per_gpu, dev, lr=1e-3, dropout_p=0.4, seed=1234)
+    tr.load_state_dict(synth.mla_state_dict(conf, 128, 600, N_CLASSES, 10, seed=2))
+    for it in range(13):
         ev[0].record()
         tr.forward_backward(x, labels)
         ev[1].record()
@@ -463,13 +480,17 @@ def leg_train(dev, rank, world, barrier, max_over_ranks):
         ev[3].record()
         torch.cuda.synchronize()
         for i in range(3):
-            phases[i] += ev[i].elapsed_time(ev[i + 1]) / 10
-    loss = float(tr.loss.item())
+            if it >= 3:
+                phases[i] += ev[i].elapsed_time(ev[i + 1]) / 10
     tr.close()
     return {"value": per_gpu * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "rows_per_gpu": per_gpu,
             "global_batch": per_gpu * world, "allreduce_bytes": tr.n_params * 4 if world > 1 else 0,
             "phase_ms": {"forward_backward": phases[0], "allreduce": phases[1], "adam": phases[2]},
             "gpu_launches_per_step": launches / steps, "final_loss": loss,
+            "gradient_exchange": ("vmb_dp_adam_step: reduce-scatter + Adam + parameter all-gather in one kernel over NVLink "
+                                  "peer memory (CUDA IPC arenas), two flag barriers") if peer else "none (one rank)",
+            "ms_per_step_nccl_allreduce_then_adam": ms_serial,
+            "ms_per_step_nccl_allreduce_tail_overlapped": ms_overlap,
             "dtype": "fp32-equivalent (3-plane split bf16 on tcgen05)"}
 
 

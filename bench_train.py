@@ -52,6 +52,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--per-gpu", type=int, default=512)
     ap.add_argument("--cpu-baseline", action="store_true", help="also time the CPU oracle step on a 64-row sample")
+    ap.add_argument("--exchange", choices=("peer", "nccl-overlap", "nccl"), default="peer",
+                    help="gradient exchange at N > 1: 'peer' = reduce-scatter + Adam + all-gather in one kernel over NVLink "
+                         "peer memory (csrc/dp_adam.cu, the default); 'nccl' = one NCCL all-reduce after the backward pass "
+                         "+ Adam on every rank; 'nccl-overlap' = the tail of the bucket reduced while the backward pass "
+                         "finishes")
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     from b200 import _lib, synth, training
@@ -66,6 +71,9 @@ def main():
     x = torch.randn(args.per_gpu, 10, 128, generator=g).to(dev)
     labels = torch.randint(0, K, (args.per_gpu,), generator=g).to(dev)
 
+    if world > 1 and args.exchange == "peer":
+        tr.enable_peer_step()
+
     def sync():
         torch.cuda.synchronize()
         if world > 1:
@@ -73,7 +81,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
-        tr.step(x, labels)
+        tr.step(x, labels, overlap=args.exchange != 'nccl')
     sync()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     phases = [0.0, 0.0, 0.0]
@@ -81,12 +89,17 @@ def main():
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        tr.step(x, labels)
+        tr.step(x, labels, overlap=args.exchange != 'nccl')
     t1.record()
     sync()
     launches = _lib.lib().vmb_launch_count() - launches0
     ms = t0.elapsed_time(t1) / args.steps
     loss_end = float(tr.loss.item())
+    tr.peer_step_status()
+    if tr._dp is not None:     # phase split below uses the NCCL form on a fresh trainer
+        tr.close()
+        tr = training.HeadTrainer(conf, 128, 600, K, 10, args.per_gpu, dev, lr=1e-3, dropout_p=0.4, seed=1234)
+        tr.load_state_dict(synth.mla_state_dict(conf, 128, 600, K, 10, seed=2))
     # phase split on a few extra steps (events between phases serialise nothing: same stream)
     for _ in range(10):
         ev[0].record()
@@ -109,7 +122,8 @@ def main():
                 "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "dtype": "fp32-equivalent (3-plane split bf16 on tcgen05)", "data": "synthetic",
                 "config": {"workload": f"global batch {args.per_gpu * world} = {args.per_gpu} per GPU, Adam lr 1e-3, "
-                                       "dropout 0.4, CE on sigmoid outputs", "allreduce_bytes": tr.n_params * 4},
+                                       "dropout 0.4, CE on sigmoid outputs", "allreduce_bytes": tr.n_params * 4,
+                           "gradient_exchange": args.exchange if world > 1 else "none (one rank)"},
                 "phase_ms": {"forward_backward": phases[0], "allreduce": phases[1], "adam": phases[2]},
                 "gpu_launches": int(launches), "final_loss": loss_end}
         if args.cpu_baseline and world == 1:

@@ -235,6 +235,13 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* handle);
 int vmb_mla_train_step(vmb_mla_trainer_t* handle, const float* params_dev, float* running_dev, const float* emb_dev,
                        const long long* labels_dev, long long batch, float dropout_p, unsigned long long seed,
                        float* grads_dev, float* loss_dev, float* scores_dev, void* stream);
+/* Overlapping the gradient all-reduce with the backward pass (train.py:133-138 under data parallelism): the backward
+ * pass computes level 0's embedding chain last, and that chain's parameters come first in the flat order, so
+ * grads[vmb_mla_train_tail_offset() .. n_params) are final before it starts.  vmb_mla_train_wait_tail makes `stream`
+ * wait for that point of the most recently enqueued vmb_mla_train_step / vmb_mla_train_backward: a caller enqueues the
+ * all-reduce of the tail there and only the head of the bucket after the whole step. */
+long long vmb_mla_train_tail_offset(const vmb_mla_trainer_t* handle);
+int vmb_mla_train_wait_tail(vmb_mla_trainer_t* handle, void* stream);
 /* The same step in two calls, for callers that compute the loss themselves (the reference's `criterion(outputs,
  * labels); loss.backward()`, train.py:130-136): forward leaves its state in the handle, backward takes
  * d(loss)/d(scores) [batch][K].  One step in flight per handle.                                              */
@@ -248,6 +255,33 @@ int vmb_mla_train_backward(vmb_mla_trainer_t* handle, const float* params_dev, c
 int vmb_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, long long n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ data-parallel optimiser step
+ * (the reference trains on one device: train.py:133-138 `loss.backward(); optimizer.step()`; BASELINE configs[4] runs that
+ * step data-parallel over the GPUs of one box, which adds "average the gradients over the ranks" between the two calls).
+ * One process per GPU.  Every rank creates a vmb_dp: its arena (params | two gradient buffers | flags) is device memory
+ * owned by the library and exported through CUDA IPC; the ranks exchange the VMB_DP_IPC_HANDLE_BYTES-byte handles by any
+ * host-side means (the Python layer uses torch.distributed.all_gather_object) and call vmb_dp_connect with all `world`
+ * handles in rank order.  vmb_mla_train_step then takes vmb_dp_params() as params_dev and vmb_dp_grads(parity) as
+ * grads_dev, parity alternating 0 / 1 from step to step, and vmb_dp_adam_step(parity) replaces all-reduce + vmb_adam_step:
+ * a cross-GPU barrier, ONE kernel that sums this rank's slice (vmb_dp_slice) of all ranks' gradient buffers over NVLink
+ * peer loads in rank order, scales by 1 / world, applies the Adam update of vmb_adam_step to the slice and stores the new
+ * parameters into every rank's arena, and a second barrier.  exp_avg / exp_avg_sq: this rank's moments, (n_params + 3) / 4
+ * * 4 floats each, only the rank's slice is used.  A barrier that a rank does not reach within 10 s gives up and
+ * vmb_dp_status() reports it (non-zero) instead of hanging the GPU.  Shutdown: every rank calls vmb_dp_disconnect, the
+ * ranks synchronise on the host, then vmb_dp_destroy frees the arena. */
+#define VMB_DP_IPC_HANDLE_BYTES 64
+typedef struct vmb_dp vmb_dp_t;
+void vmb_dp_slice(long long n_params, int world, int rank, long long* begin, long long* end);
+int vmb_dp_create(vmb_dp_t** handle, long long n_params, int rank, int world, void* ipc_handle_out);
+int vmb_dp_connect(vmb_dp_t* handle, const void* all_handles);
+float* vmb_dp_params(vmb_dp_t* handle);
+float* vmb_dp_grads(vmb_dp_t* handle, int parity);
+int vmb_dp_adam_step(vmb_dp_t* handle, int parity, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, long long step, void* stream);
+int vmb_dp_status(vmb_dp_t* handle);
+void vmb_dp_disconnect(vmb_dp_t* handle);
+void vmb_dp_destroy(vmb_dp_t* handle);
 
 /* ------------------------------------------------------------------------------------------ whole path
  * Ensemble.forward for cnn_type == "vggish" (model.py:58-62) fed from raw audio:

@@ -210,6 +210,22 @@ def test_shim_error_behaviour():
         VGGish(urls={}, pretrained=False)(torch.zeros(3), 16000)              # vggish.py:175-180
 
 
+def test_dp_slices_partition_the_padded_bucket():
+    """vmb_dp_slice (csrc/dp_adam.cu): the slices of the ranks are disjoint, 16-byte aligned, in rank order, and cover
+    the bucket padded to a multiple of four floats — host arithmetic, no device."""
+    import ctypes as C
+    L = _lib.lib()
+    for n in (1, 3, 4, 5, 1023, 1989273, 823050):
+        for world in range(1, 9):
+            prev_end = 0
+            for rank in range(world):
+                b, e = C.c_longlong(-1), C.c_longlong(-1)
+                L.vmb_dp_slice(n, world, rank, C.byref(b), C.byref(e))
+                assert b.value == prev_end and e.value >= b.value and b.value % 4 == 0 and e.value % 4 == 0
+                prev_end = e.value
+            assert prev_end == (n + 3) // 4 * 4
+
+
 def test_shard_bounds_partition():
     for n in (0, 1, 7, 256, 8192, 3749):
         for world in (1, 2, 3, 4, 8):

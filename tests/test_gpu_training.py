@@ -145,6 +145,183 @@ def test_data_parallel_semantics_two_shards():
         tr.close()
 
 
+def test_tail_of_the_gradient_bucket_is_final_at_the_tail_event():
+    """vmb_mla_train_wait_tail (the hook the overlapped all-reduce hangs on): a stream that waits for the tail event sees
+    grads[tail:] exactly as they are when the whole step has finished, for every model shape; the head of the bucket
+    (level 0's embedding chain, computed last) is what is still being written."""
+    import ctypes as C
+    from b200 import _lib
+    from b200._lib import check
+    for conf, K in (((2, 1), 527), ((1, 2, 1), 10), ((1,), 33)):
+        tr = training.HeadTrainer(conf, 128, 600, K, 10, 512, DEV, dropout_p=0.4, seed=11)
+        tr.load_state_dict(synth.mla_state_dict(conf, 128, 600, K, 10, seed=2))
+        tail = int(_lib.lib().vmb_mla_train_tail_offset(tr._h))
+        first_tail_key = [k for k, _, off in tr.p_layout if off == tail]
+        assert first_tail_key == ["embedded_mappings.1.norm0.weight" if len(conf) > 1 else "attention_modules.0.fcv.weight"]
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(512, 10, 128, generator=g).to(DEV)
+        labels = torch.randint(0, K, (512,), generator=g).to(DEV)
+        side = torch.cuda.Stream(device=DEV)
+        for _ in range(3):
+            tr.forward_backward(x, labels)
+            check(_lib.lib().vmb_mla_train_wait_tail(tr._h, C.c_void_p(side.cuda_stream)), "vmb_mla_train_wait_tail")
+            with torch.cuda.stream(side):
+                early = tr.grads[tail:].clone()
+            torch.cuda.synchronize()
+            assert torch.equal(early, tr.grads[tail:]), f"conf {conf}: the tail changed after its event"
+            assert tr.grads[:tail].abs().max() > 0
+        tr.close()
+
+
+def _overlap_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    tr = training.HeadTrainer(CONF, 128, 600, 527, 10, 256, dev, dropout_p=0.4, seed=77)
+    tr.load_state_dict(synth.mla_state_dict(CONF, 128, 600, 527, 10, seed=2))
+    g = torch.Generator().manual_seed(40 + rank)
+    x = torch.randn(256, 10, 128, generator=g).to(dev)
+    labels = torch.randint(0, 527, (256,), generator=g).to(dev)
+    worst = 0.0
+    for _ in range(4):
+        # the same step (same parameters, same dropout seed) reduced both ways; the weight-gradient GEMMs add their K
+        # slices with fp32 atomics, so two runs of one step already differ in the last bits
+        tr.forward_backward(x, labels)
+        local = tr.grads.clone()
+        assert tr.all_reduce_grads_overlapped() == world
+        over = tr.grads.clone()
+        tr.forward_backward(x, labels)
+        assert tr.all_reduce_grads() == world
+        torch.cuda.synchronize()
+        worst = max(worst, float((over - tr.grads).abs().max() / tr.grads.abs().max()))
+        assert float((over - local).abs().max()) > 0          # something was added
+        tr.adam(world)
+    if rank == 0:
+        out.put(worst)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL)")
+def test_overlapped_all_reduce_matches_the_single_bucket():
+    """Two NCCL ranks: the all-reduce issued in two pieces, the tail overlapping the end of the backward pass, gives the
+    bucket of the single all-reduce after the backward pass (up to the fp32 atomics noise of two runs of one step)."""
+    import socket
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    worst = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    print(f"overlapped vs single-bucket all-reduce: max |diff| / max |grad| = {worst:.2e}")
+    assert worst < 1e-5
+
+
+def _peer_worker(rank, world, port, out):
+    import ctypes as C
+    import os
+    import torch.distributed as dist
+    from b200 import _lib
+    from b200._lib import check, ptr, stream_ptr
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sd = synth.mla_state_dict(CONF, 128, 600, 527, 10, seed=2)
+    tr = training.HeadTrainer(CONF, 128, 600, 527, 10, 256, dev, dropout_p=0.4, seed=77)
+    tr.load_state_dict(sd)
+    assert tr.enable_peer_step()
+    n = tr.n_params
+    # (1) the kernel on known inputs: three steps of "gradients of rank r = randn(seed 1000 * step + r)" against
+    # torch.optim.Adam on the mean gradient, computed on the CPU from all ranks' generators
+    p_ref = tr.params.cpu().clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    L = _lib.lib()
+    for step in range(1, 4):
+        parity = (step - 1) & 1
+        gs = [torch.randn(n, generator=torch.Generator().manual_seed(1000 * step + r)) * 0.01 for r in range(world)]
+        tr._grads2[parity].copy_(gs[rank])
+        check(L.vmb_dp_adam_step(tr._dp, parity, ptr(tr.exp_avg), ptr(tr.exp_avg_sq), 1e-3, 0.9, 0.999, 1e-8, 0.0, step,
+                                 stream_ptr()), "vmb_dp_adam_step")
+        total = gs[0].clone()
+        for r in range(1, world):
+            total += gs[r]
+        p_ref.grad = total / world
+        opt.step()
+        torch.cuda.synchronize()
+        tr.peer_step_status()
+        err = float((tr.params.cpu() - p_ref.detach()).abs().max())
+        assert err < 5e-7, f"rank {rank} step {step}: {err}"
+        every = [torch.empty_like(tr.params) for _ in range(world)]
+        dist.all_gather(every, tr.params)
+        assert all(torch.equal(every[0], e) for e in every), "replicas differ"
+    # (2) training steps through step(): the loss goes down and the replicas stay bit-identical
+    tr.load_state_dict(sd)
+    tr.exp_avg.zero_()
+    tr.exp_avg_sq.zero_()
+    tr.step_count = 0
+    dist.barrier()
+    g = torch.Generator().manual_seed(40 + rank)
+    x = torch.randn(256, 10, 128, generator=g).to(dev)
+    labels = torch.randint(0, 527, (256,), generator=g).to(dev)
+    ref = training.HeadTrainer(CONF, 128, 600, 527, 10, 256, dev, dropout_p=0.4, seed=77)     # NCCL all-reduce + Adam
+    ref.load_state_dict(sd)
+    losses, ref_losses = [], []
+    for _ in range(6):
+        losses.append(float(tr.step(x, labels).item()))
+        ref_losses.append(float(ref.step(x, labels, overlap=False).item()))
+    torch.cuda.synchronize()
+    tr.peer_step_status()
+    every = [torch.empty_like(tr.params) for _ in range(world)]
+    dist.all_gather(every, tr.params)
+    assert all(torch.equal(every[0], e) for e in every)
+    cos = float(torch.nn.functional.cosine_similarity(tr.params, ref.params, dim=0))
+    moved = float((tr.params.cpu() - torch.cat([sd[k].reshape(-1) for k, _, _ in tr.p_layout])).abs().max())
+    if rank == 0:
+        out.put((losses, ref_losses, cos, moved))
+    ref.close()
+    tr.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink peer access")
+def test_peer_memory_optimizer_step_two_ranks():
+    """vmb_dp_adam_step (csrc/dp_adam.cu): gradient reduce-scatter + Adam + parameter all-gather over NVLink peer memory.
+    Two ranks: against torch.optim.Adam on the mean gradient (5e-7 absolute over three steps, replicas bit-identical), and
+    six real training steps next to the NCCL all-reduce + Adam path (same losses to 1e-4 relative — the two runs differ
+    by the fp32-atomics noise of the weight-gradient GEMMs)."""
+    import socket
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    losses, ref_losses, cos, moved = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    print("peer-memory step losses", [f"{v:.5f}" for v in losses], "NCCL path", [f"{v:.5f}" for v in ref_losses],
+          f"params cosine {cos:.7f}, max |update| {moved:.2e}")
+    assert losses[-1] < losses[0]
+    assert all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(losses, ref_losses))
+    assert cos > 0.99999 and moved > 1e-3
+
+
 def test_dropout_is_seeded_and_inverted():
     tr, sd = _trainer(K=10, max_batch=64, dropout_p=0.4)
     g = torch.Generator().manual_seed(1)
