@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvggish_mla_b200.so")
+# VMB_LIB=<path> loads another build of the library (A/B timing of two builds on one box: tools/ab/*.so)
+LIB_PATH = os.environ.get("VMB_LIB") or os.path.join(_HERE, "libvggish_mla_b200.so")
 
 _c_p = C.c_void_p
 _ll = C.c_longlong

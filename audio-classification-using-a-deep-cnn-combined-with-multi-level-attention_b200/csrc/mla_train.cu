@@ -157,13 +157,20 @@ bn_col_stats_kernel(const float* __restrict__ x, long long ld, long long batch, 
 }
 
 // ------------------------------------------------------------------ dropout (counter-based, recomputed in backward)
+// Keep / drop decision of element idx of layer `layer` in the step seeded `seed`: a 32-bit finaliser (murmur3's fmix32)
+// over the element index keyed by (seed, layer) — 8 integer instructions per element; the first version ran a 64-bit
+// splitmix (two 64-bit multiplies = a dozen 32-bit IMADs) for every element of every element-wise kernel.
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned layer, unsigned long long idx, float p) {
   if (p <= 0.f) return 1.f;
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + (static_cast<unsigned long long>(layer) << 56);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+  const unsigned key = static_cast<unsigned>(seed) ^ (static_cast<unsigned>(seed >> 32) * 0x9E3779B1u) ^
+                       (layer * 0x85EBCA77u + 0xC2B2AE3Du);
+  unsigned h = (static_cast<unsigned>(idx) ^ key) * 0x9E3779B1u + static_cast<unsigned>(idx >> 32) * 0x27D4EB2Fu;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  const float u = static_cast<float>(h >> 8) * (1.0f / 16777216.0f);
   return u >= p ? 1.f / (1.f - p) : 0.f;
 }
 
@@ -185,54 +192,71 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
 }
 
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return __bfloat16_as_ushort(a) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+}
+// two adjacent elements of one row -> one 4-byte store per plane
+__device__ __forceinline__ void store_split_pair(float v0, float v1, __nv_bfloat16* row, long long plane_stride) {
+  __nv_bfloat16 h0, m0, l0, h1, m1, l1;
+  split_bf16(v0, h0, m0, l0);
+  split_bf16(v1, h1, m1, l1);
+  *reinterpret_cast<uint32_t*>(row) = pack2(h0, h1);
+  *reinterpret_cast<uint32_t*>(row + plane_stride) = pack2(m0, m1);
+  *reinterpret_cast<uint32_t*>(row + 2 * plane_stride) = pack2(l0, l1);
+}
+
+// 64 x 64 tile per CTA.  A thread evaluates the functor on column PAIRS (row-major outputs: a warp writes 128 contiguous
+// bytes per plane row) and, after the transpose through shared memory, writes row PAIRS of the transposed planes (again
+// 128 bytes per warp and plane row).  The functor gets the row's time step t = r % T from the kernel: one 32-bit modulo
+// per row instead of a 64-bit one per element.
+constexpr int kTile = 64;
 template <class F>
 __global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
   vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
   vmb::pdl_wait();
-  __shared__ float tile[32][33];
+  __shared__ float tile[kTile][kTile + 1];
   f.prologue();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long r0 = static_cast<long long>(blockIdx.y) * 32;
-  const int c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * kTile;
+  const int c0 = blockIdx.x * kTile;
+  const int tmod = f.time_steps();
+  {
+    const int c = c0 + 2 * tx;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long r = r0 + ty + 8 * i;
-    const int c = c0 + tx;
-    const float v = (r < o.rows && c < o.cols) ? f(r, c) : 0.f;
-    tile[ty + 8 * i][tx] = v;
-    if (r < o.rows_pad && c < o.cols_pad) {
-      if (o.planes) {
-        __nv_bfloat16 hi, mid, lo;
-        split_bf16(v, hi, mid, lo);
-        __nv_bfloat16* row = o.planes + r * (static_cast<long long>(kPl) * o.cols_pad);
-        row[c] = hi;
-        row[o.cols_pad + c] = mid;
-        row[2 * o.cols_pad + c] = lo;
+    for (int i = 0; i < kTile / 8; ++i) {
+      const int r = r0 + ty + 8 * i;
+      float v0 = 0.f, v1 = 0.f;
+      if (r < o.rows) {
+        const int t = tmod > 1 ? r % tmod : 0;
+        if (c < o.cols) v0 = f(r, t, c);
+        if (c + 1 < o.cols) v1 = f(r, t, c + 1);
       }
-      if (o.f32 && r < o.rows) o.f32[r * o.ld_f32 + c] = v;
+      tile[ty + 8 * i][2 * tx] = v0;
+      tile[ty + 8 * i][2 * tx + 1] = v1;
+      if (r < o.rows_pad && c < o.cols_pad) {
+        if (o.planes)
+          store_split_pair(v0, v1, o.planes + static_cast<long long>(r) * (static_cast<long long>(kPl) * o.cols_pad) + c,
+                           o.cols_pad);
+        if (o.f32 && r < o.rows) *reinterpret_cast<float2*>(o.f32 + static_cast<long long>(r) * o.ld_f32 + c) = make_float2(v0, v1);
+      }
     }
   }
   __syncthreads();
   if (o.planes_t) {
+    const int r = r0 + 2 * tx;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kTile / 8; ++i) {
       const int c = c0 + ty + 8 * i;
-      const long long r = r0 + tx;
-      if (c < o.cols_pad && r < o.rows_pad) {
-        __nv_bfloat16 hi, mid, lo;
-        split_bf16(tile[tx][ty + 8 * i], hi, mid, lo);
-        __nv_bfloat16* row = o.planes_t + c * (static_cast<long long>(kPl) * o.rows_pad);
-        row[r] = hi;
-        row[o.rows_pad + r] = mid;
-        row[2 * o.rows_pad + r] = lo;
-      }
+      if (c < o.cols_pad && r < o.rows_pad)
+        store_split_pair(tile[2 * tx][ty + 8 * i], tile[2 * tx + 1][ty + 8 * i],
+                         o.planes_t + static_cast<long long>(c) * (static_cast<long long>(kPl) * o.rows_pad) + r, o.rows_pad);
     }
   }
-  if (o.col_sum && ty == 0 && c0 + tx < o.cols) {
+  if (o.col_sum && threadIdx.x < kTile && c0 + threadIdx.x < o.cols) {
     float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s += tile[j][tx];
-    atomicAdd(o.col_sum + c0 + tx, s);
+#pragma unroll 8
+    for (int j = 0; j < kTile; ++j) s += tile[j][threadIdx.x];
+    atomicAdd(o.col_sum + c0 + threadIdx.x, s);
   }
 }
 
@@ -244,20 +268,22 @@ struct FIdentity {
     if (bias_dst && blockIdx.x == 0 && blockIdx.y == 0)
       for (int i = threadIdx.x; i < n_bias; i += blockDim.x) bias_dst[i] = bias_src[i];
   }
-  __device__ float operator()(long long r, int c) const { return __ldg(x + r * ld + c); }
+  __device__ int time_steps() const { return 1; }
+  __device__ float operator()(int r, int, int c) const { return __ldg(x + static_cast<long long>(r) * ld + c); }
 };
 
 // forward: a = dropout(relu?(gamma_t * (u - mu_t) * rstd_t + beta_t))
 struct FBnAct {
   const float* u; long long ld; int T, F;
   const float* stat; const float* gamma; const float* beta;
-  int relu; float p; unsigned long long seed; unsigned layer;
+  int relu; float p; const unsigned long long* seed; unsigned layer;   // *seed: the step's dropout seed (device memory)
   __device__ void prologue() {}
-  __device__ float operator()(long long r, int c) const {
-    const int t = static_cast<int>(r % T);
-    float v = fmaf(__ldg(gamma + t) * __ldg(stat + 2 * t + 1), __ldg(u + r * ld + c) - __ldg(stat + 2 * t), __ldg(beta + t));
+  __device__ int time_steps() const { return T; }
+  __device__ float operator()(int r, int t, int c) const {
+    float v = fmaf(__ldg(gamma + t) * __ldg(stat + 2 * t + 1), __ldg(u + static_cast<long long>(r) * ld + c) - __ldg(stat + 2 * t),
+                   __ldg(beta + t));
     if (relu) v = fmaxf(v, 0.f);
-    return v * dropout_scale(seed, layer, static_cast<unsigned long long>(r) * F + c, p);
+    return v * dropout_scale(p > 0.f ? __ldg(seed) : 0ull, layer, static_cast<unsigned long long>(r) * F + c, p);
   }
 };
 
@@ -266,17 +292,15 @@ struct GradIn {
   const float* da1; long long ld1; const float* da2; long long ld2;   // da2 may be null
   const float* u; long long ldu; int T, F;
   const float* stat; const float* gamma; const float* beta;
-  int relu; float p; unsigned long long seed; unsigned layer;
-  __device__ __forceinline__ float xhat(long long r, int c) const {
-    const int t = static_cast<int>(r % T);
+  int relu; float p; const unsigned long long* seed; unsigned layer;
+  __device__ __forceinline__ float xhat(long long r, int t, int c) const {
     return (__ldg(u + r * ldu + c) - __ldg(stat + 2 * t)) * __ldg(stat + 2 * t + 1);
   }
-  __device__ __forceinline__ float g(long long r, int c, float xh) const {
-    const int t = static_cast<int>(r % T);
+  __device__ __forceinline__ float g(long long r, int t, int c, float xh) const {
     float d = __ldg(da1 + r * ld1 + c);
     if (da2) d += __ldg(da2 + r * ld2 + c);
     if (relu && fmaf(__ldg(gamma + t), xh, __ldg(beta + t)) <= 0.f) return 0.f;
-    return d * dropout_scale(seed, layer, static_cast<unsigned long long>(r) * F + c, p);
+    return d * dropout_scale(p > 0.f ? __ldg(seed) : 0ull, layer, static_cast<unsigned long long>(r) * F + c, p);
   }
 };
 
@@ -293,8 +317,8 @@ bn_time_backward_reduce_kernel(GradIn in, long long batch, double* __restrict__ 
     const long long b = i / in.F;
     const int c = static_cast<int>(i - b * in.F);
     const long long r = b * in.T + t;
-    const float xh = in.xhat(r, c);
-    const float g = in.g(r, c, xh);
+    const float xh = in.xhat(r, t, c);
+    const float g = in.g(r, t, c, xh);
     s1 += g;
     s2 += double(g) * xh;
   }
@@ -333,10 +357,10 @@ struct FBnBackward {
     }
     __syncthreads();
   }
-  __device__ float operator()(long long r, int c) const {
-    const int t = static_cast<int>(r % in.T);
-    const float xh = in.xhat(r, c);
-    const float g = in.g(r, c, xh);
+  __device__ int time_steps() const { return in.T; }
+  __device__ float operator()(int r, int t, int c) const {
+    const float xh = in.xhat(r, t, c);
+    const float g = in.g(r, t, c, xh);
     return coef[3 * t] * (g - coef[3 * t + 1] - xh * coef[3 * t + 2]);
   }
 };
@@ -416,7 +440,7 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
   float* cla = att + a.T * a.K;        // [T][K]
   float* sinv = cla + a.T * a.K;       // [K]  1 / sum_t att
   __shared__ float sa_v[16], sb_v[16], sa_f[16], sb_f[16], dot[16];
-  __shared__ double red[8][4];
+  __shared__ double red[8][16][4];
   const long long clip = blockIdx.x;
   const float* zc = a.z + clip * a.T * a.ldz;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -458,7 +482,7 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
     if (lane == 0 && t < a.T) atomicAdd(&dot[t], v);
   }
   __syncthreads();
-  // second pass, one time step per iteration so the BatchNorm reductions stay per t
+  // second pass, one time step per iteration so the BatchNorm reductions stay per t (no barrier inside the loop)
   for (int t = 0; t < a.T; ++t) {
     const float mu = a.stat[2 * t], rstd = a.stat[2 * t + 1];
     double p1v = 0, p2v = 0, p1f = 0, p2f = 0;
@@ -481,17 +505,15 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
       p1f += __shfl_xor_sync(0xffffffffu, p1f, o);
       p2f += __shfl_xor_sync(0xffffffffu, p2f, o);
     }
-    if (lane == 0) { red[warp][0] = p1v; red[warp][1] = p2v; red[warp][2] = p1f; red[warp][3] = p2f; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s1v = 0, s2v = 0, s1f = 0, s2f = 0;
-      for (int w = 0; w < 8; ++w) { s1v += red[w][0]; s2v += red[w][1]; s1f += red[w][2]; s2f += red[w][3]; }
-      atomicAdd(acc_v + 2 * t, s1v);
-      atomicAdd(acc_v + 2 * t + 1, s2v);
-      atomicAdd(acc_f + 2 * t, s1f);
-      atomicAdd(acc_f + 2 * t + 1, s2f);
-    }
-    __syncthreads();
+    if (lane == 0) { red[warp][t][0] = p1v; red[warp][t][1] = p2v; red[warp][t][2] = p1f; red[warp][t][3] = p2f; }
+  }
+  // one cross-warp reduction for all time steps: thread (t, j) adds the eight warps' partial sums of quantity j
+  __syncthreads();
+  if (threadIdx.x < 4 * a.T) {
+    const int t = threadIdx.x >> 2, j = threadIdx.x & 3;
+    double sum = 0;
+    for (int w = 0; w < 8; ++w) sum += red[w][t][j];
+    atomicAdd((j < 2 ? acc_v : acc_f) + 2 * t + (j & 1), sum);
   }
 }
 
@@ -501,21 +523,34 @@ struct FAttCombine {
   AttParams a; const float* gv; const float* gf; long long ldg;
   const double* acc_v; const double* acc_f; double n;
   float *dgv, *dbv, *dgf, *dbf;
+  float* coef;   // shared memory [T][8]: mu, rstd, gamma^v rstd, S1v / n, S2v / n, gamma^f rstd, S1f / n, S2f / n
   __device__ void prologue() {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.T) {
+    __shared__ float coef_s[16 * 8];
+    coef = coef_s;
+    if (threadIdx.x < a.T) {
       const int t = threadIdx.x;
-      dbv[t] = static_cast<float>(acc_v[2 * t]); dgv[t] = static_cast<float>(acc_v[2 * t + 1]);
-      dbf[t] = static_cast<float>(acc_f[2 * t]); dgf[t] = static_cast<float>(acc_f[2 * t + 1]);
+      const float rstd = a.stat[2 * t + 1];
+      coef_s[8 * t] = a.stat[2 * t];
+      coef_s[8 * t + 1] = rstd;
+      coef_s[8 * t + 2] = a.gv[t] * rstd;
+      coef_s[8 * t + 3] = float(acc_v[2 * t] / n);
+      coef_s[8 * t + 4] = float(acc_v[2 * t + 1] / n);
+      coef_s[8 * t + 5] = a.gf[t] * rstd;
+      coef_s[8 * t + 6] = float(acc_f[2 * t] / n);
+      coef_s[8 * t + 7] = float(acc_f[2 * t + 1] / n);
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        dbv[t] = static_cast<float>(acc_v[2 * t]); dgv[t] = static_cast<float>(acc_v[2 * t + 1]);
+        dbf[t] = static_cast<float>(acc_f[2 * t]); dgf[t] = static_cast<float>(acc_f[2 * t + 1]);
+      }
     }
+    __syncthreads();
   }
-  __device__ float operator()(long long r, int c) const {
-    const int t = static_cast<int>(r % a.T);
-    const float rstd = __ldg(a.stat + 2 * t + 1);
-    const float zh = (__ldg(a.z + r * a.ldz + c) - __ldg(a.stat + 2 * t)) * rstd;
-    const float v = __ldg(a.gv + t) * rstd *
-                    (__ldg(gv + r * ldg + c) - float(acc_v[2 * t] / n) - zh * float(acc_v[2 * t + 1] / n));
-    const float f = __ldg(a.gf + t) * rstd *
-                    (__ldg(gf + r * ldg + c) - float(acc_f[2 * t] / n) - zh * float(acc_f[2 * t + 1] / n));
+  __device__ int time_steps() const { return a.T; }
+  __device__ float operator()(int r, int t, int c) const {
+    const float* k = coef + 8 * t;
+    const float zh = (__ldg(a.z + static_cast<long long>(r) * a.ldz + c) - k[0]) * k[1];
+    const float v = k[2] * (__ldg(gv + static_cast<long long>(r) * ldg + c) - k[3] - zh * k[4]);
+    const float f = k[5] * (__ldg(gf + static_cast<long long>(r) * ldg + c) - k[6] - zh * k[7]);
     return v + f;
   }
 };
@@ -627,6 +662,8 @@ out_bn_backward_kernel(const float* __restrict__ o, long long ldo, int K, const 
   }
 }
 
+__global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed) { *dst = seed; }
+
 // ------------------------------------------------------------------ Adam (torch.optim.Adam, amsgrad = False)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
@@ -704,6 +741,27 @@ struct vmb_mla_trainer {
   float *dA = nullptr, *dB = nullptr, *dEnext = nullptr;  // fp32 gradient buffers [R][Hp]
   float* dWtmp = nullptr;                          // padded dW GEMM output
   int Hp, Kp, inpad, ycols, ycols_pad;
+  // The dropout seed of the step lives in device memory, so that a captured step can be replayed with a new seed.
+  unsigned long long* seed_dev = nullptr;
+  // CUDA graph of the whole step (vmb_mla_train_step): ~110 kernel launches, memsets and stream fork / join events cost
+  // the host about as long as the GPU needs to run them; a replayed graph is one launch.  The inputs are copied into
+  // staging buffers first, so the graph does not depend on the caller's x / labels addresses; one graph per distinct
+  // (params, running, grads, loss, scores, batch, dropout_p) — the peer-memory step alternates two gradient buffers.
+  float* x_stage = nullptr;
+  long long* labels_stage = nullptr;
+  cudaStream_t gstream = nullptr;     // the graph runs here (stream capture is not allowed on the legacy default stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  struct GraphSlot {
+    const void *params, *running, *grads, *loss, *scores;
+    long long batch;
+    float dropout_p;
+    cudaGraphExec_t exec;
+    int launches;                     // kernels in the graph (for vmb_launch_count)
+  } graphs[4] = {};
+  int n_graphs = 0, next_graph = 0;
+  int eager_steps = 0;                // the first step of a handle runs eagerly: one-time set-up must not be captured
+  bool graph_broken = false;          // capture or instantiation failed once: stay on the eager path
+  bool capturing = false;
 };
 
 namespace {
@@ -756,6 +814,9 @@ void carve(vmb_mla_trainer* h, char* base) {
   h->dA = c.take<float>(size_t(R) * Hp);
   h->dB = c.take<float>(size_t(R) * Hp);
   h->dEnext = c.take<float>(size_t(R) * Hp);
+  h->seed_dev = c.take<unsigned long long>(2);
+  h->x_stage = c.take<float>(size_t(R) * h->emb_in);
+  h->labels_stage = c.take<long long>(size_t(B));
   const int widest = std::max(h->ycols_pad, std::max(Hp, inpad));
   h->dWtmp = c.take<float>(size_t(Hp) * widest);
   if (h->n_levels > 1) {
@@ -825,7 +886,7 @@ void build_layout(vmb_mla_trainer* h, const int* n_fc) {
 }
 
 dim3 tile_grid(long long rows_pad, int cols_pad) {
-  return dim3(static_cast<unsigned>((cols_pad + 31) / 32), static_cast<unsigned>((rows_pad + 31) / 32));
+  return dim3(static_cast<unsigned>((cols_pad + kTile - 1) / kTile), static_cast<unsigned>((rows_pad + kTile - 1) / kTile));
 }
 
 template <class F>
@@ -950,6 +1011,14 @@ void vmb_mla_trainer_destroy(vmb_mla_trainer_t* h) {
   for (int i = 0; h && i < kMaxLevels; ++i)
     if (h->ev_attb[i]) cudaEventDestroy(h->ev_attb[i]);
   if (!h) return;
+  for (int i = 0; i < h->n_graphs; ++i)
+    if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+  if (h->gstream) {
+    cudaStreamSynchronize(h->gstream);
+    cudaStreamDestroy(h->gstream);
+  }
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
   cudaFree(h->ws);
   delete h;
 }
@@ -973,6 +1042,10 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   if (dropout_p < 0.f || dropout_p >= 1.f) return fail("vmb_mla_train: dropout_p must be in [0, 1)");
   const bool do_fwd = phases & kPhaseForward, do_bwd = phases & kPhaseBackward;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!h->capturing) {   // a captured step reads the seed its replay was given (vmb_mla_train_step)
+    set_seed_kernel<<<1, 1, 0, st>>>(h->seed_dev, seed);
+    vmb::count_launch();
+  }
   const int T = h->T, H = h->H, K = h->K, Hp = h->Hp, inpad = h->inpad;
   const long long B = batch, R = B * T, Rp = pad64(R), Bp = pad64(B);
   int rc = 0;
@@ -1064,7 +1137,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     __nv_bfloat16* npt = l == 0 ? h->xin_pt : h->N_pt[l];
     TRY(time_stats(in, ld_in, F_in, L.norm0, true, st));
     {
-      FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, seed, 0};
+      FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
       TileOut o{np, npt, nullptr, 0, nullptr, R, Rp, F_in, in_pad};
       TRY(run_tile(f, o, st, "norm0 forward"));
     }
@@ -1078,7 +1151,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(gemm_bn(a, fc, h->U[l][j], fc.n_in_pad, H, L.norms[j], st));
       const bool last = j == L.n_fc - 1;
       FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
-               dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
+               dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
       TileOut o{h->A_p[l][j], h->A_pt[l][j], last ? h->E[l] : nullptr, Hp, nullptr, R, Rp, H, Hp};
       TRY(run_tile(f, o, st, "fc forward activation"));
       a = h->A_p[l][j];
@@ -1250,14 +1323,14 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
         vmb::set_kernel_error("cannot create the tail event");
         rc = 1;
       }
-      if (h->ev_tail) cudaEventRecord(h->ev_tail, st);
+      if (h->ev_tail) cudaEventRecordWithFlags(h->ev_tail, st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     }
     // embedding chain of this level, last Linear first; gradient wrt E_l = attention part (+ next level's input grad)
     const float* da2 = (l + 1 < h->n_levels) ? h->dEnext : nullptr;
     for (int j = L.n_fc - 1; j >= 0 && !rc; --j) {
       const FcRef& fc = L.fc[j];
       GradIn gi{da1, Hp, da2, Hp, h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g,
-                params + L.norms[j].b, 1, dropout_p, seed, unsigned(1 + l * kMaxFc + j)};
+                params + L.norms[j].b, 1, dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
       double* acc = slotacc(L.norms[j].bslot);
       const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * H + 256 * 8 - 1) / (256 * 8), 64));
       vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
@@ -1282,7 +1355,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       const long long ld_in = l == 0 ? h->emb_in : Hp;
       const int F_in = l == 0 ? h->emb_in : H;
       GradIn gi{da1, Hp, nullptr, 0, in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g,
-                params + L.norm0.b, 0, 0.f, seed, 0};
+                params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
       double* acc = slotacc(L.norm0.bslot);
       const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F_in + 256 * 8 - 1) / (256 * 8), 64));
       vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
@@ -1304,14 +1377,109 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
 }
 }  // namespace
 
+namespace {
+bool train_graph_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VMB_TRAIN_GRAPH");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// Replays (capturing it first if needed) the graph of one whole step on the trainer's own stream, between two events
+// that order it after / before the caller's stream.  Returns 0 on success, 1 on a real error, -1 when the graph path
+// cannot be used (the caller falls back to eager launches).
+int train_step_graph(vmb_mla_trainer* h, const float* params, float* running, const float* x, const long long* labels,
+                     long long batch, float dropout_p, unsigned long long seed, float* grads, float* loss, float* scores,
+                     cudaStream_t st) {
+  if (!h->gstream) {
+    if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+  }
+  vmb_mla_trainer::GraphSlot* slot = nullptr;
+  for (int i = 0; i < h->n_graphs; ++i) {
+    auto& g = h->graphs[i];
+    if (g.params == params && g.running == running && g.grads == grads && g.loss == loss && g.scores == scores &&
+        g.batch == batch && g.dropout_p == dropout_p)
+      slot = &g;
+  }
+  cudaStream_t gs = h->gstream;
+  if (cudaEventRecord(h->ev_in, st) != cudaSuccess || cudaStreamWaitEvent(gs, h->ev_in, 0) != cudaSuccess) return -1;
+  if (!slot) {
+    const long long l0 = vmb_launch_count();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    h->capturing = true;
+    const int rc = train_phases(kPhaseForward | kPhaseBackward, h, params, running, h->x_stage, h->labels_stage, nullptr,
+                                batch, dropout_p, 0, grads, loss, scores, gs);
+    h->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    const int launches = static_cast<int>(vmb_launch_count() - l0);
+    vmb::count_launch(-launches);          // nothing has run yet
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return -1;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+      cudaGetLastError();
+      return -1;
+    }
+    const int n_slots = static_cast<int>(sizeof h->graphs / sizeof h->graphs[0]);
+    int idx;
+    if (h->n_graphs < n_slots) {
+      idx = h->n_graphs++;
+    } else {
+      idx = h->next_graph;
+      h->next_graph = (h->next_graph + 1) % n_slots;
+      cudaGraphExecDestroy(h->graphs[idx].exec);
+    }
+    h->graphs[idx] = {params, running, grads, loss, scores, batch, dropout_p, exec, launches};
+    slot = &h->graphs[idx];
+  }
+  const size_t x_bytes = size_t(batch) * h->T * h->emb_in * sizeof(float);
+  if (cudaMemcpyAsync(h->x_stage, x, x_bytes, cudaMemcpyDeviceToDevice, gs) != cudaSuccess ||
+      cudaMemcpyAsync(h->labels_stage, labels, size_t(batch) * sizeof(long long), cudaMemcpyDeviceToDevice, gs) != cudaSuccess)
+    return fail("vmb_mla_train_step: staging copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  set_seed_kernel<<<1, 1, 0, gs>>>(h->seed_dev, seed);
+  if (cudaGraphLaunch(slot->exec, gs) != cudaSuccess)
+    return fail("vmb_mla_train_step: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  vmb::count_launch(1 + slot->launches);
+  if (cudaEventRecord(h->ev_out, gs) != cudaSuccess || cudaStreamWaitEvent(st, h->ev_out, 0) != cudaSuccess)
+    return fail("vmb_mla_train_step: cannot join the graph stream: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int vmb_mla_train_step(vmb_mla_trainer_t* h, const float* params, float* running, const float* x,
                        const long long* labels, long long batch, float dropout_p, unsigned long long seed,
                        float* grads, float* loss, float* scores, void* stream) {
   if (!labels) return fail("vmb_mla_train_step: labels are required");
-  return train_phases(kPhaseForward | kPhaseBackward, h, params, running, x, labels, nullptr, batch, dropout_p, seed,
-                      grads, loss, scores, stream);
+  // The first step of a handle runs eagerly (streams, events and kernel attributes are created on the way); from the
+  // second one on the step is a CUDA graph replay.  VMB_TRAIN_GRAPH=0 keeps the eager path.
+  if (h && h->eager_steps > 0 && !h->graph_broken && train_graph_enabled() && params && running && x && grads && loss &&
+      batch >= 2 && batch <= h->max_batch && dropout_p >= 0.f && dropout_p < 1.f) {
+    const int rc = train_step_graph(h, params, running, x, labels, batch, dropout_p, seed, grads, loss, scores,
+                                    static_cast<cudaStream_t>(stream));
+    if (rc >= 0) return rc;
+    h->graph_broken = true;     // fall through to the eager path, now and for the rest of the handle's life
+  }
+  const int rc = train_phases(kPhaseForward | kPhaseBackward, h, params, running, x, labels, nullptr, batch, dropout_p, seed,
+                              grads, loss, scores, stream);
+  if (!rc && h) ++h->eager_steps;
+  return rc;
 }
 
 long long vmb_mla_train_tail_offset(const vmb_mla_trainer_t* h) {

@@ -52,7 +52,8 @@ struct PCfg {
   static constexpr int kStages = 192 * 1024 / kStageBytes;               // 4 (three planes) or 6 (two)
   static constexpr int kBiasBytes = 2 * kBN * 4;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kStatBytes = kMaxStatChannels * 2 * 8 + 16;      // {sum, sum of squares} per channel + a flag
+  // statistics epilogue: {sum, sum of squares} per channel + a flag, and two buffers of per-thread partial sums
+  static constexpr int kStatBytes = kMaxStatChannels * 2 * 8 + 16 + 2 * kEpiThreads * 2 * 8;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes + kStatBytes;
   static constexpr int kTmemCols = 512;                                  // 2 buffers x (hi*hi | cross products) x 128
 };
@@ -102,6 +103,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   double* stat_s = reinterpret_cast<double*>(smem + C::kStages * C::kStageBytes + C::kBiasBytes + C::kBarBytes);
   int* last_flag = reinterpret_cast<int*>(stat_s + 2 * kMaxStatChannels);
+  double* part_s = stat_s + 2 * kMaxStatChannels + 2;   // [2][kEpiThreads][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,7 +235,9 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (p.epi.a2) { s2 = __ldg(p.epi.a2 + t); o2 = __ldg(p.epi.b2 + t); }
       }
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * kBN);
-      double st1 = 0.0, st2 = 0.0;   // EPI == 3: this row's sum / sum of squares over the tile's valid columns
+      // EPI == 3: this row's sum / sum of squares over the 64 columns this thread sees of the tile (fp32: 64 terms of
+      // similar size; everything above that level is added in double)
+      float st1 = 0.f, st2 = 0.f;
 #pragma unroll 1
       for (int ch = half; ch < kBN / 32; ch += 2) {
         uint32_t big[32], small[32];
@@ -259,7 +263,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int j = 0; j < 32; ++j)
             if (c0 + j < p.stats.cols) {
               st1 += f[j];
-              st2 += double(f[j]) * f[j];
+              st2 = fmaf(f[j], f[j], st2);
             }
         }
         if (EPI == 1) {
@@ -307,10 +311,23 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (EPI == 3 && valid) {   // channel = time step of the row
-        const int t = row % p.stats.channels;
-        atomicAdd(stat_s + 2 * t, st1);
-        atomicAdd(stat_s + 2 * t + 1, st2);
+      if (EPI == 3) {
+        // Per-channel sums without atomics: every thread leaves its row's partial sums in shared memory (the two warps
+        // of a lane quarter hold the two halves of a row's columns), then thread (t, j) adds the rows of the tile whose
+        // time step is t.  Two buffers, so one named barrier per tile is enough: a buffer is rewritten two tiles later,
+        // after the barrier of the tile in between, which the reading thread only reaches when it is done reading.
+        double* part = part_s + (it & 1) * (kEpiThreads * 2);
+        const int slot = half * kBM + q * 32 + lane;
+        part[2 * slot] = valid ? double(st1) : 0.0;
+        part[2 * slot + 1] = valid ? double(st2) : 0.0;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (ep_tid < 2 * p.stats.channels) {
+          const int t = ep_tid >> 1, j = ep_tid & 1, T = p.stats.channels;
+          const int first = (t - (m_tile * kBM) % T + T) % T;   // first row of the tile with time step t
+          double sum = 0.0;
+          for (int i = first; i < kBM; i += T) sum += part[2 * i + j] + part[2 * (kBM + i) + j];
+          stat_s[ep_tid] += sum;
+        }
       }
     }
     if (EPI == 3) {
@@ -318,8 +335,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // accumulators; the CTA that arrives last turns them into {mean, rstd} and updates the running statistics, exactly
       // as bn_time_stats_kernel does after its own pass over the matrix
       const PlanesStats& j = p.stats;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      if (ep_tid < 2 * j.channels) atomicAdd(j.acc + ep_tid, stat_s[ep_tid]);
+      if (ep_tid < 2 * j.channels) atomicAdd(j.acc + ep_tid, stat_s[ep_tid]);   // stat_s[i] belongs to thread i
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (ep_tid == 0) *last_flag = atomicAdd(j.counter, 1u) == gridDim.x - 1;

@@ -87,9 +87,12 @@ def main():
     phases = [0.0, 0.0, 0.0]
     launches0 = _lib.lib().vmb_launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     t0.record()
+    w0 = time.perf_counter()
     for _ in range(args.steps):
         tr.step(x, labels, overlap=args.exchange != 'nccl')
+    host_ms = (time.perf_counter() - w0) * 1e3 / args.steps      # host time to ENQUEUE a step (no synchronisation inside)
     t1.record()
     sync()
     launches = _lib.lib().vmb_launch_count() - launches0
@@ -125,7 +128,8 @@ def main():
                                        "dropout 0.4, CE on sigmoid outputs", "allreduce_bytes": tr.n_params * 4,
                            "gradient_exchange": args.exchange if world > 1 else "none (one rank)"},
                 "phase_ms": {"forward_backward": phases[0], "allreduce": phases[1], "adam": phases[2]},
-                "gpu_launches": int(launches), "final_loss": loss_end}
+                "gpu_launches": int(launches), "final_loss": loss_end, "host_enqueue_ms_per_step": host_ms,
+                "cuda_graph": os.environ.get("VMB_TRAIN_GRAPH", "1") != "0"}
         if args.cpu_baseline and world == 1:
             import time
             from oracle import train_torch
