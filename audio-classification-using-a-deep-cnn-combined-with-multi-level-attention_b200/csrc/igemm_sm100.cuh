@@ -103,6 +103,24 @@ int igemm_set_halo(int on);   // 1 / 0 force the choice, -1 returns to the defau
 
 const char* igemm_last_error();
 
+// Keep / drop decision of dropout element idx of layer `layer` in the step seeded `seed` (head training; counter based,
+// recomputed in the backward pass): a 32-bit finaliser (murmur3's fmix32) over the element index keyed by (seed, layer)
+// — 8 integer instructions per element; the first version ran a 64-bit splitmix (two 64-bit multiplies = a dozen 32-bit
+// IMADs) for every element of every element-wise kernel.  Returns the inverted-dropout scale: 1 / (1 - p) or 0.
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned layer, unsigned long long idx, float p) {
+  if (p <= 0.f) return 1.f;
+  const unsigned key = static_cast<unsigned>(seed) ^ (static_cast<unsigned>(seed >> 32) * 0x9E3779B1u) ^
+                       (layer * 0x85EBCA77u + 0xC2B2AE3Du);
+  unsigned h = (static_cast<unsigned>(idx) ^ key) * 0x9E3779B1u + static_cast<unsigned>(idx >> 32) * 0x27D4EB2Fu;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  const float u = static_cast<float>(h >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? 1.f / (1.f - p) : 0.f;
+}
+
 // planes_gemm_sm100.cu: the split GEMMs with every operand plane of a K-block loaded once per tile and the hi * hi
 // product in its own TMEM accumulator.  igemm_linear_split / igemm_linear_split_ksplit route to it when
 // planes_gemm_enabled() (default; env VMB_PLANES_GEMM=0 or planes_gemm_set(0) selects the long-K-loop kernel above).
@@ -136,6 +154,24 @@ struct PlanesStats {
   int channels, cols;
   float eps, momentum;
 };
+// Gradient-statistics epilogue (head training, backward): the GEMM computes d(loss)/d(activation) of a
+// BatchNorm1d(T) (+ ReLU + dropout) block, out fp32 [M][ldo]; the block's backward pass first needs, per time step
+// t = row % T, S1_t = sum g and S2_t = sum g * xhat with g = out * [BN output > 0] * dropout keep scale and
+// xhat = (u - mean_t) * rstd_t (u: the block's pre-BatchNorm input saved by the forward pass).  The epilogue adds both
+// sums into acc (double [T][2], zeroed by the caller) from the accumulator rows it holds — the separate reduction pass
+// over out and u (bn_time_backward_reduce_kernel, mla_train.cu) is not launched.
+struct PlanesGradStats {
+  const float* u;
+  long long ldu;
+  const float *stat, *gamma, *beta;     // [T][2] {mean, rstd}; [T]; [T]
+  double* acc;
+  const unsigned long long* seed;       // device memory: the step's dropout seed
+  unsigned layer;
+  float p;
+  int relu, T, F, cols;                 // F: elements per row in the dropout element index; cols: valid columns
+};
+int planes_gemm_gradstats(const void* a_planes, const void* b_planes, float* out, long long ldo, int M, int N, int K,
+                          int planes, const PlanesGradStats& gs, cudaStream_t stream);
 int planes_gemm_stats(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int M,
                       int N, int K, int planes, const PlanesStats& stats, cudaStream_t stream);
 bool planes_gemm_enabled();

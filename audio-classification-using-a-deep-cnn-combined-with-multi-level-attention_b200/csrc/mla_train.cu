@@ -157,22 +157,7 @@ bn_col_stats_kernel(const float* __restrict__ x, long long ld, long long batch, 
 }
 
 // ------------------------------------------------------------------ dropout (counter-based, recomputed in backward)
-// Keep / drop decision of element idx of layer `layer` in the step seeded `seed`: a 32-bit finaliser (murmur3's fmix32)
-// over the element index keyed by (seed, layer) — 8 integer instructions per element; the first version ran a 64-bit
-// splitmix (two 64-bit multiplies = a dozen 32-bit IMADs) for every element of every element-wise kernel.
-__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned layer, unsigned long long idx, float p) {
-  if (p <= 0.f) return 1.f;
-  const unsigned key = static_cast<unsigned>(seed) ^ (static_cast<unsigned>(seed >> 32) * 0x9E3779B1u) ^
-                       (layer * 0x85EBCA77u + 0xC2B2AE3Du);
-  unsigned h = (static_cast<unsigned>(idx) ^ key) * 0x9E3779B1u + static_cast<unsigned>(idx >> 32) * 0x27D4EB2Fu;
-  h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  const float u = static_cast<float>(h >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? 1.f / (1.f - p) : 0.f;
-}
+using vmb::dropout_scale;   // igemm_sm100.cuh: shared with the gradient-statistics epilogue of the GEMM
 
 // ------------------------------------------------------------------ 32x32 tile kernel with element functor
 struct TileOut {
@@ -939,6 +924,27 @@ int gemm_stats(const void* a_planes, const void* w_planes, const float* bias, fl
   return 0;
 }
 
+// dX GEMM + the BatchNorm-backward reductions of the block that consumes its output (planes_gemm_gradstats): replaces
+// gemm() followed by bn_time_backward_reduce_kernel when the block's only upstream gradient is this GEMM's output.
+bool gradstats_in_gemm(const GradIn& gi) {
+  static const bool env_on = [] {
+    const char* e = getenv("VMB_TRAIN_GRADSTATS_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return env_on && vmb::planes_gemm_enabled() && gi.T <= 16 && !gi.da2 && gi.ldu % 4 == 0 &&
+         (gi.F + 3) / 4 * 4 <= gi.ldu && (reinterpret_cast<uintptr_t>(gi.u) & 15) == 0;
+}
+
+int gemm_gradstats(const void* a_planes, const void* w_planes, float* out, long long ldo, long long M, int N, int K,
+                   const GradIn& gi, double* acc, cudaStream_t st) {
+  vmb::PlanesGradStats gs{gi.u, gi.ldu, gi.stat, gi.gamma, gi.beta, acc, gi.seed, gi.layer, gi.p, gi.relu, gi.T, gi.F, gi.F};
+  if (vmb::planes_gemm_gradstats(a_planes, w_planes, out, ldo, int(M), N, K, kPl, gs, st)) {
+    vmb::set_kernel_error("%s", vmb::planes_gemm_last_error());
+    return 1;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1258,6 +1264,33 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   // sends into the level's embedding (dE_att -> out_dA).  With own_side == false it runs on the caller's stream with the
   // chain's scratch (and its dW GEMM goes through dw_job); with own_side == true everything runs on `s` with the second
   // set of scratch buffers.
+  // The BatchNorm (+ ReLU + dropout) block (l, j) — j == -1: the level's norm0 — as the backward pass sees it, with its
+  // upstream gradient(s); and the slot of its two backward reductions.
+  auto block_gi = [&](int l, int j, const float* da1, const float* da2) {
+    const LevelRef& L = h->lvl[l];
+    if (j >= 0)
+      return GradIn{da1, Hp, da2, Hp, h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g,
+                    params + L.norms[j].b, 1, dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
+    const float* in = l == 0 ? x : h->E[l - 1];
+    const long long ld_in = l == 0 ? h->emb_in : Hp;
+    const int F_in = l == 0 ? h->emb_in : H;
+    return GradIn{da1, Hp, nullptr, 0, in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g,
+                  params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
+  };
+  auto block_acc = [&](int l, int j) { return slotacc(j >= 0 ? h->lvl[l].norms[j].bslot : h->lvl[l].norm0.bslot); };
+  // dX GEMM into `out`, the upstream gradient of block (l, j): when that is the block's only upstream gradient, the
+  // block's reductions ride in the GEMM's epilogue and `pre_reduced` tells the consumer not to launch its own pass
+  bool pre_reduced = false;
+  auto gemm_into_block = [&](const void* a, const void* wt, float* out, int n_pad, int l, int j, const float* da2,
+                             cudaStream_t s) {
+    const GradIn gi = block_gi(l, j, out, da2);
+    if (gradstats_in_gemm(gi)) {
+      pre_reduced = true;
+      return gemm_gradstats(a, wt, out, Hp, R, n_pad, Hp, gi, block_acc(l, j), s);
+    }
+    pre_reduced = false;
+    return gemm(a, wt, nullptr, out, Hp, R, n_pad, Hp, s);
+  };
   static std::atomic<unsigned long long> att_attr{0};   // one bit per device: the attribute is per device
   if (vmb::device_needs_setup(att_attr))
     cudaFuncSetAttribute(att_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -1293,7 +1326,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     } else {
       TRY(dw_job(gpt, e_pt, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
     }
-    TRY(gemm(gp, L.fcv.wtp, nullptr, out_dA, Hp, R, Hp, Hp, s));
+    if (own_side) {
+      TRY(gemm(gp, L.fcv.wtp, nullptr, out_dA, Hp, R, Hp, Hp, s));     // joins the chain as one of two upstream gradients
+    } else {
+      TRY(gemm_into_block(gp, L.fcv.wtp, out_dA, Hp, l, L.n_fc - 1, (l + 1 < h->n_levels) ? h->dEnext : nullptr, s));
+    }
   };
   // fork: every level below the last starts its attention branch now (dY is complete), on the second side stream
   const bool att_fork = forked && h->n_levels > 1;
@@ -1329,13 +1366,14 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     const float* da2 = (l + 1 < h->n_levels) ? h->dEnext : nullptr;
     for (int j = L.n_fc - 1; j >= 0 && !rc; --j) {
       const FcRef& fc = L.fc[j];
-      GradIn gi{da1, Hp, da2, Hp, h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g,
-                params + L.norms[j].b, 1, dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
-      double* acc = slotacc(L.norms[j].bslot);
-      const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * H + 256 * 8 - 1) / (256 * 8), 64));
-      vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
-      vmb::count_launch();
-      TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      const GradIn gi = block_gi(l, j, da1, da2);
+      double* acc = block_acc(l, j);
+      if (!pre_reduced) {
+        const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * H + 256 * 8 - 1) / (256 * 8), 64));
+        vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
+        vmb::count_launch();
+        TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      }
       FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
       TileOut o{h->G_p, h->G_pt, nullptr, Hp, grads + fc.b, R, Rp, H, Hp};
       before_g_overwrite();
@@ -1345,22 +1383,22 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(dw_job(h->G_pt, prev_pt, fc.n_in_pad, Hp, fc.n_in_pad, Rp, grads + fc.w, size_t(fc.n_in) * 4,
                  size_t(fc.n_in) * 4, H));
       float* dprev = (da1 == h->dA) ? h->dB : h->dA;
-      TRY(gemm(h->G_p, fc.wtp, nullptr, dprev, Hp, R, fc.n_in_pad, Hp, st));
+      TRY(gemm_into_block(h->G_p, fc.wtp, dprev, fc.n_in_pad, l, j - 1, nullptr, st));   // j - 1 == -1: the level's norm0
       da1 = dprev;
       da2 = nullptr;
     }
     // norm0 of this level: gradient wrt its input (= E_{l-1} for l > 0) and its affine parameters
     {
-      const float* in = l == 0 ? x : h->E[l - 1];
-      const long long ld_in = l == 0 ? h->emb_in : Hp;
       const int F_in = l == 0 ? h->emb_in : H;
-      GradIn gi{da1, Hp, nullptr, 0, in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g,
-                params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
-      double* acc = slotacc(L.norm0.bslot);
-      const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F_in + 256 * 8 - 1) / (256 * 8), 64));
-      vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
-      vmb::count_launch();
-      TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      const GradIn gi = block_gi(l, -1, da1, nullptr);
+      double* acc = block_acc(l, -1);
+      if (!pre_reduced) {
+        const unsigned chunks = static_cast<unsigned>(std::min<long long>((B * F_in + 256 * 8 - 1) / (256 * 8), 64));
+        vmb::launch_pdl(bn_time_backward_reduce_kernel, dim3(chunks, T), dim3(256), 0, st, gi, B, acc);
+        vmb::count_launch();
+        TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
+      }
+      pre_reduced = false;
       FBnBackward f{gi, acc, double(B) * F_in, grads + L.norm0.g, grads + L.norm0.b};
       // level 0: only the parameter gradients are needed (written by the prologue); still run one tile row so
       // the prologue executes.  level > 0: fp32 gradient wrt E_{l-1}

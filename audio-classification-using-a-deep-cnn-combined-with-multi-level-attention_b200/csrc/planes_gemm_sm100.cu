@@ -69,6 +69,7 @@ struct PlanesParams {
   float* out;
   PlanesEpi epi;     // EPI == 1 only
   PlanesStats stats; // EPI == 3 only
+  PlanesGradStats gs; // EPI == 4 only
 };
 
 // hi | lo bf16 split of 32 consecutive values of one row -> two 64-byte runs (full 32-byte sectors)
@@ -125,7 +126,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     mbar_fence_init();
   }
-  if (EPI == 3 && threadIdx.x < 2 * kMaxStatChannels) stat_s[threadIdx.x] = 0.0;
+  if (EPI >= 3 && threadIdx.x < 2 * kMaxStatChannels) stat_s[threadIdx.x] = 0.0;
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
@@ -229,6 +230,13 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool valid = row < p.M;
       float* out_row = p.out + static_cast<size_t>(row) * p.ldo + n0;
       float s1 = 1.f, o1 = 0.f, s2 = 1.f, o2 = 0.f;
+      if (EPI == 4 && valid) {   // s1 = mean_t, o1 = rstd_t, s2 = gamma_t, o2 = beta_t of the block being differentiated
+        const int t = row % p.gs.T;
+        s1 = __ldg(p.gs.stat + 2 * t);
+        o1 = __ldg(p.gs.stat + 2 * t + 1);
+        s2 = __ldg(p.gs.gamma + t);
+        o2 = __ldg(p.gs.beta + t);
+      }
       if (EPI == 1 && valid) {
         const int t = row % p.epi.T;
         if (p.epi.a1) { s1 = __ldg(p.epi.a1 + t); o1 = __ldg(p.epi.b1 + t); }
@@ -265,6 +273,29 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               st1 += f[j];
               st2 = fmaf(f[j], f[j], st2);
             }
+        }
+        if (EPI == 4 && valid) {
+          const int c0 = n0 + ch * 32;
+          const float* urow = p.gs.u + static_cast<size_t>(row) * p.gs.ldu + c0;
+          const unsigned long long seed = p.gs.p > 0.f ? __ldg(p.gs.seed) : 0ull;
+          const unsigned long long e0 = static_cast<unsigned long long>(row) * p.gs.F + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < p.gs.cols) {   // cols is a multiple of 4 or the row is padded: u rows are 16-byte aligned
+              const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow + j));
+              const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                if (c0 + j + q4 < p.gs.cols) {
+                  const float xh = (uu[q4] - s1) * o1;
+                  float g = f[j + q4] * dropout_scale(seed, p.gs.layer, e0 + j + q4, p.gs.p);
+                  if (p.gs.relu && fmaf(s2, xh, o2) <= 0.f) g = 0.f;
+                  st1 += g;
+                  st2 = fmaf(g, xh, st2);
+                }
+              }
+            }
+          }
         }
         if (EPI == 1) {
           // h = relu?(a1_t u + b1_t) as hi | lo planes; with dst2 also a2_t h + b2_t (the next level's norm0).  Columns
@@ -311,7 +342,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (EPI == 3) {
+      if (EPI >= 3) {
         // Per-channel sums without atomics: every thread leaves its row's partial sums in shared memory (the two warps
         // of a lane quarter hold the two halves of a row's columns), then thread (t, j) adds the rows of the tile whose
         // time step is t.  Two buffers, so one named barrier per tile is enough: a buffer is rewritten two tiles later,
@@ -321,14 +352,18 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         part[2 * slot] = valid ? double(st1) : 0.0;
         part[2 * slot + 1] = valid ? double(st2) : 0.0;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (ep_tid < 2 * p.stats.channels) {
-          const int t = ep_tid >> 1, j = ep_tid & 1, T = p.stats.channels;
+        const int T = EPI == 3 ? p.stats.channels : p.gs.T;
+        if (ep_tid < 2 * T) {
+          const int t = ep_tid >> 1, j = ep_tid & 1;
           const int first = (t - (m_tile * kBM) % T + T) % T;   // first row of the tile with time step t
           double sum = 0.0;
           for (int i = first; i < kBM; i += T) sum += part[2 * i + j] + part[2 * (kBM + i) + j];
           stat_s[ep_tid] += sum;
         }
       }
+    }
+    if (EPI == 4) {
+      if (ep_tid < 2 * p.gs.T) atomicAdd(p.gs.acc + ep_tid, stat_s[ep_tid]);   // stat_s[i] belongs to thread i
     }
     if (EPI == 3) {
       // BatchNorm statistics of the output (model.py:221 in train mode): this CTA's partial sums go to the global
@@ -419,7 +454,7 @@ int planes_gemm_set(int on) {
 // == 2, no K split) the epilogue of PlanesEpi::mode replaces the fp32 store.
 static int planes_gemm_any(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo,
                            int relu, int M, int N, int K, int planes, int ksplit, const PlanesEpi* epi,
-                           cudaStream_t stream, const PlanesStats* stats = nullptr) {
+                           cudaStream_t stream, const PlanesStats* stats = nullptr, const PlanesGradStats* gs = nullptr) {
   if (M <= 0) return 0;
   if (K % kBK != 0 || N % kBN != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_perr, sizeof g_perr, "planes_gemm: need K %% 32 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d planes=%d)", K, N,
@@ -468,6 +503,10 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
     p.epi = *epi;
     return launch_planes<2, false, 1>(ta, tb, p, stream);
   }
+  if (gs) {
+    p.gs = *gs;
+    return planes == 3 ? launch_planes<3, false, 4>(ta, tb, p, stream) : launch_planes<2, false, 4>(ta, tb, p, stream);
+  }
   if (stats) {
     if (ksplit != 0 || stats->channels <= 0 || stats->channels > kMaxStatChannels || stats->cols <= 0 || stats->cols > N ||
         !stats->acc || !stats->stat || !stats->counter || (stats->run_mean && !stats->run_var)) {
@@ -485,6 +524,16 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
 int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,
                 int N, int K, int planes, int ksplit, cudaStream_t stream) {
   return planes_gemm_any(a_planes, b_planes, bias, out, ldo, relu, M, N, K, planes, ksplit, nullptr, stream);
+}
+
+int planes_gemm_gradstats(const void* a_planes, const void* b_planes, float* out, long long ldo, int M, int N, int K,
+                          int planes, const PlanesGradStats& gs, cudaStream_t stream) {
+  if (gs.T <= 0 || gs.T > kMaxStatChannels || gs.cols <= 0 || gs.cols > N || !gs.u || !gs.stat || !gs.gamma || !gs.beta ||
+      !gs.acc || !gs.seed || gs.ldu % 4 != 0 || (gs.cols + 3) / 4 * 4 > gs.ldu || (reinterpret_cast<uintptr_t>(gs.u) & 15)) {
+    snprintf(g_perr, sizeof g_perr, "planes_gemm: bad gradient-statistics arguments");
+    return 1;
+  }
+  return planes_gemm_any(a_planes, b_planes, nullptr, out, ldo, 0, M, N, K, planes, 0, nullptr, stream, nullptr, &gs);
 }
 
 int planes_gemm_stats(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int M,
