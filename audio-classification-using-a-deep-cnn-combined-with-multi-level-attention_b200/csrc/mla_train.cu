@@ -196,14 +196,12 @@ __device__ __forceinline__ void store_split_pair(float v0, float v1, __nv_bfloat
 // per row instead of a 64-bit one per element.
 constexpr int kTile = 64;
 template <class F>
-__global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
-  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
-  vmb::pdl_wait();
+__device__ __forceinline__ void tile_body(F& f, const TileOut& o, int bx, int by) {
   __shared__ float tile[kTile][kTile + 1];
-  f.prologue();
+  f.prologue(bx == 0 && by == 0);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int r0 = blockIdx.y * kTile;
-  const int c0 = blockIdx.x * kTile;
+  const int r0 = by * kTile;
+  const int c0 = bx * kTile;
   const int tmod = f.time_steps();
   {
     const int c = c0 + 2 * tx;
@@ -245,24 +243,51 @@ __global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
   }
 }
 
+template <class F>
+__global__ void __launch_bounds__(256) tile_split_kernel(F f, TileOut o) {
+  vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
+  vmb::pdl_wait();
+  tile_body(f, o, blockIdx.x, blockIdx.y);
+}
+
 // identity (weights, plain copies)
 struct FIdentity {
   const float* x; long long ld;
   const float* bias_src = nullptr; float* bias_dst = nullptr; int n_bias = 0;   // block (0,0) copies the bias
-  __device__ void prologue() {
-    if (bias_dst && blockIdx.x == 0 && blockIdx.y == 0)
+  __device__ void prologue(bool first_block) {
+    if (bias_dst && first_block)
       for (int i = threadIdx.x; i < n_bias; i += blockDim.x) bias_dst[i] = bias_src[i];
   }
   __device__ int time_steps() const { return 1; }
   __device__ float operator()(int r, int, int c) const { return __ldg(x + static_cast<long long>(r) * ld + c); }
 };
 
+// Every weight matrix of the head -> operand planes (row-major and transposed) + padded bias, in ONE launch: the jobs'
+// tiles are laid end to end over blockIdx.x (nine launches of 20-100 CTAs each left most of the GPU idle).
+constexpr int kMaxWeightJobs = 4 * (4 + 1) + 1;
+struct WeightJobs {
+  int n;
+  int first_tile[kMaxWeightJobs + 1];
+  int tiles_x[kMaxWeightJobs];
+  FIdentity f[kMaxWeightJobs];
+  TileOut o[kMaxWeightJobs];
+};
+__global__ void __launch_bounds__(256) weights_split_kernel(const __grid_constant__ WeightJobs jobs) {
+  vmb::pdl_launch_dependents();
+  vmb::pdl_wait();
+  int j = 0;
+  while (j + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.first_tile[j + 1]) ++j;
+  const int local = blockIdx.x - jobs.first_tile[j];
+  FIdentity f = jobs.f[j];
+  tile_body(f, jobs.o[j], local % jobs.tiles_x[j], local / jobs.tiles_x[j]);
+}
+
 // forward: a = dropout(relu?(gamma_t * (u - mu_t) * rstd_t + beta_t))
 struct FBnAct {
   const float* u; long long ld; int T, F;
   const float* stat; const float* gamma; const float* beta;
   int relu; float p; const unsigned long long* seed; unsigned layer;   // *seed: the step's dropout seed (device memory)
-  __device__ void prologue() {}
+  __device__ void prologue(bool) {}
   __device__ int time_steps() const { return T; }
   __device__ float operator()(int r, int t, int c) const {
     float v = fmaf(__ldg(gamma + t) * __ldg(stat + 2 * t + 1), __ldg(u + static_cast<long long>(r) * ld + c) - __ldg(stat + 2 * t),
@@ -327,7 +352,7 @@ bn_time_backward_reduce_kernel(GradIn in, long long batch, double* __restrict__ 
 struct FBnBackward {
   GradIn in; const double* acc; double n; float* dgamma; float* dbeta;
   float* coef;   // shared memory [T][3]: gamma * rstd, S1 / n, S2 / n   (set by prologue)
-  __device__ void prologue() {
+  __device__ void prologue(bool first_block) {
     __shared__ float coef_s[16 * 3];
     coef = coef_s;
     if (threadIdx.x < in.T) {
@@ -335,7 +360,7 @@ struct FBnBackward {
       coef_s[3 * t] = in.gamma[t] * in.stat[2 * t + 1];
       coef_s[3 * t + 1] = static_cast<float>(acc[2 * t] / n);
       coef_s[3 * t + 2] = static_cast<float>(acc[2 * t + 1] / n);
-      if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (first_block) {
         dbeta[t] = static_cast<float>(acc[2 * t]);
         dgamma[t] = static_cast<float>(acc[2 * t + 1]);
       }
@@ -423,7 +448,6 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
   extern __shared__ float att_sm[];
   float* att = att_sm;                 // [T][K]
   float* cla = att + a.T * a.K;        // [T][K]
-  float* sinv = cla + a.T * a.K;       // [K]  1 / sum_t att
   __shared__ float sa_v[16], sb_v[16], sa_f[16], sb_f[16], dot[16];
   __shared__ double red[8][16][4];
   const long long clip = blockIdx.x;
@@ -437,27 +461,43 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
     dot[t] = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.T * a.K; i += blockDim.x) {
-    const int t = i / a.K, k = i - t * a.K;
-    const float zz = __ldg(zc + t * a.ldz + k);
+  // att / cla of the clip into shared memory, one time step at a time (no index division, the row's softmax statistics
+  // read once per row)
+  for (int t = 0; t < a.T; ++t) {
     const float* rs2 = row_stats + 2 * (clip * a.T + t);
-    att[i] = expf(fmaf(sa_v[t], zz, sb_v[t]) - rs2[0]) / rs2[1];
-    cla[i] = 1.f / (1.f + expf(-fmaf(sa_f[t], zz, sb_f[t])));
+    const float m = __ldg(rs2), inv = 1.f / __ldg(rs2 + 1);
+    const float av = sa_v[t], bv = sb_v[t], af = sa_f[t], bf = sb_f[t];
+    const float* zt = zc + t * a.ldz;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
+      const float zz = __ldg(zt + k);
+      att[t * a.K + k] = expf(fmaf(av, zz, bv) - m) * inv;
+      cla[t * a.K + k] = 1.f / (1.f + expf(-fmaf(af, zz, bf)));
+    }
   }
   __syncthreads();
+  // A thread owns the classes k = threadIdx.x + 256 i, i < kIter (K <= 1024): what depends on k alone — 1 / sum_t att,
+  // y and dy — stays in registers for both passes.
   // s[k] = sum_t att; datt = dy (cla - y) / s; dot[t] = sum_k datt * att  (the softmax backward needs it per row)
+  constexpr int kIter = 4;
+  float si_r[kIter], yy_r[kIter], d_r[kIter];
   float pdot[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) pdot[t] = 0.f;
-  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < a.T; ++t) s += att[t * a.K + k];
-    const float si = 1.f / s;
-    sinv[k] = si;
-    const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
 #pragma unroll
-    for (int t = 0; t < 16; ++t)
-      if (t < a.T) pdot[t] = fmaf(d * (cla[t * a.K + k] - yy) * si, att[t * a.K + k], pdot[t]);
+  for (int i = 0; i < kIter; ++i) {
+    const int k = threadIdx.x + 256 * i;
+    si_r[i] = yy_r[i] = d_r[i] = 0.f;
+    if (k < a.K) {
+      float s = 0.f;
+      for (int t = 0; t < a.T; ++t) s += att[t * a.K + k];
+      si_r[i] = 1.f / s;
+      yy_r[i] = __ldg(y + clip * ystride + col0 + k);
+      d_r[i] = __ldg(dy + clip * ystride + col0 + k);
+      const float dsi = d_r[i] * si_r[i];
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < a.T) pdot[t] = fmaf(dsi * (cla[t * a.K + k] - yy_r[i]), att[t * a.K + k], pdot[t]);
+    }
   }
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
@@ -467,22 +507,30 @@ att_backward_kernel(AttParams a, const float* __restrict__ y, const float* __res
     if (lane == 0 && t < a.T) atomicAdd(&dot[t], v);
   }
   __syncthreads();
-  // second pass, one time step per iteration so the BatchNorm reductions stay per t (no barrier inside the loop)
+  // second pass, one time step per iteration so the BatchNorm reductions stay per t (no barrier inside the loop); a
+  // thread adds its <= 4 terms in fp32, everything above that in double
   for (int t = 0; t < a.T; ++t) {
-    const float mu = a.stat[2 * t], rstd = a.stat[2 * t + 1];
-    double p1v = 0, p2v = 0, p1f = 0, p2f = 0;
-    for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-      const float at = att[t * a.K + k], cl = cla[t * a.K + k], si = sinv[k];
-      const float yy = __ldg(y + clip * ystride + col0 + k), d = __ldg(dy + clip * ystride + col0 + k);
-      const float g_f = d * at * si * cl * (1.f - cl);
-      const float g_v = at * (d * (cl - yy) * si - dot[t]);
-      const long long r = clip * a.T + t;
-      gv[r * ldg + k] = g_v;
-      gf[r * ldg + k] = g_f;
-      const float zh = (__ldg(zc + t * a.ldz + k) - mu) * rstd;
-      p1v += g_v; p2v += double(g_v) * zh;
-      p1f += g_f; p2f += double(g_f) * zh;
+    const float mu = a.stat[2 * t], rstd = a.stat[2 * t + 1], dt = dot[t];
+    float* gvr = gv + (clip * a.T + t) * ldg;
+    float* gfr = gf + (clip * a.T + t) * ldg;
+    const float* zt = zc + t * a.ldz;
+    float q1v = 0.f, q2v = 0.f, q1f = 0.f, q2f = 0.f;
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int k = threadIdx.x + 256 * i;
+      if (k < a.K) {
+        const float at = att[t * a.K + k], cl = cla[t * a.K + k];
+        const float dsi = d_r[i] * si_r[i];
+        const float g_f = dsi * at * cl * (1.f - cl);
+        const float g_v = at * (dsi * (cl - yy_r[i]) - dt);
+        gvr[k] = g_v;
+        gfr[k] = g_f;
+        const float zh = (__ldg(zt + k) - mu) * rstd;
+        q1v += g_v; q2v = fmaf(g_v, zh, q2v);
+        q1f += g_f; q2f = fmaf(g_f, zh, q2f);
+      }
     }
+    double p1v = q1v, p2v = q2v, p1f = q1f, p2f = q2f;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       p1v += __shfl_xor_sync(0xffffffffu, p1v, o);
@@ -509,7 +557,7 @@ struct FAttCombine {
   const double* acc_v; const double* acc_f; double n;
   float *dgv, *dbv, *dgf, *dbf;
   float* coef;   // shared memory [T][8]: mu, rstd, gamma^v rstd, S1v / n, S2v / n, gamma^f rstd, S1f / n, S2f / n
-  __device__ void prologue() {
+  __device__ void prologue(bool first_block) {
     __shared__ float coef_s[16 * 8];
     coef = coef_s;
     if (threadIdx.x < a.T) {
@@ -523,7 +571,7 @@ struct FAttCombine {
       coef_s[8 * t + 5] = a.gf[t] * rstd;
       coef_s[8 * t + 6] = float(acc_f[2 * t] / n);
       coef_s[8 * t + 7] = float(acc_f[2 * t + 1] / n);
-      if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (first_block) {
         dbv[t] = static_cast<float>(acc_v[2 * t]); dgv[t] = static_cast<float>(acc_v[2 * t + 1]);
         dbf[t] = static_cast<float>(acc_f[2 * t]); dgf[t] = static_cast<float>(acc_f[2 * t + 1]);
       }
@@ -1105,9 +1153,15 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   // weights -> operand planes run on the side stream: the first Linear needs them only after the level-0 norm0
   // statistics and its activation pass, which do not depend on the weights
   cudaStream_t ws_stream = forked ? h->side : st;
+  WeightJobs wj{};
   auto weights = [&](const FcRef& f) {
-    TileOut o{f.wp, f.wtp, nullptr, 0, nullptr, f.n_out, f.n_out_pad, f.n_in, f.n_in_pad};
-    return run_tile(FIdentity{params + f.w, f.n_in, params + f.b, f.bias_pad, f.n_out}, o, ws_stream, "weight split");
+    const int j = wj.n++;
+    wj.o[j] = TileOut{f.wp, f.wtp, nullptr, 0, nullptr, f.n_out, f.n_out_pad, f.n_in, f.n_in_pad};
+    wj.f[j] = FIdentity{params + f.w, f.n_in, params + f.b, f.bias_pad, f.n_out};
+    const dim3 g = tile_grid(f.n_out_pad, f.n_in_pad);
+    wj.tiles_x[j] = int(g.x);
+    wj.first_tile[j + 1] = wj.first_tile[j] + int(g.x * g.y);
+    return 0;
   };
   const bool fuse_stats = stats_in_gemm(T);
   // Linear (+ bias) into `out` and the BatchNorm statistics of its first `cols` columns
@@ -1128,6 +1182,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     TRY(weights(h->lvl[l].fcv));
   }
   TRY(weights(h->fc_out));
+  if (!rc) {
+    vmb::launch_pdl(weights_split_kernel, dim3(unsigned(wj.first_tile[wj.n])), dim3(256), 0, ws_stream, wj);
+    vmb::count_launch();
+    TRY(vmb::check_launch("weights_split_kernel"));
+  }
   if (forked) cudaEventRecord(h->ev_w, h->side);
   bool weights_pending = forked;
 
