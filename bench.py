@@ -379,16 +379,20 @@ def leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks):
     big = wave_host.repeat(reps, 1)[:per_rank].contiguous().pin_memory()     # this rank's shard (the step batch, tiled)
     out = torch.empty(per_rank, N_CLASSES).pin_memory()
     pipe.forward_host(big[:512], out[:512], clips_per_batch=256)
-    barrier()
-    t0 = time.perf_counter()
-    pipe.forward_host(big, out, clips_per_batch=256)
-    barrier()
-    ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    runs = []
+    for _ in range(5):          # five whole passes; the first one also pays the first device touch of the 5 GB shard
+        barrier()
+        t0 = time.perf_counter()
+        pipe.forward_host(big, out, clips_per_batch=256)
+        barrier()
+        runs.append(max_over_ranks(1e3 * (time.perf_counter() - t0)))
+    ms = sorted(runs)[2]        # the median pass
     nb = wave_host.shape[0]
     ok = bool(torch.isfinite(out).all().item())
     if per_rank >= 2 * nb:                       # the shard is the step batch tiled: its blocks must come out identical
         ok = ok and bool(torch.equal(out[:nb], out[nb:2 * nb]))
-    return {"value": 8192 / (ms * 1e-3), "unit": UNIT, "ms": ms, "clips_per_rank": per_rank, "microbatch_clips": 256,
+    return {"value": 8192 / (ms * 1e-3), "unit": UNIT, "ms": ms, "ms_each_pass": runs, "clips_per_rank": per_rank,
+            "microbatch_clips": 256,
             "h2d_bytes_per_rank": per_rank * CLIP_SAMPLES * 4, "scores_ok": ok,
             "api": "vmb_pipeline_forward_host (one blocking call per rank; pinned host in, pinned host out)"}
 
