@@ -39,23 +39,27 @@ namespace vmb {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32;
-constexpr int kPlaneBytes = 128 * kBK * 2;   // one plane of one K-block of one operand: 128 rows x 64 bytes = 8 KB
+constexpr int kBM = 128, kBK = 32;
+constexpr int kPlaneBytes = 128 * kBK * 2;   // one plane of one K-block of A: 128 rows x 64 bytes = 8 KB
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kMaxStatChannels = 16;         // BatchNorm1d(T) channels the statistics epilogue can carry (T = 10)
 
-template <int PLANES>
+// BN = 128, or 64 when 128-wide tiles would leave most of the last wave idle (head training: 5120 x 640 outputs are 200
+// tiles of 128 x 128 on 148 SMs — two waves, the second a third full — but 400 tiles of 128 x 64 — 2.7 waves of half the
+// work each; the narrower MMA re-reads A from shared memory twice as often per flop, which costs less than the idle SMs).
+template <int PLANES, int BN>
 struct PCfg {
-  static constexpr int kStageBytes = 2 * PLANES * kPlaneBytes;          // A planes, then B planes
-  static constexpr int kStages = 192 * 1024 / kStageBytes;               // 4 (three planes) or 6 (two)
-  static constexpr int kBiasBytes = 2 * kBN * 4;
+  static constexpr int kBPlaneBytes = BN * kBK * 2;                      // one plane of one K-block of B
+  static constexpr int kStageBytes = PLANES * (kPlaneBytes + kBPlaneBytes);   // A planes, then B planes
+  static constexpr int kStages = 192 * 1024 / kStageBytes;               // 4 / 5 (three planes), 6 / 8 (two)
+  static constexpr int kBiasBytes = 2 * BN * 4;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   // statistics epilogue: {sum, sum of squares} per channel + a flag, and two buffers of per-thread partial sums
   static constexpr int kStatBytes = kMaxStatChannels * 2 * 8 + 16 + 2 * kEpiThreads * 2 * 8;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBiasBytes + kBarBytes + kStatBytes;
-  static constexpr int kTmemCols = 512;                                  // 2 buffers x (hi*hi | cross products) x 128
+  static constexpr int kTmemCols = 4 * BN;                               // 2 buffers x (hi*hi | cross products) x BN
 };
 
 struct PlanesParams {
@@ -89,11 +93,12 @@ __device__ __forceinline__ void store_split32(const float (&v)[32], __nv_bfloat1
   st_global_256(lo_dst + 16, l[8], l[9], l[10], l[11], l[12], l[13], l[14], l[15]);
 }
 
-template <int PLANES, bool ATOMIC, int EPI>
+template <int PLANES, bool ATOMIC, int EPI, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const PlanesParams p) {
-  using C = PCfg<PLANES>;
+  using C = PCfg<PLANES, BN>;
+  constexpr int kBN = BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* bias_s = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
@@ -154,7 +159,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tma_load_2d(dst + pl * kPlaneBytes, &tmap_a, &full_bar[stage], pl * plane_cols + kb * kBK, m_tile * kBM);
 #pragma unroll
           for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_2d(dst + (PLANES + pl) * kPlaneBytes, &tmap_b, &full_bar[stage], pl * plane_cols + kb * kBK,
+            tma_load_2d(dst + PLANES * kPlaneBytes + pl * C::kBPlaneBytes, &tmap_b, &full_bar[stage], pl * plane_cols + kb * kBK,
                         n_tile * kBN);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -188,7 +193,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int pa = PLANES == 3 ? cross_a3[q] : cross_a2[q];
             const int pb = PLANES == 3 ? cross_b3[q] : cross_b2[q];
             const uint64_t a_desc = umma_desc_kmajor_sw64(a0 + pa * kPlaneBytes);
-            const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + pb * kPlaneBytes);
+            const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + pb * C::kBPlaneBytes);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (>>4 = 2) per 16-element K step
               umma_bf16_ss(d_small, a_desc + 2 * k, b_desc + 2 * k, idesc, (first | q | k) != 0);
@@ -403,11 +408,11 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 thread_local char g_perr[384] = "";
 
-template <int PLANES, bool ATOMIC, int EPI = 0>
+template <int PLANES, bool ATOMIC, int EPI = 0, int BN = 128>
 int launch_planes(const CUtensorMap& ta, const CUtensorMap& tb, const PlanesParams& p, cudaStream_t stream) {
-  auto kern = planes_gemm_kernel<PLANES, ATOMIC, EPI>;
+  auto kern = planes_gemm_kernel<PLANES, ATOMIC, EPI, BN>;
   static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
-  constexpr int smem = PCfg<PLANES>::kSmemBytes;
+  constexpr int smem = PCfg<PLANES, BN>::kSmemBytes;
   if (device_needs_setup(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -449,6 +454,18 @@ int planes_gemm_set(int on) {
   return prev;
 }
 
+// Which three-plane variants may take 128 x 64 tiles — bit 0: plain stores, bit 1: statistics epilogue, bit 2:
+// gradient-statistics epilogue.  Measured on the training step (A/B on one box, VMB_PLANES_NARROW=<mask>): 0.884 ms with
+// 128-wide tiles everywhere, 0.875 ms with mask 5 (the default), 0.895 ms with mask 7 — the statistics epilogue's
+// per-tile barrier and partial-sum pass cost more per tile than the fuller last wave gives back.
+static int narrow_tiles_mask() {
+  static const int mask = [] {
+    const char* e = getenv("VMB_PLANES_NARROW");
+    return e ? atoi(e) : 5;
+  }();
+  return mask;
+}
+
 // out fp32 [M][ldo] = act(sum of plane products + bias), or with ksplit > 1 / == -1: out += the K slices' partial sums.
 // K % 32 == 0, N % 128 == 0, planes 2 or 3; the operands' rows are planes * K bf16 long.  With epi != nullptr (planes
 // == 2, no K split) the epilogue of PlanesEpi::mode replaces the fp32 store.
@@ -456,7 +473,7 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
                            int relu, int M, int N, int K, int planes, int ksplit, const PlanesEpi* epi,
                            cudaStream_t stream, const PlanesStats* stats = nullptr, const PlanesGradStats* gs = nullptr) {
   if (M <= 0) return 0;
-  if (K % kBK != 0 || N % kBN != 0 || (planes != 2 && planes != 3)) {
+  if (K % kBK != 0 || N % 128 != 0 || (planes != 2 && planes != 3)) {
     snprintf(g_perr, sizeof g_perr, "planes_gemm: need K %% 32 == 0, N %% 128 == 0, planes 2|3 (K=%d N=%d planes=%d)", K, N,
              planes);
     return 1;
@@ -469,6 +486,18 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
       return 1;
     }
   }
+  // Tile width: 128, or 64 (three planes, the variants of narrow_tiles_mask()) when that shortens the schedule — whole
+  // waves of 148 tiles at one unit of time each against waves of half-width tiles at ~0.6 units (the narrower MMA
+  // re-reads A twice as often).
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int bn = 128;
+  if (planes == 3 && !epi && ksplit == 0 && (narrow_tiles_mask() & (gs ? 4 : stats ? 2 : 1))) {
+    const int sms = num_sms();
+    const int t128 = m_tiles * (N / 128);
+    const double cost128 = double((t128 + sms - 1) / sms), cost64 = 0.6 * double((2 * t128 + sms - 1) / sms);
+    if (cost64 < cost128) bn = 64;
+  }
+  const int kBN = bn;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(M)};
@@ -482,7 +511,7 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
   {
     uint64_t dims[2] = {uint64_t(planes) * K, uint64_t(N)};
     uint64_t str[1] = {uint64_t(planes) * K * 2};
-    uint32_t box[2] = {kBK, kBN};
+    uint32_t box[2] = {kBK, uint32_t(kBN)};
     if (make_tmap_bf16(&tb, b_planes, 2, dims, str, box, 64)) {
       snprintf(g_perr, sizeof g_perr, "planes_gemm: %s", igemm_last_error());
       return 1;
@@ -492,7 +521,7 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
   p.M = M;
   p.N = N;
   p.num_kb = K / kBK;
-  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_m_tiles = m_tiles;
   p.num_n_tiles = N / kBN;
   p.ksplit = ksplit;
   p.relu = relu;
@@ -505,6 +534,7 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
   }
   if (gs) {
     p.gs = *gs;
+    if (bn == 64) return launch_planes<3, false, 4, 64>(ta, tb, p, stream);
     return planes == 3 ? launch_planes<3, false, 4>(ta, tb, p, stream) : launch_planes<2, false, 4>(ta, tb, p, stream);
   }
   if (stats) {
@@ -514,10 +544,12 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
       return 1;
     }
     p.stats = *stats;
+    if (bn == 64) return launch_planes<3, false, 3, 64>(ta, tb, p, stream);
     return planes == 3 ? launch_planes<3, false, 3>(ta, tb, p, stream) : launch_planes<2, false, 3>(ta, tb, p, stream);
   }
   if (ksplit > 1 || ksplit == -1)
     return planes == 3 ? launch_planes<3, true>(ta, tb, p, stream) : launch_planes<2, true>(ta, tb, p, stream);
+  if (bn == 64) return launch_planes<3, false, 0, 64>(ta, tb, p, stream);
   return planes == 3 ? launch_planes<3, false>(ta, tb, p, stream) : launch_planes<2, false>(ta, tb, p, stream);
 }
 
