@@ -106,6 +106,7 @@ class HeadTrainer:
                   "vmb_mla_trainer_create")
         self.max_batch = int(max_batch)
         self._dp = None              # vmb_dp handle once enable_peer_step() has run
+        self.peer_step_error = None
         self._parity = 0
         self._comm_stream = None     # created by the first overlapped all-reduce
         self._tail = 0
@@ -141,7 +142,9 @@ class HeadTrainer:
         so that step() can use vmb_dp_adam_step: ONE kernel per rank that reduce-scatters the gradients over NVLink peer
         loads, applies Adam to the rank's slice and all-gathers the new parameters with peer stores (csrc/dp_adam.cu),
         instead of an NCCL all-reduce followed by the Adam kernel on every rank.  The Adam moments become sharded: each
-        rank keeps its slice.  Collective over the group; returns False (and changes nothing) for a single rank."""
+        rank keeps its slice.  Collective over the group; returns False (and changes nothing) for a single rank, or when
+        any rank cannot create / map the arenas (no peer access between the GPUs, IPC not permitted): then every rank
+        stays on the NCCL path together and `peer_step_error` says why."""
         import torch.distributed as dist
         if self._dp is not None:
             return True
@@ -151,12 +154,33 @@ class HeadTrainer:
         L = _lib.lib()
         handle = (C.c_char * 64)()
         dp = C.c_void_p()
+        error = None
         with torch.cuda.device(self.device):
-            check(L.vmb_dp_create(C.byref(dp), self.n_params, rank, world, C.cast(handle, C.c_void_p)), "vmb_dp_create")
+            # every rank takes part in every collective below whatever happens locally: a rank that fails reports it and
+            # ALL ranks fall back together (a half-connected group would hang in the first cross-GPU barrier)
+            try:
+                check(L.vmb_dp_create(C.byref(dp), self.n_params, rank, world, C.cast(handle, C.c_void_p)), "vmb_dp_create")
+            except B200Error as e:
+                error, dp = str(e), C.c_void_p()
             every = [None] * world
-            dist.all_gather_object(every, bytes(handle.raw), group=self.group)
-            blob = b"".join(every)
-            check(L.vmb_dp_connect(dp, C.cast(C.c_char_p(blob), C.c_void_p)), "vmb_dp_connect")
+            dist.all_gather_object(every, bytes(handle.raw) if dp.value else None, group=self.group)
+            if error is None and all(h is not None for h in every):
+                try:
+                    check(L.vmb_dp_connect(dp, C.cast(C.c_char_p(b"".join(every)), C.c_void_p)), "vmb_dp_connect")
+                except B200Error as e:
+                    error = str(e)
+            elif error is None:
+                error = "another rank could not create its arena"
+            ok = torch.tensor([0 if error else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if dp.value:
+                    L.vmb_dp_disconnect(dp)
+                dist.barrier(group=self.group)
+                if dp.value:
+                    L.vmb_dp_destroy(dp)
+                self.peer_step_error = error or "another rank could not map the arenas"
+                return False
             npad = (self.n_params + 3) // 4 * 4
             params = torch.as_tensor(_DeviceArray(L.vmb_dp_params(dp), self.n_params), device=self.device)
             params.copy_(self.params)

@@ -459,7 +459,7 @@ def leg_train(dev, rank, world, barrier, max_over_ranks):
         ms_serial = _timed(lambda: tr.step(x, labels, overlap=False), steps, barrier, max_over_ranks) / steps
         ms_overlap = _timed(lambda: tr.step(x, labels, overlap=True), steps, barrier, max_over_ranks) / steps
         # the product path: reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory (csrc/dp_adam.cu)
-        tr.enable_peer_step()
+        tr.enable_peer_step()       # False (every rank together) if the arenas cannot be mapped: the NCCL form stays
         for _ in range(5):
             tr.step(x, labels)
     l0 = _lib.lib().vmb_launch_count()
@@ -467,6 +467,7 @@ def leg_train(dev, rank, world, barrier, max_over_ranks):
     launches = _lib.lib().vmb_launch_count() - l0
     tr.peer_step_status()
     peer = tr._dp is not None
+    peer_err = tr.peer_step_error
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     phases = [0.0, 0.0, 0.0]
     loss = float(tr.loss.item())
@@ -492,7 +493,9 @@ def leg_train(dev, rank, world, barrier, max_over_ranks):
             "phase_ms": {"forward_backward": phases[0], "allreduce": phases[1], "adam": phases[2]},
             "gpu_launches_per_step": launches / steps, "final_loss": loss,
             "gradient_exchange": ("vmb_dp_adam_step: reduce-scatter + Adam + parameter all-gather in one kernel over NVLink "
-                                  "peer memory (CUDA IPC arenas), two flag barriers") if peer else "none (one rank)",
+                                  "peer memory (CUDA IPC arenas), two flag barriers") if peer else
+                                 ("none (one rank)" if world == 1 else
+                                  "NCCL all-reduce, tail overlapped (peer-memory step unavailable: %s)" % peer_err),
             "ms_per_step_nccl_allreduce_then_adam": ms_serial,
             "ms_per_step_nccl_allreduce_tail_overlapped": ms_overlap,
             "dtype": "fp32-equivalent (3-plane split bf16 on tcgen05)"}
@@ -688,10 +691,14 @@ def run_b200(args, rank, local_rank, world):
     # ---- compact legs for BASELINE.json configs[2..4] and the reference-named API
     legs = {}
     if not args.no_config_legs:
-        legs["batch8192"] = leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks)
-        legs["stream_1h"] = leg_stream_1h(dev, rank, world, barrier, max_over_ranks, vsd)
-        legs["train"] = leg_train(dev, rank, world, barrier, max_over_ranks)
-        legs["e2e_dropin"] = leg_dropin(dev, vsd, msd, wave_host, barrier, max_over_ranks, world)
+        for name, leg in (("batch8192", lambda: leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks)),
+                          ("stream_1h", lambda: leg_stream_1h(dev, rank, world, barrier, max_over_ranks, vsd)),
+                          ("train", lambda: leg_train(dev, rank, world, barrier, max_over_ranks)),
+                          ("e2e_dropin", lambda: leg_dropin(dev, vsd, msd, wave_host, barrier, max_over_ranks, world))):
+            try:
+                legs[name] = leg()
+            except Exception as e:  # noqa: BLE001 — a leg that fails must not take the headline line with it
+                legs[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
 
     if rank != 0:
         if world > 1:
