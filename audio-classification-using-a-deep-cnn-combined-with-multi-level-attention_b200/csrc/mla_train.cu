@@ -930,6 +930,36 @@ int run_tile(F f, TileOut o, cudaStream_t st, const char* what) {
 }
 
 // dW = A^T B over the rows: tall contraction, few output tiles -> split-K with atomic accumulation into a zeroed buffer
+// The weight-gradient GEMMs read the ROW-major planes (the ones the forward / dX GEMMs consume) as MN-major UMMA operands
+// (planes_gemm_mn): no transposed copy of any activation or gradient is written.  VMB_TRAIN_MN_DW=0, or the planes GEMM
+// switched off, brings back the transposed planes and the K-major kernel (A/B timing).
+bool mn_dw_enabled() {
+  static const bool env_on = [] {
+    const char* e = getenv("VMB_TRAIN_MN_DW");
+    return !(e && e[0] == '0');
+  }();
+  return env_on && vmb::planes_gemm_enabled();
+}
+
+// dW [M][ldo] = sum over rows r of a[r][m] b[r][n]: a_planes [K][kPl * a_cols], b_planes [K][kPl * b_cols]
+int gemm_dw_mn(const void* a_planes, int a_cols, const void* b_planes, int b_cols, float* out, long long ldo, int M, int N,
+               long long K, cudaStream_t st) {
+  if (cudaMemsetAsync(out, 0, size_t(M) * ldo * sizeof(float), st) != cudaSuccess) {
+    vmb::set_kernel_error("dW buffer clear failed");
+    return 1;
+  }
+  // one wave of (K slice, tile) work items, each slice at least four 32-row K-blocks long
+  const int mn = (M / 128) * (N / 128);
+  int ks = vmb::num_sms() / mn;
+  if (ks > K / 32 / 4) ks = int(K / 32 / 4);
+  if (ks < 1) ks = 1;
+  if (vmb::planes_gemm_mn(a_planes, a_cols, b_planes, b_cols, out, ldo, M, N, int(K), kPl, ks > 1 ? ks : -1, st)) {
+    vmb::set_kernel_error("%s", vmb::planes_gemm_last_error());
+    return 1;
+  }
+  return 0;
+}
+
 int gemm_dw(const void* at_planes, const void* bt_planes, float* out, long long ldo, int M, int N, long long K,
             cudaStream_t st) {
   if (cudaMemsetAsync(out, 0, size_t(M) * ldo * sizeof(float), st) != cudaSuccess) {
@@ -1164,6 +1194,8 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     return 0;
   };
   const bool fuse_stats = stats_in_gemm(T);
+  const bool mn_dw = mn_dw_enabled();   // weight-gradient GEMMs read the row-major planes: no transposed planes are written
+  auto tplanes = [&](__nv_bfloat16* pt) { return mn_dw ? static_cast<__nv_bfloat16*>(nullptr) : pt; };
   // Linear (+ bias) into `out` and the BatchNorm statistics of its first `cols` columns
   auto gemm_bn = [&](const void* a, const FcRef& fc, float* out, int k_pad, int cols, const BnRef& bn, cudaStream_t ss) {
     if (fuse_stats) return gemm_stats(a, fc.wp, fc.bias_pad, out, Hp, R, Hp, k_pad, statjob(bn, double(B) * cols), cols, ss);
@@ -1199,7 +1231,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     const int F_in = l == 0 ? h->emb_in : H;
     const int in_pad = l == 0 ? inpad : Hp;
     __nv_bfloat16* np = l == 0 ? h->xin_p : h->N_p[l];
-    __nv_bfloat16* npt = l == 0 ? h->xin_pt : h->N_pt[l];
+    __nv_bfloat16* npt = tplanes(l == 0 ? h->xin_pt : h->N_pt[l]);
     TRY(time_stats(in, ld_in, F_in, L.norm0, true, st));
     {
       FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
@@ -1217,7 +1249,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       const bool last = j == L.n_fc - 1;
       FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
                dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
-      TileOut o{h->A_p[l][j], h->A_pt[l][j], last ? h->E[l] : nullptr, Hp, nullptr, R, Rp, H, Hp};
+      TileOut o{h->A_p[l][j], tplanes(h->A_pt[l][j]), last ? h->E[l] : nullptr, Hp, nullptr, R, Rp, H, Hp};
       TRY(run_tile(f, o, st, "fc forward activation"));
       a = h->A_p[l][j];
     }
@@ -1253,7 +1285,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   if (att_pending) cudaStreamWaitEvent(st, h->ev_att, 0);   // join: the concatenation below reads every level's pooling
   // output layer
   {
-    TileOut o{h->Y_p, h->Y_pt, nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
+    TileOut o{h->Y_p, tplanes(h->Y_pt), nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
     TRY(run_tile(FIdentity{h->Y, h->ycols_pad}, o, st, "y split"));
   }
   TRY(gemm(h->Y_p, h->fc_out.wp, h->fc_out.bias_pad, h->O, Hp, B, Hp, h->ycols_pad, st));
@@ -1276,14 +1308,20 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   // The chain only has to wait (ev_dw) before the NEXT tile kernel overwrites G_pt, one dX GEMM and one reduction later.
   bool dw_pending = false;
   // dW (M x N, contraction over the rows) -> dst [rows_out][cols_out] of `grads`
-  auto dw_job = [&](const void* at, const void* bt, long long ldo, int M, int N, long long Kc, float* dst,
+  // operands of a dW GEMM in both forms: transposed planes (K-major kernel) and the row-major planes with their widths
+  struct DwOps { const void *at, *bt, *a; int a_cols; const void* b; int b_cols; };
+  auto dw_gemm = [&](const DwOps& ops, float* out, long long ldo, int M, int N, long long Kc, cudaStream_t s) {
+    return mn_dw ? gemm_dw_mn(ops.a, ops.a_cols, ops.b, ops.b_cols, out, ldo, M, N, Kc, s)
+                 : gemm_dw(ops.at, ops.bt, out, ldo, M, N, Kc, s);
+  };
+  auto dw_job = [&](const DwOps& ops, long long ldo, int M, int N, long long Kc, float* dst,
                     size_t dst_pitch, size_t width, size_t height) {
     cudaStream_t s = forked ? h->side : st;
     if (forked) {
       cudaEventRecord(h->ev_fork, st);
       cudaStreamWaitEvent(h->side, h->ev_fork, 0);
     }
-    int r = gemm_dw(at, bt, h->dWtmp, ldo, M, N, Kc, s);
+    int r = dw_gemm(ops, h->dWtmp, ldo, M, N, Kc, s);
     if (!r && cudaMemcpy2DAsync(dst, dst_pitch, h->dWtmp, size_t(ldo) * 4, width, height, cudaMemcpyDeviceToDevice, s) !=
                   cudaSuccess) {
       vmb::set_kernel_error("dW copy failed");
@@ -1311,10 +1349,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   }
   {
     // dO planes (+ transposed) and d(bias) = column sums
-    TileOut o{h->G_p, h->G_pt, nullptr, 0, grads + h->fc_out.b, B, Bp, K, Hp};
+    TileOut o{h->G_p, tplanes(h->G_pt), nullptr, 0, grads + h->fc_out.b, B, Bp, K, Hp};
     TRY(run_tile(FIdentity{h->dO, Hp}, o, st, "dO split"));
     // dW_fc [K][L*K] = dO^T [K x B] * Y^T [L*K x B]^T
-    TRY(dw_job(h->G_pt, h->Y_pt, h->ycols_pad, Hp, h->ycols_pad, Bp, grads + h->fc_out.w, size_t(h->ycols) * 4,
+    TRY(dw_job(DwOps{h->G_pt, h->Y_pt, h->G_p, Hp, h->Y_p, h->ycols_pad}, h->ycols_pad, Hp, h->ycols_pad, Bp,
+               grads + h->fc_out.w, size_t(h->ycols) * 4,
                size_t(h->ycols) * 4, K));
     // dY [B][L*K] = dO [B x K] * W_fc [K x L*K]
     TRY(gemm(h->G_p, h->fc_out.wtp, nullptr, h->dY, h->ycols_pad, B, h->ycols_pad, Hp, st));
@@ -1372,18 +1411,19 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     {
       FAttCombine f{ap, gv, gf, Hp, acc_v, acc_f, double(B) * K, grads + L.normv.g, grads + L.normv.b,
                     grads + L.normf.g, grads + L.normf.b};
-      TileOut o{gp, gpt, nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
+      TileOut o{gp, tplanes(gpt), nullptr, 0, grads + L.fcv.b, R, Rp, K, Hp};
       if (!own_side) before_g_overwrite();
       TRY(run_tile(f, o, s, "attention BN backward"));
     }
     // dWv [K][H] = dZ^T * E^T ; dE_att [R][H] = dZ * Wv
+    const DwOps att_ops{gpt, e_pt, gp, Hp, h->A_p[l][L.n_fc - 1], Hp};
     if (own_side) {
-      TRY(gemm_dw(gpt, e_pt, h->dWtmp2, Hp, Hp, Hp, Rp, s));
+      TRY(dw_gemm(att_ops, h->dWtmp2, Hp, Hp, Hp, Rp, s));
       if (!rc && cudaMemcpy2DAsync(grads + L.fcv.w, size_t(H) * 4, h->dWtmp2, size_t(Hp) * 4, size_t(H) * 4, K,
                                    cudaMemcpyDeviceToDevice, s) != cudaSuccess)
         rc = 1;
     } else {
-      TRY(dw_job(gpt, e_pt, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
+      TRY(dw_job(att_ops, Hp, Hp, Hp, Rp, grads + L.fcv.w, size_t(H) * 4, size_t(H) * 4, K));
     }
     if (own_side) {
       TRY(gemm(gp, L.fcv.wtp, nullptr, out_dA, Hp, R, Hp, Hp, s));     // joins the chain as one of two upstream gradients
@@ -1434,12 +1474,13 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
         TRY(vmb::check_launch("bn_time_backward_reduce_kernel"));
       }
       FBnBackward f{gi, acc, double(B) * H, grads + L.norms[j].g, grads + L.norms[j].b};
-      TileOut o{h->G_p, h->G_pt, nullptr, Hp, grads + fc.b, R, Rp, H, Hp};
+      TileOut o{h->G_p, tplanes(h->G_pt), nullptr, Hp, grads + fc.b, R, Rp, H, Hp};
       before_g_overwrite();
       TRY(run_tile(f, o, st, "fc BN backward"));
       // dW [H][n_in] = dU^T * A_prev^T ; dA_prev [R][n_in] = dU * W
       const __nv_bfloat16* prev_pt = j > 0 ? h->A_pt[l][j - 1] : (l == 0 ? h->xin_pt : h->N_pt[l]);
-      TRY(dw_job(h->G_pt, prev_pt, fc.n_in_pad, Hp, fc.n_in_pad, Rp, grads + fc.w, size_t(fc.n_in) * 4,
+      const __nv_bfloat16* prev_p = j > 0 ? h->A_p[l][j - 1] : (l == 0 ? h->xin_p : h->N_p[l]);
+      TRY(dw_job(DwOps{h->G_pt, prev_pt, h->G_p, Hp, prev_p, fc.n_in_pad}, fc.n_in_pad, Hp, fc.n_in_pad, Rp, grads + fc.w, size_t(fc.n_in) * 4,
                  size_t(fc.n_in) * 4, H));
       float* dprev = (da1 == h->dA) ? h->dB : h->dA;
       TRY(gemm_into_block(h->G_p, fc.wtp, dprev, fc.n_in_pad, l, j - 1, nullptr, st));   // j - 1 == -1: the level's norm0

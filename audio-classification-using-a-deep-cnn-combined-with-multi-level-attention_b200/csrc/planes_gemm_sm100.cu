@@ -65,6 +65,7 @@ struct PCfg {
 struct PlanesParams {
   int M, N;
   int num_kb;        // K / 32 (of one plane)
+  int a_plane_cols, b_plane_cols;   // MN-major operands: padded width of one plane of A / B
   int num_m_tiles, num_n_tiles;
   int ksplit;        // <= 1: none
   int relu;
@@ -93,7 +94,7 @@ __device__ __forceinline__ void store_split32(const float (&v)[32], __nv_bfloat1
   st_global_256(lo_dst + 16, l[8], l[9], l[10], l[11], l[12], l[13], l[14], l[15]);
 }
 
-template <int PLANES, bool ATOMIC, int EPI, int BN>
+template <int PLANES, bool ATOMIC, int EPI, int BN, bool MNMAJOR>
 __global__ void __launch_bounds__(kThreads, 1)
 planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const PlanesParams p) {
@@ -154,20 +155,39 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* dst = smem + stage * C::kStageBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (MNMAJOR) {
+            // operands stored [K rows][planes * width]: a plane tile is two boxes of {64 elements along M / N, 32 rows}
 #pragma unroll
-          for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_2d(dst + pl * kPlaneBytes, &tmap_a, &full_bar[stage], pl * plane_cols + kb * kBK, m_tile * kBM);
+            for (int pl = 0; pl < PLANES; ++pl)
 #pragma unroll
-          for (int pl = 0; pl < PLANES; ++pl)
-            tma_load_2d(dst + PLANES * kPlaneBytes + pl * C::kBPlaneBytes, &tmap_b, &full_bar[stage], pl * plane_cols + kb * kBK,
-                        n_tile * kBN);
+              for (int hh = 0; hh < kBM / 64; ++hh)
+                tma_load_2d(dst + pl * kPlaneBytes + hh * (64 * kBK * 2), &tmap_a, &full_bar[stage],
+                            pl * p.a_plane_cols + m_tile * kBM + hh * 64, kb * kBK);
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl)
+#pragma unroll
+              for (int hh = 0; hh < kBN / 64; ++hh)
+                tma_load_2d(dst + PLANES * kPlaneBytes + pl * C::kBPlaneBytes + hh * (64 * kBK * 2), &tmap_b, &full_bar[stage],
+                            pl * p.b_plane_cols + n_tile * kBN + hh * 64, kb * kBK);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_2d(dst + pl * kPlaneBytes, &tmap_a, &full_bar[stage], pl * plane_cols + kb * kBK, m_tile * kBM);
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_2d(dst + PLANES * kPlaneBytes + pl * C::kBPlaneBytes, &tmap_b, &full_bar[stage],
+                          pl * plane_cols + kb * kBK, n_tile * kBN);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    constexpr uint32_t idesc =
+        umma_idesc_bf16_f32(kBM, kBN) | (MNMAJOR ? (kUmmaIdescAMnMajor | kUmmaIdescBMnMajor) : 0u);
+    constexpr uint32_t kBoxBytes = 64 * kBK * 2;       // MN-major: one box of 64 elements x 32 rows
+    constexpr uint32_t kStep = MNMAJOR ? (16 * 128) >> 4 : 2;   // descriptor advance per 16-element K step
     // cross products (a plane, b plane), smallest magnitude first; hi * hi has its own accumulator
     constexpr int kCross = PLANES == 3 ? 5 : 2;
     constexpr int cross_a3[5] = {2, 1, 0, 1, 0}, cross_b3[5] = {0, 1, 2, 0, 1};
@@ -192,18 +212,20 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int q = 0; q < kCross; ++q) {
             const int pa = PLANES == 3 ? cross_a3[q] : cross_a2[q];
             const int pb = PLANES == 3 ? cross_b3[q] : cross_b2[q];
-            const uint64_t a_desc = umma_desc_kmajor_sw64(a0 + pa * kPlaneBytes);
-            const uint64_t b_desc = umma_desc_kmajor_sw64(b0 + pb * C::kBPlaneBytes);
+            const uint64_t a_desc = MNMAJOR ? umma_desc_mnmajor_sw128(a0 + pa * kPlaneBytes, kBoxBytes)
+                                            : umma_desc_kmajor_sw64(a0 + pa * kPlaneBytes);
+            const uint64_t b_desc = MNMAJOR ? umma_desc_mnmajor_sw128(b0 + pb * C::kBPlaneBytes, kBoxBytes)
+                                            : umma_desc_kmajor_sw64(b0 + pb * C::kBPlaneBytes);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (>>4 = 2) per 16-element K step
-              umma_bf16_ss(d_small, a_desc + 2 * k, b_desc + 2 * k, idesc, (first | q | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k)   // K-major: +32 bytes per 16-element K step; MN-major: +16 rows of 128 bytes
+              umma_bf16_ss(d_small, a_desc + kStep * k, b_desc + kStep * k, idesc, (first | q | k) != 0);
           }
           {
-            const uint64_t a_desc = umma_desc_kmajor_sw64(a0);
-            const uint64_t b_desc = umma_desc_kmajor_sw64(b0);
+            const uint64_t a_desc = MNMAJOR ? umma_desc_mnmajor_sw128(a0, kBoxBytes) : umma_desc_kmajor_sw64(a0);
+            const uint64_t b_desc = MNMAJOR ? umma_desc_mnmajor_sw128(b0, kBoxBytes) : umma_desc_kmajor_sw64(b0);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_ss(d_big, a_desc + 2 * k, b_desc + 2 * k, idesc, (first | k) != 0);
+              umma_bf16_ss(d_big, a_desc + kStep * k, b_desc + kStep * k, idesc, (first | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
@@ -408,9 +430,9 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 thread_local char g_perr[384] = "";
 
-template <int PLANES, bool ATOMIC, int EPI = 0, int BN = 128>
+template <int PLANES, bool ATOMIC, int EPI = 0, int BN = 128, bool MNMAJOR = false>
 int launch_planes(const CUtensorMap& ta, const CUtensorMap& tb, const PlanesParams& p, cudaStream_t stream) {
-  auto kern = planes_gemm_kernel<PLANES, ATOMIC, EPI, BN>;
+  auto kern = planes_gemm_kernel<PLANES, ATOMIC, EPI, BN, MNMAJOR>;
   static std::atomic<unsigned long long> attr_set{0};   // one bit per device: the attribute is per device
   constexpr int smem = PCfg<PLANES, BN>::kSmemBytes;
   if (device_needs_setup(attr_set)) {
@@ -551,6 +573,44 @@ static int planes_gemm_any(const void* a_planes, const void* b_planes, const flo
     return planes == 3 ? launch_planes<3, true>(ta, tb, p, stream) : launch_planes<2, true>(ta, tb, p, stream);
   if (bn == 64) return launch_planes<3, false, 0, 64>(ta, tb, p, stream);
   return planes == 3 ? launch_planes<3, false>(ta, tb, p, stream) : launch_planes<2, false>(ta, tb, p, stream);
+}
+
+// out [M][ldo] += sum_r A[r][m] B[r][n] over plane products: both operands stored ROW-major over the contraction index,
+// a_planes bf16 [K][planes * a_cols], b_planes bf16 [K][planes * b_cols] (the layout the forward / dX GEMMs consume), read
+// as MN-major UMMA operands — the weight-gradient GEMMs need no transposed copies of the activations and gradients.
+// M <= a_cols, N <= b_cols, both multiples of 128; K % 32 == 0; ksplit as in planes_gemm (> 1 or -1: out is added to).
+int planes_gemm_mn(const void* a_planes, int a_cols, const void* b_planes, int b_cols, float* out, long long ldo, int M,
+                   int N, int K, int planes, int ksplit, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBK != 0 || M % 128 != 0 || N % 128 != 0 || M > a_cols || N > b_cols || (planes != 2 && planes != 3) ||
+      (ksplit <= 1 && ksplit != -1)) {
+    snprintf(g_perr, sizeof g_perr, "planes_gemm_mn: bad shape (M=%d N=%d K=%d planes=%d ksplit=%d)", M, N, K, planes, ksplit);
+    return 1;
+  }
+  CUtensorMap ta, tb;
+  for (int which = 0; which < 2; ++which) {
+    const int cols = which ? b_cols : a_cols;
+    uint64_t dims[2] = {uint64_t(planes) * cols, uint64_t(K)};
+    uint64_t str[1] = {uint64_t(planes) * cols * 2};
+    uint32_t box[2] = {64, kBK};
+    if (make_tmap_bf16(which ? &tb : &ta, which ? b_planes : a_planes, 2, dims, str, box, 128)) {
+      snprintf(g_perr, sizeof g_perr, "planes_gemm_mn: %s", igemm_last_error());
+      return 1;
+    }
+  }
+  PlanesParams p{};
+  p.M = M;
+  p.N = N;
+  p.num_kb = K / kBK;
+  p.a_plane_cols = a_cols;
+  p.b_plane_cols = b_cols;
+  p.num_m_tiles = M / kBM;
+  p.num_n_tiles = N / 128;
+  p.ksplit = ksplit;
+  p.ldo = ldo;
+  p.out = out;
+  return planes == 3 ? launch_planes<3, true, 0, 128, true>(ta, tb, p, stream)
+                     : launch_planes<2, true, 0, 128, true>(ta, tb, p, stream);
 }
 
 int planes_gemm(const void* a_planes, const void* b_planes, const float* bias, float* out, long long ldo, int relu, int M,

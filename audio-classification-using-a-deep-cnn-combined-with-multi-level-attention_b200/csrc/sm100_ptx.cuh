@@ -181,6 +181,21 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
   d |= 4ull << 61;                               // layout type 4 = SWIZZLE_64B
   return d;
 }
+// MN-major operand (the M / N index is contiguous in memory, K strides): what a TMA box of {64 elements along M, K rows}
+// with SWIZZLE_128B leaves in shared memory — rows of 128 bytes = 64 consecutive M elements at one K, 8-row atoms of
+// 1024 B.  Canonical form (CUTLASS mma_traits_sm100: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 bf16): the stride
+// byte offset is the distance between 8-row K groups (1024 B), the leading byte offset the distance between the
+// 64-element M chunks (`lbo_bytes`: the size of one box).  A 16-element K step advances the start address by 16 rows.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+constexpr uint32_t kUmmaIdescAMnMajor = 1u << 15, kUmmaIdescBMnMajor = 1u << 16;
 // Instruction descriptor, kind::f16, A = B = bf16 (K-major), D = fp32, M x N tile.
 //   bits 4-5 D format (1 = f32)  bits 7-9 A format (1 = bf16)  bits 10-12 B format (1 = bf16)
 //   bit 15/16 A/B major (0 = K)  bits 17-22 N >> 3  bits 24-28 M >> 4
