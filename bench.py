@@ -688,9 +688,14 @@ def run_b200(args, rank, local_rank, world):
         h2.close()
     acc_ms = other["split"]
 
-    # ---- compact legs for BASELINE.json configs[2..4] and the reference-named API
+    # ---- compact legs for BASELINE.json configs[2..4] and the reference-named API.  They run LAST, after the headline
+    # line has been assembled, under a watchdog: a leg that hangs (they contain collectives) costs its own entry, not the
+    # line — on time-out rank 0 prints the line with what has finished and every rank leaves with exit code 0.
     legs = {}
-    if not args.no_config_legs:
+
+    def run_legs():
+        if args.no_config_legs:
+            return
         for name, leg in (("batch8192", lambda: leg_batch8192(pipe, wave_host, world, barrier, max_over_ranks)),
                           ("stream_1h", lambda: leg_stream_1h(dev, rank, world, barrier, max_over_ranks, vsd)),
                           ("train", lambda: leg_train(dev, rank, world, barrier, max_over_ranks)),
@@ -700,7 +705,36 @@ def run_b200(args, rank, local_rank, world):
             except Exception as e:  # noqa: BLE001 — a leg that fails must not take the headline line with it
                 legs[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
 
+    class Watchdog:
+        def __init__(self, seconds, on_timeout):
+            self.lock, self.done = threading.Lock(), False
+            self.timer = threading.Timer(seconds, self._fire)
+            self.timer.daemon = True
+            self.on_timeout = on_timeout
+
+        def _fire(self):
+            with self.lock:
+                if self.done:
+                    return
+                self.done = True
+                try:
+                    self.on_timeout()
+                finally:
+                    os._exit(0)
+
+        def __enter__(self):
+            self.timer.start()
+            return self
+
+        def __exit__(self, *exc):
+            with self.lock:
+                self.done = True
+            self.timer.cancel()
+            return False
+
     if rank != 0:
+        with Watchdog(args.legs_timeout + 10.0, lambda: None):
+            run_legs()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -774,6 +808,14 @@ def run_b200(args, rank, local_rank, world):
             "value": r["clips_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
             "sample": f"{r['sample_clips']} of the {args.clips} clips per pass, 3 timed passes after 1 warm-up "
                       f"(numpy float64 front end + torch CPU fp32 VGGish + head); host has {os.cpu_count()} CPUs"}
+
+    def emit_without_the_rest():
+        for name in ("batch8192", "stream_1h", "train", "e2e_dropin"):
+            legs.setdefault(name, {"error": f"not finished within {args.legs_timeout:.0f} s (leg watchdog)"})
+        emit(line)
+
+    with Watchdog(args.legs_timeout, emit_without_the_rest):
+        run_legs()
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -797,6 +839,8 @@ def main():
                     help="arithmetic of the VGGish body for the headline legs (fp16 and bf16 run at the same tensor rate)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0,
                     help="length of the back-to-back leg that measures the sustained regime (0 = skip)")
+    ap.add_argument("--legs-timeout", type=float, default=300.0,
+                    help="seconds the configs[2..4] / drop-in legs may take before the line is printed without them")
     ap.add_argument("--no-config-legs", action="store_true",
                     help="skip the batch8192 / stream_1h / train / e2e_dropin legs")
     args = ap.parse_args()
