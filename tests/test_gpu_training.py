@@ -227,6 +227,48 @@ def test_overlapped_all_reduce_matches_the_single_bucket():
     assert worst < 1e-5
 
 
+def test_peer_memory_optimizer_step_single_rank_arithmetic():
+    """vmb_dp_adam_step with world = 1 (no peer mapping needed, so it runs on the one-GPU test box): the barrier / reduce
+    / Adam / gather kernels against torch.optim.Adam over three steps with alternating gradient buffers, on a bucket
+    whose length is not a multiple of four (the padded tail must stay zero and harmless)."""
+    import ctypes as C
+    from b200 import _lib
+    from b200._lib import check, ptr, stream_ptr
+    L = _lib.lib()
+    n = 10007
+    handle = (C.c_char * 64)()
+    dp = C.c_void_p()
+    check(L.vmb_dp_create(C.byref(dp), n, 0, 1, C.cast(handle, C.c_void_p)), "vmb_dp_create")
+    params = grads = None
+    try:
+        params = torch.as_tensor(training._DeviceArray(L.vmb_dp_params(dp), n), device=DEV)
+        grads = [torch.as_tensor(training._DeviceArray(L.vmb_dp_grads(dp, i), n), device=DEV) for i in (0, 1)]
+        g = torch.Generator().manual_seed(3)
+        p0 = torch.randn(n, generator=g)
+        params.copy_(p0)
+        npad = (n + 3) // 4 * 4
+        m, v = torch.zeros(npad, device=DEV), torch.zeros(npad, device=DEV)
+        ref = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-3)
+        for step in range(1, 4):
+            gr = torch.randn(n, generator=g) * 0.02
+            grads[(step - 1) & 1].copy_(gr)
+            check(L.vmb_dp_adam_step(dp, (step - 1) & 1, ptr(m), ptr(v), 1e-3, 0.9, 0.999, 1e-8, 0.0, step, stream_ptr()),
+                  "vmb_dp_adam_step")
+            ref.grad = gr.clone()
+            opt.step()
+            torch.cuda.synchronize()
+            check(L.vmb_dp_status(dp), "vmb_dp_status")
+            assert float((params.cpu() - ref.detach()).abs().max()) < 5e-7, f"step {step}"
+        assert float(m[n:].abs().max()) == 0.0 and float(v[n:].abs().max()) == 0.0
+        b, e = C.c_longlong(0), C.c_longlong(0)
+        L.vmb_dp_slice(n, 1, 0, C.byref(b), C.byref(e))
+        assert (b.value, e.value) == (0, npad)
+    finally:
+        del params, grads
+        L.vmb_dp_destroy(dp)
+
+
 def _peer_worker(rank, world, port, out):
     import ctypes as C
     import os
