@@ -168,6 +168,10 @@ struct TileOut {
   float* col_sum;           // [cols] += sum over rows (atomic)   (may be null)
   long long rows, rows_pad;
   int cols, cols_pad;
+  // BatchNorm1d(T) batch statistics of the values this pass produces (channel = row % stats_T), accumulated from the
+  // tile in shared memory and finalised by the last block like bn_time_stats_kernel does: stats_T > 0 switches it on
+  StatJob stats = {};
+  int stats_T = 0;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
@@ -203,6 +207,7 @@ __device__ __forceinline__ void tile_body(F& f, const TileOut& o, int bx, int by
   const int r0 = by * kTile;
   const int c0 = bx * kTile;
   const int tmod = f.time_steps();
+  const bool need_tile = o.planes_t || o.col_sum || o.stats_T > 0;   // nothing else reads the shared-memory copy
   {
     const int c = c0 + 2 * tx;
 #pragma unroll
@@ -214,8 +219,10 @@ __device__ __forceinline__ void tile_body(F& f, const TileOut& o, int bx, int by
         if (c < o.cols) v0 = f(r, t, c);
         if (c + 1 < o.cols) v1 = f(r, t, c + 1);
       }
-      tile[ty + 8 * i][2 * tx] = v0;
-      tile[ty + 8 * i][2 * tx + 1] = v1;
+      if (need_tile) {
+        tile[ty + 8 * i][2 * tx] = v0;
+        tile[ty + 8 * i][2 * tx + 1] = v1;
+      }
       if (r < o.rows_pad && c < o.cols_pad) {
         if (o.planes)
           store_split_pair(v0, v1, o.planes + static_cast<long long>(r) * (static_cast<long long>(kPl) * o.cols_pad) + c,
@@ -224,7 +231,29 @@ __device__ __forceinline__ void tile_body(F& f, const TileOut& o, int bx, int by
       }
     }
   }
+  if (!need_tile) return;
   __syncthreads();
+  if (o.stats_T > 0) {
+    // per-row sums in fp32 (64 terms; columns past `cols` hold zeros), per-time-step sums of the tile in double
+    __shared__ double st_s[32];
+    if (threadIdx.x < 32) st_s[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < kTile && r0 + static_cast<int>(threadIdx.x) < o.rows) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < kTile; ++j) {
+        const float v = tile[threadIdx.x][j];
+        s1 += v;
+        s2 = fmaf(v, v, s2);
+      }
+      const int t = (r0 + static_cast<int>(threadIdx.x)) % o.stats_T;
+      atomicAdd(&st_s[2 * t], static_cast<double>(s1));
+      atomicAdd(&st_s[2 * t + 1], static_cast<double>(s2));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * o.stats_T) atomicAdd(o.stats.acc + threadIdx.x, st_s[threadIdx.x]);
+    if (last_block_done(o.stats.counter, gridDim.x * gridDim.y)) finalize_stats(o.stats);
+  }
   if (o.planes_t) {
     const int r = r0 + 2 * tx;
 #pragma unroll
@@ -1194,6 +1223,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     return 0;
   };
   const bool fuse_stats = stats_in_gemm(T);
+  static const bool estats_env = [] {
+    const char* e = getenv("VMB_TRAIN_ESTATS_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  const bool estats_fused = estats_env && T <= 16;   // norm0 statistics of levels >= 1 from the pass that writes the embedding
   const bool mn_dw = mn_dw_enabled();   // weight-gradient GEMMs read the row-major planes: no transposed planes are written
   auto tplanes = [&](__nv_bfloat16* pt) { return mn_dw ? static_cast<__nv_bfloat16*>(nullptr) : pt; };
   // Linear (+ bias) into `out` and the BatchNorm statistics of its first `cols` columns
@@ -1232,7 +1266,7 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
     const int in_pad = l == 0 ? inpad : Hp;
     __nv_bfloat16* np = l == 0 ? h->xin_p : h->N_p[l];
     __nv_bfloat16* npt = tplanes(l == 0 ? h->xin_pt : h->N_pt[l]);
-    TRY(time_stats(in, ld_in, F_in, L.norm0, true, st));
+    if (!(l > 0 && estats_fused)) TRY(time_stats(in, ld_in, F_in, L.norm0, true, st));
     {
       FBnAct f{in, ld_in, T, F_in, slotstat(L.norm0.slot), params + L.norm0.g, params + L.norm0.b, 0, 0.f, h->seed_dev, 0};
       TileOut o{np, npt, nullptr, 0, nullptr, R, Rp, F_in, in_pad};
@@ -1250,6 +1284,11 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       FBnAct f{h->U[l][j], Hp, T, H, slotstat(L.norms[j].slot), params + L.norms[j].g, params + L.norms[j].b, 1,
                dropout_p, h->seed_dev, unsigned(1 + l * kMaxFc + j)};
       TileOut o{h->A_p[l][j], tplanes(h->A_pt[l][j]), last ? h->E[l] : nullptr, Hp, nullptr, R, Rp, H, Hp};
+      if (last && l + 1 < h->n_levels && estats_fused) {
+        // the embedding this pass writes is the input of the next level's norm0: its batch statistics ride along
+        o.stats = statjob(h->lvl[l + 1].norm0, double(B) * H);
+        o.stats_T = T;
+      }
       TRY(run_tile(f, o, st, "fc forward activation"));
       a = h->A_p[l][j];
     }
