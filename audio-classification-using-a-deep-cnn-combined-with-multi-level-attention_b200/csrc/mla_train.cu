@@ -91,7 +91,8 @@ __device__ bool last_block_done(unsigned* counter, unsigned total) {
   return is_last;
 }
 
-// BatchNorm1d(T) on [rows = (b, t)][F]: channel = r % T.  grid = (chunks, T); block 256.
+// BatchNorm1d(T) on [rows = (b, t)][F]: channel = r % T.  grid = (chunks, T); block 256.  Rows of a multiple of four
+// floats at 16-byte aligned addresses are read as float4 with 32-bit index arithmetic.
 __global__ void __launch_bounds__(256)
 bn_time_stats_kernel(const float* __restrict__ x, long long ld, long long batch, int F, int T, StatJob job) {
   vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
@@ -99,13 +100,25 @@ bn_time_stats_kernel(const float* __restrict__ x, long long ld, long long batch,
   const int t = blockIdx.y;
   const long long per_t = batch * F;
   double s1 = 0, s2 = 0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_t;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long b = i / F;
-    const int c = static_cast<int>(i - b * F);
-    const float v = __ldg(x + (b * T + t) * ld + c);
-    s1 += v;
-    s2 += double(v) * v;
+  if (F % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && per_t < 0x7fffffffLL) {
+    const unsigned f4 = static_cast<unsigned>(F) / 4, n4 = static_cast<unsigned>(per_t / 4);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const unsigned b = i / f4, c = (i - b * f4) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * T + t) * ld + c));
+      const float a1 = (v.x + v.y) + (v.z + v.w);
+      const float a2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+      s1 += a1;
+      s2 += a2;
+    }
+  } else {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_t;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long b = i / F;
+      const int c = static_cast<int>(i - b * F);
+      const float v = __ldg(x + (b * T + t) * ld + c);
+      s1 += v;
+      s2 += double(v) * v;
+    }
   }
   __shared__ double r1[8], r2[8];
 #pragma unroll
@@ -422,13 +435,22 @@ struct AttParams {
   const float *gv, *bv, *gf, *bf;          // normv / normf affine parameters [T]
 };
 
-// y[clip][col0 + k] = sum_t cla * att / sum_t att; row_stats[r] = {max, sum} of the class softmax of row r
+// y[clip][col0 + k] = sum_t cla * att / sum_t att; row_stats[r] = {max, sum} of the class softmax of row r.
+// With yp != nullptr the same values also go out as the operand planes of the output Linear, yp [rows_pad][3 * yp_cols]
+// (the separate split pass over y is not launched); the grid then covers the padded rows, which are written as zeros.
 __global__ void __launch_bounds__(256)
-att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int col0, float* __restrict__ row_stats) {
+att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int col0, float* __restrict__ row_stats,
+                   __nv_bfloat16* __restrict__ yp, int yp_cols, long long batch) {
   vmb::pdl_launch_dependents();   // programmatic dependent launch: see sm100_ptx.cuh
   vmb::pdl_wait();
   __shared__ float rmax[16], rsum[16], sa_v[16], sb_v[16], sa_f[16], sb_f[16];
   const long long clip = blockIdx.x;
+  if (clip >= batch) {   // padding row of the planes (only reached with yp != nullptr)
+    __nv_bfloat16* row = yp + clip * (static_cast<long long>(kPl) * yp_cols) + col0;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x)
+      for (int pl = 0; pl < kPl; ++pl) row[pl * yp_cols + k] = __float2bfloat16_rn(0.f);
+    return;
+  }
   const float* zc = a.z + clip * a.T * a.ldz;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < a.T) {
@@ -461,7 +483,16 @@ att_forward_kernel(AttParams a, float* __restrict__ y, long long ystride, int co
       num = fmaf(cla, att, num);
       den += att;
     }
-    y[clip * ystride + col0 + k] = num / den;
+    const float val = num / den;
+    y[clip * ystride + col0 + k] = val;
+    if (yp) {
+      __nv_bfloat16 hi, mid, lo;
+      split_bf16(val, hi, mid, lo);
+      __nv_bfloat16* row = yp + clip * (static_cast<long long>(kPl) * yp_cols) + col0 + k;
+      row[0] = hi;
+      row[yp_cols] = mid;
+      row[2 * yp_cols] = lo;
+    }
   }
 }
 
@@ -1311,8 +1342,10 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
       TRY(vmb::check_launch("bn_running_only_kernel"));
       AttParams ap{h->Z[l], Hp, K, T, slotstat(L.normv.slot), params + L.normv.g, params + L.normv.b,
                    params + L.normf.g, params + L.normf.b};
-      vmb::launch_pdl(att_forward_kernel, dim3(static_cast<unsigned>(B)), dim3(256), 0, as, ap, h->Y, h->ycols_pad, l * K,
-                      h->row_stats[l]);
+      // with row-major planes only (mn_dw) the pooling kernel writes the output Linear's operand planes itself
+      vmb::launch_pdl(att_forward_kernel, dim3(static_cast<unsigned>(mn_dw ? Bp : B)), dim3(256), 0, as, ap, h->Y,
+                      static_cast<long long>(h->ycols_pad), l * K, h->row_stats[l],
+                      mn_dw ? h->Y_p : static_cast<__nv_bfloat16*>(nullptr), h->ycols_pad, B);
       vmb::count_launch();
       TRY(vmb::check_launch("att_forward_kernel"));
     }
@@ -1323,8 +1356,8 @@ int train_phases(int phases, vmb_mla_trainer* h, const float* params, float* run
   }
   if (att_pending) cudaStreamWaitEvent(st, h->ev_att, 0);   // join: the concatenation below reads every level's pooling
   // output layer
-  {
-    TileOut o{h->Y_p, tplanes(h->Y_pt), nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
+  if (!mn_dw) {
+    TileOut o{h->Y_p, h->Y_pt, nullptr, 0, nullptr, B, Bp, h->ycols, h->ycols_pad};
     TRY(run_tile(FIdentity{h->Y, h->ycols_pad}, o, st, "y split"));
   }
   TRY(gemm(h->Y_p, h->fc_out.wp, h->fc_out.bias_pad, h->O, Hp, B, Hp, h->ycols_pad, st));
