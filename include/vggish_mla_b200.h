@@ -226,7 +226,13 @@ int vmb_mla_forward_fp32(vmb_mla_t* handle, const float* emb_dev, long long batc
  *     nn.BatchNorm1d does (momentum 0.1, unbiased variance).
  * vmb_mla_train_step zeroes `grads` and `loss`, then writes d(loss)/d(params) of THIS rank's batch into grads (ready
  * for one flat NCCL all-reduce across data-parallel ranks) and the mean loss into *loss_dev.  scores_dev (optional)
- * receives the train-mode outputs [batch][K].  Dropout uses a counter-based generator keyed by (seed, layer, element). */
+ * receives the train-mode outputs [batch][K].  Dropout uses a counter-based generator keyed by (seed, layer, element).
+ * The first vmb_mla_train_step of a handle launches its kernels one by one; from the second call on the whole step —
+ * ~47 kernels, memsets and the fork / join of the handle's side streams — is replayed as ONE CUDA graph on a stream
+ * owned by the handle, ordered after / before `stream` by events.  x / labels are copied into staging buffers owned by
+ * the handle first and the seed is written to device memory, so any input addresses and any seed may follow; a distinct
+ * (params, running, grads, loss, scores, batch, dropout_p) captures its own graph (four are kept).  Environment
+ * VMB_TRAIN_GRAPH=0 keeps the eager launches; the results are the same either way. */
 long long vmb_mla_train_param_count(int n_levels, const int* n_fc, int emb_in, int hidden, int n_classes, int t_steps,
                                     long long* n_running_out);
 int vmb_mla_trainer_create(vmb_mla_trainer_t** handle, int n_levels, const int* n_fc, int emb_in, int hidden,
