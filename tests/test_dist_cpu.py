@@ -1,7 +1,8 @@
 """world_size-2 gloo tests (CPU): the host-side logic of the multi-GPU paths.
    * inference: contiguous batch shards, results gathered in rank order == unsharded result (no collective on the
      data path; the gather here is only the test's way of comparing)
-   * head training: flat gradient bucket layout + ONE all-reduce(SUM) / world == average of per-shard gradients
+   * head training: flat gradient bucket layout + ONE all-reduce(SUM) / world == average of per-shard gradients; the
+     sharded optimiser step (reduce-scatter + Adam + all-gather over the library's slice partition) == all-reduce + Adam
 The arithmetic on each rank is the CPU oracle (this container has no GPU); what is under test is the sharding,
 packing and collective plumbing that the GPU ranks use unchanged."""
 import os
@@ -54,10 +55,36 @@ def _worker(rank, world, port, out_dir):
     for key, shape, off in p_layout:
         bucket[off:off + grads[key].numel()] = grads[key].reshape(-1)
     assert all(".fcf." not in key for key, _, _ in p_layout)
+    local = bucket.clone()
     dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
     bucket /= world
+    # ---- the sharded optimiser step (csrc/dp_adam.cu) in the library's own partition (vmb_dp_slice): every rank sums ITS
+    # slice of all ranks' gradients in rank order, applies Adam to the slice, and the slices are gathered into every
+    # replica — the same parameters as all-reduce + Adam on every rank
+    import ctypes as C
+    from b200 import _lib
+    b, e = C.c_longlong(0), C.c_longlong(0)
+    _lib.lib().vmb_dp_slice(n_p, world, rank, C.byref(b), C.byref(e))
+    npad = (n_p + 3) // 4 * 4
+    everyone = [torch.zeros(npad) for _ in range(world)]
+    padded = torch.zeros(npad)
+    padded[:n_p] = local
+    dist.all_gather(everyone, padded)                       # stands in for the peer loads
+    params0 = torch.cat([sd[key].reshape(-1) for key, _, _ in p_layout] + [torch.zeros(npad - n_p)])
+    mine = torch.zeros(e.value - b.value)
+    for r in range(world):
+        mine += everyone[r][b.value:e.value]
+    new_slice = train_torch.adam_update(params0[b.value:e.value], mine / world)
+    slices = [None] * world
+    dist.all_gather_object(slices, (b.value, e.value, new_slice))      # stands in for the peer stores
+    sharded = torch.zeros(npad)
+    for lo_, hi_, sl in slices:
+        sharded[lo_:hi_] = sl
+    replicated = train_torch.adam_update(params0[:n_p], bucket)
     if rank == 0:
-        torch.save({"scores": torch.cat(parts), "bucket": bucket}, os.path.join(out_dir, "rank0.pt"))
+        torch.save({"scores": torch.cat(parts), "bucket": bucket, "sharded": sharded[:n_p], "replicated": replicated,
+                    "slices": [(lo_, hi_) for lo_, hi_, _ in slices], "npad": npad},
+                   os.path.join(out_dir, "rank0.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,6 +112,10 @@ def test_two_rank_gloo(tmp_path):
         for key, shape, off in p_layout:
             want[off:off + grads[key].numel()] += grads[key].reshape(-1) / world
     assert torch.allclose(got["bucket"], want, rtol=1e-4, atol=1e-6)      # thread counts differ between processes
+    # sharded optimiser step == all-reduce + Adam on every rank; the slices tile the padded bucket in rank order
+    assert got["slices"][0][0] == 0 and got["slices"][-1][1] == got["npad"]
+    assert all(a[1] == b[0] for a, b in zip(got["slices"], got["slices"][1:]))
+    assert torch.allclose(got["sharded"], got["replicated"], rtol=0, atol=1e-7)
     # local BatchNorm statistics: the data-parallel average is NOT the single-process full-batch gradient (H6)
     _, _, full = train_torch.head_step(sd, x, labels, conf)
     key, shape, off = p_layout[2]
