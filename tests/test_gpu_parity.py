@@ -12,6 +12,7 @@ Tolerances (BASELINE.json north_star):
   * mAP on the fixed synthetic label set (SURVEY 8d's recipe): identical to 3 decimals for the benchmarked (fp16) mode
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -471,7 +472,8 @@ def test_head_fused_epilogues_are_bit_identical(K, conf, emb_in, seed):
             n_plain = L.vmb_launch_count() - n0
             torch.cuda.synchronize()
             assert torch.equal(fused, plain), f"K={K} conf={conf} batch={batch}"
-            assert n_fused < n_plain
+            # (with VMB_PLANES_GEMM=0 the fused epilogues do not exist and both runs take the separate kernels)
+            assert n_fused < n_plain or (os.environ.get("VMB_PLANES_GEMM") == "0" and n_fused == n_plain)
         print(f"head {conf} K={K}: {n_fused} launches fused, {n_plain} as separate kernels")
     finally:
         L.vmb_mla_fuse_enable(-1)
